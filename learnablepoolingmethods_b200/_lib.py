@@ -1,0 +1,64 @@
+"""ctypes binding of liblpm_b200.so (the C-ABI declared in include/lpm_b200.h).
+
+The library is built in-tree by `learnablepoolingmethods_b200.build`.  There is no fallback: if the
+shared object is missing or a call fails, a `LpmError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblpm_b200.so")
+
+
+class LpmError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_mn", C.c_int), ("lda", C.c_longlong), ("a_batch_stride", C.c_longlong),
+        ("B", C.c_void_p), ("b_mn", C.c_int), ("ldb", C.c_longlong), ("b_batch_stride", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("splits", C.c_int),
+        ("force_bn", C.c_int),
+        ("out", C.c_void_p), ("out_f32", C.c_int), ("ldc", C.c_longlong),
+        ("out_batch_stride", C.c_longlong), ("out_split_stride", C.c_longlong),
+        ("bias", C.c_void_p), ("row_scale", C.c_void_p), ("row_scale_batch_stride", C.c_longlong),
+        ("relu", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float),
+        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load liblpm_b200.so (building is a separate, explicit step)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LpmError(
+            f"{LIB_PATH} not found: build it with `python -m learnablepoolingmethods_b200.build` "
+            "(there is no CPU or PyTorch fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.lpm_last_error.restype = C.c_char_p
+    lib.lpm_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().lpm_last_error().decode("utf-8", "replace")
+        raise LpmError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr() -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,339 @@
+// Generic fp16 x fp16 -> fp32 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma with
+// TMEM accumulators (double buffered) -> fused epilogue.  Persistent, warp specialised:
+//   warp 0   : TMA producer (one lane)
+//   warp 1   : TMEM allocator + MMA issuer (one lane)
+//   warps 2-5: epilogue (TMEM -> registers -> bias / row-scale / ReLU / row statistics -> global)
+// Either operand may be K-major or MN-major in memory, so NN / NT / TN products (forward, dX, dW)
+// need no transposes.  Batched (3-D tensor maps) and split-K (fp32 partials) variants included.
+//
+// Replaces the tf.matmul / tf.layers.dense / slim.fully_connected call sites of the hot path:
+//   frame_level_models.py:2319,2347  transformer_utils.py:559-561,583-585,701-711
+//   video_level_models.py:86-114 and their autodiff transposes.
+#include "lpm_common.cuh"
+#include "lpm_kernels.h"
+
+namespace lpm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int batch, splits;
+  int m_tiles, n_tiles;
+  int kb_total, kb_per_split;
+  int a_batched, b_batched;
+  // epilogue
+  void* out;
+  int out_f32;
+  long long ldc, out_batch_stride, out_split_stride;
+  const float* bias;
+  const float* row_scale;
+  long long row_scale_batch_stride;
+  int relu;
+  int accumulate;
+  float alpha;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmKernelParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_per_batch * p.batch * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int mt = t % p.m_tiles; t /= p.m_tiles;
+        const int nt = t % p.n_tiles; t /= p.n_tiles;
+        const int bz = t % p.batch;   t /= p.batch;
+        const int sp = t;
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int za = p.a_batched ? bz : 0, zb = p.b_batched ? bz : 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (A_MN == 0) {
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, za);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_3d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, za);
+          }
+          if (B_MN == 0) {
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * BK, n0, zb);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK, zb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int sp = tile / (tiles_per_batch * p.batch);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(sa + ks * 2048, 8192, 1024)
+                                        : umma_smem_desc(sa + ks * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + ks * 2048, 8192, 1024)
+                                        : umma_smem_desc(sb + ks * 32, 16, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int quarter = warp & 3;  // TMEM sub-partition this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int mt = t % p.m_tiles; t /= p.m_tiles;
+      const int nt = t % p.n_tiles; t /= p.n_tiles;
+      const int bz = t % p.batch;   t /= p.batch;
+      const int sp = t;
+      const int row = mt * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float rs = (p.row_scale != nullptr && row_ok)
+                           ? __ldg(p.row_scale + (long long)bz * p.row_scale_batch_stride + row) * p.alpha
+                           : p.alpha;
+      const long long obase = (long long)sp * p.out_split_stride + (long long)bz * p.out_batch_stride +
+                              (long long)row * p.ldc;
+      float s_sum = 0.f, s_sq = 0.f;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nt * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]) * rs;
+          if (p.bias != nullptr && col0 + i < p.N) x += __ldg(p.bias + col0 + i);
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[i] = x;
+        }
+        if (p.stat_sum != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) { s_sum += v[i]; s_sq += v[i] * v[i]; }
+        }
+        if (p.out != nullptr && row_ok) {
+          const bool full = (col0 + 32 <= p.N);
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + obase + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 w = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                float4* dst = reinterpret_cast<float4*>(o) + i;
+                if (p.accumulate) { float4 old = *dst; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+                *dst = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = p.accumulate ? o[i] + v[i] : v[i];
+            }
+          } else {
+            __half* o = reinterpret_cast<__half*>(p.out) + obase + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+                w.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+                w.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+                w.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+                reinterpret_cast<uint4*>(o)[i] = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = __float2half_rn(v[i]);
+            }
+          }
+        }
+      }
+      if (p.stat_sum != nullptr && row_ok) {
+        const long long si = ((long long)(sp * p.batch + bz) * p.n_tiles + nt) * p.M + row;
+        p.stat_sum[si] = s_sum;
+        p.stat_sq[si] = s_sq;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launcher
+// ----------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, cudaStream_t st) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_f16_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.batch * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, p);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+template <int BN, int STAGES>
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+                          const GemmKernelParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, 0, 0>(ta, tb, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, 0, 1>(ta, tb, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, 1, 0>(ta, tb, p, st);
+  return launch_gemm<BN, STAGES, 1, 1>(ta, tb, p, st);
+}
+
+int gemm_pick_bn(int N) {
+  if (N >= 256 || N > 192) return 256;
+  if (N > 64) return 128;
+  return 64;
+}
+
+int gemm_f16(const GemmArgs& g, cudaStream_t st) {
+  LPM_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0, "gemm: bad dims M=%d N=%d K=%d batch=%d", g.M, g.N, g.K, g.batch);
+  LPM_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (TMA 16B strides), got %lld %lld", g.lda, g.ldb);
+  LPM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0, "gemm: A/B must be 16B aligned");
+  LPM_REQUIRE(g.a_batch_stride % 8 == 0 && g.b_batch_stride % 8 == 0, "gemm: batch strides must be multiples of 8");
+  const int BN = g.force_bn ? g.force_bn : gemm_pick_bn(g.N);
+  LPM_REQUIRE(BN == 256 || BN == 128 || BN == 64, "gemm: unsupported BN %d", BN);
+
+  GemmKernelParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.m_tiles = (g.M + BM - 1) / BM;
+  p.n_tiles = (g.N + BN - 1) / BN;
+  p.kb_total = (g.K + BK - 1) / BK;
+  int splits = g.splits > 0 ? g.splits : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  LPM_REQUIRE(p.splits == 1 || (g.out_f32 && g.out_split_stride > 0 && !g.bias && !g.relu && !g.stat_sum),
+              "gemm: split-K needs fp32 partial output with a split stride and a plain epilogue");
+  p.a_batched = g.a_batch_stride != 0; p.b_batched = g.b_batch_stride != 0;
+  p.out = g.out; p.out_f32 = g.out_f32; p.ldc = g.ldc; p.out_batch_stride = g.out_batch_stride;
+  p.out_split_stride = g.out_split_stride;
+  p.bias = g.bias; p.row_scale = g.row_scale; p.row_scale_batch_stride = g.row_scale_batch_stride;
+  p.relu = g.relu; p.accumulate = g.accumulate; p.alpha = g.alpha;
+  p.stat_sum = g.stat_sum; p.stat_sq = g.stat_sq;
+
+  CUtensorMap ta, tb;
+  int rc;
+  // A: K-major = memory [M][K]; MN-major = memory [K][M]
+  if (!g.a_mn) rc = make_tmap_3d(&ta, g.A, 2, g.K, g.M, p.a_batched ? g.batch : 1, g.lda, g.a_batch_stride, BK, BM);
+  else         rc = make_tmap_3d(&ta, g.A, 2, g.M, g.K, p.a_batched ? g.batch : 1, g.lda, g.a_batch_stride, 64, BK);
+  if (rc) return rc;
+  if (!g.b_mn) rc = make_tmap_3d(&tb, g.B, 2, g.K, g.N, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, BK, BN);
+  else         rc = make_tmap_3d(&tb, g.B, 2, g.N, g.K, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, 64, BK);
+  if (rc) return rc;
+
+  if (BN == 256) return dispatch_major<256, 4>(g.a_mn, g.b_mn, ta, tb, p, st);
+  if (BN == 128) return dispatch_major<128, 6>(g.a_mn, g.b_mn, ta, tb, p, st);
+  return dispatch_major<64, 8>(g.a_mn, g.b_mn, ta, tb, p, st);
+}
+
+int gemm_effective_splits(int K, int splits) {
+  const int kb_total = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  const int per = (kb_total + splits - 1) / splits;
+  return (kb_total + per - 1) / per;
+}
+
+}  // namespace lpm
