@@ -65,6 +65,99 @@ int lpm_gemm_tile_n(int N);
 /* Number of non-empty K splits the kernel will use. */
 int lpm_gemm_splits(int K, int requested_splits);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split-K reduction:  out[r][c] = act(alpha * sum_s part[s][r][c] + bias[c]) -> fp32 and/or fp16.
+ * Completes the hidden projection (frame_level_models.py:2319,2329-2334) and split-K weight
+ * gradients.  n = rows*cols elements per split, splits are split_stride elements apart.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols,
+                      const float* bias, int relu, float alpha, int accumulate, float* out_f32,
+                      void* out_f16, lpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame sampling + input batch norm.
+ *   lpm_sample_bn_stats : per-feature sum / sum-of-squares partials of the uniformly sampled frames
+ *                         (model_utils.py:101-122 gather; frame_level_models.py:2265-2271 statistics).
+ *                         partial must hold lpm_sample_stats_blocks()*2*F floats.
+ *   lpm_sample_bn_apply : y[b*T+i][:] = fp16(x[b, idx(b,i), :] * scale + shift), idx = int32(fl32(i/T)*nf).
+ * x: fp32 [B][max_frames][F] (already L2-normalised by the caller, train.py:264); num_frames int32 [B].
+ * ------------------------------------------------------------------------------------------- */
+int lpm_sample_stats_blocks(void);
+int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
+                        float* partial, lpm_stream_t stream);
+int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
+                        const float* scale, const float* shift, void* y_f16, lpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * slim.batch_norm finalisation (eps 1e-3, decay 0.999 passed by the caller): reduces P partial
+ * (sum, sumsq) rows (pstride floats apart) over `count` samples into the folded affine
+ * y = x*scale + shift, updates the moving statistics (Bessel-corrected variance when bessel!=0),
+ * or (training==0) folds the moving statistics.  frame_level_models.py:2266,2784; slim semantics.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
+                           const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                           float decay, float eps, int bessel, int training, float* scale, float* shift,
+                           float* save_mean, float* save_rstd, lpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused NetVLAD pooling forward (K1): soft-assignment + residual aggregation + norms.
+ * frame_level_models.py:2775-2822 (NetVLAD.forward) for one modality.
+ *   x            fp16 [B][T][D] (row stride ldx, video stride x_batch_stride), the batch-normed frames
+ *   wc           fp16 [D][K] cluster_weights (row stride ldw)
+ *   logit_scale/shift  fp32 [K]: cluster_bn folded affine, or (1, cluster_biases)
+ *   centers_t    fp32 [K][D]: cluster_weights2 transposed
+ *   valid_frames int32 [B] or NULL: frames t >= valid_frames[b] get zero assignment (masked mode)
+ *   z            fp16 [B][K][D]  un-normalised cluster-major descriptor V^T
+ *   rscale       fp32 [B][K]     vlad[b,k,:] = z[b,k,:]*rscale[b,k]  (intra-norm x global norm)
+ *   a_sum        fp32 [B][K] or NULL;  assign fp16 [B][T][K] or NULL (saved for the backward)
+ * Limits: T <= 256, D % 64 == 0, K % 8 == 0, K <= 256.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
+                         const float* logit_scale, const float* logit_shift, const float* centers_t,
+                         const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
+                         float* a_sum, void* assign, lpm_stream_t stream);
+/* vlad = z * rscale as fp32: d_major!=0 -> [B][D*K] (reference flatten, :2821), else [B][K][D]. */
+int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
+                         lpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention core: out = softmax(scale*QK^T [*key_scale + key_shift]) V per (sample, head).
+ * transformer_utils.py:563-581 (V1) and :641-664 (V2, logits batch norm = per-key affine).
+ *   qkv fp16 [B*L][ld] with q | k | v blocks of Dm columns; head h = columns [h*depth, (h+1)*depth).
+ *   depth = Dm/H in {8,16}; L % 16 == 0.  lse fp32 [B][H][L] or NULL.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_mha_core_fwd(const void* qkv, long long ld, int B, int L, int Dm, int H, float scale,
+                     const float* key_scale, const float* key_shift, void* out, long long ldo, float* lse,
+                     lpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Joint-axis layer norm with fused residual (tf.contrib.layers.layer_norm, begin_norm_axis=1):
+ *   u = a + b*b_row_scale (written back over a, fp16);  y = (u-mean_b)*rstd_b*gamma[d] + beta[d].
+ * transformer_utils.py:406-411,712-713.  partial: B*64 floats; save_mean_rstd: [B][2] or NULL.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, int B, int rows, int D,
+                            long long a_stride, long long b_stride, const float* gamma, const float* beta,
+                            float eps, void* y, long long y_stride, float* partial, float* save_mean_rstd,
+                            lpm_stream_t stream);
+
+/* Context gating (frame_level_models.py:2342-2368): act * sigmoid(BN_batch(g - diag*act)). */
+int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
+                   const float* beta, float* moving_mean, float* moving_var, float decay, float eps,
+                   int training, float* out_f32, void* out_f16, float* save_mean, float* save_rstd,
+                   lpm_stream_t stream);
+
+/* MoE mixing (video_level_models.py:116-126): logits fp32 [B][ld] = [gates V*(M+1) | experts V*M]. */
+int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, float* pred, lpm_stream_t stream);
+
+/* CrossEntropyLoss (losses.py:44-51): labels uint8 [B][V]; row_loss [B]; loss scalar = mean_b. */
+int lpm_xent_fwd(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss,
+                 lpm_stream_t stream);
+
+/* fp32 -> fp16 2-D copy with zero column padding (parameter shadows) and fp32 transpose. */
+int lpm_cast_f32_to_f16(const float* src, long long ld_src, int rows, int cols, void* dst, long long ld_dst,
+                        int cols_dst, lpm_stream_t stream);
+int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,4 +108,116 @@ int lpm_gemm_tile_n(int N) { return gemm_pick_bn(N); }
 
 int lpm_gemm_splits(int K, int requested_splits) { return gemm_effective_splits(K, requested_splits); }
 
+#define ST(s) static_cast<cudaStream_t>(s)
+#define H16(p) reinterpret_cast<__half*>(p)
+#define CH16(p) reinterpret_cast<const __half*>(p)
+#define DEVCHK() do { if (int rc_ = check_device()) return rc_; } while (0)
+
+int lpm_splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols,
+                      const float* bias, int relu, float alpha, int accumulate, float* out_f32,
+                      void* out_f16, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(part && splits > 0 && n > 0 && cols > 0, "lpm_splitk_reduce: bad arguments");
+  return splitk_reduce(part, splits, split_stride, n, cols, bias, relu, alpha, accumulate, out_f32, H16(out_f16), ST(stream));
+}
+
+int lpm_sample_stats_blocks(void) { return sample_stats_blocks(); }
+
+int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
+                        float* partial, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && num_frames && partial && B > 0 && T > 0 && max_frames > 0, "lpm_sample_bn_stats: bad arguments");
+  return sample_stats(x, num_frames, B, max_frames, F, T, partial, ST(stream));
+}
+
+int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
+                        const float* scale, const float* shift, void* y_f16, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply: bad arguments");
+  return sample_apply(x, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), ST(stream));
+}
+
+int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
+                           const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                           float decay, float eps, int bessel, int training, float* scale, float* shift,
+                           float* save_mean, float* save_rstd, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(scale && shift && C > 0, "lpm_batchnorm_finalize: bad arguments");
+  LPM_REQUIRE(training ? (psum && psq && P > 0 && count > 0) : (moving_mean && moving_var),
+              "lpm_batchnorm_finalize: training needs partial sums, inference needs moving statistics");
+  return bn_finalize(psum, psq, P, pstride, C, count, gamma, beta, moving_mean, moving_var, decay, eps, bessel,
+                     training, scale, shift, save_mean, save_rstd, ST(stream));
+}
+
+int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
+                         const float* logit_scale, const float* logit_shift, const float* centers_t,
+                         const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
+                         float* a_sum, void* assign, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && wc && logit_scale && logit_shift && centers_t && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
+  return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, centers_t,
+                          valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), ST(stream));
+}
+
+int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
+                         lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(z && rscale && out, "lpm_netvlad_finalize: null pointer");
+  return vlad_finalize(CH16(z), rscale, B, K, D, d_major, out, ST(stream));
+}
+
+int lpm_mha_core_fwd(const void* qkv, long long ld, int B, int L, int Dm, int H, float scale,
+                     const float* key_scale, const float* key_shift, void* out, long long ldo, float* lse,
+                     lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(qkv && out && B > 0 && H > 0, "lpm_mha_core_fwd: bad arguments");
+  return mha_fwd(CH16(qkv), ld, B, L, Dm, H, scale, key_scale, key_shift, H16(out), ldo, lse, ST(stream));
+}
+
+int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, int B, int rows, int D,
+                            long long a_stride, long long b_stride, const float* gamma, const float* beta,
+                            float eps, void* y, long long y_stride, float* partial, float* save_mean_rstd,
+                            lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(a && gamma && beta && y && partial && B > 0 && rows > 0, "lpm_layernorm_joint_fwd: bad arguments");
+  return layernorm_joint(H16(a), CH16(b), b_row_scale, B, rows, D, a_stride, b_stride, gamma, beta, eps, H16(y),
+                         y_stride, partial, save_mean_rstd, ST(stream));
+}
+
+int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
+                   const float* beta, float* moving_mean, float* moving_var, float decay, float eps,
+                   int training, float* out_f32, void* out_f16, float* save_mean, float* save_rstd,
+                   lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(act && g && gamma && beta && moving_mean && moving_var && out_f32, "lpm_gating_fwd: null pointer");
+  return gating_fwd(act, g, B, H, wg_diag, gamma, beta, moving_mean, moving_var, decay, eps, training, out_f32,
+                    H16(out_f16), save_mean, save_rstd, ST(stream));
+}
+
+int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, float* pred, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(logits && pred && B > 0 && V > 0 && M > 0, "lpm_moe_mix_fwd: bad arguments");
+  return moe_mix(logits, ld, B, V, M, pred, ST(stream));
+}
+
+int lpm_xent_fwd(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss,
+                 lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(pred && labels && row_loss && loss, "lpm_xent_fwd: null pointer");
+  return xent_loss(pred, labels, B, V, row_loss, loss, ST(stream));
+}
+
+int lpm_cast_f32_to_f16(const float* src, long long ld_src, int rows, int cols, void* dst, long long ld_dst,
+                        int cols_dst, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(src && dst && rows > 0 && cols > 0 && cols_dst >= cols, "lpm_cast_f32_to_f16: bad arguments");
+  return cast_2d(src, ld_src, rows, cols, H16(dst), ld_dst, cols_dst, ST(stream));
+}
+
+int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(src && dst && rows > 0 && cols > 0, "lpm_transpose_f32: bad arguments");
+  return transpose_2d(src, rows, cols, dst, ST(stream));
+}
+
 }  // extern "C"

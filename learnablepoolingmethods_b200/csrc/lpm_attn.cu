@@ -1,0 +1,186 @@
+// Multi-head attention core for short sequences and tiny heads (length <= 512, depth 8 or 16):
+//   O = softmax(scale * Q K^T [* key_scale + key_shift]) V        per (sample, head)
+// transformer_utils.py:563-581 (V1, q scaled by depth^-0.5) and :641-664 (V2, batch-norm on the
+// logits = per-key affine).  One CTA per (sample, head); Q/K/V of the head staged in shared memory;
+// each warp owns 16-query blocks, FA2-style online softmax in registers, mma.sync m16n8k16 fp16
+// with fp32 accumulation (depth-16 heads make one k-step per score tile: the op is exp/LSU bound,
+// not tensor bound, so the legacy warp-level MMA is the right-sized tool here).
+#include "lpm_common.cuh"
+#include "lpm_kernels.h"
+
+namespace lpm {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// smem tile [L][16] halves, 32 B per row, the two 16-byte chunks swapped on rows with bit 2 set
+// (conflict-free ldmatrix).
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
+
+template <int DH>
+__device__ __forceinline__ void load_head_tile(uint8_t* dst, const __half* src, long long ld, int L) {
+  // src: first element of this head's columns in row 0; DH halves per row
+  constexpr int CH = DH / 8;
+  for (int i = threadIdx.x; i < L * 2; i += blockDim.x) {
+    const int r = i >> 1, c = i & 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c < CH) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
+    *reinterpret_cast<uint4*>(dst + tile_off(r, c)) = v;
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__ qkv, long long ld, int L, int Dm,
+                                                      int H, float scale_log2, const float* __restrict__ key_scale,
+                                                      const float* __restrict__ key_shift, __half* __restrict__ out,
+                                                      long long ldo, float* __restrict__ lse) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + L * 32;
+  uint8_t* sV = sK + L * 32;
+  float* sKs = reinterpret_cast<float*>(sV + L * 32);  // per-key affine in log2 domain (optional)
+  float* sKb = sKs + L;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const __half* base = qkv + (long long)b * L * ld + h * DH;
+  load_head_tile<DH>(sQ, base, ld, L);
+  load_head_tile<DH>(sK, base + Dm, ld, L);
+  load_head_tile<DH>(sV, base + 2 * Dm, ld, L);
+  const bool affine = key_scale != nullptr;
+  if (affine)
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      sKs[i] = key_scale[i] * 1.4426950408889634f;
+      sKb[i] = key_shift[i] * 1.4426950408889634f;
+    }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV);
+  const int nkb = L / 16;  // 16-key blocks
+
+  for (int qb = warp; qb < L / 16; qb += 4) {
+    uint32_t qa0, qa1, qa2, qa3;
+    {
+      const int row = qb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4(q_s + tile_off(row, lane >> 4), qa0, qa1, qa2, qa3);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[DH / 8][4];
+#pragma unroll
+    for (int j = 0; j < DH / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+
+    for (int kb0 = 0; kb0 < nkb; kb0 += 4) {  // up to 64 keys per step
+      const int nb = min(4, nkb - kb0);
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nb) {
+          uint32_t b0, b1, b2, b3;
+          const int key = (kb0 + j) * 16 + (lane & 7) + (lane >> 4) * 8;
+          ldsm_x4(k_s + tile_off(key, (lane >> 3) & 1), b0, b1, b2, b3);
+          s[2 * j][0] = s[2 * j][1] = s[2 * j][2] = s[2 * j][3] = 0.f;
+          s[2 * j + 1][0] = s[2 * j + 1][1] = s[2 * j + 1][2] = s[2 * j + 1][3] = 0.f;
+          mma16816(s[2 * j], qa0, qa1, qa2, qa3, b0, b1);
+          mma16816(s[2 * j + 1], qa0, qa1, qa2, qa3, b2, b3);
+        }
+      }
+      // scale to log2 domain (+ optional per-key affine), block row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < 2 * nb) {
+          const int key = kb0 * 16 + j * 8 + (lane & 3) * 2;
+          if (affine) {
+            const float ks0 = sKs[key], ks1 = sKs[key + 1], kb_0 = sKb[key], kb_1 = sKb[key + 1];
+            s[j][0] = s[j][0] * ks0 + kb_0; s[j][1] = s[j][1] * ks1 + kb_1;
+            s[j][2] = s[j][2] * ks0 + kb_0; s[j][3] = s[j][3] * ks1 + kb_1;
+          } else {
+            s[j][0] *= scale_log2; s[j][1] *= scale_log2; s[j][2] *= scale_log2; s[j][3] *= scale_log2;
+          }
+          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < 2 * nb) {
+          s[j][0] = exp2f(s[j][0] - m0); s[j][1] = exp2f(s[j][1] - m0);
+          s[j][2] = exp2f(s[j][2] - m1); s[j][3] = exp2f(s[j][3] - m1);
+          l0 += s[j][0] + s[j][1];
+          l1 += s[j][2] + s[j][3];
+        }
+      }
+      // O += P V
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nb) {
+          const uint32_t a0 = pack_half2(s[2 * j][0], s[2 * j][1]), a1 = pack_half2(s[2 * j][2], s[2 * j][3]);
+          const uint32_t a2 = pack_half2(s[2 * j + 1][0], s[2 * j + 1][1]), a3 = pack_half2(s[2 * j + 1][2], s[2 * j + 1][3]);
+          uint32_t b0, b1, b2, b3;
+          const int key = (kb0 + j) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          ldsm_x4_t(v_s + tile_off(key, lane >> 4), b0, b1, b2, b3);
+          mma16816(o[0], a0, a1, a2, a3, b0, b1);
+          if (DH == 16) mma16816(o[DH / 8 - 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = qb * 16 + (lane >> 2), r1 = r0 + 8;
+    __half* o0 = out + ((long long)b * L + r0) * ldo + h * DH + (lane & 3) * 2;
+    __half* o1 = out + ((long long)b * L + r1) * ldo + h * DH + (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < DH / 8; ++j) {
+      *reinterpret_cast<__half2*>(o0 + j * 8) = __floats2half2_rn(o[j][0] * i0, o[j][1] * i0);
+      *reinterpret_cast<__half2*>(o1 + j * 8) = __floats2half2_rn(o[j][2] * i1, o[j][3] * i1);
+    }
+    if (lse != nullptr && (lane & 3) == 0) {
+      // natural-log log-sum-exp of the (scaled / affine) logits
+      lse[((long long)b * H + h) * L + r0] = (m0 + log2f(l0)) * 0.6931471805599453f;
+      lse[((long long)b * H + h) * L + r1] = (m1 + log2f(l1)) * 0.6931471805599453f;
+    }
+  }
+}
+
+int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float scale, const float* key_scale,
+            const float* key_shift, __half* out, long long ldo, float* lse, cudaStream_t st) {
+  const int DH = Dm / H;
+  LPM_REQUIRE(DH * H == Dm && (DH == 8 || DH == 16), "mha_fwd: head depth must be 8 or 16 (Dm=%d H=%d)", Dm, H);
+  LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 1024, "mha_fwd: length must be a multiple of 16 in [16,1024] (got %d)", L);
+  LPM_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, "mha_fwd: leading dimensions must be multiples of 8");
+  const size_t smem = (size_t)L * 96 + (size_t)L * 8;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  if (DH == 16) {
+    static bool set16 = false;
+    if (!set16) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); set16 = true; }
+    mha_fwd_kernel<16><<<B * H, 128, smem, st>>>(qkv, ld, L, Dm, H, scale_log2, key_scale, key_shift, out, ldo, lse);
+  } else {
+    static bool set8 = false;
+    if (!set8) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); set8 = true; }
+    mha_fwd_kernel<8><<<B * H, 128, smem, st>>>(qkv, ld, L, Dm, H, scale_log2, key_scale, key_shift, out, ldo, lse);
+  }
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+}  // namespace lpm

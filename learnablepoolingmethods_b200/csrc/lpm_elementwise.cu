@@ -1,0 +1,491 @@
+// HBM-bound kernels of the hot path: frame sampling + input batch-norm, batch-norm finalisation,
+// joint-axis layer-norm (+ residual), split-K reduction, context gating, MoE mixing, cross-entropy,
+// fp32 -> fp16 parameter shadows.  Vectorised, coalesced, grid sized in multiples of the SM count.
+#include "lpm_common.cuh"
+#include "lpm_kernels.h"
+
+namespace lpm {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  // red: >= 32 floats of shared memory
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  return red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2 + a3: SampleUniformFrames (model_utils.py:101-122) + input_bn (frame_level_models.py:2265-2271)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sample_index(int i, float step, int nf, int max_frames) {
+  // int32( fl32(fl32(i*step) * fl32(nf)) ), truncation toward zero: the TF float32 arithmetic
+  const float g = __fmul_rn(static_cast<float>(i), step);
+  int idx = __float2int_rz(__fmul_rn(g, static_cast<float>(nf)));
+  return min(max(idx, 0), max_frames - 1);
+}
+
+// partial[blockIdx][0][c] = sum, partial[blockIdx][1][c] = sum of squares over this block's rows
+__global__ void __launch_bounds__(256) sample_stats_kernel(const float* __restrict__ x,
+                                                           const int* __restrict__ num_frames, int B,
+                                                           int max_frames, int F, int T, float step,
+                                                           float* __restrict__ partial) {
+  const int rows = B * T;
+  float4 s[2], q[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { s[j] = make_float4(0, 0, 0, 0); q[j] = make_float4(0, 0, 0, 0); }
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / T, i = r - b * T;
+    const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
+    const float* src = x + ((size_t)b * max_frames + idx) * F;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = threadIdx.x * 4 + j * 1024;
+      if (c < F) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+        s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
+        q[j].x += v.x * v.x; q[j].y += v.y * v.y; q[j].z += v.z * v.z; q[j].w += v.w * v.w;
+      }
+    }
+  }
+  float* ps = partial + (size_t)blockIdx.x * 2 * F;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = threadIdx.x * 4 + j * 1024;
+    if (c < F) {
+      *reinterpret_cast<float4*>(ps + c) = s[j];
+      *reinterpret_cast<float4*>(ps + F + c) = q[j];
+    }
+  }
+}
+
+// y[r][c] = fp16( x[b, idx(b,i), c] * scale[c] + shift[c] )
+__global__ void __launch_bounds__(256) sample_apply_kernel(const float* __restrict__ x,
+                                                           const int* __restrict__ num_frames, int B,
+                                                           int max_frames, int F, int T, float step,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           __half* __restrict__ y) {
+  const int rows = B * T;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / T, i = r - b * T;
+    const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
+    const float* src = x + ((size_t)b * max_frames + idx) * F;
+    __half* dst = y + (size_t)r * F;
+    for (int c = threadIdx.x * 4; c < F; c += blockDim.x * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+      uint2 o;
+      o.x = pack_half2(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y));
+      o.y = pack_half2(fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+      *reinterpret_cast<uint2*>(dst + c) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slim.batch_norm finalisation: partial sums -> mean / biased var -> affine (scale, shift); moving
+// statistics update (decay 0.999; Bessel-corrected variance when `bessel`).  Inference: affine from
+// the moving statistics.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int P,
+                                   long long pstride, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, float decay, float eps, int bessel,
+                                   int training, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < P; ++p) {
+      s += static_cast<double>(psum[(size_t)p * pstride + c]);
+      q += static_cast<double>(psq[(size_t)p * pstride + c]);
+    }
+    const double m = s / count;
+    double v = q / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = static_cast<float>(m);
+    var = static_cast<float>(v);
+    if (moving_mean != nullptr) {
+      const double corr = (bessel && count > 1.0) ? count / (count - 1.0) : 1.0;
+      moving_mean[c] = moving_mean[c] * decay + mean * (1.f - decay);
+      moving_var[c] = moving_var[c] * decay + static_cast<float>(v * corr) * (1.f - decay);
+    }
+  } else {
+    mean = moving_mean[c];
+    var = moving_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  scale[c] = g * rstd;
+  shift[c] = bt - mean * g * rstd;
+  if (save_mean) save_mean[c] = mean;
+  if (save_rstd) save_rstd[c] = rstd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Joint-axis layer norm (tf.contrib.layers.layer_norm, begin_norm_axis=1) with fused residual:
+//   u = a + b * row_scale ;  y = (u - mean_b) * rstd_b * gamma[d] + beta[d]
+// pass 1 writes u (fp16, in place over a) and per-(sample, chunk) partial sums;
+// pass 2 reduces the partials (fixed order) and normalises.  transformer_utils.py:406-411,712-713.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_CHUNKS = 32;
+
+__global__ void __launch_bounds__(256) ln_stats_kernel(__half* __restrict__ a, const __half* __restrict__ b,
+                                                       const float* __restrict__ b_row_scale, int rows, int D,
+                                                       long long a_sample_stride, long long b_sample_stride,
+                                                       float* __restrict__ partial) {
+  __shared__ float red[32];
+  const int sample = blockIdx.y, chunk = blockIdx.x;
+  const long long n8 = (long long)rows * D / 8;
+  const long long per = (n8 + LN_CHUNKS - 1) / LN_CHUNKS;
+  const long long i0 = chunk * per, i1 = min(n8, i0 + per);
+  uint4* pa = reinterpret_cast<uint4*>(a + sample * a_sample_stride);
+  const uint4* pb = b ? reinterpret_cast<const uint4*>(b + sample * b_sample_stride) : nullptr;
+  float s = 0.f, q = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint4 va = pa[i];
+    __half2* ha = reinterpret_cast<__half2*>(&va);
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(ha[j]); u[2 * j] = f.x; u[2 * j + 1] = f.y; }
+    if (pb) {
+      const uint4 vb = __ldg(pb + i);
+      const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+      const float rs = b_row_scale ? __ldg(b_row_scale + (long long)sample * rows + (i * 8) / D) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hb[j]); u[2 * j] += f.x * rs; u[2 * j + 1] += f.y * rs; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ha[j] = __floats2half2_rn(u[2 * j], u[2 * j + 1]);
+      pa[i] = va;
+      // statistics of the stored (fp16-rounded) u, which is what pass 2 normalises
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(ha[j]); u[2 * j] = f.x; u[2 * j + 1] = f.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += u[j]; q += u[j] * u[j]; }
+  }
+  s = block_sum(s, red);
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    partial[((size_t)sample * LN_CHUNKS + chunk) * 2 + 0] = s;
+    partial[((size_t)sample * LN_CHUNKS + chunk) * 2 + 1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_apply_kernel(const __half* __restrict__ u, int rows, int D,
+                                                       long long u_sample_stride, const float* __restrict__ partial,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, __half* __restrict__ y, long long y_sample_stride,
+                                                       float* __restrict__ save_mean_rstd) {
+  const int sample = blockIdx.y, chunk = blockIdx.x;
+  double ds = 0.0, dq = 0.0;
+  for (int c = 0; c < LN_CHUNKS; ++c) {
+    ds += partial[((size_t)sample * LN_CHUNKS + c) * 2 + 0];
+    dq += partial[((size_t)sample * LN_CHUNKS + c) * 2 + 1];
+  }
+  const double n = (double)rows * D;
+  const double m = ds / n;
+  double var = dq / n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  if (save_mean_rstd && chunk == 0 && threadIdx.x == 0) {
+    save_mean_rstd[sample * 2 + 0] = mean;
+    save_mean_rstd[sample * 2 + 1] = rstd;
+  }
+  const long long n8 = (long long)rows * D / 8;
+  const long long per = (n8 + gridDim.x - 1) / gridDim.x;
+  const long long i0 = chunk * per, i1 = min(n8, i0 + per);
+  const uint4* pu = reinterpret_cast<const uint4*>(u + sample * u_sample_stride);
+  uint4* py = reinterpret_cast<uint4*>(y + sample * y_sample_stride);
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const uint4 vu = __ldg(pu + i);
+    const __half2* hu = reinterpret_cast<const __half2*>(&vu);
+    const int d = (int)((i * 8) % D);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + d));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + d + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + d));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + d + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 vo;
+    __half2* ho = reinterpret_cast<__half2*>(&vo);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(hu[j]);
+      ho[j] = __floats2half2_rn((f.x - mean) * rstd * gg[2 * j] + bb[2 * j],
+                                (f.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+    }
+    py[i] = vo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-K reduction + bias (+ReLU):  out[r][c] = act( sum_s part[s][r][c] + bias[c] )  -> fp32 and/or fp16
+// (hidden projection, frame_level_models.py:2319,2329-2334, and split-K weight gradients)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits,
+                                                            long long split_stride, long long n, int cols,
+                                                            const float* __restrict__ bias, int relu, float alpha,
+                                                            int accumulate, float* __restrict__ out32,
+                                                            __half* __restrict__ out16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[k * split_stride + i];
+    s *= alpha;
+    if (bias) s += __ldg(bias + (i % cols));
+    if (relu) s = fmaxf(s, 0.f);
+    if (out32) out32[i] = accumulate ? out32[i] + s : s;
+    if (out16) out16[i] = __float2half_rn(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Context gating (frame_level_models.py:2342-2368): gates = BN_batch(g [- diag(Wg) * act]) ;
+// act *= sigmoid(gates).  One thread per hidden unit, loops over the (small) batch.
+// ------------------------------------------------------------------------------------------------
+__global__ void gating_fwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
+                                  const float* __restrict__ wg_diag, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                  float* __restrict__ moving_var, float decay, float eps, int training,
+                                  float* __restrict__ out32, __half* __restrict__ out16,
+                                  float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  const float dg = wg_diag ? wg_diag[c] : 0.f;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < B; ++b) {
+      const float v = g[(size_t)b * H + c] - dg * act[(size_t)b * H + c];
+      s += v; q += (double)v * v;
+    }
+    const double m = s / B;
+    double vv = q / B - m * m;
+    if (vv < 0.0) vv = 0.0;
+    mean = (float)m; var = (float)vv;
+    const double corr = B > 1 ? (double)B / (B - 1) : 1.0;
+    moving_mean[c] = moving_mean[c] * decay + mean * (1.f - decay);
+    moving_var[c] = moving_var[c] * decay + (float)(vv * corr) * (1.f - decay);
+  } else {
+    mean = moving_mean[c]; var = moving_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  if (save_mean) { save_mean[c] = mean; save_rstd[c] = rstd; }
+  const float sc = gamma[c] * rstd, sh = beta[c] - mean * sc;
+  for (int b = 0; b < B; ++b) {
+    const float a = act[(size_t)b * H + c];
+    const float v = (g[(size_t)b * H + c] - dg * a) * sc + sh;
+    const float o = a / (1.f + __expf(-v));
+    out32[(size_t)b * H + c] = o;
+    if (out16) out16[(size_t)b * H + c] = __float2half_rn(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MoE mixing (video_level_models.py:116-126): logits [B][ld] = [gates V*(M+1) | experts V*M]
+//   p[b,v] = sum_m softmax(gate[b,v,:])[m] * sigmoid(expert[b,v,m])
+// ------------------------------------------------------------------------------------------------
+__global__ void moe_mix_kernel(const float* __restrict__ logits, long long ld, int B, int V, int M,
+                               float* __restrict__ pred) {
+  const long long n = (long long)B * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / V), v = (int)(i - (long long)b * V);
+    const float* gl = logits + b * ld + (long long)v * (M + 1);
+    const float* el = logits + b * ld + (long long)V * (M + 1) + (long long)v * M;
+    float mx = gl[0];
+    for (int m = 1; m <= M; ++m) mx = fmaxf(mx, gl[m]);
+    float den = 0.f, num = 0.f;
+    for (int m = 0; m <= M; ++m) {
+      const float e = __expf(gl[m] - mx);
+      den += e;
+      if (m < M) num += e / (1.f + __expf(-el[m]));
+    }
+    pred[i] = num / den;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CrossEntropyLoss (losses.py:44-51): per-sample sums -> loss = mean_b ; labels as uint8 {0,1}
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xent_rows_kernel(const float* __restrict__ pred,
+                                                        const uint8_t* __restrict__ labels, int V,
+                                                        float* __restrict__ row_loss) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float p = pred[(size_t)b * V + v];
+    const float y = labels[(size_t)b * V + v] ? 1.f : 0.f;
+    s -= y * logf(p + 1e-5f) + (1.f - y) * logf(1.f - p + 1e-5f);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) row_loss[b] = s;
+}
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += v[i];
+    *out = (float)(s / n);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> fp16 2-D copy with destination leading dimension / zero column padding (parameter shadows)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_2d_kernel(const float* __restrict__ src, long long ld_src, int rows,
+                                                      int cols, __half* __restrict__ dst, long long ld_dst,
+                                                      int cols_dst) {
+  const long long n = (long long)rows * cols_dst;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_dst), c = (int)(i - (long long)r * cols_dst);
+    dst[r * ld_dst + c] = __float2half_rn(c < cols ? src[r * ld_src + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NetVLAD descriptor finalisation (frame_level_models.py:2819-2822): z[b,k,:] (un-normalised, fp16)
+// times rscale[b,k] -> fp32 [B][D*K] d-major (reference flatten) or [B][K][D].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vlad_finalize_kernel(const __half* __restrict__ z, const float* __restrict__ rscale,
+                                                            int B, int K, int D, int d_major, float* __restrict__ out) {
+  const long long n = (long long)B * K * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((long long)K * D));
+    const int rem = (int)(i - (long long)b * K * D);
+    int k, d;
+    if (d_major) { d = rem / K; k = rem - d * K; } else { k = rem / D; d = rem - k * D; }
+    out[i] = __half2float(z[((long long)b * K + k) * D + d]) * rscale[b * K + k];
+  }
+}
+
+// fp32 2-D transpose (parameter layout preparation, e.g. cluster_weights2 [D][K] -> [K][D])
+__global__ void transpose_2d_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------------------------
+static inline int grid_for(long long n, int threads, int per_sm = 8) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int sample_stats_blocks() { return num_sms() * 4; }
+
+int sample_stats(const float* x, const int* nf, int B, int max_frames, int F, int T, float* partial, cudaStream_t st) {
+  LPM_REQUIRE(F % 4 == 0 && F <= 2048, "sample_stats: feature size must be a multiple of 4 and <= 2048 (got %d)", F);
+  sample_stats_kernel<<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, partial);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, int T, const float* scale,
+                 const float* shift, __half* y, cudaStream_t st) {
+  LPM_REQUIRE(F % 4 == 0, "sample_apply: feature size must be a multiple of 4 (got %d)", F);
+  int grid = B * T < num_sms() * 8 ? B * T : num_sms() * 8;
+  sample_apply_kernel<<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, scale, shift, y);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
+                const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
+                int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(psum, psq, P, pstride, C, count, gamma, beta, mm, mv, decay,
+                                                      eps, bessel, training, scale, shift, save_mean, save_rstd);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, int B, int rows, int D,
+                    long long a_stride, long long b_stride, const float* gamma, const float* beta, float eps,
+                    __half* y, long long y_stride, float* partial, float* save_mean_rstd, cudaStream_t st) {
+  LPM_REQUIRE(D % 8 == 0 && a_stride % 8 == 0 && b_stride % 8 == 0 && y_stride % 8 == 0,
+              "layernorm_joint: D and sample strides must be multiples of 8");
+  dim3 g1(LN_CHUNKS, B);
+  ln_stats_kernel<<<g1, 256, 0, st>>>(a, b, b_row_scale, rows, D, a_stride, b_stride, partial);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  int chunks = (num_sms() * 8 + B - 1) / B;
+  const long long n8 = (long long)rows * D / 8;
+  if (chunks > (n8 + 255) / 256) chunks = (int)((n8 + 255) / 256);
+  if (chunks < 1) chunks = 1;
+  dim3 g2(chunks, B);
+  ln_apply_kernel<<<g2, 256, 0, st>>>(a, rows, D, a_stride, partial, gamma, beta, eps, y, y_stride, save_mean_rstd);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols, const float* bias,
+                  int relu, float alpha, int accumulate, float* out32, __half* out16, cudaStream_t st) {
+  splitk_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(part, splits, split_stride, n, cols, bias, relu, alpha,
+                                                         accumulate, out32, out16);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
+               const float* beta, float* mm, float* mv, float decay, float eps, int training, float* out32,
+               __half* out16, float* save_mean, float* save_rstd, cudaStream_t st) {
+  gating_fwd_kernel<<<(H + 63) / 64, 64, 0, st>>>(act, g, B, H, wg_diag, gamma, beta, mm, mv, decay, eps, training,
+                                                  out32, out16, save_mean, save_rstd);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int moe_mix(const float* logits, long long ld, int B, int V, int M, float* pred, cudaStream_t st) {
+  moe_mix_kernel<<<grid_for((long long)B * V, 256), 256, 0, st>>>(logits, ld, B, V, M, pred);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss, cudaStream_t st) {
+  xent_rows_kernel<<<B, 256, 0, st>>>(pred, labels, V, row_loss);
+  mean_kernel<<<1, 32, 0, st>>>(row_loss, B, loss);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
+            cudaStream_t st) {
+  cast_2d_kernel<<<grid_for((long long)rows * cols_dst, 256), 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, cols_dst);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int transpose_2d(const float* src, int rows, int cols, float* dst, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_2d_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int vlad_finalize(const __half* z, const float* rscale, int B, int K, int D, int d_major, float* out, cudaStream_t st) {
+  vlad_finalize_kernel<<<grid_for((long long)B * K * D, 256), 256, 0, st>>>(z, rscale, B, K, D, d_major, out);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+}  // namespace lpm

@@ -78,3 +78,175 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     if stats:
         return out, st
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+BN_EPS = 1e-3      # slim.batch_norm default
+BN_DECAY = 0.999   # slim.batch_norm default
+LN_EPS = 1e-12     # tf.contrib.layers.layer_norm
+
+
+def _f32(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+def _f16(shape, dev):
+    return torch.empty(shape, dtype=torch.float16, device=dev)
+
+
+def splitk_reduce(parts, *, bias=None, relu=False, alpha=1.0, out32=None, out16=None, accumulate=False):
+    lib = _lib.load()
+    splits = parts.shape[0]
+    n = parts[0].numel()
+    cols = parts.shape[-1]
+    check(lib.lpm_splitk_reduce(ptr(parts), splits, C.c_longlong(parts.stride(0)), C.c_longlong(n), cols, ptr(bias),
+                                int(relu), C.c_float(alpha), int(accumulate), ptr(out32), ptr(out16), stream_ptr()),
+          "lpm_splitk_reduce")
+
+
+def cast_f16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, cols_dst: Optional[int] = None):
+    """fp32 [rows, cols] -> fp16 [rows, cols_dst >= cols] (zero padded)."""
+    lib = _lib.load()
+    src2 = src.reshape(-1, src.shape[-1])
+    rows, cols = src2.shape
+    if dst is None:
+        cols_dst = cols_dst or cols
+        dst = torch.empty((rows, cols_dst), dtype=torch.float16, device=src.device)
+    cols_dst = cols_dst or dst.shape[-1]
+    check(lib.lpm_cast_f32_to_f16(ptr(src2), C.c_longlong(src2.stride(0)), rows, cols, ptr(dst),
+                                  C.c_longlong(dst.stride(0)), cols_dst, stream_ptr()), "lpm_cast_f32_to_f16")
+    return dst
+
+
+def transpose_f32(src: torch.Tensor):
+    lib = _lib.load()
+    rows, cols = src.shape
+    dst = _f32((cols, rows), src.device)
+    check(lib.lpm_transpose_f32(ptr(src), rows, cols, ptr(dst), stream_ptr()), "lpm_transpose_f32")
+    return dst
+
+
+def bn_finalize(psum, psq, count, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False,
+                decay=BN_DECAY, eps=BN_EPS):
+    """Reduce (sum, sumsq) partial rows [P, C] -> folded affine (scale, shift) [C]."""
+    lib = _lib.load()
+    Cn = gamma.numel()
+    dev = gamma.device
+    scale, shift = _f32((Cn,), dev), _f32((Cn,), dev)
+    sm = _f32((2, Cn), dev) if save else None
+    P = 0 if psum is None else psum.reshape(-1, Cn).shape[0]
+    check(lib.lpm_batchnorm_finalize(ptr(psum), ptr(psq), P, C.c_longlong(Cn), Cn, C.c_double(count), ptr(gamma),
+                                     ptr(beta), ptr(moving_mean), ptr(moving_var), C.c_float(decay), C.c_float(eps),
+                                     int(bessel), int(training), ptr(scale), ptr(shift),
+                                     ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
+          "lpm_batchnorm_finalize")
+    return (scale, shift, sm) if save else (scale, shift)
+
+
+def sample_bn_stats(x, num_frames, T):
+    lib = _lib.load()
+    B, Fmax, F = x.shape
+    blocks = lib.lpm_sample_stats_blocks()
+    partial = _f32((blocks, 2, F), x.device)
+    check(lib.lpm_sample_bn_stats(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(partial), stream_ptr()),
+          "lpm_sample_bn_stats")
+    return partial
+
+
+def sample_bn_apply(x, num_frames, T, scale, shift, out=None):
+    lib = _lib.load()
+    B, Fmax, F = x.shape
+    if out is None:
+        out = _f16((B * T, F), x.device)
+    check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out),
+                                  stream_ptr()), "lpm_sample_bn_apply")
+    return out
+
+
+def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers_t, *, valid_frames=None,
+                     save_assign=False):
+    """x16: fp16 view [B*T, D] (row stride may exceed D).  Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign."""
+    lib = _lib.load()
+    D = x16.shape[1]
+    K = wc16.shape[1]
+    dev = x16.device
+    z = _f16((B, K, D), dev)
+    rscale = _f32((B, K), dev)
+    a_sum = _f32((B, K), dev)
+    assign = _f16((B, T, K), dev) if save_assign else None
+    ldx = x16.stride(0)
+    check(lib.lpm_netvlad_pool_fwd(ptr(x16), C.c_longlong(ldx), C.c_longlong(ldx * T), ptr(wc16),
+                                   C.c_longlong(wc16.stride(0)), ptr(logit_scale), ptr(logit_shift), ptr(centers_t),
+                                   ptr(valid_frames), B, T, D, K, ptr(z), ptr(rscale), ptr(a_sum), ptr(assign),
+                                   stream_ptr()), "lpm_netvlad_pool_fwd")
+    return z, rscale, a_sum, assign
+
+
+def netvlad_finalize(z, rscale, d_major=True):
+    lib = _lib.load()
+    B, K, D = z.shape
+    out = _f32((B, D * K) if d_major else (B, K, D), z.device)
+    check(lib.lpm_netvlad_finalize(ptr(z), ptr(rscale), B, K, D, int(d_major), ptr(out), stream_ptr()),
+          "lpm_netvlad_finalize")
+    return out
+
+
+def mha_core_fwd(qkv, B, L, Dm, H, *, scale, key_scale=None, key_shift=None, want_lse=False):
+    lib = _lib.load()
+    out = _f16((B * L, Dm), qkv.device)
+    lse = _f32((B, H, L), qkv.device) if want_lse else None
+    check(lib.lpm_mha_core_fwd(ptr(qkv), C.c_longlong(qkv.stride(0)), B, L, Dm, H, C.c_float(scale), ptr(key_scale),
+                               ptr(key_shift), ptr(out), C.c_longlong(out.stride(0)), ptr(lse), stream_ptr()),
+          "lpm_mha_core_fwd")
+    return (out, lse) if want_lse else out
+
+
+def layernorm_joint_fwd(a, b, b_row_scale, B, rows, D, gamma, beta, *, out=None, out_stride=None, save=False,
+                        eps=LN_EPS):
+    """u = a + b*row_scale (stored over a); returns y = LN_joint(u) (fp16) [, (mean, rstd) [B,2]]."""
+    lib = _lib.load()
+    dev = a.device
+    if out is None:
+        out = _f16((B, rows, D), dev)
+        out_stride = rows * D
+    partial = _f32((B, 64), dev)
+    sm = _f32((B, 2), dev) if save else None
+    check(lib.lpm_layernorm_joint_fwd(ptr(a), ptr(b), ptr(b_row_scale), B, rows, D, C.c_longlong(rows * D),
+                                      C.c_longlong(rows * D), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out),
+                                      C.c_longlong(out_stride), ptr(partial), ptr(sm), stream_ptr()),
+          "lpm_layernorm_joint_fwd")
+    return (out, sm) if save else out
+
+
+def gating_fwd(act, g, gamma, beta, moving_mean, moving_var, *, training, wg_diag=None, save=False,
+               decay=BN_DECAY, eps=BN_EPS):
+    lib = _lib.load()
+    B, H = act.shape
+    dev = act.device
+    out32, out16 = _f32((B, H), dev), _f16((B, H), dev)
+    sm = _f32((2, H), dev) if save else None
+    check(lib.lpm_gating_fwd(ptr(act), ptr(g), B, H, ptr(wg_diag), ptr(gamma), ptr(beta), ptr(moving_mean),
+                             ptr(moving_var), C.c_float(decay), C.c_float(eps), int(training), ptr(out32), ptr(out16),
+                             ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
+          "lpm_gating_fwd")
+    return (out32, out16, sm) if save else (out32, out16)
+
+
+def moe_mix_fwd(logits, V, M):
+    lib = _lib.load()
+    B = logits.shape[0]
+    pred = _f32((B, V), logits.device)
+    check(lib.lpm_moe_mix_fwd(ptr(logits), C.c_longlong(logits.stride(0)), B, V, M, ptr(pred), stream_ptr()),
+          "lpm_moe_mix_fwd")
+    return pred
+
+
+def xent_fwd(pred, labels_u8):
+    lib = _lib.load()
+    B, V = pred.shape
+    row = _f32((B,), pred.device)
+    loss = _f32((1,), pred.device)
+    check(lib.lpm_xent_fwd(ptr(pred), ptr(labels_u8), B, V, ptr(row), ptr(loss), stream_ptr()), "lpm_xent_fwd")
+    return loss, row

@@ -1,0 +1,165 @@
+"""Per-kernel GPU parity: each C-ABI kernel against the CPU oracle's restatement of the same
+reference lines, on the same seeded inputs.  Tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_sample_and_input_bn(cuda):
+    """model_utils.py:101-122 + frame_level_models.py:2265-2271 (train and inference statistics)."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    B, Fmax, F, T = 6, 300, 1152, 256
+    x, nf, _ = O.synthetic_batch(B, seed=5, max_frames=Fmax, feat=F, vocab=10)
+    nf[0] = 1
+    nf[1] = 300
+    g = torch.Generator().manual_seed(0)
+    P = {"input_bn/gamma": torch.rand(F, generator=g) + 0.5, "input_bn/beta": torch.randn(F, generator=g) * 0.1}
+    S = {"input_bn/moving_mean": torch.randn(F, generator=g) * 0.01, "input_bn/moving_variance": torch.rand(F, generator=g) * 0.01 + 0.001}
+    S0 = {k: v.clone() for k, v in S.items()}
+    xs = O.sample_uniform_frames(x, nf, T).reshape(-1, F)
+    xd, nfd = x.to(cuda), nf.to(cuda)
+    for training in (True, False):
+        Sref = {k: v.clone() for k, v in S0.items()}
+        ref = O.batch_norm(xs, P, Sref, "input_bn", training)
+        mm, mv = S0["input_bn/moving_mean"].clone().to(cuda), S0["input_bn/moving_variance"].clone().to(cuda)
+        part = ops.sample_bn_stats(xd, nfd, T) if training else None
+        scale, shift = ops.bn_finalize(None if part is None else part[:, 0].contiguous(), None if part is None else part[:, 1].contiguous(),
+                                       B * T, P["input_bn/gamma"].to(cuda), P["input_bn/beta"].to(cuda), mm, mv,
+                                       training=training, bessel=True)
+        y = ops.sample_bn_apply(xd, nfd, T, scale, shift)
+        assert rel(y.float(), ref) < 6e-4          # fp16 output rounding (2^-11) only
+        if training:
+            assert rel(mm, Sref["input_bn/moving_mean"]) < 1e-5
+            assert rel(mv, Sref["input_bn/moving_variance"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,D,K", [(3, 256, 1024, 256), (2, 256, 128, 64), (2, 200, 256, 128), (2, 96, 128, 32), (1, 30, 64, 8)])
+def test_netvlad_pool_fwd(cuda, B, T, D, K):
+    """NetVLAD.forward (frame_level_models.py:2775-2822) fused kernel vs oracle: rel-L2 <= 1e-3 on the descriptor."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    g = torch.Generator().manual_seed(B * 1000 + T + D + K)
+    x = torch.randn(B * T, D, generator=g)
+    P = {"v/cluster_weights": torch.randn(D, K, generator=g) / D ** 0.5,
+         "v/cluster_weights2": torch.randn(1, D, K, generator=g) / D ** 0.5,
+         "v/cluster_bn/gamma": torch.rand(K, generator=g) + 0.5, "v/cluster_bn/beta": torch.randn(K, generator=g) * 0.2}
+    S = {"v/cluster_bn/moving_mean": torch.randn(K, generator=g) * 0.1, "v/cluster_bn/moving_variance": torch.rand(K, generator=g) + 0.5}
+    x16 = x.half()
+    ref, A_ref = O.netvlad_forward(x16.float(), P, S, "v", T, True, False, return_assign=True)
+    dev = cuda
+    scale, shift = ops.bn_finalize(None, None, 1, P["v/cluster_bn/gamma"].to(dev), P["v/cluster_bn/beta"].to(dev),
+                                   S["v/cluster_bn/moving_mean"].to(dev), S["v/cluster_bn/moving_variance"].to(dev),
+                                   training=False, bessel=True)
+    wc16 = ops.cast_f16(P["v/cluster_weights"].to(dev))
+    ct = ops.transpose_f32(P["v/cluster_weights2"][0].contiguous().to(dev))
+    z, rs, a_sum, assign = ops.netvlad_pool_fwd(x16.to(dev), B, T, wc16, scale, shift, ct, save_assign=True)
+    torch.cuda.synchronize()
+    assert rel(assign.float(), A_ref) < 2e-3
+    assert rel(a_sum, A_ref.sum(dim=1)) < 1e-3
+    vlad = ops.netvlad_finalize(z, rs, d_major=True)
+    err = rel(vlad, ref)
+    print(f"\n[pool B={B} T={T} D={D} K={K}] vlad rel-L2 {err:.2e}")
+    assert err < 1e-3
+    vk = ops.netvlad_finalize(z, rs, d_major=False)
+    assert rel(vk, ref.reshape(B, D, K).transpose(1, 2)) < 1e-3
+
+
+def test_netvlad_pool_masked_frames(cuda):
+    """Masked mode (extension): frames t >= valid_frames[b] contribute nothing."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    B, T, D, K = 3, 256, 128, 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B * T, D, generator=g).half()
+    P = {"v/cluster_weights": torch.randn(D, K, generator=g) / D ** 0.5, "v/cluster_weights2": torch.randn(1, D, K, generator=g) / D ** 0.5,
+         "v/cluster_biases": torch.randn(K, generator=g) * 0.1}
+    valid = torch.tensor([256, 100, 1], dtype=torch.int32)
+    dev = cuda
+    one = torch.ones(K, device=dev)
+    z, rs, a_sum, _ = ops.netvlad_pool_fwd(x.to(dev), B, T, ops.cast_f16(P["v/cluster_weights"].to(dev)), one,
+                                           P["v/cluster_biases"].to(dev), ops.transpose_f32(P["v/cluster_weights2"][0].contiguous().to(dev)),
+                                           valid_frames=valid.to(dev))
+    out = ops.netvlad_finalize(z, rs)
+    for b in range(B):
+        n = int(valid[b])
+        ref = O.netvlad_forward(x.float().reshape(B, T, D)[b, :n], P, None, "v", n, False, False)
+        assert rel(out[b], ref[0]) < 1e-3
+
+
+@pytest.mark.parametrize("B,L,Dm,H", [(3, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (2, 256, 128, 8), (1, 80, 64, 4)])
+def test_mha_core_fwd(cuda, B, L, Dm, H):
+    """transformer_utils.py:563-581: softmax(q*depth^-0.5 k^T) v per head."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(L + Dm + H)
+    qkv = (torch.randn(B * L, 3 * Dm, generator=g)).half()
+    dh = Dm // H
+    q, k, v = [t.float().reshape(B, L, H, dh).permute(0, 2, 1, 3) for t in qkv.split(Dm, dim=1)]
+    logits = (q * dh ** -0.5) @ k.transpose(-1, -2)
+    ref = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
+    out, lse = ops.mha_core_fwd(qkv.to(cuda), B, L, Dm, H, scale=dh ** -0.5, want_lse=True)
+    assert rel(out.float(), ref) < 2e-3
+    assert rel(lse, torch.logsumexp(logits, -1)) < 1e-4
+    # per-key affine (V2: batch norm on the logits)
+    ks, kb = torch.rand(L, generator=g) + 0.5, torch.randn(L, generator=g)
+    ref2 = (torch.softmax((q @ k.transpose(-1, -2)) * ks + kb, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
+    out2 = ops.mha_core_fwd(qkv.to(cuda), B, L, Dm, H, scale=1.0, key_scale=ks.to(cuda), key_shift=kb.to(cuda))
+    assert rel(out2.float(), ref2) < 2e-3
+
+
+def test_layernorm_joint(cuda):
+    """tf.contrib.layers.layer_norm (begin_norm_axis=1) + residual (transformer_utils.py:406-407)."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    B, R, D = 3, 64, 128
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(B, R, D, generator=g).half(), torch.randn(B, R, D, generator=g).half()
+    rs = torch.rand(B, R, generator=g) + 0.5
+    P = {"ln/gamma": torch.rand(D, generator=g) + 0.5, "ln/beta": torch.randn(D, generator=g)}
+    ref = O.layer_norm_joint(a.float() + b.float() * rs[:, :, None], P, "ln")
+    ad = a.to(cuda).clone()
+    y, sm = ops.layernorm_joint_fwd(ad, b.to(cuda), rs.to(cuda), B, R, D, P["ln/gamma"].to(cuda), P["ln/beta"].to(cuda), save=True)
+    assert rel(y.float(), ref) < 1e-3
+    u = a.float() + b.float() * rs[:, :, None]
+    assert rel(ad.float(), u) < 1e-3
+    assert rel(sm[:, 0], u.reshape(B, -1).mean(1)) < 1e-2
+    # no residual, strided output
+    out = torch.zeros(B, 2 * R * D, dtype=torch.float16, device=cuda)
+    ops.layernorm_joint_fwd(a.to(cuda).clone(), None, None, B, R, D, P["ln/gamma"].to(cuda), P["ln/beta"].to(cuda),
+                            out=out[:, R * D:], out_stride=2 * R * D)
+    assert rel(out[:, R * D:].float().reshape(B, R, D), O.layer_norm_joint(a.float(), P, "ln")) < 1e-3
+    assert float(out[:, :R * D].abs().max()) == 0.0
+
+
+def test_head_kernels(cuda):
+    """Context gating (frame_level_models.py:2342-2368), MoE mix (video_level_models.py:116-126), xent (losses.py:44-51)."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    B, H, V, M = 10, 64, 37, 2
+    g = torch.Generator().manual_seed(11)
+    act, gt = torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
+    P = {"gating_bn/gamma": torch.rand(H, generator=g) + 0.5, "gating_bn/beta": torch.randn(H, generator=g)}
+    for training in (True, False):
+        S = {"gating_bn/moving_mean": torch.randn(H, generator=g) * 0.1, "gating_bn/moving_variance": torch.rand(H, generator=g) + 0.5}
+        mm, mv = S["gating_bn/moving_mean"].clone().to(cuda), S["gating_bn/moving_variance"].clone().to(cuda)
+        ref = act * torch.sigmoid(O.batch_norm(gt, P, S, "gating_bn", training))
+        o32, o16 = ops.gating_fwd(act.to(cuda), gt.to(cuda), P["gating_bn/gamma"].to(cuda), P["gating_bn/beta"].to(cuda), mm, mv, training=training)
+        assert rel(o32, ref) < 1e-5
+        assert rel(mv, S["gating_bn/moving_variance"]) < 1e-5
+    logits = torch.randn(B, V * (2 * M + 1) + 3, generator=g)
+    Pm = {"gates/weights": torch.eye(1), "experts/weights": torch.eye(1)}
+    gate = logits[:, :V * (M + 1)].reshape(-1, M + 1)
+    ex = logits[:, V * (M + 1):V * (2 * M + 1)].reshape(-1, M)
+    ref = (torch.softmax(gate, -1)[:, :M] * torch.sigmoid(ex)).sum(1).reshape(B, V)
+    pred = ops.moe_mix_fwd(logits.to(cuda), V, M)
+    assert rel(pred, ref) < 1e-5
+    labels = torch.rand(B, V, generator=g) < 0.1
+    loss, _ = ops.xent_fwd(pred, labels.to(torch.uint8).to(cuda))
+    assert abs(float(loss) - float(O.cross_entropy_loss(ref, labels))) < 1e-4 * float(O.cross_entropy_loss(ref, labels))
