@@ -44,6 +44,8 @@ const char* lpm_last_error(void);
  *   batch strides of 0 share the operand across the batch.  lda/ldb/batch strides: multiples of 8.
  *   splits>1: split-K; out must be an fp32 workspace [splits][batch][M][ldc] (out_split_stride
  *   elements apart) reduced afterwards with lpm_splitk_reduce.
+ *   mask / add1 / add2 (optional, fp16, batch stride = out_batch_stride): fused ReLU-backward mask and
+ *   residual-gradient sums, applied after bias/ReLU in the order "+= add1 + add2, then mask".
  *   stat_sum/stat_sq (optional): per-row sum / sum of squares of the epilogue values over the N
  *   columns of each N-tile, written to [batch][n_tiles][M] (deterministic partials).
  * ------------------------------------------------------------------------------------------- */
@@ -57,6 +59,8 @@ typedef struct lpm_gemm_desc {
   long long row_scale_batch_stride;
   int relu; int accumulate; float alpha;
   float* stat_sum; float* stat_sq;
+  const void* mask; long long ld_mask;                     /* fp16 [M][ld_mask]: out = mask>0 ? out : 0 */
+  const void* add1; const void* add2; long long ld_add;    /* fp16 addends [M][ld_add]: out += add1 (+ add2) */
 } lpm_gemm_desc;
 
 int lpm_gemm_f16(const lpm_gemm_desc* desc, lpm_stream_t stream);
@@ -132,10 +136,11 @@ int lpm_mha_core_fwd(const void* qkv, long long ld, int B, int L, int Dm, int H,
 
 /* ---------------------------------------------------------------------------------------------
  * Joint-axis layer norm with fused residual (tf.contrib.layers.layer_norm, begin_norm_axis=1):
- *   u = a + b*b_row_scale (written back over a, fp16);  y = (u-mean_b)*rstd_b*gamma[d] + beta[d].
+ *   u = a + b*b_row_scale (fp16, written to u_out, or over a when u_out is NULL);
+ *   y = (u-mean_b)*rstd_b*gamma[d] + beta[d].
  * transformer_utils.py:406-411,712-713.  partial: B*64 floats; save_mean_rstd: [B][2] or NULL.
  * ------------------------------------------------------------------------------------------- */
-int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, int B, int rows, int D,
+int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, void* u_out, int B, int rows, int D,
                             long long a_stride, long long b_stride, const float* gamma, const float* beta,
                             float eps, void* y, long long y_stride, float* partial, float* save_mean_rstd,
                             lpm_stream_t stream);
@@ -146,17 +151,72 @@ int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* 
                    int training, float* out_f32, void* out_f16, float* save_mean, float* save_rstd,
                    lpm_stream_t stream);
 
-/* MoE mixing (video_level_models.py:116-126): logits fp32 [B][ld] = [gates V*(M+1) | experts V*M]. */
-int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, float* pred, lpm_stream_t stream);
+/* MoE mixing (video_level_models.py:116-126): logits fp32 [B][ld]; gates V*(M+1) at column 0, experts V*M at
+ * column expert_off (lets the caller pad the gate block to a 16-byte boundary). */
+int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred,
+                    lpm_stream_t stream);
 
 /* CrossEntropyLoss (losses.py:44-51): labels uint8 [B][V]; row_loss [B]; loss scalar = mean_b. */
 int lpm_xent_fwd(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss,
                  lpm_stream_t stream);
 
+/* y[r][:] = fp16(x[r][:] * row_scale[r]): materialises vlad = z*rscale for the training path. */
+int lpm_scale_rows_f16(const void* x, const float* row_scale, long long rows, int D, void* y, lpm_stream_t stream);
+
 /* fp32 -> fp16 2-D copy with zero column padding (parameter shadows) and fp32 transpose. */
 int lpm_cast_f32_to_f16(const float* src, long long ld_src, int rows, int cols, void* dst, long long ld_dst,
                         int cols_dst, lpm_stream_t stream);
 int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stream_t stream);
+
+/* =============================================================================================
+ * Backward entry points (autodiff of the reference lines cited by the matching forward call).
+ * Activation gradients are fp16 scaled by the caller's loss scale; parameter gradients are fp32 and
+ * unscaled (inv_scale = 1/loss_scale).
+ * ============================================================================================= */
+/* losses.py:44-51: dpred = -(y/(p+1e-5) - (1-y)/(1-p+1e-5)) * gscale  (gscale = upstream/B). */
+int lpm_xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred,
+                 lpm_stream_t stream);
+/* video_level_models.py:116-126: dlogits fp16 [B][ldo] (x loss_scale), padding columns zeroed. */
+int lpm_moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
+                    float loss_scale, void* dlogits_f16, long long ldo, int ncols, lpm_stream_t stream);
+/* out[c] (+)= alpha*sum_r x[r][c]; partial: lpm_colsum_chunks(rows)*cols floats. */
+int lpm_colsum_chunks(long long rows);
+int lpm_colsum(const void* x, int is_f32, long long ld, long long rows, int cols, float alpha, int accumulate,
+               float* partial, float* out, lpm_stream_t stream);
+int lpm_colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
+                     float* out, lpm_stream_t stream);
+/* frame_level_models.py:2342-2368 backward. */
+int lpm_gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
+                   const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact,
+                   void* dg_f16, float* dgamma, float* dbeta, lpm_stream_t stream);
+/* Joint layer norm backward: du = rstd*(dy*gamma - c1/N - xhat*c2/N); with `mask`, du_masked = du o (mask>0)
+ * (ReLU backward of the pre-residual branch).  part_sample: B*chunks*2, part_cols: B*chunks*2*D (sum dy*xhat |
+ * sum dy per column), part_cols_du (optional): B*chunks*D column sums of du_masked (du without mask);
+ * chunks = lpm_layernorm_bwd_chunks(). */
+int lpm_layernorm_bwd_chunks(void);
+int lpm_layernorm_joint_bwd(const void* u, const void* dy, long long dy_stride, int B, int rows, int D,
+                            const float* mean_rstd, const float* gamma, const void* mask, void* du,
+                            void* du_masked, float* part_sample, float* part_cols, float* part_cols_du,
+                            lpm_stream_t stream);
+/* frame_level_models.py:2819-2822 backward: dz fp16 [rows][D], q[rows] = dz . C[:,k]. */
+int lpm_netvlad_norm_bwd(const void* z, const float* rscale, const void* dvhat, long long rows, int K, int D,
+                         const float* centers_t, void* dz, float* q, lpm_stream_t stream);
+/* Soft-assignment (softmax + cluster_bn) backward, two passes; partial: lpm_assign_bwd_blocks()*2*K. */
+int lpm_assign_bwd_blocks(void);
+int lpm_assign_bwd1(const float* G, const void* assign, const float* q, const void* S, const float* mean,
+                    const float* rstd, long long rows, int T, int K, void* dshat, float* partial,
+                    lpm_stream_t stream);
+int lpm_assign_bwd2(void* dshat, const void* S, const float* mean, const float* rstd, const float* gamma,
+                    const float* csum, long long rows, int K, lpm_stream_t stream);
+/* cluster_weights2 / input_bn parameter gradients (see lpm_backward.cu for the algebra). */
+int lpm_center_bwd(const void* dV, const void* Z, const float* a_sum, int B, int K, int D, const float* centers_t,
+                   const float* beta_in, float inv_scale, float* dCt, float* E, lpm_stream_t stream);
+int lpm_input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const float* E, int D, int K,
+                      const float* gamma_in, float* dgamma_in, float* dbeta_in, lpm_stream_t stream);
+int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_stream_t stream);
+/* transformer_utils.py:563-581 backward: dqkv fp16 [B*L][ldd] in the qkv layout; L <= 256. */
+int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* dout, long long ldo, const float* lse,
+                     int B, int L, int Dm, int H, float scale, void* dqkv, long long ldd, lpm_stream_t stream);
 
 #ifdef __cplusplus
 }

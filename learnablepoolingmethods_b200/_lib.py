@@ -27,6 +27,8 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("row_scale", C.c_void_p), ("row_scale_batch_stride", C.c_longlong),
         ("relu", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float),
         ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
+        ("mask", C.c_void_p), ("ld_mask", C.c_longlong),
+        ("add1", C.c_void_p), ("add2", C.c_void_p), ("ld_add", C.c_longlong),
     ]
 
 

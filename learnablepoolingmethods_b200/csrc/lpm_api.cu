@@ -174,13 +174,19 @@ int lpm_mha_core_fwd(const void* qkv, long long ld, int B, int L, int Dm, int H,
   return mha_fwd(CH16(qkv), ld, B, L, Dm, H, scale, key_scale, key_shift, H16(out), ldo, lse, ST(stream));
 }
 
-int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, int B, int rows, int D,
+int lpm_scale_rows_f16(const void* x, const float* row_scale, long long rows, int D, void* y, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && row_scale && y && rows > 0, "lpm_scale_rows_f16: bad arguments");
+  return scale_rows(CH16(x), row_scale, rows, D, H16(y), ST(stream));
+}
+
+int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, void* u_out, int B, int rows, int D,
                             long long a_stride, long long b_stride, const float* gamma, const float* beta,
                             float eps, void* y, long long y_stride, float* partial, float* save_mean_rstd,
                             lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(a && gamma && beta && y && partial && B > 0 && rows > 0, "lpm_layernorm_joint_fwd: bad arguments");
-  return layernorm_joint(H16(a), CH16(b), b_row_scale, B, rows, D, a_stride, b_stride, gamma, beta, eps, H16(y),
+  return layernorm_joint(H16(a), CH16(b), b_row_scale, H16(u_out), B, rows, D, a_stride, b_stride, gamma, beta, eps, H16(y),
                          y_stride, partial, save_mean_rstd, ST(stream));
 }
 
@@ -194,10 +200,11 @@ int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* 
                     H16(out_f16), save_mean, save_rstd, ST(stream));
 }
 
-int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, float* pred, lpm_stream_t stream) {
+int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred,
+                    lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(logits && pred && B > 0 && V > 0 && M > 0, "lpm_moe_mix_fwd: bad arguments");
-  return moe_mix(logits, ld, B, V, M, pred, ST(stream));
+  return moe_mix(logits, ld, B, V, M, expert_off, pred, ST(stream));
 }
 
 int lpm_xent_fwd(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss,
@@ -218,6 +225,92 @@ int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stre
   DEVCHK();
   LPM_REQUIRE(src && dst && rows > 0 && cols > 0, "lpm_transpose_f32: bad arguments");
   return transpose_2d(src, rows, cols, dst, ST(stream));
+}
+
+int lpm_xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred,
+                 lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(pred && labels && dpred && n > 0, "lpm_xent_bwd: bad arguments");
+  return xent_bwd(pred, labels, n, gscale, dpred, ST(stream));
+}
+int lpm_moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
+                    float loss_scale, void* dlogits_f16, long long ldo, int ncols, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(logits && dpred && dlogits_f16, "lpm_moe_mix_bwd: null pointer");
+  return moe_mix_bwd(logits, ld, B, V, M, expert_off, dpred, loss_scale, H16(dlogits_f16), ldo, ncols, ST(stream));
+}
+int lpm_colsum_chunks(long long rows) { return colsum_chunks(rows); }
+int lpm_colsum(const void* x, int is_f32, long long ld, long long rows, int cols, float alpha, int accumulate,
+               float* partial, float* out, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && partial && out && rows > 0 && cols > 0, "lpm_colsum: bad arguments");
+  return colsum(x, is_f32, ld, rows, cols, alpha, accumulate, partial, out, ST(stream));
+}
+int lpm_colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
+                     float* out, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(partial && out && chunks > 0 && cols > 0, "lpm_colsum_final: bad arguments");
+  return colsum_final(partial, chunks, pstride, cols, alpha, accumulate, out, ST(stream));
+}
+int lpm_gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
+                   const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact,
+                   void* dg_f16, float* dgamma, float* dbeta, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(act && g && gamma && beta && mean && rstd && dout && dact && dg_f16 && dgamma && dbeta, "lpm_gating_bwd: null pointer");
+  return gating_bwd(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, H16(dg_f16), dgamma, dbeta, ST(stream));
+}
+int lpm_layernorm_bwd_chunks(void) { return ln_bwd_chunks(); }
+int lpm_layernorm_joint_bwd(const void* u, const void* dy, long long dy_stride, int B, int rows, int D,
+                            const float* mean_rstd, const float* gamma, const void* mask, void* du,
+                            void* du_masked, float* part_sample, float* part_cols, float* part_cols_du,
+                            lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(u && dy && mean_rstd && gamma && du && part_sample && part_cols, "lpm_layernorm_joint_bwd: null pointer");
+  return layernorm_joint_bwd(CH16(u), CH16(dy), dy_stride, B, rows, D, mean_rstd, gamma, CH16(mask), H16(du),
+                             H16(du_masked), part_sample, part_cols, part_cols_du, ST(stream));
+}
+int lpm_netvlad_norm_bwd(const void* z, const float* rscale, const void* dvhat, long long rows, int K, int D,
+                         const float* centers_t, void* dz, float* q, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(z && rscale && dvhat && centers_t && dz && q, "lpm_netvlad_norm_bwd: null pointer");
+  return vlad_norm_bwd(CH16(z), rscale, CH16(dvhat), rows, K, D, centers_t, H16(dz), q, ST(stream));
+}
+int lpm_assign_bwd_blocks(void) { return assign_bwd_blocks(); }
+int lpm_assign_bwd1(const float* G, const void* assign, const float* q, const void* S, const float* mean,
+                    const float* rstd, long long rows, int T, int K, void* dshat, float* partial,
+                    lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(G && assign && q && S && mean && rstd && dshat && partial, "lpm_assign_bwd1: null pointer");
+  return assign_bwd1(G, CH16(assign), q, CH16(S), mean, rstd, rows, T, K, H16(dshat), partial, ST(stream));
+}
+int lpm_assign_bwd2(void* dshat, const void* S, const float* mean, const float* rstd, const float* gamma,
+                    const float* csum, long long rows, int K, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(dshat && S && mean && rstd && gamma && csum, "lpm_assign_bwd2: null pointer");
+  return assign_bwd2(H16(dshat), CH16(S), mean, rstd, gamma, csum, rows, K, ST(stream));
+}
+int lpm_center_bwd(const void* dV, const void* Z, const float* a_sum, int B, int K, int D, const float* centers_t,
+                   const float* beta_in, float inv_scale, float* dCt, float* E, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(dV && Z && a_sum && centers_t && beta_in && dCt && E, "lpm_center_bwd: null pointer");
+  return center_bwd(CH16(dV), CH16(Z), a_sum, B, K, D, centers_t, beta_in, inv_scale, dCt, E, ST(stream));
+}
+int lpm_input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const float* E, int D, int K,
+                      const float* gamma_in, float* dgamma_in, float* dbeta_in, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(Wc && dWc && dCt && E && gamma_in && dgamma_in && dbeta_in, "lpm_input_bn_grad: null pointer");
+  return input_bn_grad(Wc, dWc, dCt, E, D, K, gamma_in, dgamma_in, dbeta_in, ST(stream));
+}
+int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && y && n > 0, "lpm_cast_scaled_f16: bad arguments");
+  return cast_scaled(x, n, alpha, H16(y), ST(stream));
+}
+int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* dout, long long ldo, const float* lse,
+                     int B, int L, int Dm, int H, float scale, void* dqkv, long long ldd, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(qkv && o && dout && lse && dqkv, "lpm_mha_core_bwd: null pointer");
+  return mha_bwd(CH16(qkv), ld, CH16(o), CH16(dout), ldo, lse, B, L, Dm, H, scale, H16(dqkv), ldd, ST(stream));
 }
 
 }  // extern "C"

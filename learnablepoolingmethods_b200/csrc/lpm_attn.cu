@@ -183,4 +183,177 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
   return LPM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the attention core (V1 scaling mode).  One CTA (8 warps) per (sample, head); L <= 256.
+//   pass A (warp owns a 16-key block j, loops over query blocks i):
+//       S^T = K_j Q_i^T ; P^T = exp2(S^T*scale - lse_i) ; dP^T = V_j dO_i^T ; dS^T = P^T o (dP^T - delta_i)
+//       dV_j += P^T dO_i ; dK_j += dS^T Q_i ; dS^T parked in shared memory (fp16, [key][query])
+//   pass B (warp owns a 16-query block i): dQ_i = sum_j dS_ij K_j with dS read back transposed (ldmatrix.trans)
+// Gradients arrive / leave scaled by the caller's loss scale (the kernel is linear in dO).
+// ------------------------------------------------------------------------------------------------
+constexpr int DS_STRIDE = 264;  // halves per dS row (256 + 8 padding -> conflict-free stores and ldmatrix)
+
+template <int DH>
+__global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
+                                                      const __half* __restrict__ o, const __half* __restrict__ dout,
+                                                      long long ldo, const float* __restrict__ lse, int L, int Dm,
+                                                      int H, float scale, __half* __restrict__ dqkv, long long ldd) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + L * 32;
+  uint8_t* sV = sK + L * 32;
+  uint8_t* sdO = sV + L * 32;
+  float* sLse = reinterpret_cast<float*>(sdO + L * 32);   // lse in log2 units
+  float* sDel = sLse + L;
+  __half* sdS = reinterpret_cast<__half*>(sDel + L);       // [L keys][DS_STRIDE]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const __half* base = qkv + (long long)b * L * ld + h * DH;
+  load_head_tile<DH>(sQ, base, ld, L);
+  load_head_tile<DH>(sK, base + Dm, ld, L);
+  load_head_tile<DH>(sV, base + 2 * Dm, ld, L);
+  load_head_tile<DH>(sdO, dout + (long long)b * L * ldo + h * DH, ldo, L);
+  for (int r = threadIdx.x; r < L; r += blockDim.x) {
+    const __half* orow = o + ((long long)b * L + r) * ldo + h * DH;
+    const __half* drow = dout + ((long long)b * L + r) * ldo + h * DH;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH; c += 8) {
+      const uint4 vo = __ldg(reinterpret_cast<const uint4*>(orow + c));
+      const uint4 vd = __ldg(reinterpret_cast<const uint4*>(drow + c));
+      const __half2* ho = reinterpret_cast<const __half2*>(&vo);
+      const __half2* hd = reinterpret_cast<const __half2*>(&vd);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 a = __half22float2(ho[j]), g = __half22float2(hd[j]); d += a.x * g.x + a.y * g.y; }
+    }
+    sDel[r] = d;
+    sLse[r] = lse[((long long)b * H + h) * L + r] * 1.4426950408889634f;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV), do_s = smem_u32(sdO);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  const int nb = L / 16;
+
+  // ------------------------------- pass A: dK, dV, dS -------------------------------
+  for (int j = warp; j < nb; j += 8) {
+    uint32_t ka0, ka1, ka2, ka3, va0, va1, va2, va3;
+    {
+      const int row = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4(k_s + tile_off(row, lane >> 4), ka0, ka1, ka2, ka3);
+      ldsm_x4(v_s + tile_off(row, lane >> 4), va0, va1, va2, va3);
+    }
+    float dk[2][4], dv[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+    for (int i = 0; i < nb; ++i) {
+      float st[2][4], dp[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) st[n][0] = st[n][1] = st[n][2] = st[n][3] = dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      {
+        uint32_t b0, b1, b2, b3;
+        const int qrow = i * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldsm_x4(q_s + tile_off(qrow, (lane >> 3) & 1), b0, b1, b2, b3);
+        mma16816(st[0], ka0, ka1, ka2, ka3, b0, b1);
+        mma16816(st[1], ka0, ka1, ka2, ka3, b2, b3);
+        ldsm_x4(do_s + tile_off(qrow, (lane >> 3) & 1), b0, b1, b2, b3);
+        mma16816(dp[0], va0, va1, va2, va3, b0, b1);
+        mma16816(dp[1], va0, va1, va2, va3, b2, b3);
+      }
+      // columns of the transposed tiles are queries: n-tile n -> queries i*16 + n*8 + (lane&3)*2 + {0,1}
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int qc = i * 16 + n * 8 + (lane & 3) * 2;
+        const float l0 = sLse[qc], l1 = sLse[qc + 1], d0 = sDel[qc], d1 = sDel[qc + 1];
+        const float p0 = exp2f(st[n][0] * scale_log2 - l0), p1 = exp2f(st[n][1] * scale_log2 - l1);
+        const float p2 = exp2f(st[n][2] * scale_log2 - l0), p3 = exp2f(st[n][3] * scale_log2 - l1);
+        st[n][0] = p0; st[n][1] = p1; st[n][2] = p2; st[n][3] = p3;
+        dp[n][0] = p0 * (dp[n][0] - d0); dp[n][1] = p1 * (dp[n][1] - d1);
+        dp[n][2] = p2 * (dp[n][2] - d0); dp[n][3] = p3 * (dp[n][3] - d1);
+      }
+      // A fragments (rows = keys, k = queries) from the accumulator layout
+      const uint32_t pa0 = pack_half2(st[0][0], st[0][1]), pa1 = pack_half2(st[0][2], st[0][3]);
+      const uint32_t pa2 = pack_half2(st[1][0], st[1][1]), pa3 = pack_half2(st[1][2], st[1][3]);
+      const uint32_t sa0 = pack_half2(dp[0][0], dp[0][1]), sa1 = pack_half2(dp[0][2], dp[0][3]);
+      const uint32_t sa2 = pack_half2(dp[1][0], dp[1][1]), sa3 = pack_half2(dp[1][2], dp[1][3]);
+      {
+        uint32_t b0, b1, b2, b3;
+        const int qrow = i * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(do_s + tile_off(qrow, lane >> 4), b0, b1, b2, b3);
+        mma16816(dv[0], pa0, pa1, pa2, pa3, b0, b1);
+        if (DH == 16) mma16816(dv[1], pa0, pa1, pa2, pa3, b2, b3);
+        ldsm_x4_t(q_s + tile_off(qrow, lane >> 4), b0, b1, b2, b3);
+        mma16816(dk[0], sa0, sa1, sa2, sa3, b0, b1);
+        if (DH == 16) mma16816(dk[1], sa0, sa1, sa2, sa3, b2, b3);
+      }
+      // park dS^T: element (key = j*16 + lane/4 (+8), query = i*16 + n*8 + (lane&3)*2)
+      {
+        __half* r0 = sdS + (size_t)(j * 16 + (lane >> 2)) * DS_STRIDE + i * 16 + (lane & 3) * 2;
+        __half* r1 = r0 + 8 * DS_STRIDE;
+        *reinterpret_cast<uint32_t*>(r0) = sa0;
+        *reinterpret_cast<uint32_t*>(r1) = sa1;
+        *reinterpret_cast<uint32_t*>(r0 + 8) = sa2;
+        *reinterpret_cast<uint32_t*>(r1 + 8) = sa3;
+      }
+    }
+    const int r0 = j * 16 + (lane >> 2), r1 = r0 + 8;
+    __half* dk0 = dqkv + ((long long)b * L + r0) * ldd + Dm + h * DH + (lane & 3) * 2;
+    __half* dk1 = dqkv + ((long long)b * L + r1) * ldd + Dm + h * DH + (lane & 3) * 2;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<__half2*>(dk0 + n * 8) = __floats2half2_rn(dk[n][0] * scale, dk[n][1] * scale);
+      *reinterpret_cast<__half2*>(dk1 + n * 8) = __floats2half2_rn(dk[n][2] * scale, dk[n][3] * scale);
+      *reinterpret_cast<__half2*>(dk0 + Dm + n * 8) = __floats2half2_rn(dv[n][0], dv[n][1]);
+      *reinterpret_cast<__half2*>(dk1 + Dm + n * 8) = __floats2half2_rn(dv[n][2], dv[n][3]);
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------- pass B: dQ -------------------------------
+  const uint32_t ds_s = smem_u32(sdS);
+  for (int i = warp; i < nb; i += 8) {
+    float dq[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      const int key = j * 16 + (lane & 7) + (lane >> 4) * 8;
+      const int qcol = i * 16 + ((lane >> 3) & 1) * 8;
+      ldsm_x4_t(ds_s + (uint32_t)(key * DS_STRIDE + qcol) * 2, a0, a1, a2, a3);
+      const int krow = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4_t(k_s + tile_off(krow, lane >> 4), b0, b1, b2, b3);
+      mma16816(dq[0], a0, a1, a2, a3, b0, b1);
+      if (DH == 16) mma16816(dq[1], a0, a1, a2, a3, b2, b3);
+    }
+    const int r0 = i * 16 + (lane >> 2), r1 = r0 + 8;
+    __half* q0 = dqkv + ((long long)b * L + r0) * ldd + h * DH + (lane & 3) * 2;
+    __half* q1 = dqkv + ((long long)b * L + r1) * ldd + h * DH + (lane & 3) * 2;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<__half2*>(q0 + n * 8) = __floats2half2_rn(dq[n][0] * scale, dq[n][1] * scale);
+      *reinterpret_cast<__half2*>(q1 + n * 8) = __floats2half2_rn(dq[n][2] * scale, dq[n][3] * scale);
+    }
+  }
+}
+
+int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
+            int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st) {
+  const int DH = Dm / H;
+  LPM_REQUIRE(DH * H == Dm && (DH == 8 || DH == 16), "mha_bwd: head depth must be 8 or 16 (Dm=%d H=%d)", Dm, H);
+  LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 256, "mha_bwd: length must be a multiple of 16 in [16,256] (got %d)", L);
+  LPM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0, "mha_bwd: leading dimensions must be multiples of 8");
+  const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (size_t)L * DS_STRIDE * 2;
+  if (DH == 16) {
+    static bool set16 = false;
+    if (!set16) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set16 = true; }
+    mha_bwd_kernel<16><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd);
+  } else {
+    static bool set8 = false;
+    if (!set8) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set8 = true; }
+    mha_bwd_kernel<8><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd);
+  }
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
 }  // namespace lpm

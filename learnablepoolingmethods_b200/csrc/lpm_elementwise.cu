@@ -139,17 +139,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_CHUNKS = 32;
 
-__global__ void __launch_bounds__(256) ln_stats_kernel(__half* __restrict__ a, const __half* __restrict__ b,
-                                                       const float* __restrict__ b_row_scale, int rows, int D,
-                                                       long long a_sample_stride, long long b_sample_stride,
-                                                       float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __half* a, const __half* __restrict__ b,
+                                                       const float* __restrict__ b_row_scale, __half* u_out,
+                                                       int rows, int D, long long a_sample_stride,
+                                                       long long b_sample_stride, float* __restrict__ partial) {
   __shared__ float red[32];
   const int sample = blockIdx.y, chunk = blockIdx.x;
   const long long n8 = (long long)rows * D / 8;
   const long long per = (n8 + LN_CHUNKS - 1) / LN_CHUNKS;
   const long long i0 = chunk * per, i1 = min(n8, i0 + per);
-  uint4* pa = reinterpret_cast<uint4*>(a + sample * a_sample_stride);
+  const uint4* pa = reinterpret_cast<const uint4*>(a + sample * a_sample_stride);
+  uint4* pu = reinterpret_cast<uint4*>(u_out + sample * a_sample_stride);   // u_out may alias a
   const uint4* pb = b ? reinterpret_cast<const uint4*>(b + sample * b_sample_stride) : nullptr;
+  const bool copy_only = (pb == nullptr) && (u_out != a);
   float s = 0.f, q = 0.f;
   for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     uint4 va = pa[i];
@@ -165,11 +167,12 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(__half* __restrict__ a, c
       for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hb[j]); u[2 * j] += f.x * rs; u[2 * j + 1] += f.y * rs; }
 #pragma unroll
       for (int j = 0; j < 4; ++j) ha[j] = __floats2half2_rn(u[2 * j], u[2 * j + 1]);
-      pa[i] = va;
+      pu[i] = va;
       // statistics of the stored (fp16-rounded) u, which is what pass 2 normalises
 #pragma unroll
       for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(ha[j]); u[2 * j] = f.x; u[2 * j + 1] = f.y; }
     }
+    if (copy_only) pu[i] = va;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s += u[j]; q += u[j] * u[j]; }
   }
@@ -292,15 +295,15 @@ __global__ void gating_fwd_kernel(const float* __restrict__ act, const float* __
 
 // ------------------------------------------------------------------------------------------------
 // MoE mixing (video_level_models.py:116-126): logits [B][ld] = [gates V*(M+1) | experts V*M]
-//   p[b,v] = sum_m softmax(gate[b,v,:])[m] * sigmoid(expert[b,v,m])
+//   p[b,v] = sum_m softmax(gate[b,v,:])[m] * sigmoid(expert[b,v,m]);  experts start at column expert_off
 // ------------------------------------------------------------------------------------------------
 __global__ void moe_mix_kernel(const float* __restrict__ logits, long long ld, int B, int V, int M,
-                               float* __restrict__ pred) {
+                               int expert_off, float* __restrict__ pred) {
   const long long n = (long long)B * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / V), v = (int)(i - (long long)b * V);
     const float* gl = logits + b * ld + (long long)v * (M + 1);
-    const float* el = logits + b * ld + (long long)V * (M + 1) + (long long)v * M;
+    const float* el = logits + b * ld + expert_off + (long long)v * M;
     float mx = gl[0];
     for (int m = 1; m <= M; ++m) mx = fmaxf(mx, gl[m]);
     float den = 0.f, num = 0.f;
@@ -367,6 +370,20 @@ __global__ void __launch_bounds__(256) vlad_finalize_kernel(const __half* __rest
   }
 }
 
+// y[r][:] = fp16(x[r][:] * row_scale[r])   (materialises the normalised VLAD descriptor for training)
+__global__ void __launch_bounds__(256) scale_rows_kernel(const __half* __restrict__ x, const float* __restrict__ rs,
+                                                         long long rows, int D, __half* __restrict__ y) {
+  const long long n8 = rows * D / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float sc = __ldg(rs + (i * 8) / D);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); h[j] = __floats2half2_rn(f.x * sc, f.y * sc); }
+    reinterpret_cast<uint4*>(y)[i] = v;
+  }
+}
+
 // fp32 2-D transpose (parameter layout preparation, e.g. cluster_weights2 [D][K] -> [K][D])
 __global__ void transpose_2d_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
   __shared__ float tile[32][33];
@@ -420,20 +437,21 @@ int bn_finalize(const float* psum, const float* psq, int P, long long pstride, i
   return LPM_OK;
 }
 
-int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, int B, int rows, int D,
+int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, __half* u_out, int B, int rows, int D,
                     long long a_stride, long long b_stride, const float* gamma, const float* beta, float eps,
                     __half* y, long long y_stride, float* partial, float* save_mean_rstd, cudaStream_t st) {
+  if (u_out == nullptr) u_out = a;
   LPM_REQUIRE(D % 8 == 0 && a_stride % 8 == 0 && b_stride % 8 == 0 && y_stride % 8 == 0,
               "layernorm_joint: D and sample strides must be multiples of 8");
   dim3 g1(LN_CHUNKS, B);
-  ln_stats_kernel<<<g1, 256, 0, st>>>(a, b, b_row_scale, rows, D, a_stride, b_stride, partial);
+  ln_stats_kernel<<<g1, 256, 0, st>>>(a, b, b_row_scale, u_out, rows, D, a_stride, b_stride, partial);
   LPM_CUDA_CHECK(cudaGetLastError());
   int chunks = (num_sms() * 8 + B - 1) / B;
   const long long n8 = (long long)rows * D / 8;
   if (chunks > (n8 + 255) / 256) chunks = (int)((n8 + 255) / 256);
   if (chunks < 1) chunks = 1;
   dim3 g2(chunks, B);
-  ln_apply_kernel<<<g2, 256, 0, st>>>(a, rows, D, a_stride, partial, gamma, beta, eps, y, y_stride, save_mean_rstd);
+  ln_apply_kernel<<<g2, 256, 0, st>>>(u_out, rows, D, a_stride, partial, gamma, beta, eps, y, y_stride, save_mean_rstd);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -455,8 +473,8 @@ int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_d
   return LPM_OK;
 }
 
-int moe_mix(const float* logits, long long ld, int B, int V, int M, float* pred, cudaStream_t st) {
-  moe_mix_kernel<<<grid_for((long long)B * V, 256), 256, 0, st>>>(logits, ld, B, V, M, pred);
+int moe_mix(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred, cudaStream_t st) {
+  moe_mix_kernel<<<grid_for((long long)B * V, 256), 256, 0, st>>>(logits, ld, B, V, M, expert_off, pred);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -471,6 +489,13 @@ int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
             cudaStream_t st) {
   cast_2d_kernel<<<grid_for((long long)rows * cols_dst, 256), 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, cols_dst);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int scale_rows(const __half* x, const float* rs, long long rows, int D, __half* y, cudaStream_t st) {
+  LPM_REQUIRE(D % 8 == 0, "scale_rows: D must be a multiple of 8");
+  scale_rows_kernel<<<grid_for(rows * D / 8, 256), 256, 0, st>>>(x, rs, rows, D, y);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

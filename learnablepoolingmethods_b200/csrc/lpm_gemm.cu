@@ -35,6 +35,11 @@ struct GemmKernelParams {
   float alpha;
   float* stat_sum;
   float* stat_sq;
+  const __half* mask;   // optional: v = mask > 0 ? v : 0   (ReLU backward fused into the producing GEMM)
+  long long ld_mask;
+  const __half* add1;   // optional fp16 addends (fused residual-gradient sums)
+  const __half* add2;
+  long long ld_add;
 };
 
 template <int BN, int STAGES>
@@ -195,6 +200,53 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (p.relu) x = fmaxf(x, 0.f);
           v[i] = x;
         }
+        if ((p.add1 != nullptr || p.mask != nullptr) && row_ok) {
+          const long long bofs = (long long)bz * p.out_batch_stride;
+          if (p.add1 != nullptr) {
+            const __half* a1 = p.add1 + bofs + (long long)row * p.ld_add + col0;
+            const __half* a2 = p.add2 ? p.add2 + bofs + (long long)row * p.ld_add + col0 : nullptr;
+            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(a1) & 15) == 0) &&
+                (a2 == nullptr || (reinterpret_cast<uintptr_t>(a2) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(a1) + i);
+                const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+                if (a2) {
+                  const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(a2) + i);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&w2);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+                }
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
+                v[i] += __half2float(a1[i]);
+                if (a2) v[i] += __half2float(a2[i]);
+              }
+            }
+          }
+          if (p.mask != nullptr) {
+            const __half* mk = p.mask + (long long)bz * p.out_batch_stride + (long long)row * p.ld_mask + col0;
+            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(mk) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(mk) + i);
+                const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h[j]);
+                  if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+                  if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+                }
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i)
+                if (!(__half2float(mk[i]) > 0.f)) v[i] = 0.f;
+            }
+          }
+        }
         if (p.stat_sum != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -312,6 +364,9 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
   p.bias = g.bias; p.row_scale = g.row_scale; p.row_scale_batch_stride = g.row_scale_batch_stride;
   p.relu = g.relu; p.accumulate = g.accumulate; p.alpha = g.alpha;
   p.stat_sum = g.stat_sum; p.stat_sq = g.stat_sq;
+  p.mask = reinterpret_cast<const __half*>(g.mask); p.ld_mask = g.ld_mask;
+  p.add1 = reinterpret_cast<const __half*>(g.add1); p.add2 = reinterpret_cast<const __half*>(g.add2); p.ld_add = g.ld_add;
+  LPM_REQUIRE(!(g.add2 && !g.add1), "gemm: add2 requires add1");
 
   CUtensorMap ta, tb;
   int rc;

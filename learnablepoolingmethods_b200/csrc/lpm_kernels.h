@@ -22,7 +22,8 @@ int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, in
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
                 int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st);
-int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, int B, int rows, int D,
+int scale_rows(const __half* x, const float* rs, long long rows, int D, __half* y, cudaStream_t st);
+int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, __half* u_out, int B, int rows, int D,
                     long long a_stride, long long b_stride, const float* gamma, const float* beta, float eps,
                     __half* y, long long y_stride, float* partial, float* save_mean_rstd, cudaStream_t st);
 int splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols, const float* bias,
@@ -30,7 +31,7 @@ int splitk_reduce(const float* part, int splits, long long split_stride, long lo
 int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
                const float* beta, float* mm, float* mv, float decay, float eps, int training, float* out32,
                __half* out16, float* save_mean, float* save_rstd, cudaStream_t st);
-int moe_mix(const float* logits, long long ld, int B, int V, int M, float* pred, cudaStream_t st);
+int moe_mix(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred, cudaStream_t st);
 int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss, cudaStream_t st);
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
             cudaStream_t st);
@@ -40,6 +41,39 @@ int vlad_finalize(const __half* z, const float* rscale, int B, int K, int D, int
 // lpm_attn.cu
 int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float scale, const float* key_scale,
             const float* key_shift, __half* out, long long ldo, float* lse, cudaStream_t st);
+
+int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
+            int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st);
+
+// lpm_backward.cu
+int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred, cudaStream_t st);
+int moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
+                float loss_scale, __half* dl, long long ldo, int ncols, cudaStream_t st);
+int colsum_chunks(long long rows);
+int colsum(const void* x, int is_f32, long long ld, long long rows, int cols, float alpha, int accumulate,
+           float* partial, float* out, cudaStream_t st);
+int colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
+                 float* out, cudaStream_t st);
+int gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
+               const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact, __half* dg,
+               float* dgamma, float* dbeta, cudaStream_t st);
+int ln_bwd_chunks();
+int layernorm_joint_bwd(const __half* u, const __half* dy, long long dy_stride, int B, int rows, int D,
+                        const float* mean_rstd, const float* gamma, const __half* mask, __half* du,
+                        __half* du_masked, float* part_sample, float* part_cols, float* part_cols_du,
+                        cudaStream_t st);
+int vlad_norm_bwd(const __half* z, const float* rs, const __half* dvh, long long rows, int K, int D,
+                  const float* centers_t, __half* dz, float* q, cudaStream_t st);
+int assign_bwd_blocks();
+int assign_bwd1(const float* G, const __half* A, const float* q, const __half* S, const float* mean,
+                const float* rstd, long long rows, int T, int K, __half* dsh, float* partial, cudaStream_t st);
+int assign_bwd2(__half* dsh, const __half* S, const float* mean, const float* rstd, const float* gamma,
+                const float* csum, long long rows, int K, cudaStream_t st);
+int center_bwd(const __half* dV, const __half* Z, const float* a_sum, int B, int K, int D, const float* centers_t,
+               const float* beta_in, float inv_scale, float* dCt, float* E, cudaStream_t st);
+int input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const float* E, int D, int K,
+                  const float* gamma_in, float* dgamma_in, float* dbeta_in, cudaStream_t st);
+int cast_scaled(const float* x, long long n, float alpha, __half* y, cudaStream_t st);
 
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,

@@ -1,0 +1,433 @@
+"""Execution engine for the NetVladV1 / NetVladV2 hot path.
+
+Sequences the C-ABI kernels (liblpm_b200.so) for the forward pass and -- in training -- records what
+the hand-written backward needs.  torch owns memory and the autograd edge at the model boundary
+(`NetVladFunction`); all arithmetic runs in the CUDA kernels.  There is no fallback path.
+
+Reference lines mirrored: frame_level_models.py:2222-2377 (V1), :2383-2513 (V2), :2765-2824 (NetVLAD),
+transformer_utils.py:374-457,507-767, video_level_models.py:48-159, model_utils.py:101-122.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .variables import VariableStore
+
+
+def _ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+@dataclass
+class NetVladConfig:
+    model: str = "NetVladV1"
+    iterations: int = 256
+    cluster_size: int = 256
+    hidden_size: int = 512
+    vocab_size: int = 3862
+    num_mixtures: int = 2
+    rgb_dim: int = 1024
+    audio_dim: int = 128
+    rgb_heads: int = 64        # frame_level_models.py:2285
+    audio_heads: int = 16      # frame_level_models.py:2297
+    add_batch_norm: bool = True
+    gating: bool = True
+    remove_diag: bool = False
+    moe_l2: float = 1e-8
+    d5_raw_reshape: bool = False   # SURVEY.md defect D5 switch (raw reinterpret instead of transpose)
+    dropout_rate: float = 0.9      # D7: tf.layers.dropout(rate=1-0.1) in TransformerEncoderMod
+    loss_scale: float = 1024.0     # fp16 activation-gradient scaling inside the backward
+    hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
+
+    def modalities(self):
+        ka = self.cluster_size // 4          # D7: integer division (frame_level_models.py:2263)
+        return (("video", 0, self.rgb_dim, self.cluster_size, self.rgb_heads, "encode1"),
+                ("audio", self.rgb_dim, self.audio_dim, ka, self.audio_heads, "encode2"))
+
+    @property
+    def feature_size(self):
+        return self.rgb_dim + self.audio_dim
+
+    @property
+    def vlad_dim(self):
+        return sum(D * K for _, _, D, K, _, _ in self.modalities())
+
+
+class NetVladEngine:
+    def __init__(self, cfg: NetVladConfig, store: VariableStore):
+        self.cfg = cfg
+        self.store = store
+        if cfg.model not in ("NetVladV1", "NetVladV2"):
+            raise ValueError(f"unknown model {cfg.model}")
+        if not cfg.add_batch_norm:
+            # frame_level_models.py:2236 `add_batch_norm or FLAGS...` can never be False and the no-BN
+            # gating branch raises in TF.
+            raise NotImplementedError("netvlad_add_batch_norm=False is unreachable in the reference (D7)")
+        self.build_variables()
+
+    # ------------------------------------------------------------------------------------------
+    # variables (names = TF variable names)
+    # ------------------------------------------------------------------------------------------
+    def build_variables(self):
+        c, s = self.cfg, self.store
+        s.batch_norm_vars("input_bn", c.feature_size)
+        for name, _, D, K, H, sid in c.modalities():
+            with s.variable_scope(name + "_VLAD"):
+                if c.model == "NetVladV1":
+                    s.get_variable("cluster_weights", (D, K), "normal", 1 / math.sqrt(D))
+                    s.batch_norm_vars("cluster_bn", K)
+                    s.get_variable("cluster_weights2", (1, D, K), "normal", 1 / math.sqrt(D))
+                else:
+                    with s.variable_scope("cluster_attention"):
+                        self._dense_vars("q", D, D, False); self._dense_vars("k", D, D, False); self._dense_vars("v", D, D, False)
+                        s.batch_norm_vars("logits_bn", c.iterations)
+                        s.batch_norm_vars("attention_bn", D)
+                        self._dense_vars("output_transform", D, D, True)
+                        self._ln_vars("LayerNorm", D)
+                        self._dense_vars("filter_outputencode", D, 4 * D, True)
+                        s.batch_norm_vars("filter_bn", 4 * D)
+                        self._dense_vars("ff_outputencode", 4 * D, K, True)
+                        s.batch_norm_vars("feed_output_bn", K)
+                    s.get_variable("cluster_centers", (D, K), "normal", 1 / math.sqrt(D))
+            if c.model == "NetVladV1":
+                with s.variable_scope(name + "_attention"):
+                    self._dense_vars("q", D, D, False); self._dense_vars("k", D, D, False); self._dense_vars("v", D, D, False)
+                    self._dense_vars("output_transform", D, D, True)
+                    for ln in ("LayerNorm", "LayerNorm_1", "LayerNorm_2"):
+                        self._ln_vars(ln, D)
+                    self._dense_vars("filter_output" + sid, D, 4 * D, True)
+                    self._dense_vars("ff_output" + sid, 4 * D, D, True)
+        s.get_variable("hidden1_weights", (c.vlad_dim, c.hidden_size), "normal", 1 / math.sqrt(c.cluster_size))
+        s.get_variable("hidden1_biases", (c.hidden_size,), "normal", 0.01)
+        s.get_variable("gating_weights_2", (c.hidden_size, c.hidden_size), "normal", 1 / math.sqrt(c.hidden_size))
+        s.batch_norm_vars("gating_bn", c.hidden_size)
+        V, M = c.vocab_size, c.num_mixtures
+        with s.variable_scope("gates"):
+            s.get_variable("weights", (c.hidden_size, V * (M + 1)), "glorot")
+        with s.variable_scope("experts"):
+            s.get_variable("weights", (c.hidden_size, V * M), "glorot")
+            s.get_variable("biases", (V * M,), "zeros")
+
+    def _dense_vars(self, scope, i, o, bias):
+        s = self.store
+        with s.variable_scope(scope):
+            s.get_variable("kernel", (i, o), "glorot")
+            if bias:
+                s.get_variable("bias", (o,), "zeros")
+
+    def _ln_vars(self, scope, c):
+        s = self.store
+        with s.variable_scope(scope):
+            s.get_variable("beta", (c,), "zeros")
+            s.get_variable("gamma", (c,), "ones")
+
+    # ------------------------------------------------------------------------------------------
+    # fp16 operand shadows
+    # ------------------------------------------------------------------------------------------
+    def refresh_shadows(self, force=False):
+        s, c = self.store, self.cfg
+        if not force and s.shadow_version == s.version:
+            return s.shadows
+        v, sh = s.vars, s.shadows
+        dev = s.device
+
+        def buf(key, shape, dtype=torch.float16):
+            t = sh.get(key)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = torch.zeros(shape, dtype=dtype, device=dev)
+                sh[key] = t
+            return t
+
+        for name, _, D, K, H, sid in c.modalities():
+            vs = name + "_VLAD"
+            if c.model == "NetVladV1":
+                ops.cast_f16(v[vs + "/cluster_weights"], buf(vs + "/wc16", (D, K)))
+                sh[vs + "/centers_t"] = ops.transpose_f32(v[vs + "/cluster_weights2"][0])
+                a = name + "_attention"
+                w1, w2 = a + "/filter_output" + sid, a + "/ff_output" + sid
+            else:
+                sh[vs + "/centers_t"] = ops.transpose_f32(v[vs + "/cluster_centers"])
+                a = vs + "/cluster_attention"
+                w1, w2 = a + "/filter_outputencode", a + "/ff_outputencode"
+            qkv = buf(a + "/wqkv16", (D, 3 * D))
+            for i, n in enumerate(("q", "k", "v")):
+                ops.cast_f16(v[f"{a}/{n}/kernel"], qkv[:, i * D:(i + 1) * D], cols_dst=D)
+            ops.cast_f16(v[a + "/output_transform/kernel"], buf(a + "/wo16", (D, D)))
+            ops.cast_f16(v[w1 + "/kernel"], buf(a + "/w1_16", (D, 4 * D)))
+            n2 = v[w2 + "/kernel"].shape[1]
+            ops.cast_f16(v[w2 + "/kernel"], buf(a + "/w2_16", (4 * D, _ceil8(n2))), cols_dst=_ceil8(n2))
+        ops.cast_f16(v["hidden1_weights"], buf("wh16", (c.vlad_dim, c.hidden_size)))
+        ops.cast_f16(v["gating_weights_2"], buf("wg16", (c.hidden_size, c.hidden_size)))
+        V, M = c.vocab_size, c.num_mixtures
+        g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
+        wm = buf("wmoe16", (c.hidden_size, g8 + e8))
+        ops.cast_f16(v["gates/weights"], wm[:, :g8], cols_dst=g8)
+        ops.cast_f16(v["experts/weights"], wm[:, g8:], cols_dst=e8)
+        bm = buf("bmoe", (g8 + e8,), torch.float32)
+        bm[g8:g8 + V * M].copy_(v["experts/biases"])
+        sh["moe_g8"] = g8
+        s.shadow_version = s.version
+        return sh
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
+                save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False):
+        """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264);
+        num_frames int [B].  Returns (predictions fp32 [B, vocab], ctx)."""
+        c, s = self.cfg, self.store
+        v = s.vars
+        sh = self.refresh_shadows()
+        if model_input.dim() != 3 or model_input.shape[2] != c.feature_size:
+            raise ValueError(f"model_input must be [B, frames, {c.feature_size}], got {tuple(model_input.shape)}")
+        if not model_input.is_cuda:
+            raise RuntimeError("model_input must live on the GPU (there is no CPU path)")
+        x = model_input.contiguous().float()
+        nf = num_frames.to(device=x.device, dtype=torch.int32).contiguous()
+        B, T, F = x.shape[0], c.iterations, c.feature_size
+        ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}}
+        save = save_for_backward
+
+        # ---- a2 + a3: uniform frame sampling + input_bn -> fp16 frames [B*T, F] -----------------
+        if is_training:
+            part = ops.sample_bn_stats(x, nf, T)
+            r = ops.bn_finalize(part[:, 0], part[:, 1], B * T, v["input_bn/gamma"], v["input_bn/beta"],
+                                v["input_bn/moving_mean"], v["input_bn/moving_variance"], training=True,
+                                bessel=True, save=save, psum_stride=2 * F)
+        else:
+            r = ops.bn_finalize(None, None, 1, v["input_bn/gamma"], v["input_bn/beta"], v["input_bn/moving_mean"],
+                                v["input_bn/moving_variance"], training=False, bessel=True, save=save)
+        in_scale, in_shift = r[0], r[1]
+        xb = ops.sample_bn_apply(x, nf, T, in_scale, in_shift)
+        if save:
+            ctx["xb"] = xb
+            ctx["input_bn_stats"] = r[2]
+
+        vlad = torch.empty((B, c.vlad_dim), dtype=torch.float16, device=x.device)
+        off = 0
+        for name, col0, D, K, H, sid in c.modalities():
+            X = xb[:, col0:col0 + D]
+            if c.model == "NetVladV1":
+                m = self._v1_modality(name, X, B, T, D, K, H, sid, is_training, save, vlad[:, off:off + K * D], ctx,
+                                      return_intermediates)
+            else:
+                raise NotImplementedError("NetVladV2 forward is wired in engine_v2")
+            if save:
+                ctx[name] = m
+            off += K * D
+
+        pred = self._head(vlad, B, is_training, save, ctx, return_intermediates)
+        return pred, ctx
+
+    def _v1_modality(self, name, X, B, T, D, K, H, sid, training, save, out_view, ctx, want_inter):
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        vs, a = name + "_VLAD", name + "_attention"
+        m: Dict[str, object] = {}
+        wc16 = sh[vs + "/wc16"]
+        # ---- cluster_bn statistics over all B*T rows (recompute pass, nothing stored) ------------
+        bn = vs + "/cluster_bn"
+        if training:
+            _, st = ops.gemm(wc16, X, a_mn=True, b_mn=False, out="none", stats=True)    # S^T = Wc^T X^T
+            r = ops.bn_finalize(st[0].reshape(-1, K), st[1].reshape(-1, K), B * T, v[bn + "/gamma"], v[bn + "/beta"],
+                                v[bn + "/moving_mean"], v[bn + "/moving_variance"], training=True, bessel=True, save=save)
+        else:
+            r = ops.bn_finalize(None, None, 1, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"],
+                                v[bn + "/moving_variance"], training=False, bessel=True, save=save)
+        lscale, lshift = r[0], r[1]
+        # ---- K1: fused soft-assignment + aggregation + norms -----------------------------------
+        z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, lscale, lshift, sh[vs + "/centers_t"],
+                                                        save_assign=save)
+        if want_inter:
+            ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
+        if c.d5_raw_reshape:
+            raise NotImplementedError("d5_raw_reshape: the raw-reshape alternative of SURVEY D5 is not wired yet")
+        # ---- a9: attention block over the K cluster descriptors (rows = (b,k), cols = d) -------
+        Z2 = z.view(B * K, D)
+        rs = rscale.view(B * K)
+        if save:
+            # training keeps the normalised descriptor as a GEMM operand for the weight gradients
+            zn = ops.scale_rows_f16(Z2, rs)
+            qkv = ops.gemm(zn, sh[a + "/wqkv16"])
+            resid, resid_rs = zn, None
+        else:
+            qkv = ops.gemm(Z2, sh[a + "/wqkv16"], row_scale=rs)
+            resid, resid_rs = Z2, rs
+        dh = D // H
+        o = ops.mha_core_fwd(qkv, B, K, D, H, scale=dh ** -0.5, want_lse=save)
+        lse = None
+        if save:
+            o, lse = o
+        att = ops.gemm(o, sh[a + "/wo16"], bias=v[a + "/output_transform/bias"])
+        h1 = ops.layernorm_joint_fwd(att, resid, resid_rs, B, K, D, v[a + "/LayerNorm/gamma"], v[a + "/LayerNorm/beta"], save=save)
+        st1 = None
+        if save:
+            h1, st1 = h1
+        f1 = ops.gemm(h1.view(B * K, D), sh[a + "/w1_16"], bias=v[f"{a}/filter_output{sid}/bias"], relu=True)
+        f2 = ops.gemm(f1, sh[a + "/w2_16"], bias=v[f"{a}/ff_output{sid}/bias"], relu=True)
+        u2 = torch.empty_like(f2) if save else f2
+        h2 = ops.layernorm_joint_fwd(f2, h1, None, B, K, D, v[a + "/LayerNorm_1/gamma"], v[a + "/LayerNorm_1/beta"],
+                                     save=save, u_out=u2)
+        st2 = None
+        if save:
+            h2, st2 = h2
+        r3 = ops.layernorm_joint_fwd(h2, h1, None, B, K, D, v[a + "/LayerNorm_2/gamma"], v[a + "/LayerNorm_2/beta"],
+                                     out=out_view, out_stride=out_view.stride(0), save=save)
+        if want_inter:
+            ctx["inter"]["att_" + name] = out_view.float().reshape(B, K, D)
+        if save:
+            m.update(dict(X=X, z=z, rscale=rscale, a_sum=a_sum, assign=assign, cluster_bn_stats=r[2], lscale=lscale,
+                          zn=zn, qkv=qkv, o=o, lse=lse, u1=att, st1=st1, h1=h1, f1=f1, f2=f2, u2=u2, st2=st2,
+                          u3=h2, st3=r3[1]))
+        return m
+
+    def _head(self, vlad, B, training, save, ctx, want_inter):
+        """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        Hn = c.hidden_size
+        parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
+        act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
+        act16 = torch.empty((B, Hn), dtype=torch.float16, device=vlad.device)
+        ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=act16)
+        if c.gating:
+            gates = ops.gemm(act16, sh["wg16"], out_dtype=torch.float32)
+            diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
+            r = ops.gating_fwd(act32, gates, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
+                               v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save)
+            gated32, gated16 = r[0], r[1]
+        else:
+            gates, gated32, gated16, r = None, act32, act16, (None, None, None)
+        logits = ops.gemm(gated16, sh["wmoe16"], bias=sh["bmoe"], out_dtype=torch.float32)
+        pred = ops.moe_mix_fwd(logits, c.vocab_size, c.num_mixtures, expert_off=sh["moe_g8"])
+        if want_inter:
+            ctx["inter"].update(hidden=act32, gated=gated32)
+        if save:
+            ctx["head"] = dict(vlad=vlad, act32=act32, act16=act16, gates=gates, gating_stats=r[2] if c.gating else None,
+                               gated32=gated32, gated16=gated16, logits=logits, pred=pred)
+        return pred
+
+    # ------------------------------------------------------------------------------------------
+    # backward (NetVladV1): hand-written autodiff of the forward above
+    # ------------------------------------------------------------------------------------------
+    def backward(self, ctx, dpred: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
+        Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        if c.model != "NetVladV1":
+            raise NotImplementedError("backward is implemented for NetVladV1 in this round")
+        if c.remove_diag:
+            raise NotImplementedError("gating_remove_diag backward")
+        S, inv = float(c.loss_scale), 1.0 / float(c.loss_scale)
+        B, hd = ctx["B"], ctx["head"]
+        V, M, Hn = c.vocab_size, c.num_mixtures, c.hidden_size
+        g8 = sh["moe_g8"]
+        f32 = torch.float32
+        grads: Dict[str, torch.Tensor] = {}
+        hook = ctx.get("grad_hook")
+
+        def put(name, g):
+            grads[name] = g
+            if hook is not None:
+                hook(name, g)
+
+        # ---- MoE (video_level_models.py:86-126) ------------------------------------------------
+        dl16 = ops.moe_mix_bwd(hd["logits"], dpred, V, M, g8, S)
+        gated16 = hd["gated16"]
+        put("experts/biases", ops.colsum(dl16[:, g8:], alpha=inv, cols=V * M))
+        put("gates/weights", ops.gemm(gated16, dl16[:, :g8], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * (M + 1)))
+        put("experts/weights", ops.gemm(gated16, dl16[:, g8:], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * M))
+        dgated = ops.gemm(dl16, sh["wmoe16"], b_mn=False, out_dtype=f32)
+        # ---- context gating (frame_level_models.py:2342-2368) -----------------------------------
+        if c.gating:
+            dact, dg16, dgam, dbet = ops.gating_bwd(hd["act32"], hd["gates"], v["gating_bn/gamma"], v["gating_bn/beta"],
+                                                    hd["gating_stats"], dgated, inv)
+            put("gating_bn/gamma", dgam)
+            put("gating_bn/beta", dbet)
+            put("gating_weights_2", ops.gemm(hd["act16"], dg16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+            ops.gemm(dg16, sh["wg16"], b_mn=False, out=dact, accumulate=True)
+        else:
+            dact = dgated
+        # ---- hidden projection (frame_level_models.py:2314-2334) --------------------------------
+        put("hidden1_biases", ops.colsum(dact, alpha=inv))
+        dact16 = ops.cast_scaled_f16(dact)
+        put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        dvlad = ops.gemm(dact16, sh["wh16"], b_mn=False)                      # [B, vlad_dim] fp16
+        dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
+        dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
+        off = 0
+        mods = list(c.modalities())
+        offs = []
+        for name, col0, D, K, H, sid in mods:
+            offs.append(off)
+            off += K * D
+        for (name, col0, D, K, H, sid), o0 in reversed(list(zip(mods, offs))):
+            self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put)
+        put("input_bn/gamma", dgamma_in)
+        put("input_bn/beta", dbeta_in)
+        return grads
+
+    def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        S, inv = float(c.loss_scale), 1.0 / float(c.loss_scale)
+        m, B, T = ctx[name], ctx["B"], c.iterations
+        a, vs = name + "_attention", name + "_VLAD"
+        f32 = torch.float32
+        rows = B * K
+        # ---- LN3: out = LN(u3), u3 = h2 + h1 ----------------------------------------------------
+        du3, dg, db = ops.layernorm_joint_bwd(m["u3"], dv, dv.stride(0), B, K, D, m["st3"], v[a + "/LayerNorm_2/gamma"],
+                                              inv_scale=inv)
+        put(a + "/LayerNorm_2/gamma", dg); put(a + "/LayerNorm_2/beta", db)
+        # ---- LN2: h2 = LN(u2), u2 = relu(f2pre) + h1 -------------------------------------------
+        (du2, dpre2), dg, db, db2 = ops.layernorm_joint_bwd(m["u2"], du3, K * D, B, K, D, m["st2"],
+                                                            v[a + "/LayerNorm_1/gamma"], inv_scale=inv, mask=m["f2"],
+                                                            want_du_colsum=True)
+        put(a + "/LayerNorm_1/gamma", dg); put(a + "/LayerNorm_1/beta", db)
+        put(f"{a}/ff_output{sid}/bias", db2)
+        h1 = m["h1"].view(rows, D)
+        f1 = m["f1"]
+        dpre2 = dpre2.view(rows, D)
+        put(f"{a}/ff_output{sid}/kernel", ops.gemm(f1, dpre2, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
+        put(f"{a}/filter_output{sid}/bias", ops.colsum(dpre1, alpha=inv))
+        put(f"{a}/filter_output{sid}/kernel", ops.gemm(h1, dpre1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
+        # ---- LN1: h1 = LN(u1), u1 = att + vlad --------------------------------------------------
+        du1, dg, db, dbo = ops.layernorm_joint_bwd(m["u1"], dh1, K * D, B, K, D, m["st1"], v[a + "/LayerNorm/gamma"],
+                                                   inv_scale=inv, want_du_colsum=True)
+        put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
+        put(a + "/output_transform/bias", dbo)
+        du1 = du1.view(rows, D)
+        put(a + "/output_transform/kernel", ops.gemm(m["o"], du1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
+        dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
+        zn = m["zn"]
+        for i, n in enumerate(("q", "k", "v")):
+            put(f"{a}/{n}/kernel", ops.gemm(zn, dqkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
+        # ---- NetVLAD normalisation + aggregation + soft-assignment ------------------------------
+        ct = sh[vs + "/centers_t"]
+        dz, q = ops.netvlad_norm_bwd(m["z"], m["rscale"], dzn.view(B, K, D), ct)
+        X = m["X"]                                                            # [B*T, D] view, row stride = feature size
+        wc16 = sh[vs + "/wc16"]
+        S16 = ops.gemm(X, wc16)                                               # logits recomputed: [B*T, K]
+        X3 = ctx["xb"].view(B, T, -1)[:, :, col0:col0 + D]
+        G = ops.gemm(X3, dz, b_mn=False, out_dtype=f32)                       # [B, T, K] = X dV^T per video
+        bn = vs + "/cluster_bn"
+        dS, dg, db = ops.assign_bwd(G.view(B * T, K), m["assign"].view(B * T, K), q, S16, m["cluster_bn_stats"],
+                                    v[bn + "/gamma"], T, inv_scale=inv)
+        put(bn + "/gamma", dg); put(bn + "/beta", db)
+        m_tiles = (D + 127) // 128
+        splits = max(2, min(64, 148 // max(1, m_tiles)))
+        parts = ops.gemm(X, dS, a_mn=True, b_mn=True, splits=splits)           # [s, D, K] fp32
+        dWc = torch.empty((D, K), dtype=f32, device=X.device)
+        ops.splitk_reduce(parts, alpha=inv, out32=dWc)
+        put(vs + "/cluster_weights", dWc)
+        dCt, E = ops.center_bwd(dz, m["z"], m["a_sum"], ct, v["input_bn/beta"][col0:col0 + D], inv)
+        put(vs + "/cluster_weights2", ops.transpose_f32(dCt).view(1, D, K))
+        ops.input_bn_grad(v[vs + "/cluster_weights"], dWc, dCt, E, v["input_bn/gamma"][col0:col0 + D],
+                          dgamma_in[col0:col0 + D], dbeta_in[col0:col0 + D])

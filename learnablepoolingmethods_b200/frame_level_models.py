@@ -1,0 +1,104 @@
+"""Frame-level models of the hot path with the reference's registry names and call signatures.
+
+Drop-in for `frame_level_models.NetVladV1` / `NetVladV2` (frame_level_models.py:2222-2377, 2383-2513)
+and the `NetVLAD` pooling module (:2765-2824).  `create_model` executes eagerly on the GPU (there is no
+graph): it returns `{"predictions": tensor [B, vocab]}`; when called with `is_training=True` under
+torch autograd the tensor carries the backward of the whole path (hand-written CUDA).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import models, ops, variables
+from .engine import NetVladConfig, NetVladEngine
+from .flags import FLAGS, ensure_parsed
+
+
+def _resolve(cls_name, model_input, vocab_size, iterations, cluster_size, hidden_size, unused):
+    ensure_parsed()
+    # kwargs resolve as `kw or FLAGS.<name>` (frame_level_models.py:2235-2242)
+    iterations = iterations or FLAGS.iterations
+    cluster_size = cluster_size or FLAGS.netvlad_cluster_size
+    hidden_size = hidden_size or FLAGS.netvlad_hidden_size
+    feat = int(model_input.shape[2])
+    rgb_dim = int(unused.get("rgb_dim", 1024))      # the reference hard-codes 1024 (:2261,2274)
+    return NetVladConfig(model=cls_name, iterations=int(iterations), cluster_size=int(cluster_size),
+                         hidden_size=int(hidden_size), vocab_size=int(vocab_size),
+                         num_mixtures=int(unused.get("num_mixtures") or FLAGS.moe_num_mixtures),
+                         rgb_dim=rgb_dim, audio_dim=feat - rgb_dim,
+                         rgb_heads=int(unused.get("rgb_heads", 64)), audio_heads=int(unused.get("audio_heads", 16)),
+                         add_batch_norm=True, gating=FLAGS.gating, remove_diag=FLAGS.gating_remove_diag,
+                         moe_l2=FLAGS.moe_l2)
+
+
+def get_engine(cfg: NetVladConfig, store=None) -> NetVladEngine:
+    """One engine per (store, config): calling create_model again reuses the variables (tower reuse)."""
+    store = store or variables.default_store()
+    cache = store.__dict__.setdefault("_engines", {})
+    key = tuple(sorted(cfg.__dict__.items()))
+    if key not in cache:
+        cache[key] = NetVladEngine(cfg, store)
+    return cache[key]
+
+
+class _NetVladBase(models.BaseModel):
+    _NAME = None
+
+    def create_model(self, model_input, vocab_size, num_frames, iterations=None, add_batch_norm=None,
+                     sample_random_frames=None, cluster_size=None, hidden_size=None, is_training=True,
+                     **unused_params):
+        cfg = _resolve(self._NAME, model_input, vocab_size, iterations, cluster_size, hidden_size, unused_params)
+        engine = get_engine(cfg, unused_params.get("store"))
+        from .autograd import netvlad_apply
+        pred = netvlad_apply(engine, model_input, num_frames, is_training,
+                             dropout_masks=unused_params.get("dropout_masks"))
+        return {"predictions": pred}
+
+
+class NetVladV1(_NetVladBase):
+    """ NetVlad with Context Gating + attention over the cluster descriptors (paper 3.1). """
+    _NAME = "NetVladV1"
+
+
+class NetVladV2(_NetVladBase):
+    """ NetVlad with attention-based cluster similarities (paper 3.2). """
+    _NAME = "NetVladV2"
+
+
+class NetVLAD():
+    """frame_level_models.py:2765-2824; the 6th ctor argument of the call sites (:2261-2264) is a scope label."""
+
+    def __init__(self, feature_size, max_frames, cluster_size, add_batch_norm, is_training, scope_id=None):
+        self.feature_size = feature_size
+        self.max_frames = max_frames
+        self.is_training = is_training
+        self.add_batch_norm = add_batch_norm
+        self.cluster_size = int(cluster_size)
+        self.scope_id = scope_id
+
+    def forward(self, reshaped_input, store=None):
+        """reshaped_input: [(B*max_frames), feature_size] (fp32 or fp16, GPU) -> [B, cluster_size*feature_size]
+        fp32, d-major flatten (index d*K + k) as in the reference."""
+        s = store or variables.default_store()
+        D, K, T = self.feature_size, self.cluster_size, self.max_frames
+        import math
+        wc = s.get_variable("cluster_weights", (D, K), "normal", 1 / math.sqrt(D))
+        if self.add_batch_norm:
+            beta, gamma, mm, mv = s.batch_norm_vars("cluster_bn", K)
+        else:
+            bias = s.get_variable("cluster_biases", (K,), "normal", 1 / math.sqrt(D))
+        c2 = s.get_variable("cluster_weights2", (1, D, K), "normal", 1 / math.sqrt(D))
+        x16 = reshaped_input if reshaped_input.dtype == torch.float16 else ops.cast_f16(reshaped_input.contiguous())
+        B = x16.shape[0] // T
+        wc16 = ops.cast_f16(wc)
+        if self.add_batch_norm:
+            if self.is_training:
+                _, st = ops.gemm(wc16, x16, a_mn=True, b_mn=False, out="none", stats=True)
+                scale, shift = ops.bn_finalize(st[0].reshape(-1, K), st[1].reshape(-1, K), B * T, gamma, beta, mm, mv,
+                                               training=True, bessel=True)
+            else:
+                scale, shift = ops.bn_finalize(None, None, 1, gamma, beta, mm, mv, training=False, bessel=True)
+        else:
+            scale, shift = torch.ones(K, device=x16.device), bias
+        z, rs, _, _ = ops.netvlad_pool_fwd(x16, B, T, wc16, scale, shift, ops.transpose_f32(c2[0]))
+        return ops.netvlad_finalize(z, rs, d_major=True)

@@ -22,7 +22,7 @@ def _lda(t: torch.Tensor) -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = True,
          out: Optional[torch.Tensor] = None, out_dtype=torch.float16, bias=None, row_scale=None,
          relu: bool = False, alpha: float = 1.0, accumulate: bool = False, splits: int = 1,
-         stats: bool = False, force_bn: int = 0, M=None, N=None, K=None):
+         stats: bool = False, force_bn: int = 0, M=None, N=None, K=None, mask=None, add1=None, add2=None):
     """D = epilogue(alpha * A x B).
 
     a: [.., M, K] (a_mn=False) or [.., K, M] (a_mn=True), fp16, last dim contiguous.
@@ -52,7 +52,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     eff_splits = lib.lpm_gemm_splits(K, splits)
     d.splits = eff_splits
     shape = (batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N)
-    if eff_splits > 1:
+    if splits > 1:   # fp32 partials [eff_splits, ...] (eff_splits may be 1 for a short K)
         assert out is None and bias is None and not relu and not stats
         out = torch.empty((eff_splits,) + shape, dtype=torch.float32, device=a.device)
         d.out_split_stride = out.stride(0)
@@ -61,14 +61,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
         if out is None:
             out = torch.empty(shape, dtype=out_dtype, device=a.device)
         view = out
-    d.out = ptr(out)
-    d.out_f32 = int(out.dtype == torch.float32)
-    d.ldc = _lda(view)
-    d.out_batch_stride = view.stride(0) if view.dim() == 3 else 0
+    if isinstance(out, str):   # out="none": statistics only
+        out = None
+        d.out = None
+    else:
+        d.out = ptr(out)
+        d.out_f32 = int(out.dtype == torch.float32)
+        d.ldc = _lda(view)
+        d.out_batch_stride = view.stride(0) if view.dim() == 3 else 0
     d.bias = ptr(bias)
     d.row_scale = ptr(row_scale)
     d.row_scale_batch_stride = M if row_scale is not None else 0
     d.relu, d.accumulate, d.alpha = int(relu), int(accumulate), float(alpha)
+    if mask is not None:
+        d.mask, d.ld_mask = ptr(mask), _lda(mask)
+    if add1 is not None:
+        d.add1, d.ld_add = ptr(add1), _lda(add1)
+        if add2 is not None:
+            assert _lda(add2) == _lda(add1)
+            d.add2 = ptr(add2)
     st = None
     if stats:
         n_tiles = -(-N // (force_bn or lib.lpm_gemm_tile_n(N)))
@@ -129,15 +140,16 @@ def transpose_f32(src: torch.Tensor):
 
 
 def bn_finalize(psum, psq, count, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False,
-                decay=BN_DECAY, eps=BN_EPS):
-    """Reduce (sum, sumsq) partial rows [P, C] -> folded affine (scale, shift) [C]."""
+                decay=BN_DECAY, eps=BN_EPS, psum_stride=None):
+    """Reduce (sum, sumsq) partial rows [P, C] (row stride psum_stride) -> folded affine (scale, shift) [C]."""
     lib = _lib.load()
     Cn = gamma.numel()
     dev = gamma.device
     scale, shift = _f32((Cn,), dev), _f32((Cn,), dev)
     sm = _f32((2, Cn), dev) if save else None
-    P = 0 if psum is None else psum.reshape(-1, Cn).shape[0]
-    check(lib.lpm_batchnorm_finalize(ptr(psum), ptr(psq), P, C.c_longlong(Cn), Cn, C.c_double(count), ptr(gamma),
+    P = 0 if psum is None else psum.shape[0]
+    pstride = psum_stride or Cn
+    check(lib.lpm_batchnorm_finalize(ptr(psum), ptr(psq), P, C.c_longlong(pstride), Cn, C.c_double(count), ptr(gamma),
                                      ptr(beta), ptr(moving_mean), ptr(moving_var), C.c_float(decay), C.c_float(eps),
                                      int(bessel), int(training), ptr(scale), ptr(shift),
                                      ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
@@ -203,8 +215,16 @@ def mha_core_fwd(qkv, B, L, Dm, H, *, scale, key_scale=None, key_shift=None, wan
     return (out, lse) if want_lse else out
 
 
+def scale_rows_f16(x, rs):
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    check(lib.lpm_scale_rows_f16(ptr(x), ptr(rs), C.c_longlong(x.shape[0]), x.shape[1], ptr(y), stream_ptr()),
+          "lpm_scale_rows_f16")
+    return y
+
+
 def layernorm_joint_fwd(a, b, b_row_scale, B, rows, D, gamma, beta, *, out=None, out_stride=None, save=False,
-                        eps=LN_EPS):
+                        eps=LN_EPS, u_out=None):
     """u = a + b*row_scale (stored over a); returns y = LN_joint(u) (fp16) [, (mean, rstd) [B,2]]."""
     lib = _lib.load()
     dev = a.device
@@ -213,7 +233,7 @@ def layernorm_joint_fwd(a, b, b_row_scale, B, rows, D, gamma, beta, *, out=None,
         out_stride = rows * D
     partial = _f32((B, 64), dev)
     sm = _f32((B, 2), dev) if save else None
-    check(lib.lpm_layernorm_joint_fwd(ptr(a), ptr(b), ptr(b_row_scale), B, rows, D, C.c_longlong(rows * D),
+    check(lib.lpm_layernorm_joint_fwd(ptr(a), ptr(b), ptr(b_row_scale), ptr(u_out), B, rows, D, C.c_longlong(rows * D),
                                       C.c_longlong(rows * D), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out),
                                       C.c_longlong(out_stride), ptr(partial), ptr(sm), stream_ptr()),
           "lpm_layernorm_joint_fwd")
@@ -234,11 +254,12 @@ def gating_fwd(act, g, gamma, beta, moving_mean, moving_var, *, training, wg_dia
     return (out32, out16, sm) if save else (out32, out16)
 
 
-def moe_mix_fwd(logits, V, M):
+def moe_mix_fwd(logits, V, M, expert_off=None):
     lib = _lib.load()
     B = logits.shape[0]
     pred = _f32((B, V), logits.device)
-    check(lib.lpm_moe_mix_fwd(ptr(logits), C.c_longlong(logits.stride(0)), B, V, M, ptr(pred), stream_ptr()),
+    expert_off = V * (M + 1) if expert_off is None else expert_off
+    check(lib.lpm_moe_mix_fwd(ptr(logits), C.c_longlong(logits.stride(0)), B, V, M, expert_off, ptr(pred), stream_ptr()),
           "lpm_moe_mix_fwd")
     return pred
 
@@ -250,3 +271,143 @@ def xent_fwd(pred, labels_u8):
     loss = _f32((1,), pred.device)
     check(lib.lpm_xent_fwd(ptr(pred), ptr(labels_u8), B, V, ptr(row), ptr(loss), stream_ptr()), "lpm_xent_fwd")
     return loss, row
+
+
+# ------------------------------------------------------------------------------------------------
+# backward wrappers
+# ------------------------------------------------------------------------------------------------
+def _ll(v):
+    return C.c_longlong(int(v))
+
+
+def xent_bwd(pred, labels_u8, gscale):
+    lib = _lib.load()
+    dpred = torch.empty_like(pred)
+    check(lib.lpm_xent_bwd(ptr(pred), ptr(labels_u8), _ll(pred.numel()), C.c_float(gscale), ptr(dpred), stream_ptr()),
+          "lpm_xent_bwd")
+    return dpred
+
+
+def moe_mix_bwd(logits, dpred, V, M, expert_off, loss_scale):
+    lib = _lib.load()
+    B, ncols = logits.shape
+    dl = _f16((B, ncols), logits.device)
+    check(lib.lpm_moe_mix_bwd(ptr(logits), _ll(logits.stride(0)), B, V, M, expert_off, ptr(dpred), C.c_float(loss_scale),
+                              ptr(dl), _ll(dl.stride(0)), ncols, stream_ptr()), "lpm_moe_mix_bwd")
+    return dl
+
+
+def colsum(x, *, alpha=1.0, out=None, accumulate=False, rows=None, cols=None):
+    """out[c] (+)= alpha * sum_r x[r, c]; x fp16 or fp32 2-D (row stride may exceed cols)."""
+    lib = _lib.load()
+    rows = rows or x.shape[0]
+    cols = cols or x.shape[1]
+    if out is None:
+        out = _f32((cols,), x.device)
+    partial = _f32((lib.lpm_colsum_chunks(_ll(rows)), cols), x.device)
+    check(lib.lpm_colsum(ptr(x), int(x.dtype == torch.float32), _ll(x.stride(0)), _ll(rows), cols, C.c_float(alpha),
+                         int(accumulate), ptr(partial), ptr(out), stream_ptr()), "lpm_colsum")
+    return out
+
+
+def colsum_final(partial, chunks, pstride, cols, *, alpha=1.0, out=None, accumulate=False):
+    lib = _lib.load()
+    if out is None:
+        out = _f32((cols,), partial.device)
+    check(lib.lpm_colsum_final(ptr(partial), chunks, _ll(pstride), cols, C.c_float(alpha), int(accumulate), ptr(out),
+                               stream_ptr()), "lpm_colsum_final")
+    return out
+
+
+def gating_bwd(act, g, gamma, beta, stats, dout, inv_scale):
+    lib = _lib.load()
+    B, H = act.shape
+    dev = act.device
+    dact, dg = _f32((B, H), dev), _f16((B, H), dev)
+    dgamma, dbeta = _f32((H,), dev), _f32((H,), dev)
+    check(lib.lpm_gating_bwd(ptr(act), ptr(g), B, H, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]), ptr(dout),
+                             C.c_float(inv_scale), ptr(dact), ptr(dg), ptr(dgamma), ptr(dbeta), stream_ptr()),
+          "lpm_gating_bwd")
+    return dact, dg, dgamma, dbeta
+
+
+def layernorm_joint_bwd(u, dy, dy_stride, B, rows, D, mean_rstd, gamma, *, inv_scale, mask=None, want_du_colsum=False):
+    """Returns du (fp16 [B, rows, D]) or (du, du_masked) with a mask, dgamma, dbeta (fp32, unscaled)
+    [, colsum(du_masked or du) unscaled]."""
+    lib = _lib.load()
+    dev = u.device
+    ch = lib.lpm_layernorm_bwd_chunks()
+    du = _f16((B, rows, D), dev)
+    dum = _f16((B, rows, D), dev) if mask is not None else None
+    ps = _f32((B * ch * 2,), dev)
+    pc = _f32((B * ch, 2, D), dev)
+    pdu = _f32((B * ch, D), dev) if want_du_colsum else None
+    check(lib.lpm_layernorm_joint_bwd(ptr(u), ptr(dy), _ll(dy_stride), B, rows, D, ptr(mean_rstd), ptr(gamma), ptr(mask),
+                                      ptr(du), ptr(dum), ptr(ps), ptr(pc), ptr(pdu), stream_ptr()), "lpm_layernorm_joint_bwd")
+    if mask is not None:
+        du = (du, dum)
+    dgamma = colsum_final(pc, B * ch, 2 * D, D, alpha=inv_scale)
+    dbeta = colsum_final(pc[:, 1], B * ch, 2 * D, D, alpha=inv_scale)
+    if want_du_colsum:
+        return du, dgamma, dbeta, colsum_final(pdu, B * ch, D, D, alpha=inv_scale)
+    return du, dgamma, dbeta
+
+
+def netvlad_norm_bwd(z, rscale, dvhat, centers_t):
+    lib = _lib.load()
+    B, K, D = z.shape
+    dz = torch.empty_like(z)
+    q = _f32((B, K), z.device)
+    check(lib.lpm_netvlad_norm_bwd(ptr(z), ptr(rscale), ptr(dvhat), _ll(B * K), K, D, ptr(centers_t), ptr(dz), ptr(q),
+                                   stream_ptr()), "lpm_netvlad_norm_bwd")
+    return dz, q
+
+
+def assign_bwd(G, assign, q, S, stats, gamma, T, *, inv_scale):
+    """Soft-assignment + cluster_bn backward.  Returns dS (fp16 [rows, K]), dgamma, dbeta (unscaled)."""
+    lib = _lib.load()
+    rows, K = G.shape
+    dev = G.device
+    nb = lib.lpm_assign_bwd_blocks()
+    dsh = _f16((rows, K), dev)
+    partial = _f32((nb, 2, K), dev)
+    check(lib.lpm_assign_bwd1(ptr(G), ptr(assign), ptr(q), ptr(S), ptr(stats[0]), ptr(stats[1]), _ll(rows), T, K,
+                              ptr(dsh), ptr(partial), stream_ptr()), "lpm_assign_bwd1")
+    csum = _f32((2, K), dev)
+    colsum_final(partial, nb, 2 * K, 2 * K, out=csum.view(-1))
+    check(lib.lpm_assign_bwd2(ptr(dsh), ptr(S), ptr(stats[0]), ptr(stats[1]), ptr(gamma), ptr(csum), _ll(rows), K,
+                              stream_ptr()), "lpm_assign_bwd2")
+    dgamma = colsum_final(partial[:, 1], nb, 2 * K, K, alpha=inv_scale)
+    dbeta = colsum_final(partial, nb, 2 * K, K, alpha=inv_scale)
+    return dsh, dgamma, dbeta
+
+
+def center_bwd(dV, Z, a_sum, centers_t, beta_in, inv_scale):
+    lib = _lib.load()
+    B, K, D = Z.shape
+    dCt, E = _f32((K, D), Z.device), _f32((K, D), Z.device)
+    check(lib.lpm_center_bwd(ptr(dV), ptr(Z), ptr(a_sum), B, K, D, ptr(centers_t), ptr(beta_in), C.c_float(inv_scale),
+                             ptr(dCt), ptr(E), stream_ptr()), "lpm_center_bwd")
+    return dCt, E
+
+
+def input_bn_grad(Wc, dWc, dCt, E, gamma_in, dgamma_in, dbeta_in):
+    lib = _lib.load()
+    D, K = Wc.shape
+    check(lib.lpm_input_bn_grad(ptr(Wc), ptr(dWc), ptr(dCt), ptr(E), D, K, ptr(gamma_in), ptr(dgamma_in), ptr(dbeta_in),
+                                stream_ptr()), "lpm_input_bn_grad")
+
+
+def cast_scaled_f16(x, alpha=1.0):
+    lib = _lib.load()
+    y = _f16(x.shape, x.device)
+    check(lib.lpm_cast_scaled_f16(ptr(x), _ll(x.numel()), C.c_float(alpha), ptr(y), stream_ptr()), "lpm_cast_scaled_f16")
+    return y
+
+
+def mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, *, scale):
+    lib = _lib.load()
+    dqkv = torch.empty_like(qkv)
+    check(lib.lpm_mha_core_bwd(ptr(qkv), _ll(qkv.stride(0)), ptr(o), ptr(dout), _ll(o.stride(0)), ptr(lse), B, L, Dm, H,
+                               C.c_float(scale), ptr(dqkv), _ll(dqkv.stride(0)), stream_ptr()), "lpm_mha_core_bwd")
+    return dqkv

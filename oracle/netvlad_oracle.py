@@ -278,7 +278,7 @@ def _shell(model_input, num_frames, iterations, P, S, is_training):
 
 def netvlad_v1(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size,
                is_training, num_mixtures=2, rgb_dim=1024, rgb_heads=64, audio_heads=16,
-               d5_raw_reshape=False, remove_diag=False, return_intermediates=False):
+               d5_raw_reshape=False, remove_diag=False, gating=True, return_intermediates=False):
     """NetVladV1.create_model forward.  model_input [B, max_frames, rgb+audio] is
     already L2-normalised by the caller (train.py:264)."""
     x, B, T = _shell(model_input, num_frames, iterations, P, S, is_training)
@@ -298,7 +298,7 @@ def netvlad_v1(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
         inter["att_" + name] = z
         outs.append(z.reshape(B, K * D))                            # :2292, :2304 k-major flatten
     vlad = torch.cat(outs, dim=1)                                   # :2309
-    pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures,
+    pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
                             remove_diag=remove_diag, return_intermediates=True)
     inter.update(hi)
     return (pred, inter) if return_intermediates else pred

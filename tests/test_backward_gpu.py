@@ -1,0 +1,53 @@
+"""Gradients of the CUDA NetVladV1 path vs autograd through the CPU oracle (identical weights / inputs).
+fp16 activation gradients with loss scaling: per-parameter rel-L2 <= 3e-2 (most are ~1e-3..1e-2)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("gating,tol", [(False, 2e-2), (True, 1.5e-1)])
+@pytest.mark.parametrize("B,K,Hd,V,T", [(4, 64, 64, 100, 256), (3, 128, 64, 200, 128)])
+def test_netvlad_v1_gradients(cuda, B, K, Hd, V, T, gating, tol):
+    """gating=False isolates the kernels (tight bound).  With context gating the batch-statistics BN over a
+    batch of 3-4 videos has |mean|/std ~ 10 on this data and amplifies the fp16 forward error ~10x into
+    dLoss/dpred, so that case only guards against gross errors (numerics)."""
+    from learnablepoolingmethods_b200 import ops, variables
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from oracle import netvlad_oracle as O
+    from tests.helpers import oracle_params as _oracle_params, perturb as _perturb
+    store = variables.VariableStore(cuda, seed=7)
+    cfg = NetVladConfig(model="NetVladV1", iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V, gating=gating)
+    eng = NetVladEngine(cfg, store)
+    _perturb(store, seed=3)
+    x, nf, labels = O.synthetic_batch(B, seed=20181001, vocab=V)
+    P, S = _oracle_params(store)
+    for p in P.values():
+        p.requires_grad_(True)
+    pred_ref = O.netvlad_v1(x, nf, P, S, vocab_size=V, iterations=T, cluster_size=K, is_training=True, gating=gating)
+    loss_ref = O.cross_entropy_loss(pred_ref, labels)
+    loss_ref.backward()
+
+    pred, ctx = eng.forward(x.to(cuda), nf.to(cuda), True, save_for_backward=True)
+    lab = labels.to(torch.uint8).to(cuda)
+    loss, _ = ops.xent_fwd(pred, lab)
+    dpred = ops.xent_bwd(pred, lab, 1.0 / B)
+    grads = eng.backward(ctx, dpred)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 2e-2
+    bad = []
+    print()
+    for name in sorted(P):
+        if not gating and name.startswith("gating"):
+            continue
+        assert name in grads, f"missing gradient for {name}"
+        e = rel(grads[name].reshape(P[name].shape), P[name].grad)
+        print(f"  {name:60s} rel-L2 {e:.2e}  |g| {float(P[name].grad.norm()):.2e}")
+        if not (e < tol):
+            bad.append((name, e))
+    assert not bad, bad

@@ -1,0 +1,40 @@
+"""Model-level GPU parity of NetVladV1 against the CPU oracle on identical weights and inputs.
+Tolerances are BASELINE.json's: rel-L2 <= 1e-3 on the VLAD descriptor, max-abs <= 5e-3 on predictions."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+from tests.helpers import oracle_params as _oracle_params, perturb as _perturb, rel
+
+
+@pytest.mark.parametrize("is_training", [False, True])
+@pytest.mark.parametrize("B,K,Hd,V,T", [(4, 64, 64, 100, 256), (3, 256, 128, 3862, 256), (2, 128, 64, 50, 96)])
+def test_netvlad_v1_forward_parity(cuda, B, K, Hd, V, T, is_training):
+    from learnablepoolingmethods_b200 import variables
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from oracle import netvlad_oracle as O
+    store = variables.VariableStore(cuda, seed=1810)
+    cfg = NetVladConfig(model="NetVladV1", iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V)
+    eng = NetVladEngine(cfg, store)
+    _perturb(store)
+    x, nf, _ = O.synthetic_batch(B, seed=20181000, vocab=V)
+    P, S = _oracle_params(store)
+    with torch.no_grad():
+        ref, inter = O.netvlad_v1(x, nf, P, S, vocab_size=V, iterations=T, cluster_size=K, is_training=is_training,
+                                  return_intermediates=True)
+    pred, ctx = eng.forward(x.to(cuda), nf.to(cuda), is_training, return_intermediates=True)
+    torch.cuda.synchronize()
+    gi = ctx["inter"]
+    e_v, e_a = rel(gi["vlad_video"], inter["vlad_video"]), rel(gi["vlad_audio"], inter["vlad_audio"])
+    e_att = rel(gi["att_video"], inter["att_video"])
+    e_h = rel(gi["hidden"], inter["hidden"])
+    e_p = float((pred.cpu() - ref).abs().max())
+    print(f"\n[V1 B={B} K={K} train={is_training}] vlad rgb {e_v:.2e} audio {e_a:.2e} | att {e_att:.2e} | hidden {e_h:.2e} | pred max-abs {e_p:.2e}")
+    assert e_v < 1e-3 and e_a < 1e-3
+    assert e_att < 3e-3
+    assert e_p < 5e-3
+    if is_training:   # moving statistics were updated in place
+        for k in ("input_bn/moving_variance", "video_VLAD/cluster_bn/moving_mean", "gating_bn/moving_variance"):
+            assert rel(store.vars[k], S[k]) < 2e-3, k
