@@ -218,6 +218,18 @@ int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_s
 int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* dout, long long ldo, const float* lse,
                      int B, int L, int Dm, int H, float scale, void* dqkv, long long ldd, lpm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser step on a flat fp32 buffer (train.py:321-336, utils.py:170-189, tf.train.AdamOptimizer):
+ * per-tensor L2-regulariser term (wd[t]*p), per-tensor clip_by_norm(clip), Adam with the TF bias-corrected
+ * step lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  table: int32 [n_chunks][3] = {tensor id, start/32, length};
+ * chunk_begin: int32 [n_tensors+1].  Scratch: partial [n_chunks], factor/norms [n_tensors], flag [1] (set to
+ * 1 and the update skipped when a gradient norm is non-finite).
+ * ------------------------------------------------------------------------------------------- */
+int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
+                       const int* chunk_begin, int n_tensors, const float* wd, float clip, float lr_t, float b1,
+                       float b2, float eps, float* partial, float* factor, float* norms, int* flag,
+                       lpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,11 @@ int input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const flo
                   const float* gamma_in, float* dgamma_in, float* dbeta_in, cudaStream_t st);
 int cast_scaled(const float* x, long long n, float alpha, __half* y, cudaStream_t st);
 
+// lpm_optim.cu
+int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
+                   const int* chunk_begin, int n_tensors, const float* wd, float clip, float lr_t, float b1,
+                   float b2, float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
+
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const float* centers_t,

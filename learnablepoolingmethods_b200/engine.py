@@ -329,8 +329,16 @@ class NetVladEngine:
         f32 = torch.float32
         grads: Dict[str, torch.Tensor] = {}
         hook = ctx.get("grad_hook")
+        views = ctx.get("grad_views")       # optional {name: preallocated fp32 view} (flat gradient buffer)
+        ctx["_gout"] = (lambda n: views.get(n) if views is not None else None)
+        gout = ctx["_gout"]
 
         def put(name, g):
+            if views is not None and name in views:
+                dst = views[name]
+                if g.data_ptr() != dst.data_ptr():
+                    dst.copy_(g.reshape(dst.shape))
+                g = dst
             grads[name] = g
             if hook is not None:
                 hook(name, g)
@@ -339,8 +347,10 @@ class NetVladEngine:
         dl16 = ops.moe_mix_bwd(hd["logits"], dpred, V, M, g8, S)
         gated16 = hd["gated16"]
         put("experts/biases", ops.colsum(dl16[:, g8:], alpha=inv, cols=V * M))
-        put("gates/weights", ops.gemm(gated16, dl16[:, :g8], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * (M + 1)))
-        put("experts/weights", ops.gemm(gated16, dl16[:, g8:], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * M))
+        put("gates/weights", ops.gemm(gated16, dl16[:, :g8], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * (M + 1),
+                                      out=gout("gates/weights")))
+        put("experts/weights", ops.gemm(gated16, dl16[:, g8:], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, N=V * M,
+                                        out=gout("experts/weights")))
         dgated = ops.gemm(dl16, sh["wmoe16"], b_mn=False, out_dtype=f32)
         # ---- context gating (frame_level_models.py:2342-2368) -----------------------------------
         if c.gating:
@@ -348,14 +358,16 @@ class NetVladEngine:
                                                     hd["gating_stats"], dgated, inv)
             put("gating_bn/gamma", dgam)
             put("gating_bn/beta", dbet)
-            put("gating_weights_2", ops.gemm(hd["act16"], dg16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+            put("gating_weights_2", ops.gemm(hd["act16"], dg16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                             out=gout("gating_weights_2")))
             ops.gemm(dg16, sh["wg16"], b_mn=False, out=dact, accumulate=True)
         else:
             dact = dgated
         # ---- hidden projection (frame_level_models.py:2314-2334) --------------------------------
         put("hidden1_biases", ops.colsum(dact, alpha=inv))
         dact16 = ops.cast_scaled_f16(dact)
-        put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                        out=gout("hidden1_weights")))
         dvlad = ops.gemm(dact16, sh["wh16"], b_mn=False)                      # [B, vlad_dim] fp16
         dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
         dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
@@ -377,6 +389,7 @@ class NetVladEngine:
         m, B, T = ctx[name], ctx["B"], c.iterations
         a, vs = name + "_attention", name + "_VLAD"
         f32 = torch.float32
+        gout = ctx["_gout"]
         rows = B * K
         # ---- LN3: out = LN(u3), u3 = h2 + h1 ----------------------------------------------------
         du3, dg, db = ops.layernorm_joint_bwd(m["u3"], dv, dv.stride(0), B, K, D, m["st3"], v[a + "/LayerNorm_2/gamma"],
@@ -391,10 +404,12 @@ class NetVladEngine:
         h1 = m["h1"].view(rows, D)
         f1 = m["f1"]
         dpre2 = dpre2.view(rows, D)
-        put(f"{a}/ff_output{sid}/kernel", ops.gemm(f1, dpre2, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        put(f"{a}/ff_output{sid}/kernel", ops.gemm(f1, dpre2, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                   out=gout(f"{a}/ff_output{sid}/kernel")))
         dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
         put(f"{a}/filter_output{sid}/bias", ops.colsum(dpre1, alpha=inv))
-        put(f"{a}/filter_output{sid}/kernel", ops.gemm(h1, dpre1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        put(f"{a}/filter_output{sid}/kernel", ops.gemm(h1, dpre1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                       out=gout(f"{a}/filter_output{sid}/kernel")))
         dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
         # ---- LN1: h1 = LN(u1), u1 = att + vlad --------------------------------------------------
         du1, dg, db, dbo = ops.layernorm_joint_bwd(m["u1"], dh1, K * D, B, K, D, m["st1"], v[a + "/LayerNorm/gamma"],
@@ -402,12 +417,14 @@ class NetVladEngine:
         put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
         put(a + "/output_transform/bias", dbo)
         du1 = du1.view(rows, D)
-        put(a + "/output_transform/kernel", ops.gemm(m["o"], du1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+        put(a + "/output_transform/kernel", ops.gemm(m["o"], du1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                     out=gout(a + "/output_transform/kernel")))
         do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
         dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
         zn = m["zn"]
         for i, n in enumerate(("q", "k", "v")):
-            put(f"{a}/{n}/kernel", ops.gemm(zn, dqkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv))
+            put(f"{a}/{n}/kernel", ops.gemm(zn, dqkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                            out=gout(f"{a}/{n}/kernel")))
         dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
         # ---- NetVLAD normalisation + aggregation + soft-assignment ------------------------------
         ct = sh[vs + "/centers_t"]
@@ -424,7 +441,9 @@ class NetVladEngine:
         m_tiles = (D + 127) // 128
         splits = max(2, min(64, 148 // max(1, m_tiles)))
         parts = ops.gemm(X, dS, a_mn=True, b_mn=True, splits=splits)           # [s, D, K] fp32
-        dWc = torch.empty((D, K), dtype=f32, device=X.device)
+        dWc = gout(vs + "/cluster_weights")
+        if dWc is None:
+            dWc = torch.empty((D, K), dtype=f32, device=X.device)
         ops.splitk_reduce(parts, alpha=inv, out32=dWc)
         put(vs + "/cluster_weights", dWc)
         dCt, E = ops.center_bwd(dz, m["z"], m["a_sum"], ct, v["input_bn/beta"][col0:col0 + D], inv)

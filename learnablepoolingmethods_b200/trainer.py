@@ -1,0 +1,153 @@
+"""Training step of the reference trainer for the hot path (train.py:193-345, utils.py:170-213).
+
+One process per GPU.  Reference semantics kept: `--batch_size` is per tower (= per rank), batch-norm
+statistics are per tower, gradients are SUMMED over towers (utils.py:205-211 -> NCCL all-reduce SUM,
+bucketed and overlapped with the backward), per-tensor clip_by_norm after the sum (utils.py:170-189),
+Adam, learning rate decayed on global examples (train.py:244-249).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import NetVladConfig, NetVladEngine
+from .variables import VariableStore
+
+CHUNK = 32768           # elements per optimiser chunk
+ALIGN = 32              # segment alignment inside the flat buffers (elements)
+
+
+class FlatState:
+    """Parameters, gradients and Adam moments as views of four flat fp32 buffers (fixed addresses)."""
+
+    def __init__(self, store: VariableStore, order: List[str], wd: Dict[str, float]):
+        self.store, self.order = store, list(order)
+        tr = store.trainable()
+        missing = [n for n in tr if n not in self.order]
+        self.order += missing
+        dev = store.device
+        offs, off = {}, 0
+        for n in self.order:
+            offs[n] = off
+            off += (tr[n].numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total, self.offsets = off, offs
+        self.p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views: Dict[str, torch.Tensor] = {}
+        table, chunk_begin = [], [0]
+        for t, n in enumerate(self.order):
+            numel, o = tr[n].numel(), offs[n]
+            view = self.p[o:o + numel].view(tr[n].shape)
+            view.copy_(tr[n])
+            store.vars[n] = view                       # re-home the variable into the flat buffer
+            self.grad_views[n] = self.g[o:o + numel].view(tr[n].shape)
+            for c0 in range(0, numel, CHUNK):
+                table.append((t, (o + c0) // ALIGN, min(CHUNK, numel - c0)))
+            chunk_begin.append(len(table))
+        self.table = torch.tensor(table, dtype=torch.int32, device=dev)
+        self.chunk_begin = torch.tensor(chunk_begin, dtype=torch.int32, device=dev)
+        self.wd = torch.tensor([wd.get(n, 0.0) for n in self.order], dtype=torch.float32, device=dev)
+        nt = len(self.order)
+        self.scratch = (torch.zeros(len(table), dtype=torch.float32, device=dev), torch.zeros(nt, dtype=torch.float32, device=dev),
+                        torch.zeros(nt, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+        store.mark_dirty()
+
+    def end_offset(self, name: str) -> int:
+        return self.offsets[name] + self.store.vars[name].numel()
+
+
+class Trainer:
+    def __init__(self, engine: NetVladEngine, *, base_learning_rate=0.0002, learning_rate_decay=0.85,
+                 learning_rate_decay_examples=4000000, clip_gradient_norm=1.0, regularization_penalty=1.0,
+                 batch_size: int = 80, process_group=None, bucket_elems: int = 48 * 1024 * 1024):
+        self.engine, self.store, self.cfg = engine, engine.store, engine.cfg
+        self.base_lr, self.decay, self.decay_examples = base_learning_rate, learning_rate_decay, learning_rate_decay_examples
+        self.clip, self.reg_penalty, self.batch_size = clip_gradient_norm, regularization_penalty, batch_size
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.global_step = 0
+        self.flat: Optional[FlatState] = None
+        self.bucket_elems = bucket_elems
+        self._handles = []
+        self._done_upto = 0
+        self._next_bucket = 0
+        self.launches = 0
+
+    # -- learning rate (train.py:244-249, tf.train.exponential_decay staircase) -------------------
+    def learning_rate(self) -> float:
+        ex = self.global_step * self.batch_size * self.world
+        return self.base_lr * self.decay ** math.floor(ex / self.decay_examples)
+
+    def _wd(self) -> Dict[str, float]:
+        l2 = self.cfg.moe_l2 * self.reg_penalty     # slim.l2_regularizer(moe_l2) * regularization_penalty
+        return {"gates/weights": l2, "experts/weights": l2}
+
+    # -- gradient all-reduce (SUM), bucketed over the flat buffer, overlapped with the backward -----
+    def _hook(self, name, g):
+        if self.world == 1 or self.flat is None:
+            return
+        self._done_upto = max(self._done_upto, self.flat.end_offset(name))
+        self._launch_ready_buckets(final=False)
+
+    def _launch_ready_buckets(self, final: bool):
+        import torch.distributed as dist
+        f = self.flat
+        while self._next_bucket < f.total:
+            b0 = self._next_bucket
+            b1 = min(f.total, b0 + self.bucket_elems)
+            if not final and self._done_upto < b1:
+                break
+            self._handles.append(dist.all_reduce(f.g[b0:b1], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            self._next_bucket = b1
+
+    def train_step(self, model_input, num_frames, labels_u8):
+        """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32)."""
+        eng = self.engine
+        pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True)
+        B = pred.shape[0]
+        loss, _ = ops.xent_fwd(pred, labels_u8)
+        dpred = ops.xent_bwd(pred, labels_u8, 1.0 / B)
+        order: List[str] = []
+        if self.flat is None:
+            ctx["grad_hook"] = lambda n, g: order.append(n)
+            grads = eng.backward(ctx, dpred)
+            self.flat = FlatState(self.store, order, self._wd())
+            for n, g in grads.items():
+                self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
+            if self.world > 1:
+                self._done_upto, self._next_bucket = self.flat.total, 0
+                self._launch_ready_buckets(final=True)
+        else:
+            ctx["grad_views"] = self.flat.grad_views
+            ctx["grad_hook"] = self._hook
+            self._done_upto, self._next_bucket = 0, 0
+            eng.backward(ctx, dpred)
+            if self.world > 1:
+                self._launch_ready_buckets(final=True)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        f = self.flat
+        t = self.global_step + 1
+        lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=lr_t, scratch=f.scratch)
+        self.store.mark_dirty()
+        self.global_step += 1
+        return loss
+
+    def overflowed(self) -> bool:
+        """True if any step since the last call saw a non-finite gradient norm (host sync)."""
+        if self.flat is None:
+            return False
+        flag = self.flat.scratch[3]
+        r = bool(int(flag.item()))
+        if r:
+            flag.zero_()
+        return r
