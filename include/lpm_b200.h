@@ -221,14 +221,16 @@ int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* d
 /* ---------------------------------------------------------------------------------------------
  * Optimiser step on a flat fp32 buffer (train.py:321-336, utils.py:170-189, tf.train.AdamOptimizer):
  * per-tensor L2-regulariser term (wd[t]*p), per-tensor clip_by_norm(clip), Adam with the TF bias-corrected
- * step lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  table: int32 [n_chunks][3] = {tensor id, start/32, length};
- * chunk_begin: int32 [n_tensors+1].  Scratch: partial [n_chunks], factor/norms [n_tensors], flag [1] (set to
- * 1 and the update skipped when a gradient norm is non-finite).
+ * step lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  table: int32 [n_chunks][4] = {tensor id, start/32, length, element
+ * offset inside the tensor / 32}; chunk_begin: int32 [n_tensors+1].  Optional fused refresh of the fp16 operand
+ * shadows: sh_ptr[t] (device address or 0), sh_cols[t] (inner dimension), sh_ld[t] (shadow row stride).
+ * Scratch: partial [n_chunks], factor/norms [n_tensors], flag [1] (set to 1 and the update skipped when a
+ * gradient norm is non-finite).
  * ------------------------------------------------------------------------------------------- */
 int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
-                       const int* chunk_begin, int n_tensors, const float* wd, float clip, float lr_t, float b1,
-                       float b2, float eps, float* partial, float* factor, float* norms, int* flag,
-                       lpm_stream_t stream);
+                       const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
+                       const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
+                       float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,16 @@ def load() -> C.CDLL:
     return lib
 
 
+launch_count = 0   # kernels launched through the C-ABI by this process (bench.py's gpu_launches)
+
+# kernels per C-ABI call (everything not listed launches exactly one)
+_LAUNCHES = {"lpm_layernorm_joint_fwd": 2, "lpm_layernorm_joint_bwd": 2, "lpm_colsum": 2, "lpm_xent_fwd": 2,
+             "lpm_adam_clip_step": 3}
+
+
 def check(rc: int, what: str = "") -> None:
+    global launch_count
+    launch_count += _LAUNCHES.get(what, 1)
     if rc != 0:
         msg = load().lpm_last_error().decode("utf-8", "replace")
         raise LpmError(f"{what} failed (code {rc}): {msg}")

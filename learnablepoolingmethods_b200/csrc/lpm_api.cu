@@ -314,13 +314,13 @@ int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* d
 }
 
 int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
-                       const int* chunk_begin, int n_tensors, const float* wd, float clip, float lr_t, float b1,
-                       float b2, float eps, float* partial, float* factor, float* norms, int* flag,
-                       lpm_stream_t stream) {
+                       const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
+                       const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
+                       float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(p && g && m && v && table && chunk_begin && wd && partial && factor && norms && flag && n_chunks > 0 && n_tensors > 0,
               "lpm_adam_clip_step: bad arguments");
-  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, clip, lr_t, b1, b2, eps, partial,
+  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, lr_t, b1, b2, eps, partial,
                         factor, norms, flag, ST(stream));
 }
 

@@ -80,14 +80,25 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   for (long long r = r0; r < r1; ++r) s += to_f<T>(x[r * ld + c]);
   partial[(size_t)blockIdx.y * cols + c] = s;
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, long long pstride, int cols,
-                                    float alpha, int accumulate, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// 32 columns x 8 partial-row lanes per block: the partial rows are summed in parallel, then across lanes
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int chunks,
+                                                           long long pstride, int cols, float alpha, int accumulate,
+                                                           float* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double s = 0.0;
-  for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * pstride + c];
-  const float r = (float)(s * alpha);
-  out[c] = accumulate ? out[c] + r : r;
+  if (c < cols)
+    for (int k = ky; k < chunks; k += 8) s += partial[(size_t)k * pstride + c];
+  red[ky][cx] = s;
+  __syncthreads();
+  if (ky == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    const float r = (float)(t * alpha);
+    out[c] = accumulate ? out[c] + r : r;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,21 +405,24 @@ __global__ void __launch_bounds__(256) center_bwd_kernel(const __half* __restric
   E[(size_t)k * D + d] = s2 + s1 * (centers_t[(size_t)k * D + d] - beta_in[d]);
 }
 
-__global__ void input_bn_grad_kernel(const float* __restrict__ Wc, const float* __restrict__ dWc,
-                                     const float* __restrict__ dCt, const float* __restrict__ E, int D, int K,
-                                     const float* __restrict__ gamma_in, float* __restrict__ dgamma_in,
-                                     float* __restrict__ dbeta_in) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) input_bn_grad_kernel(const float* __restrict__ Wc, const float* __restrict__ dWc,
+                                                            const float* __restrict__ dCt, const float* __restrict__ E,
+                                                            int D, int K, const float* __restrict__ gamma_in,
+                                                            float* __restrict__ dgamma_in, float* __restrict__ dbeta_in) {
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (d >= D) return;
-  double t1 = 0.0, t2 = 0.0, sdc = 0.0;
-  for (int k = 0; k < K; ++k) {
-    t1 += (double)Wc[(size_t)d * K + k] * dWc[(size_t)d * K + k];
-    t2 += E[(size_t)k * D + d];
+  float t = 0.f, sdc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    t += Wc[(size_t)d * K + k] * dWc[(size_t)d * K + k] + E[(size_t)k * D + d];
     sdc += dCt[(size_t)k * D + d];
   }
-  const float g = gamma_in[d];
-  dgamma_in[d] = g != 0.f ? (float)((t1 + t2) / g) : 0.f;
-  dbeta_in[d] = (float)(-sdc);
+  t = warp_sum(t);
+  sdc = warp_sum(sdc);
+  if (lane == 0) {
+    const float g = gamma_in[d];
+    dgamma_in[d] = g != 0.f ? t / g : 0.f;
+    dbeta_in[d] = -sdc;
+  }
 }
 
 // fp32 -> fp16 elementwise (scaled activation gradients entering a GEMM)
@@ -447,14 +461,14 @@ int colsum(const void* x, int is_f32, long long ld, long long rows, int cols, fl
   dim3 grid((cols + 255) / 256, chunks);
   if (is_f32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), ld, rows, cols, partial);
   else colsum_partial_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), ld, rows, cols, partial);
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, chunks, cols, cols, alpha, accumulate, out);
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, chunks, cols, cols, alpha, accumulate, out);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
 int colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
                  float* out, cudaStream_t st) {
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, chunks, pstride, cols, alpha, accumulate, out);
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, chunks, pstride, cols, alpha, accumulate, out);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -532,7 +546,7 @@ int center_bwd(const __half* dV, const __half* Z, const float* a_sum, int B, int
 
 int input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const float* E, int D, int K,
                   const float* gamma_in, float* dgamma_in, float* dbeta_in, cudaStream_t st) {
-  input_bn_grad_kernel<<<(D + 127) / 128, 128, 0, st>>>(Wc, dWc, dCt, E, D, K, gamma_in, dgamma_in, dbeta_in);
+  input_bn_grad_kernel<<<(D + 7) / 8, 256, 0, st>>>(Wc, dWc, dCt, E, D, K, gamma_in, dgamma_in, dbeta_in);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

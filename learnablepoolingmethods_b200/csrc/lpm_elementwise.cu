@@ -94,21 +94,32 @@ __global__ void __launch_bounds__(256) sample_apply_kernel(const float* __restri
 // statistics update (decay 0.999; Bessel-corrected variance when `bessel`).  Inference: affine from
 // the moving statistics.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int P,
-                                   long long pstride, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
-                                   float* __restrict__ moving_var, float decay, float eps, int bessel,
-                                   int training, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float mean, var;
-  if (training) {
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < P; ++p) {
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq,
+                                                          int P, long long pstride, int C, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                                          float decay, float eps, int bessel, int training,
+                                                          float* __restrict__ scale, float* __restrict__ shift,
+                                                          float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  // 32 channels x 8 partial-row lanes per block
+  __shared__ double red[2][8][33];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0, q = 0.0;
+  if (training && c < C)
+    for (int p = ky; p < P; p += 8) {
       s += static_cast<double>(psum[(size_t)p * pstride + c]);
       q += static_cast<double>(psq[(size_t)p * pstride + c]);
     }
+  red[0][ky][cx] = s;
+  red[1][ky][cx] = q;
+  __syncthreads();
+  if (ky != 0 || c >= C) return;
+  float mean, var;
+  if (training) {
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += red[0][k][cx]; q += red[1][k][cx]; }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -353,6 +364,21 @@ __global__ void __launch_bounds__(256) cast_2d_kernel(const float* __restrict__ 
     dst[r * ld_dst + c] = __float2half_rn(c < cols ? src[r * ld_src + c] : 0.f);
   }
 }
+// fast path: cols == cols_dst, multiple of 8, all strides / bases 16-byte friendly
+__global__ void __launch_bounds__(256) cast_2d_vec_kernel(const float* __restrict__ src, long long ld_src, int rows,
+                                                          int cols, __half* __restrict__ dst, long long ld_dst) {
+  const int c8 = cols / 8;
+  const long long n = (long long)rows * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c + 4));
+    uint4 o;
+    o.x = pack_half2(a.x, a.y); o.y = pack_half2(a.z, a.w); o.z = pack_half2(b.x, b.y); o.w = pack_half2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = o;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // NetVLAD descriptor finalisation (frame_level_models.py:2819-2822): z[b,k,:] (un-normalised, fp16)
@@ -431,7 +457,7 @@ int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, in
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
                 int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(psum, psq, P, pstride, C, count, gamma, beta, mm, mv, decay,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(psum, psq, P, pstride, C, count, gamma, beta, mm, mv, decay,
                                                       eps, bessel, training, scale, shift, save_mean, save_rstd);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
@@ -488,7 +514,12 @@ int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row
 
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
             cudaStream_t st) {
-  cast_2d_kernel<<<grid_for((long long)rows * cols_dst, 256), 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, cols_dst);
+  const bool vec = cols == cols_dst && cols % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (vec)
+    cast_2d_vec_kernel<<<grid_for((long long)rows * cols / 8, 256), 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst);
+  else
+    cast_2d_kernel<<<grid_for((long long)rows * cols_dst, 256), 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, cols_dst);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

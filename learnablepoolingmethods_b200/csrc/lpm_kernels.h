@@ -77,8 +77,9 @@ int cast_scaled(const float* x, long long n, float alpha, __half* y, cudaStream_
 
 // lpm_optim.cu
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
-                   const int* chunk_begin, int n_tensors, const float* wd, float clip, float lr_t, float b1,
-                   float b2, float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
+                   const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
+                   const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2, float eps,
+                   float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
 
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,

@@ -41,7 +41,7 @@ class NetVladConfig:
     moe_l2: float = 1e-8
     d5_raw_reshape: bool = False   # SURVEY.md defect D5 switch (raw reinterpret instead of transpose)
     dropout_rate: float = 0.9      # D7: tf.layers.dropout(rate=1-0.1) in TransformerEncoderMod
-    loss_scale: float = 1024.0     # fp16 activation-gradient scaling inside the backward
+    loss_scale: float = 0.0        # fp16 activation-gradient scale inside the backward; 0 = auto (8 x batch)
     hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
 
     def modalities(self):
@@ -129,50 +129,67 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     # fp16 operand shadows
     # ------------------------------------------------------------------------------------------
-    def refresh_shadows(self, force=False):
-        s, c = self.store, self.cfg
-        if not force and s.shadow_version == s.version:
-            return s.shadows
-        v, sh = s.vars, s.shadows
-        dev = s.device
-
-        def buf(key, shape, dtype=torch.float16):
-            t = sh.get(key)
-            if t is None or tuple(t.shape) != tuple(shape):
-                t = torch.zeros(shape, dtype=dtype, device=dev)
-                sh[key] = t
-            return t
-
+    def shadow_specs(self):
+        """[(variable name, shadow key, shadow shape, column offset)]: fp16 row-major copies (possibly one
+        column block of a wider, zero-padded shadow) consumed as tcgen05 operands."""
+        c = self.cfg
+        specs = []
         for name, _, D, K, H, sid in c.modalities():
             vs = name + "_VLAD"
             if c.model == "NetVladV1":
-                ops.cast_f16(v[vs + "/cluster_weights"], buf(vs + "/wc16", (D, K)))
-                sh[vs + "/centers_t"] = ops.transpose_f32(v[vs + "/cluster_weights2"][0])
+                specs.append((vs + "/cluster_weights", vs + "/wc16", (D, K), 0))
                 a = name + "_attention"
-                w1, w2 = a + "/filter_output" + sid, a + "/ff_output" + sid
+                w1, w2, n2 = a + "/filter_output" + sid, a + "/ff_output" + sid, D
             else:
-                sh[vs + "/centers_t"] = ops.transpose_f32(v[vs + "/cluster_centers"])
                 a = vs + "/cluster_attention"
-                w1, w2 = a + "/filter_outputencode", a + "/ff_outputencode"
-            qkv = buf(a + "/wqkv16", (D, 3 * D))
+                w1, w2, n2 = a + "/filter_outputencode", a + "/ff_outputencode", K
             for i, n in enumerate(("q", "k", "v")):
-                ops.cast_f16(v[f"{a}/{n}/kernel"], qkv[:, i * D:(i + 1) * D], cols_dst=D)
-            ops.cast_f16(v[a + "/output_transform/kernel"], buf(a + "/wo16", (D, D)))
-            ops.cast_f16(v[w1 + "/kernel"], buf(a + "/w1_16", (D, 4 * D)))
-            n2 = v[w2 + "/kernel"].shape[1]
-            ops.cast_f16(v[w2 + "/kernel"], buf(a + "/w2_16", (4 * D, _ceil8(n2))), cols_dst=_ceil8(n2))
-        ops.cast_f16(v["hidden1_weights"], buf("wh16", (c.vlad_dim, c.hidden_size)))
-        ops.cast_f16(v["gating_weights_2"], buf("wg16", (c.hidden_size, c.hidden_size)))
+                specs.append((f"{a}/{n}/kernel", a + "/wqkv16", (D, 3 * D), i * D))
+            specs.append((a + "/output_transform/kernel", a + "/wo16", (D, D), 0))
+            specs.append((w1 + "/kernel", a + "/w1_16", (D, 4 * D), 0))
+            specs.append((w2 + "/kernel", a + "/w2_16", (4 * D, _ceil8(n2)), 0))
+        specs.append(("hidden1_weights", "wh16", (c.vlad_dim, c.hidden_size), 0))
+        specs.append(("gating_weights_2", "wg16", (c.hidden_size, c.hidden_size), 0))
         V, M = c.vocab_size, c.num_mixtures
         g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
-        wm = buf("wmoe16", (c.hidden_size, g8 + e8))
-        ops.cast_f16(v["gates/weights"], wm[:, :g8], cols_dst=g8)
-        ops.cast_f16(v["experts/weights"], wm[:, g8:], cols_dst=e8)
-        bm = buf("bmoe", (g8 + e8,), torch.float32)
+        specs.append(("gates/weights", "wmoe16", (c.hidden_size, g8 + e8), 0))
+        specs.append(("experts/weights", "wmoe16", (c.hidden_size, g8 + e8), g8))
+        return specs
+
+    def _shadow_buf(self, key, shape, dtype=torch.float16):
+        sh = self.store.shadows
+        t = sh.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, dtype=dtype, device=self.store.device)
+            sh[key] = t
+        return t
+
+    def refresh_small_shadows(self):
+        """Layouts that are not plain fp16 copies: transposed fp32 cluster centres, padded MoE bias."""
+        s, c = self.store, self.cfg
+        v, sh = s.vars, s.shadows
+        for name, _, D, K, H, sid in c.modalities():
+            vs = name + "_VLAD"
+            src = v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else v[vs + "/cluster_centers"]
+            sh[vs + "/centers_t"] = ops.transpose_f32(src)
+        V, M = c.vocab_size, c.num_mixtures
+        g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
+        bm = self._shadow_buf("bmoe", (g8 + e8,), torch.float32)
         bm[g8:g8 + V * M].copy_(v["experts/biases"])
         sh["moe_g8"] = g8
+
+    def refresh_shadows(self, force=False):
+        s = self.store
+        if not force and s.shadow_version == s.version:
+            return s.shadows
+        for var, key, shape, col0 in self.shadow_specs():
+            src = s.vars[var]
+            dst = self._shadow_buf(key, shape)
+            ops.cast_f16(src, dst[:, col0:col0 + min(shape[1] - col0, _ceil8(src.shape[1]))],
+                         cols_dst=min(shape[1] - col0, _ceil8(src.shape[1])))
+        self.refresh_small_shadows()
         s.shadow_version = s.version
-        return sh
+        return s.shadows
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -322,8 +339,12 @@ class NetVladEngine:
             raise NotImplementedError("backward is implemented for NetVladV1 in this round")
         if c.remove_diag:
             raise NotImplementedError("gating_remove_diag backward")
-        S, inv = float(c.loss_scale), 1.0 / float(c.loss_scale)
         B, hd = ctx["B"], ctx["head"]
+        # dLoss/dpred scales as 1/B; LayerNorm over the L2-normalised descriptor has rstd ~ 200, so the scale
+        # is kept modest (see DESIGN.md "numerics"): auto = 8*B clamped to [8, 4096]
+        S = float(c.loss_scale) if c.loss_scale else float(min(4096, max(8, 8 * B)))
+        ctx["loss_scale"] = S
+        inv = 1.0 / S
         V, M, Hn = c.vocab_size, c.num_mixtures, c.hidden_size
         g8 = sh["moe_g8"]
         f32 = torch.float32
@@ -385,7 +406,8 @@ class NetVladEngine:
 
     def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
-        S, inv = float(c.loss_scale), 1.0 / float(c.loss_scale)
+        S = ctx["loss_scale"]
+        inv = 1.0 / S
         m, B, T = ctx[name], ctx["B"], c.iterations
         a, vs = name + "_attention", name + "_VLAD"
         f32 = torch.float32

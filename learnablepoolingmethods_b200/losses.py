@@ -1,0 +1,35 @@
+"""Loss functions with the reference's interface (losses.py:22-51)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class BaseLoss(object):
+    """Inherit from this class when implementing new losses."""
+
+    def calculate_loss(self, unused_predictions, unused_labels, **unused_params):
+        raise NotImplementedError()
+
+
+class _XentFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, labels_u8):
+        loss, _ = ops.xent_fwd(pred, labels_u8)
+        ctx.save_for_backward(pred, labels_u8)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred, labels = ctx.saved_tensors
+        # dloss is a device scalar; the kernel takes the scale as a host float (one tiny sync, training API only)
+        return ops.xent_bwd(pred, labels, float(dloss) / pred.shape[0]), None
+
+
+class CrossEntropyLoss(BaseLoss):
+    """mean_b sum_v -(y log(p + 1e-5) + (1 - y) log(1 - p + 1e-5))   (losses.py:44-51)."""
+
+    def calculate_loss(self, predictions, labels, **unused_params):
+        lab = labels.to(device=predictions.device, dtype=torch.uint8).contiguous()
+        return _XentFunction.apply(predictions.contiguous(), lab)

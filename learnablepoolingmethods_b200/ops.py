@@ -414,12 +414,13 @@ def mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, *, scale):
 
 
 def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, clip, lr_t, scratch,
-                   b1=0.9, b2=0.999, eps=1e-8):
+                   shadow=None, b1=0.9, b2=0.999, eps=1e-8):
     """Per-tensor (grad + wd*p) -> clip_by_norm -> Adam over the flat buffers (three launches)."""
     lib = _lib.load()
     n_chunks, n_tensors = table.shape[0], wd.numel()
     partial, factor, norms, flag = scratch
+    sp, sc, sl = shadow if shadow is not None else (None, None, None)
     check(lib.lpm_adam_clip_step(ptr(flat_p), ptr(flat_g), ptr(flat_m), ptr(flat_v), ptr(table), n_chunks,
-                                 ptr(chunk_begin), n_tensors, ptr(wd), C.c_float(clip), C.c_float(lr_t), C.c_float(b1),
+                                 ptr(chunk_begin), n_tensors, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), C.c_float(lr_t), C.c_float(b1),
                                  C.c_float(b2), C.c_float(eps), ptr(partial), ptr(factor), ptr(norms), ptr(flag),
                                  stream_ptr()), "lpm_adam_clip_step")

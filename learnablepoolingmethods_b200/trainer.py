@@ -13,6 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
+from .dp import BucketedAllReduce
 from .engine import NetVladConfig, NetVladEngine
 from .variables import VariableStore
 
@@ -47,7 +48,7 @@ class FlatState:
             store.vars[n] = view                       # re-home the variable into the flat buffer
             self.grad_views[n] = self.g[o:o + numel].view(tr[n].shape)
             for c0 in range(0, numel, CHUNK):
-                table.append((t, (o + c0) // ALIGN, min(CHUNK, numel - c0)))
+                table.append((t, (o + c0) // ALIGN, min(CHUNK, numel - c0), c0 // ALIGN))
             chunk_begin.append(len(table))
         self.table = torch.tensor(table, dtype=torch.int32, device=dev)
         self.chunk_begin = torch.tensor(chunk_begin, dtype=torch.int32, device=dev)
@@ -55,7 +56,24 @@ class FlatState:
         nt = len(self.order)
         self.scratch = (torch.zeros(len(table), dtype=torch.float32, device=dev), torch.zeros(nt, dtype=torch.float32, device=dev),
                         torch.zeros(nt, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+        self.shadow = None
         store.mark_dirty()
+
+    def bind_shadows(self, engine):
+        """Per-tensor fp16 shadow destinations so the Adam kernel refreshes the GEMM operands in the same pass."""
+        engine.refresh_shadows(force=True)
+        dev = self.store.device
+        ptrs, cols, lds = [0] * len(self.order), [1] * len(self.order), [0] * len(self.order)
+        idx = {n: i for i, n in enumerate(self.order)}
+        for var, key, shape, col0 in engine.shadow_specs():
+            dst = self.store.shadows[key]
+            i = idx[var]
+            ptrs[i] = dst.data_ptr() + col0 * 2
+            cols[i] = self.store.vars[var].shape[-1]
+            lds[i] = dst.stride(0)
+        self.shadow = (torch.tensor(ptrs, dtype=torch.int64, device=dev).view(torch.uint64) if hasattr(torch, "uint64")
+                       else torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                       torch.tensor(cols, dtype=torch.int32, device=dev), torch.tensor(lds, dtype=torch.int64, device=dev))
 
     def end_offset(self, name: str) -> int:
         return self.offsets[name] + self.store.vars[name].numel()
@@ -75,10 +93,7 @@ class Trainer:
         self.global_step = 0
         self.flat: Optional[FlatState] = None
         self.bucket_elems = bucket_elems
-        self._handles = []
-        self._done_upto = 0
-        self._next_bucket = 0
-        self.launches = 0
+        self.reducer: Optional[BucketedAllReduce] = None
 
     # -- learning rate (train.py:244-249, tf.train.exponential_decay staircase) -------------------
     def learning_rate(self) -> float:
@@ -91,21 +106,8 @@ class Trainer:
 
     # -- gradient all-reduce (SUM), bucketed over the flat buffer, overlapped with the backward -----
     def _hook(self, name, g):
-        if self.world == 1 or self.flat is None:
-            return
-        self._done_upto = max(self._done_upto, self.flat.end_offset(name))
-        self._launch_ready_buckets(final=False)
-
-    def _launch_ready_buckets(self, final: bool):
-        import torch.distributed as dist
-        f = self.flat
-        while self._next_bucket < f.total:
-            b0 = self._next_bucket
-            b1 = min(f.total, b0 + self.bucket_elems)
-            if not final and self._done_upto < b1:
-                break
-            self._handles.append(dist.all_reduce(f.g[b0:b1], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-            self._next_bucket = b1
+        if self.reducer is not None:
+            self.reducer.mark_done(self.flat.end_offset(name))
 
     def train_step(self, model_input, num_frames, labels_u8):
         """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32)."""
@@ -119,26 +121,31 @@ class Trainer:
             ctx["grad_hook"] = lambda n, g: order.append(n)
             grads = eng.backward(ctx, dpred)
             self.flat = FlatState(self.store, order, self._wd())
+            self.flat.bind_shadows(eng)
             for n, g in grads.items():
                 self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
             if self.world > 1:
-                self._done_upto, self._next_bucket = self.flat.total, 0
-                self._launch_ready_buckets(final=True)
+                self.reducer = BucketedAllReduce(self.flat.g, self.bucket_elems, self.pg)
+                self.reducer.flush()
         else:
             ctx["grad_views"] = self.flat.grad_views
             ctx["grad_hook"] = self._hook
-            self._done_upto, self._next_bucket = 0, 0
+            if self.reducer is not None:
+                self.reducer.reset()
             eng.backward(ctx, dpred)
-            if self.world > 1:
-                self._launch_ready_buckets(final=True)
-        for h in self._handles:
-            h.wait()
-        self._handles = []
+            if self.reducer is not None:
+                self.reducer.flush()
+        if self.reducer is not None:
+            self.reducer.wait()
         f = self.flat
         t = self.global_step + 1
         lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
-        ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=lr_t, scratch=f.scratch)
-        self.store.mark_dirty()
+        ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=lr_t, scratch=f.scratch,
+                           shadow=f.shadow)
+        # the fp16 GEMM operands were refreshed by the Adam kernel; only the two odd layouts remain
+        self.store.version += 1
+        eng.refresh_small_shadows()
+        self.store.shadow_version = self.store.version
         self.global_step += 1
         return loss
 

@@ -1,0 +1,18 @@
+import sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from learnablepoolingmethods_b200 import ops
+dev = torch.device("cuda:0")
+T, D, Kc = 256, 1024, 256
+for B in (80, 1184):
+    xb = torch.randn(B * T, D, device=dev).half()
+    wc = (torch.randn(D, Kc, device=dev) / 32).half()
+    ct = torch.randn(Kc, D, device=dev) / 32
+    one, zero = torch.ones(Kc, device=dev), torch.zeros(Kc, device=dev)
+    for _ in range(3):
+        ops.netvlad_pool_fwd(xb, B, T, wc, one, zero, ct)
+    torch.cuda.synchronize()
+M, N, K = 20480, 4096, 1024
+a = torch.randn(M, K, device=dev).half(); w = (torch.randn(K, N, device=dev) * 0.03).half()
+for _ in range(3):
+    ops.gemm(a, w)
+torch.cuda.synchronize()

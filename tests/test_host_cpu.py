@@ -1,0 +1,142 @@
+"""CPU tests of the host-side mirror of the reference interface: flags, registry, variable names/shapes,
+C-ABI surface (symbols only: no compute without a GPU), data-parallel bucket logic on gloo (world size 2)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_flags_have_reference_names_and_defaults():
+    from learnablepoolingmethods_b200.flags import FLAGS, ensure_parsed
+    ensure_parsed()
+    # frame_level_models.py:35-36,2197-2216 ; video_level_models.py:26-45
+    assert FLAGS.iterations == 30
+    assert FLAGS.netvlad_cluster_size == 256 and FLAGS.netvlad_hidden_size == 1024
+    assert FLAGS.netvlad_add_batch_norm is True and FLAGS.netvlad_relu is False
+    assert FLAGS.gating is True and FLAGS.gating_remove_diag is False
+    assert FLAGS.moe_num_mixtures == 2 and FLAGS.moe_l2 == 1e-8 and FLAGS.moe_low_rank_gating == -1
+    assert FLAGS.moe_prob_gating is False and FLAGS.sample_random_frames is True
+
+
+def test_registry_lookup_like_train_py():
+    from learnablepoolingmethods_b200 import frame_level_models, models, utils, video_level_models
+    for name in ("NetVladV1", "NetVladV2"):
+        cls = utils.find_class_by_name(name, [frame_level_models, video_level_models])
+        assert issubclass(cls, models.BaseModel)
+        import inspect
+        sig = inspect.signature(cls().create_model)
+        assert list(sig.parameters)[:9] == ["model_input", "vocab_size", "num_frames", "iterations", "add_batch_norm",
+                                            "sample_random_frames", "cluster_size", "hidden_size", "is_training"]
+        assert sig.parameters["is_training"].default is True
+    assert utils.find_class_by_name("MoeModel", [frame_level_models, video_level_models]) is video_level_models.MoeModel
+    with pytest.raises(StopIteration):
+        utils.find_class_by_name("NoSuchModel", [frame_level_models, video_level_models])
+
+
+@pytest.mark.parametrize("model", ["NetVladV1", "NetVladV2"])
+def test_variable_names_and_shapes_match_tf_naming(model):
+    """State-dict keys = the reference's TF variable names; the oracle lists them independently."""
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from learnablepoolingmethods_b200.variables import VariableStore
+    from oracle import netvlad_oracle as O
+    store = VariableStore("cpu")
+    NetVladEngine(NetVladConfig(model=model, iterations=32, cluster_size=16, hidden_size=24, vocab_size=40), store)
+    specs = O.param_specs(model, iterations=32, cluster_size=16, hidden_size=24, vocab_size=40)
+    assert set(store.vars) == set(specs)
+    for k, (shape, kind, arg) in specs.items():
+        assert tuple(store.vars[k].shape) == tuple(shape), k
+    assert store.vars["audio_VLAD/cluster_weights" if model == "NetVladV1" else "audio_VLAD/cluster_centers"].shape[1] == 4
+    # initialisers: BN/LN affine at (1, 0), biases at 0, cluster weights ~ N(0, 1/sqrt(D))
+    assert float(store.vars["gating_bn/gamma"].min()) == 1.0 and float(store.vars["experts/biases"].abs().max()) == 0.0
+    sd = store.state_dict(prefix="tower/")
+    assert all(k.startswith("tower/") for k in sd)
+    store.load_state_dict(sd, prefix="tower/")
+
+
+def test_same_seed_same_weights_on_every_rank():
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from learnablepoolingmethods_b200.variables import VariableStore
+    a, b = VariableStore("cpu", seed=1810), VariableStore("cpu", seed=1810)
+    cfg = NetVladConfig(iterations=16, cluster_size=8, hidden_size=16, vocab_size=10)
+    NetVladEngine(cfg, a); NetVladEngine(cfg, b)
+    assert all(torch.equal(a.vars[k], b.vars[k]) for k in a.vars)
+
+
+def test_learning_rate_schedule_matches_reference():
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from learnablepoolingmethods_b200.trainer import Trainer
+    from learnablepoolingmethods_b200.variables import VariableStore
+    from oracle import netvlad_oracle as O
+    eng = NetVladEngine(NetVladConfig(iterations=16, cluster_size=8, hidden_size=16, vocab_size=10), VariableStore("cpu"))
+    tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, learning_rate_decay_examples=4000000, batch_size=80)
+    for step in (0, 1, 49999, 50000, 100001):
+        tr.global_step = step
+        assert tr.learning_rate() == O.learning_rate(2e-4, 0.85, 4000000, step, 80, 1)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """include/lpm_b200.h is the boundary: every function it declares must be exported (no compute calls here)."""
+    from learnablepoolingmethods_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "lpm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lpm_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 35, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.lpm_version.restype = ctypes.c_int
+    assert lib.lpm_version() >= 100
+    lib.lpm_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.lpm_last_error(), bytes)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "learnablepoolingmethods_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r"#.*", "", src).replace("the oracle", ""), fn
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from learnablepoolingmethods_b200.dp import BucketedAllReduce
+    n = 1000
+    g = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    red = BucketedAllReduce(g, bucket_elems=256)
+    launched_at = []
+    for end in (100, 300, 512, 900, 1000):       # gradients become final in flat order
+        red.mark_done(end)
+        launched_at.append(len(red.launched))
+    red.flush()
+    red.wait()
+    expect = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok = torch.equal(g, expect)
+    q.put((rank, ok, launched_at, list(red.launched)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_sum_world2_gloo():
+    """utils.py:205-211 sums the tower gradients: all-reduce SUM; buckets launch only when fully produced."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, launched_at, launched in res:
+        assert ok, rank
+        assert launched_at == [0, 1, 2, 3, 4]      # buckets complete at 256, 512, 768 and the 232-element tail at 1000
+        assert launched == [(0, 256), (256, 512), (512, 768), (768, 1000)]
