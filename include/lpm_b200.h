@@ -47,7 +47,8 @@ const char* lpm_last_error(void);
  *   mask / add1 / add2 (optional, fp16, batch stride = out_batch_stride): fused ReLU-backward mask and
  *   residual-gradient sums, applied after bias/ReLU in the order "+= add1 + add2, then mask".
  *   stat_sum/stat_sq (optional): per-row sum / sum of squares of the epilogue values over the N
- *   columns of each N-tile, written to [batch][n_tiles][M] (deterministic partials).
+ *   columns of each N-tile half-set, written to [batch][2*n_tiles][M] (deterministic partials, one row per
+ *   N-tile and epilogue warp group; rows of groups without columns stay untouched: zero them first).
  * ------------------------------------------------------------------------------------------- */
 typedef struct lpm_gemm_desc {
   const void* A; int a_mn; long long lda; long long a_batch_stride;
@@ -61,6 +62,7 @@ typedef struct lpm_gemm_desc {
   float* stat_sum; float* stat_sq;
   const void* mask; long long ld_mask;                     /* fp16 [M][ld_mask]: out = mask>0 ? out : 0 */
   const void* add1; const void* add2; long long ld_add;    /* fp16 addends [M][ld_add]: out += add1 (+ add2) */
+  int no_tma_store;                                        /* debug: force the direct-store epilogue */
 } lpm_gemm_desc;
 
 int lpm_gemm_f16(const lpm_gemm_desc* desc, lpm_stream_t stream);

@@ -29,6 +29,7 @@ class GemmDesc(C.Structure):
         ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
         ("mask", C.c_void_p), ("ld_mask", C.c_longlong),
         ("add1", C.c_void_p), ("add2", C.c_void_p), ("ld_add", C.c_longlong),
+        ("no_tma_store", C.c_int),
     ]
 
 

@@ -2,13 +2,16 @@
 // TMEM accumulators (double buffered) -> fused epilogue.  Persistent, warp specialised:
 //   warp 0   : TMA producer (one lane)
 //   warp 1   : TMEM allocator + MMA issuer (one lane)
-//   warps 2-5: epilogue (TMEM -> registers -> bias / row-scale / ReLU / row statistics -> global)
+//   warps 2-9: epilogue, two groups of four (TMEM -> registers -> bias / row-scale / ReLU / masks -> swizzled
+//              smem slab -> TMA store; the groups take alternate 64-column slabs)
 // Either operand may be K-major or MN-major in memory, so NN / NT / TN products (forward, dX, dW)
 // need no transposes.  Batched (3-D tensor maps) and split-K (fp32 partials) variants included.
 //
 // Replaces the tf.matmul / tf.layers.dense / slim.fully_connected call sites of the hot path:
 //   frame_level_models.py:2319,2347  transformer_utils.py:559-561,583-585,701-711
 //   video_level_models.py:86-114 and their autodiff transposes.
+#include <cstring>
+
 #include "lpm_common.cuh"
 #include "lpm_kernels.h"
 
@@ -40,6 +43,7 @@ struct GemmKernelParams {
   const __half* add1;   // optional fp16 addends (fused residual-gradient sums)
   const __half* add2;
   long long ld_add;
+  int tma_store;        // 1: epilogue stages 128-byte-row slabs in smem and writes them with TMA
 };
 
 template <int BN, int STAGES>
@@ -47,14 +51,131 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SLAB_BYTES = BM * 128;                 // per epilogue group: 128 rows x 128 B (64 fp16 / 32 fp32 columns)
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;        // one staging slab per epilogue group
+  static constexpr int BAR_OFF = STG_OFF + 2 * SLAB_BYTES;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
+// Epilogue math on one 32-column chunk held in registers: v = acc*rs (+bias) (ReLU) (+add1 +add2) (mask).
+__device__ __forceinline__ void epi_chunk(const uint32_t* r, float* v, const GemmKernelParams& p, float rs, int col0,
+                                          int row, bool row_ok, int bz) {
+  const bool full = (col0 + 32 <= p.N);                    // warp-uniform
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * rs;
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + min(col0 + i, p.N - 1));
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.add1 != nullptr || p.mask != nullptr) {
+    const long long rofs = (long long)bz * p.out_batch_stride;
+    if (p.add1 != nullptr && row_ok) {
+      const __half* a1 = p.add1 + rofs + (long long)row * p.ld_add + col0;
+      const __half* a2 = p.add2 ? p.add2 + rofs + (long long)row * p.ld_add + col0 : nullptr;
+      if (full && (p.ld_add & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(a1) + i);
+          const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+        }
+        if (a2 != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(a2) + i);
+            const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) {
+            v[i] += __half2float(a1[i]);
+            if (a2 != nullptr) v[i] += __half2float(a2[i]);
+          }
+      }
+    }
+    if (p.mask != nullptr && row_ok) {
+      const __half* mk = p.mask + rofs + (long long)row * p.ld_mask + col0;
+      if (full && (p.ld_mask & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(mk) + i);
+          const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+            if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N && !(__half2float(mk[i]) > 0.f)) v[i] = 0.f;
+      }
+    }
+  }
+}
+
+// direct (non-TMA) store of one chunk: unaligned pitch / accumulate
+__device__ __forceinline__ void epi_store_direct(const float* v, const GemmKernelParams& p, long long obase, int col0) {
+  const bool full = (col0 + 32 <= p.N);
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + obase + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 w = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        float4* dst = reinterpret_cast<float4*>(o) + i;
+        if (p.accumulate) { const float4 old = *dst; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+        *dst = w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) o[i] = p.accumulate ? o[i] + v[i] : v[i];
+    }
+  } else {
+    __half* o = reinterpret_cast<__half*>(p.out) + obase + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+        w.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+        w.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+        w.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(o)[i] = w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) o[i] = __float2half_rn(v[i]);
+    }
+  }
+}
+
 template <int BN, int STAGES, int A_MN, int B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmKernelParams p) {
+                const __grid_constant__ CUtensorMap tmap_c, const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,13 +192,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_c);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     mbar_fence_init();
   }
@@ -165,7 +287,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
-    const int quarter = warp & 3;  // TMEM sub-partition this warp may read
+    // 8 warps = 2 groups x 4 TMEM lane quarters; the groups take alternate 64-column slabs of the tile.
+    const int quarter = warp & 3;            // TMEM sub-partition this warp may read
+    const int grp = (warp - 2) >> 2;         // 0 / 1
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+    uint8_t* slab = smem + L::STG_OFF + grp * L::SLAB_BYTES;
+    const int trow = quarter * 32 + lane;    // row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -174,7 +302,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int nt = t % p.n_tiles; t /= p.n_tiles;
       const int bz = t % p.batch;   t /= p.batch;
       const int sp = t;
-      const int row = mt * BM + quarter * 32 + lane;
+      const int row = mt * BM + trow;
       const bool row_ok = row < p.M;
       const float rs = (p.row_scale != nullptr && row_ok)
                            ? __ldg(p.row_scale + (long long)bz * p.row_scale_batch_stride + row) * p.alpha
@@ -182,94 +310,55 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const long long obase = (long long)sp * p.out_split_stride + (long long)bz * p.out_batch_stride +
                               (long long)row * p.ldc;
       float s_sum = 0.f, s_sq = 0.f;
+      const int cols_here = min(BN, p.N - nt * BN);
+      const int slab_cols = (p.tma_store && p.out_f32) ? 32 : 64;   // one 128-byte-row TMA box per slab
+      const int n_slabs = (cols_here + slab_cols - 1) / slab_cols;
+      const int my_last = ((n_slabs - 1 - grp) >= 0) ? grp + ((n_slabs - 1 - grp) / 2) * 2 : -1;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (my_last < 0) {                      // this group has no slab in a narrow tail tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = nt * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+      for (int sl = grp; sl < n_slabs; sl += 2) {
+        const int col0 = nt * BN + sl * slab_cols;
+        const bool second = (slab_cols == 64) && (col0 + 32 < p.N);   // second 32-column chunk has valid columns
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + sl * slab_cols);
+        tmem_ld32(taddr, r0);
+        if (second) tmem_ld32(taddr + 32, r1);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]) * rs;
-          if (p.bias != nullptr && col0 + i < p.N) x += __ldg(p.bias + col0 + i);
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[i] = x;
+        if (sl == my_last) {
+          // accumulator fully read by this warp: hand the TMEM buffer back before finishing the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if ((p.add1 != nullptr || p.mask != nullptr) && row_ok) {
-          const long long bofs = (long long)bz * p.out_batch_stride;
-          if (p.add1 != nullptr) {
-            const __half* a1 = p.add1 + bofs + (long long)row * p.ld_add + col0;
-            const __half* a2 = p.add2 ? p.add2 + bofs + (long long)row * p.ld_add + col0 : nullptr;
-            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(a1) & 15) == 0) &&
-                (a2 == nullptr || (reinterpret_cast<uintptr_t>(a2) & 15) == 0)) {
+        if (p.tma_store) {
+          if (leader) bulk_wait_read<0>();                   // this group's previous slab has left smem
+          named_barrier(bar_a, 128);
+        }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(a1) + i);
-                const __half2* h = reinterpret_cast<const __half2*>(&w);
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !second) break;
+          float v[32];
+          const int c0 = col0 + 32 * h;
+          epi_chunk(h == 0 ? r0 : r1, v, p, rs, c0, row, row_ok, bz);
+          if (p.stat_sum != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
-                if (a2) {
-                  const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(a2) + i);
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&w2);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
-                }
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
-                v[i] += __half2float(a1[i]);
-                if (a2) v[i] += __half2float(a2[i]);
-              }
-            }
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.N) { s_sum += v[i]; s_sq += v[i] * v[i]; }
           }
-          if (p.mask != nullptr) {
-            const __half* mk = p.mask + (long long)bz * p.out_batch_stride + (long long)row * p.ld_mask + col0;
-            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(mk) & 15) == 0)) {
+          if (p.tma_store) {
+            if (p.out_f32) {                                  // 32 fp32 columns = one 128-byte row
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(mk) + i);
-                const __half2* h = reinterpret_cast<const __half2*>(&w);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __half22float2(h[j]);
-                  if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
-                  if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
-                }
-              }
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(slab + trow * 128 + ((i ^ (trow & 7)) << 4)) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i)
-                if (!(__half2float(mk[i]) > 0.f)) v[i] = 0.f;
-            }
-          }
-        }
-        if (p.stat_sum != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) { s_sum += v[i]; s_sq += v[i] * v[i]; }
-        }
-        if (p.out != nullptr && row_ok) {
-          const bool full = (col0 + 32 <= p.N);
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + obase + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 w = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                float4* dst = reinterpret_cast<float4*>(o) + i;
-                if (p.accumulate) { float4 old = *dst; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
-                *dst = w;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = p.accumulate ? o[i] + v[i] : v[i];
-            }
-          } else {
-            __half* o = reinterpret_cast<__half*>(p.out) + obase + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 uint4 w;
@@ -277,24 +366,30 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 w.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
                 w.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
                 w.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-                reinterpret_cast<uint4*>(o)[i] = w;
+                *reinterpret_cast<uint4*>(slab + trow * 128 + (((h * 4 + i) ^ (trow & 7)) << 4)) = w;
               }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) o[i] = __float2half_rn(v[i]);
             }
+          } else if (p.out != nullptr && row_ok) {
+            epi_store_direct(v, p, obase, c0);
+          }
+        }
+        if (p.tma_store) {
+          fence_proxy_async_smem();
+          named_barrier(bar_b, 128);
+          if (leader) {
+            tma_store_3d(&tmap_c, slab, col0, mt * BM, sp * p.batch + bz);
+            bulk_commit();
           }
         }
       }
       if (p.stat_sum != nullptr && row_ok) {
-        const long long si = ((long long)(sp * p.batch + bz) * p.n_tiles + nt) * p.M + row;
+        const long long si = ((long long)(sp * p.batch + bz) * (p.n_tiles * 2) + nt * 2 + grp) * p.M + row;
         p.stat_sum[si] = s_sum;
         p.stat_sq[si] = s_sq;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && leader) bulk_wait<0>();   // all output slabs written before exit
   }
 
   tc_fence_before();
@@ -309,7 +404,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // host launcher
 // ----------------------------------------------------------------------------------------------
 template <int BN, int STAGES, int A_MN, int B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKernelParams& p,
+                       cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   auto kern = gemm_f16_kernel<BN, STAGES, A_MN, B_MN>;
   static bool attr_set = false;
@@ -319,18 +415,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   }
   const int total = p.m_tiles * p.n_tiles * p.batch * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, p);
+  kern<<<grid, 320, L::TOTAL, st>>>(ta, tb, tc, p);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
 template <int BN, int STAGES>
-static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                           const GemmKernelParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, 0, 0>(ta, tb, p, st);
-  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, 0, 1>(ta, tb, p, st);
-  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, 1, 0>(ta, tb, p, st);
-  return launch_gemm<BN, STAGES, 1, 1>(ta, tb, p, st);
+  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, 0, 0>(ta, tb, tc, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, 0, 1>(ta, tb, tc, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, 1, 0>(ta, tb, tc, p, st);
+  return launch_gemm<BN, STAGES, 1, 1>(ta, tb, tc, p, st);
 }
 
 int gemm_pick_bn(int N) {
@@ -367,6 +463,9 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
   p.mask = reinterpret_cast<const __half*>(g.mask); p.ld_mask = g.ld_mask;
   p.add1 = reinterpret_cast<const __half*>(g.add1); p.add2 = reinterpret_cast<const __half*>(g.add2); p.ld_add = g.ld_add;
   LPM_REQUIRE(!(g.add2 && !g.add1), "gemm: add2 requires add1");
+  LPM_REQUIRE(!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  LPM_REQUIRE(!g.add1 || ((reinterpret_cast<uintptr_t>(g.add1) & 15) == 0 && (!g.add2 || (reinterpret_cast<uintptr_t>(g.add2) & 15) == 0)), "gemm: addends must be 16-byte aligned");
+  LPM_REQUIRE(!g.mask || (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0, "gemm: mask must be 16-byte aligned");
 
   CUtensorMap ta, tb;
   int rc;
@@ -378,9 +477,24 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
   else         rc = make_tmap_3d(&tb, g.B, 2, g.N, g.K, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, 64, BK);
   if (rc) return rc;
 
-  if (BN == 256) return dispatch_major<256, 4>(g.a_mn, g.b_mn, ta, tb, p, st);
-  if (BN == 128) return dispatch_major<128, 6>(g.a_mn, g.b_mn, ta, tb, p, st);
-  return dispatch_major<64, 8>(g.a_mn, g.b_mn, ta, tb, p, st);
+  // TMA-store epilogue when the output is TMA-addressable: 16-byte aligned base and row pitch, no read-modify-write
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  const int es = g.out_f32 ? 4 : 2;
+  long long zstride = 0;
+  bool z_ok = true;
+  if (p.splits > 1 && p.batch > 1) { zstride = g.out_batch_stride; z_ok = (g.out_split_stride == g.out_batch_stride * p.batch); }
+  else if (p.splits > 1) zstride = g.out_split_stride;
+  else if (p.batch > 1) zstride = g.out_batch_stride;
+  p.tma_store = (g.out != nullptr && !g.accumulate && z_ok && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 &&
+                 (g.ldc * es) % 16 == 0 && (zstride * es) % 16 == 0 && !g.no_tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    rc = make_tmap_3d(&tc, g.out, es, g.N, g.M, (uint64_t)p.splits * p.batch, g.ldc, zstride, g.out_f32 ? 32 : 64, BM);
+    if (rc) return rc;
+  }
+  if (BN == 256) return dispatch_major<256, 4>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  if (BN == 128) return dispatch_major<128, 6>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  return dispatch_major<64, 8>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
 }
 
 int gemm_effective_splits(int K, int splits) {

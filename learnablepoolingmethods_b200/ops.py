@@ -22,7 +22,8 @@ def _lda(t: torch.Tensor) -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = True,
          out: Optional[torch.Tensor] = None, out_dtype=torch.float16, bias=None, row_scale=None,
          relu: bool = False, alpha: float = 1.0, accumulate: bool = False, splits: int = 1,
-         stats: bool = False, force_bn: int = 0, M=None, N=None, K=None, mask=None, add1=None, add2=None):
+         stats: bool = False, force_bn: int = 0, M=None, N=None, K=None, mask=None, add1=None, add2=None,
+         no_tma_store: bool = False):
     """D = epilogue(alpha * A x B).
 
     a: [.., M, K] (a_mn=False) or [.., K, M] (a_mn=True), fp16, last dim contiguous.
@@ -73,6 +74,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     d.row_scale = ptr(row_scale)
     d.row_scale_batch_stride = M if row_scale is not None else 0
     d.relu, d.accumulate, d.alpha = int(relu), int(accumulate), float(alpha)
+    d.no_tma_store = int(no_tma_store)
     if mask is not None:
         d.mask, d.ld_mask = ptr(mask), _lda(mask)
     if add1 is not None:
@@ -83,7 +85,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     st = None
     if stats:
         n_tiles = -(-N // (force_bn or lib.lpm_gemm_tile_n(N)))
-        st = torch.empty((2, batch, n_tiles, M), dtype=torch.float32, device=a.device)
+        st = torch.zeros((2, batch, 2 * n_tiles, M), dtype=torch.float32, device=a.device)   # x2: epilogue groups
         d.stat_sum, d.stat_sq = ptr(st[0]), ptr(st[1])
     check(lib.lpm_gemm_f16(C.byref(d), stream_ptr()), "lpm_gemm_f16")
     if stats:

@@ -11,7 +11,7 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("gating,tol", [(False, 2e-2), (True, 1.5e-1)])
+@pytest.mark.parametrize("gating,tol", [(False, 2e-2), (True, 3e-1)])
 @pytest.mark.parametrize("B,K,Hd,V,T", [(4, 64, 64, 100, 256), (3, 128, 64, 200, 128)])
 def test_netvlad_v1_gradients(cuda, B, K, Hd, V, T, gating, tol):
     """gating=False isolates the kernels (tight bound).  With context gating the batch-statistics BN over a
