@@ -50,6 +50,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     d.B, d.b_mn, d.ldb = ptr(b), int(b_mn), _lda(b)
     d.b_batch_stride = b.stride(0) if b.dim() == 3 else 0
     d.M, d.N, d.K, d.batch, d.force_bn = M, N, K, batch, force_bn
+    # automatic split-K: fp32-output products with a plain epilogue that would occupy only a few of the 148 SMs
+    # (weight gradients with a long reduction, skinny dX products) are split over K and reduced deterministically
+    want_f32 = (out.dtype == torch.float32) if torch.is_tensor(out) else (out_dtype == torch.float32)
+    plain = bias is None and row_scale is None and not relu and not stats and mask is None and add1 is None
+    auto = None
+    if splits == 1 and want_f32 and plain and not accumulate and not isinstance(out, str):
+        bn_t = force_bn or lib.lpm_gemm_tile_n(N)
+        tiles = -(-M // 128) * -(-N // bn_t) * batch
+        kb = -(-K // 64)
+        if tiles <= 64 and kb >= 16:
+            auto = max(2, min(148 // tiles, kb // 4))
+    if auto is not None:
+        parts = gemm(a, b, a_mn=a_mn, b_mn=b_mn, splits=auto, force_bn=force_bn, M=M, N=N, K=K)
+        shape_ = (batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N)
+        if out is None:
+            out = torch.empty(shape_, dtype=torch.float32, device=a.device)
+        assert out.is_contiguous()
+        splitk_reduce(parts, alpha=alpha, out32=out)
+        return out
     eff_splits = lib.lpm_gemm_splits(K, splits)
     d.splits = eff_splits
     shape = (batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N)
