@@ -91,8 +91,10 @@ int lpm_splitk_reduce(const float* part, int splits, long long split_stride, lon
 int lpm_sample_stats_blocks(void);
 int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
                         float* partial, lpm_stream_t stream);
+/* y2_f16 == NULL: one [B*T][F] matrix; else columns [0,split_col) -> y_f16 [B*T][split_col], rest -> y2_f16. */
 int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
-                        const float* scale, const float* shift, void* y_f16, lpm_stream_t stream);
+                        const float* scale, const float* shift, void* y_f16, int split_col, void* y2_f16,
+                        lpm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * slim.batch_norm finalisation (eps 1e-3, decay 0.999 passed by the caller): reduces P partial
@@ -116,12 +118,14 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
  *   z            fp16 [B][K][D]  un-normalised cluster-major descriptor V^T
  *   rscale       fp32 [B][K]     vlad[b,k,:] = z[b,k,:]*rscale[b,k]  (intra-norm x global norm)
  *   a_sum        fp32 [B][K] or NULL;  assign fp16 [B][T][K] or NULL (saved for the backward)
+ *   assign_in    fp16 [B][T][K] or NULL: externally supplied cluster similarities (NetVladAttenCluster,
+ *                video_pooling_modules.py:1628-1652): the logits/softmax phase is skipped, wc/logit_* unused
  * Limits: T <= 256, D % 64 == 0, K % 8 == 0, K <= 256.
  * ------------------------------------------------------------------------------------------- */
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
                          const float* logit_scale, const float* logit_shift, const float* centers_t,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
-                         float* a_sum, void* assign, lpm_stream_t stream);
+                         float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream);
 /* vlad = z * rscale as fp32: d_major!=0 -> [B][D*K] (reference flatten, :2821), else [B][K][D]. */
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
                          lpm_stream_t stream);
@@ -233,6 +237,26 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                        const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                        const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
                        float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
+
+/* =============================================================================================
+ * NetVladV2 (attention-based cluster similarities) helpers
+ * ============================================================================================= */
+/* Batch-norm statistics of the attention logits q.k^T per key channel without materialising them
+ * (transformer_utils.py:646-654): partial [B*H][2][L] = (sum_i q_i.k_j | sum_i (q_i.k_j)^2); head depth 16. */
+int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int H, float* partial, lpm_stream_t stream);
+/* Per-column (sum | sum of squares) partials of an fp16 matrix: partial [lpm_colstats_chunks(rows)][2][C]
+ * (attention_bn, filter_bn, feed_output_bn: transformer_utils.py:666,747,760). */
+int lpm_colstats_chunks(long long rows);
+int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* partial, lpm_stream_t stream);
+/* x[r][c] = x[r][c]*scale[c] + shift[c] in place (applies a folded batch norm). */
+int lpm_affine_cols_f16(void* x, long long rows, int C, const float* scale, const float* shift, lpm_stream_t stream);
+/* tf.layers.dropout (transformer_utils.py:450): x *= keep/(1-rate); keep from mask_in (fp16 0/1) or a hash of
+ * (seed, index); the mask used is written to mask_out when given. */
+int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed, float rate,
+                    lpm_stream_t stream);
+/* out[b][d*K + k] = fp16(z[b][k][d]*rscale[b][k]): the reference's d-major flatten as an fp16 GEMM operand. */
+int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, int D, void* out, long long out_stride,
+                             lpm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -131,10 +131,11 @@ int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_fr
 }
 
 int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
-                        const float* scale, const float* shift, void* y_f16, lpm_stream_t stream) {
+                        const float* scale, const float* shift, void* y_f16, int split_col, void* y2_f16,
+                        lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply: bad arguments");
-  return sample_apply(x, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), ST(stream));
+  return sample_apply(x, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
 }
 
 int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
@@ -152,11 +153,12 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
                          const float* logit_scale, const float* logit_shift, const float* centers_t,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
-                         float* a_sum, void* assign, lpm_stream_t stream) {
+                         float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream) {
   DEVCHK();
-  LPM_REQUIRE(x && wc && logit_scale && logit_shift && centers_t && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
+  LPM_REQUIRE(x && centers_t && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
+  LPM_REQUIRE(assign_in || (wc && logit_scale && logit_shift), "lpm_netvlad_pool_fwd: need cluster weights or assign_in");
   return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, centers_t,
-                          valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), ST(stream));
+                          valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), CH16(assign_in), ST(stream));
 }
 
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
@@ -322,6 +324,35 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
               "lpm_adam_clip_step: bad arguments");
   return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, lr_t, b1, b2, eps, partial,
                         factor, norms, flag, ST(stream));
+}
+
+int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int H, float* partial, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(qkv && partial && B > 0 && L > 0, "lpm_mha_logit_stats: bad arguments");
+  return mha_logit_stats(CH16(qkv), ld, B, L, Dm, H, partial, ST(stream));
+}
+int lpm_colstats_chunks(long long rows) { return colstats_chunks(rows); }
+int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* partial, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && partial && rows > 0 && C > 0, "lpm_colstats_f16: bad arguments");
+  return colstats(CH16(x), ld, rows, C, partial, ST(stream));
+}
+int lpm_affine_cols_f16(void* x, long long rows, int C, const float* scale, const float* shift, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && scale && shift && rows > 0, "lpm_affine_cols_f16: bad arguments");
+  return affine_cols(H16(x), rows, C, scale, shift, ST(stream));
+}
+int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed, float rate,
+                    lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && n > 0, "lpm_dropout_f16: bad arguments");
+  return dropout_f16(H16(x), n, CH16(mask_in), H16(mask_out), seed, rate, ST(stream));
+}
+int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, int D, void* out, long long out_stride,
+                             lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(z && rscale && out, "lpm_netvlad_finalize_f16: null pointer");
+  return vlad_dmajor_f16(CH16(z), rscale, B, K, D, H16(out), out_stride, ST(stream));
 }
 
 }  // extern "C"

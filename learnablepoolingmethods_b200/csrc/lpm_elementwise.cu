@@ -70,14 +70,17 @@ __global__ void __launch_bounds__(256) sample_apply_kernel(const float* __restri
                                                            int max_frames, int F, int T, float step,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
-                                                           __half* __restrict__ y) {
+                                                           __half* __restrict__ y, int split_col,
+                                                           __half* __restrict__ y2) {
+  // y2 == null: one [rows][F] matrix.  Otherwise columns [0, split_col) go to y ([rows][split_col]) and the rest
+  // to y2 ([rows][F - split_col]): contiguous per-modality matrices for NetVladV2's residual / layer norm.
   const int rows = B * T;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const int b = r / T, i = r - b * T;
     const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
     const float* src = x + ((size_t)b * max_frames + idx) * F;
-    __half* dst = y + (size_t)r * F;
     for (int c = threadIdx.x * 4; c < F; c += blockDim.x * 4) {
+      __half* dst = y2 == nullptr ? y + (size_t)r * F : (c < split_col ? y + (size_t)r * split_col : y2 + (size_t)r * (F - split_col) - split_col);
       const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
@@ -446,10 +449,11 @@ int sample_stats(const float* x, const int* nf, int B, int max_frames, int F, in
 }
 
 int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, int T, const float* scale,
-                 const float* shift, __half* y, cudaStream_t st) {
+                 const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st) {
   LPM_REQUIRE(F % 4 == 0, "sample_apply: feature size must be a multiple of 4 (got %d)", F);
+  LPM_REQUIRE(y2 == nullptr || (split_col % 4 == 0 && split_col > 0 && split_col < F), "sample_apply: bad split column");
   int grid = B * T < num_sms() * 8 ? B * T : num_sms() * 8;
-  sample_apply_kernel<<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, scale, shift, y);
+  sample_apply_kernel<<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, scale, shift, y, split_col, y2);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

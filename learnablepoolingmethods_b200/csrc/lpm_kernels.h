@@ -18,7 +18,7 @@ int gemm_effective_splits(int K, int splits);
 int sample_stats_blocks();
 int sample_stats(const float* x, const int* nf, int B, int max_frames, int F, int T, float* partial, cudaStream_t st);
 int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, int T, const float* scale,
-                 const float* shift, __half* y, cudaStream_t st);
+                 const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st);
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
                 int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st);
@@ -85,6 +85,16 @@ int adam_clip_step(float* p, const float* g, float* m, float* v, const int* tabl
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const float* centers_t,
                      const int* valid_frames, int B, int T, int D, int K, __half* z, float* rscale, float* a_sum,
-                     __half* assign, cudaStream_t st);
+                     __half* assign, const __half* assign_in, cudaStream_t st);
+
+// lpm_v2.cu
+int mha_logit_stats(const __half* qkv, long long ld, int B, int L, int Dm, int H, float* partial, cudaStream_t st);
+int colstats_chunks(long long rows);
+int colstats(const __half* x, long long ld, long long rows, int C, float* partial, cudaStream_t st);
+int affine_cols(__half* x, long long rows, int C, const float* scale, const float* shift, cudaStream_t st);
+int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed, float rate,
+                cudaStream_t st);
+int vlad_dmajor_f16(const __half* z, const float* rscale, int B, int K, int D, __half* out, long long out_stride,
+                    cudaStream_t st);
 
 }  // namespace lpm

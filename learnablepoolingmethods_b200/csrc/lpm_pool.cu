@@ -52,6 +52,7 @@ struct PoolParams {
   float* rscale;                  // [B][K]
   float* a_sum;                   // [B][K] or null
   __half* assign;                 // [B][T][K] or null (saved for backward)
+  const __half* assign_in;        // [B][T][K] or null: externally supplied assignments (NetVladV2), phase 1 skipped
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -88,6 +89,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const int b = blockIdx.x;
   const int n_ft = (p.T + 127) / 128;          // 1 or 2 frame tiles
   const int n_dc = p.D / 64;
+  const int n_dc1 = p.assign_in ? 0 : n_dc;    // phase 1 (logits) is skipped when assignments are supplied
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -105,7 +107,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   // folded logit affine in the log2 domain; padded clusters get -inf
   for (int k = threadIdx.x; k < KCT; k += blockDim.x) {
     float2 a;
-    if (k < p.K) {
+    if (k < p.K && p.assign_in == nullptr) {
       a.x = p.logit_scale[k] * 1.4426950408889634f;
       a.y = p.logit_shift[k] * 1.4426950408889634f;
     } else {
@@ -122,7 +124,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int dc = 0; dc < n_dc; ++dc) {
+      for (int dc = 0; dc < n_dc1; ++dc) {
         mbar_wait(&empty1[stage], phase ^ 1);
         uint8_t* sx = smem + stage * Cfg::ST1_BYTES;
         uint8_t* sw = sx + Cfg::XS_BYTES;
@@ -133,7 +135,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         if (++stage == Cfg::NS1) { stage = 0; phase ^= 1; }
       }
       // phase 2 reuses the shared memory of phase 1: wait until every phase-1 MMA has retired
-      mbar_wait(s_full, 0);
+      if (!p.assign_in) mbar_wait(s_full, 0);
       stage = 0; phase = 0;
       for (int db = 0; db < n_dc; ++db) {
         mbar_wait(&empty2[stage], phase ^ 1);
@@ -149,7 +151,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       constexpr uint32_t idesc1 = umma_idesc_f16(128, KCT, 0, 1);   // A = X (K-major), B = Wc (MN-major)
       constexpr uint32_t idesc2 = umma_idesc_f16(128, 64, 1, 1);    // A = P^T (MN-major), B = X (MN-major)
       int stage = 0; uint32_t phase = 0;
-      for (int dc = 0; dc < n_dc; ++dc) {
+      for (int dc = 0; dc < n_dc1; ++dc) {
         mbar_wait(&full1[stage], phase);
         tc_fence_after();
         const uint32_t sx = smem_u32(smem + stage * Cfg::ST1_BYTES);
@@ -165,7 +167,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         umma_commit(&empty1[stage]);
         if (++stage == Cfg::NS1) { stage = 0; phase ^= 1; }
       }
-      umma_commit(s_full);
+      if (!p.assign_in) umma_commit(s_full);
 
       mbar_wait(p_ready, 0);
       tc_fence_after();
@@ -201,8 +203,10 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
 
     // ---------------- softmax over clusters, one thread per frame ----------------
-    mbar_wait(s_full, 0);
-    tc_fence_after();
+    if (!p.assign_in) {
+      mbar_wait(s_full, 0);
+      tc_fence_after();
+    }
     {
       const int t = grp * 128 + row;
       int tv = p.T;
@@ -214,7 +218,17 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       uint8_t* prow = sP + t_row * 128;
       const int sw = t_row & 7;
       float inv = 0.f;
-      if (active) {
+      if (active && p.assign_in) {
+        // NetVladV2: the assignment row comes from the encoder (video_pooling_modules.py:1628-1638)
+        inv = (t_row < tv) ? 1.f : 0.f;
+        const __half* arow = p.assign_in + ((size_t)b * p.T + min(t_row, p.T - 1)) * p.K;
+#pragma unroll 4
+        for (int ch = 0; ch < KCT / 8; ++ch) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (ch * 8 < p.K && t_row < tv) v = __ldg(reinterpret_cast<const uint4*>(arow + ch * 8));
+          *reinterpret_cast<uint4*>(prow + (ch >> 3) * (TP * 128) + (((ch & 7) ^ sw) << 4)) = v;
+        }
+      } else if (active) {
         const uint32_t s_addr = tmem_base + lane_addr + grp * KCT;
         float m = -INFINITY;
 #pragma unroll 1
@@ -370,7 +384,7 @@ static int launch_pool(const CUtensorMap& tx, const CUtensorMap& tw, const PoolP
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const float* centers_t,
                      const int* valid_frames, int B, int T, int D, int K, __half* z, float* rscale, float* a_sum,
-                     __half* assign, cudaStream_t st) {
+                     __half* assign, const __half* assign_in, cudaStream_t st) {
   LPM_REQUIRE(B > 0 && T > 0 && T <= TP, "netvlad_pool_fwd: frames per video must be in [1,%d] (got %d)", TP, T);
   LPM_REQUIRE(D % 64 == 0 && D >= 64, "netvlad_pool_fwd: feature size must be a multiple of 64 (got %d)", D);
   LPM_REQUIRE(K % 8 == 0 && K >= 8 && K <= 256, "netvlad_pool_fwd: cluster size must be a multiple of 8 in [8,256] (got %d)", K);
@@ -379,9 +393,11 @@ int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, c
   p.B = B; p.T = T; p.D = D; p.K = K;
   p.logit_scale = logit_scale; p.logit_shift = logit_shift; p.centers_t = centers_t;
   p.valid_frames = valid_frames; p.z = z; p.rscale = rscale; p.a_sum = a_sum; p.assign = assign;
+  p.assign_in = assign_in;
   CUtensorMap tx, tw;
   if (int rc = make_tmap_3d(&tx, x, 2, D, T, B, ldx, x_batch_stride, 64, 128)) return rc;
-  if (int rc = make_tmap_3d(&tw, wc, 2, K, D, 1, ldw, 0, 64, 64)) return rc;
+  if (assign_in != nullptr) tw = tx;   // unused in this mode
+  else if (int rc = make_tmap_3d(&tw, wc, 2, K, D, 1, ldw, 0, 64, 64)) return rc;
   if (K <= 64) return launch_pool<64>(tx, tw, p, st);
   if (K <= 128) return launch_pool<128>(tx, tw, p, st);
   return launch_pool<256>(tx, tw, p, st);

@@ -221,20 +221,28 @@ class NetVladEngine:
             r = ops.bn_finalize(None, None, 1, v["input_bn/gamma"], v["input_bn/beta"], v["input_bn/moving_mean"],
                                 v["input_bn/moving_variance"], training=False, bessel=True, save=save)
         in_scale, in_shift = r[0], r[1]
-        xb = ops.sample_bn_apply(x, nf, T, in_scale, in_shift)
+        if c.model == "NetVladV1":
+            xb = ops.sample_bn_apply(x, nf, T, in_scale, in_shift)
+            xmods = [xb[:, col0:col0 + D] for _, col0, D, _, _, _ in c.modalities()]
+        else:
+            # V2 adds the frames as a residual inside the encoder: contiguous per-modality matrices
+            xb = None
+            xmods = list(ops.sample_bn_apply(x, nf, T, in_scale, in_shift, split_col=c.rgb_dim))
         if save:
             ctx["xb"] = xb
             ctx["input_bn_stats"] = r[2]
 
         vlad = torch.empty((B, c.vlad_dim), dtype=torch.float16, device=x.device)
         off = 0
-        for name, col0, D, K, H, sid in c.modalities():
-            X = xb[:, col0:col0 + D]
+        for (name, col0, D, K, H, sid), X in zip(c.modalities(), xmods):
             if c.model == "NetVladV1":
                 m = self._v1_modality(name, X, B, T, D, K, H, sid, is_training, save, vlad[:, off:off + K * D], ctx,
                                       return_intermediates)
             else:
-                raise NotImplementedError("NetVladV2 forward is wired in engine_v2")
+                if save:
+                    raise NotImplementedError("NetVladV2 backward (training graph) is not implemented in this round")
+                mask = None if dropout_masks is None else dropout_masks.get(name)
+                m = self._v2_modality(name, X, B, T, D, K, is_training, vlad[:, off:off + K * D], ctx, return_intermediates, mask)
             if save:
                 ctx[name] = m
             off += K * D
@@ -302,6 +310,56 @@ class NetVladEngine:
                           zn=zn, qkv=qkv, o=o, lse=lse, u1=att, st1=st1, h1=h1, f1=f1, f2=f2, u2=u2, st2=st2,
                           u3=h2, st3=r3[1]))
         return m
+
+    def _v2_modality(self, name, X, B, T, D, K, training, out_view, ctx, want_inter, dropout_mask):
+        """NetVladAttenCluster.forward (video_pooling_modules.py:1617-1663): cluster similarities from
+        TransformerEncoderMod over the frames (transformer_utils.py:443-457, 634-677, 737-767), then the same
+        residual aggregation / norms as V1 through the pooling kernel's external-assignment mode."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        vs = name + "_VLAD"
+        a = vs + "/cluster_attention"
+        H = D // 16                                                   # video_pooling_modules.py:1612
+        if T != c.iterations:
+            raise ValueError("logits_bn is tied to iterations")
+        qkv = ops.gemm(X, sh[a + "/wqkv16"])                          # [B*T, 3D]; no q scaling (batch-normed logits)
+        bn = a + "/logits_bn"
+        if training:
+            part = ops.mha_logit_stats(qkv, B, T, D, H)
+            ks, kb = ops.bn_finalize(part[:, 0], part[:, 1], B * H * T, v[bn + "/gamma"], v[bn + "/beta"],
+                                     v[bn + "/moving_mean"], v[bn + "/moving_variance"], training=True, bessel=True,
+                                     psum_stride=2 * T)
+        else:
+            ks, kb = ops.bn_finalize(None, None, 1, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"],
+                                     v[bn + "/moving_variance"], training=False, bessel=True)
+        o = ops.mha_core_fwd(qkv, B, T, D, H, scale=1.0, key_scale=ks, key_shift=kb)
+        bn = a + "/attention_bn"                                      # rank-3 input: biased moving variance
+        ops.batch_norm_cols_f16(o, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
+                                training=training, bessel=False)
+        att = ops.gemm(o, sh[a + "/wo16"], bias=v[a + "/output_transform/bias"])
+        if training and c.dropout_rate > 0:                           # D7: drop probability 0.9
+            ops.dropout_f16(att, c.dropout_rate, mask_in=dropout_mask, seed=ctx.get("seed", 0) * 2 + (name == "audio"))
+        h1 = ops.layernorm_joint_fwd(att, X, None, B, T, D, v[a + "/LayerNorm/gamma"], v[a + "/LayerNorm/beta"])
+        f = ops.gemm(h1.view(B * T, D), sh[a + "/w1_16"], bias=v[a + "/filter_outputencode/bias"], relu=True)
+        bn = a + "/filter_bn"
+        ops.batch_norm_cols_f16(f, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
+                                training=training, bessel=False)
+        k8 = _ceil8(K)
+        b2 = v[a + "/ff_outputencode/bias"]
+        if k8 != K:
+            b2 = torch.zeros(k8, dtype=torch.float32, device=X.device)
+            b2[:K].copy_(v[a + "/ff_outputencode/bias"])
+        A = ops.gemm(f, sh[a + "/w2_16"], bias=b2, relu=True)         # [B*T, ceil8(K)]
+        if k8 != K:
+            raise NotImplementedError("cluster sizes that are not multiples of 8")
+        bn = a + "/feed_output_bn"
+        ops.batch_norm_cols_f16(A, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
+                                training=training, bessel=False)
+        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, sh[vs + "/centers_t"], assign_in=A)
+        ops.netvlad_finalize_f16(z, rscale, out_view, out_view.stride(0))    # d-major flatten, normalised, fp16
+        if want_inter:
+            ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
+            ctx["inter"]["assign_" + name] = A.float().reshape(B, T, K)
+        return {}
 
     def _head(self, vlad, B, training, save, ctx, want_inter):
         """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""

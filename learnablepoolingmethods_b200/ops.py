@@ -188,22 +188,30 @@ def sample_bn_stats(x, num_frames, T):
     return partial
 
 
-def sample_bn_apply(x, num_frames, T, scale, shift, out=None):
+def sample_bn_apply(x, num_frames, T, scale, shift, out=None, split_col=None):
+    """Sampled + batch-normed frames as fp16: one [B*T, F] matrix, or (split_col given) two contiguous
+    per-modality matrices ([B*T, split_col], [B*T, F - split_col])."""
     lib = _lib.load()
     B, Fmax, F = x.shape
-    if out is None:
-        out = _f16((B * T, F), x.device)
-    check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out),
-                                  stream_ptr()), "lpm_sample_bn_apply")
-    return out
+    if split_col is None:
+        if out is None:
+            out = _f16((B * T, F), x.device)
+        check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out), 0, None,
+                                      stream_ptr()), "lpm_sample_bn_apply")
+        return out
+    ya, yb = _f16((B * T, split_col), x.device), _f16((B * T, F - split_col), x.device)
+    check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(ya), split_col,
+                                  ptr(yb), stream_ptr()), "lpm_sample_bn_apply")
+    return ya, yb
 
 
 def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers_t, *, valid_frames=None,
-                     save_assign=False):
-    """x16: fp16 view [B*T, D] (row stride may exceed D).  Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign."""
+                     save_assign=False, assign_in=None):
+    """x16: fp16 view [B*T, D] (row stride may exceed D).  Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign.
+    assign_in (fp16 [B*T, K] contiguous): NetVladV2 mode, the soft-assignment phase is skipped."""
     lib = _lib.load()
     D = x16.shape[1]
-    K = wc16.shape[1]
+    K = wc16.shape[1] if assign_in is None else assign_in.shape[-1]
     dev = x16.device
     z = _f16((B, K, D), dev)
     rscale = _f32((B, K), dev)
@@ -211,9 +219,9 @@ def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers_t, *, va
     assign = _f16((B, T, K), dev) if save_assign else None
     ldx = x16.stride(0)
     check(lib.lpm_netvlad_pool_fwd(ptr(x16), C.c_longlong(ldx), C.c_longlong(ldx * T), ptr(wc16),
-                                   C.c_longlong(wc16.stride(0)), ptr(logit_scale), ptr(logit_shift), ptr(centers_t),
-                                   ptr(valid_frames), B, T, D, K, ptr(z), ptr(rscale), ptr(a_sum), ptr(assign),
-                                   stream_ptr()), "lpm_netvlad_pool_fwd")
+                                   C.c_longlong(wc16.stride(0) if wc16 is not None else 0), ptr(logit_scale),
+                                   ptr(logit_shift), ptr(centers_t), ptr(valid_frames), B, T, D, K, ptr(z), ptr(rscale),
+                                   ptr(a_sum), ptr(assign), ptr(assign_in), stream_ptr()), "lpm_netvlad_pool_fwd")
     return z, rscale, a_sum, assign
 
 
@@ -445,3 +453,60 @@ def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, cl
                                  ptr(chunk_begin), n_tensors, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), C.c_float(lr_t), C.c_float(b1),
                                  C.c_float(b2), C.c_float(eps), ptr(partial), ptr(factor), ptr(norms), ptr(flag),
                                  stream_ptr()), "lpm_adam_clip_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# NetVladV2 helpers
+# ------------------------------------------------------------------------------------------------
+def mha_logit_stats(qkv, B, L, Dm, H):
+    """(sum | sumsq) partials [B*H, 2, L] of the un-scaled attention logits per key channel."""
+    lib = _lib.load()
+    partial = _f32((B * H, 2, L), qkv.device)
+    check(lib.lpm_mha_logit_stats(ptr(qkv), _ll(qkv.stride(0)), B, L, Dm, H, ptr(partial), stream_ptr()),
+          "lpm_mha_logit_stats")
+    return partial
+
+
+def colstats_f16(x, rows=None, cols=None):
+    lib = _lib.load()
+    rows = rows or x.shape[0]
+    cols = cols or x.shape[1]
+    partial = _f32((lib.lpm_colstats_chunks(_ll(rows)), 2, cols), x.device)
+    check(lib.lpm_colstats_f16(ptr(x), _ll(x.stride(0)), _ll(rows), cols, ptr(partial), stream_ptr()), "lpm_colstats_f16")
+    return partial
+
+
+def affine_cols_f16(x, scale, shift):
+    lib = _lib.load()
+    assert x.is_contiguous()
+    check(lib.lpm_affine_cols_f16(ptr(x), _ll(x.shape[0]), x.shape[1], ptr(scale), ptr(shift), stream_ptr()),
+          "lpm_affine_cols_f16")
+    return x
+
+
+def dropout_f16(x, rate, *, mask_in=None, mask_out=None, seed=0):
+    lib = _lib.load()
+    check(lib.lpm_dropout_f16(ptr(x), _ll(x.numel()), ptr(mask_in), ptr(mask_out), C.c_ulonglong(seed), C.c_float(rate),
+                              stream_ptr()), "lpm_dropout_f16")
+    return x
+
+
+def netvlad_finalize_f16(z, rscale, out, out_stride):
+    lib = _lib.load()
+    B, K, D = z.shape
+    check(lib.lpm_netvlad_finalize_f16(ptr(z), ptr(rscale), B, K, D, ptr(out), _ll(out_stride), stream_ptr()),
+          "lpm_netvlad_finalize_f16")
+    return out
+
+
+def batch_norm_cols_f16(x, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False):
+    """slim.batch_norm over the rows of an fp16 matrix, applied in place.  Returns (scale, shift[, (mean, rstd)])."""
+    rows, cols = x.shape
+    if training:
+        part = colstats_f16(x)
+        r = bn_finalize(part[:, 0], part[:, 1], rows, gamma, beta, moving_mean, moving_var, training=True,
+                        bessel=bessel, save=save, psum_stride=2 * cols)
+    else:
+        r = bn_finalize(None, None, 1, gamma, beta, moving_mean, moving_var, training=False, bessel=bessel, save=save)
+    affine_cols_f16(x, r[0], r[1])
+    return r
