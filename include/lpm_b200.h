@@ -113,7 +113,7 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
  *   x            fp16 [B][T][D] (row stride ldx, video stride x_batch_stride), the batch-normed frames
  *   wc           fp16 [D][K] cluster_weights (row stride ldw)
  *   logit_scale/shift  fp32 [K]: cluster_bn folded affine, or (1, cluster_biases)
- *   centers_t    fp32 [K][D]: cluster_weights2 transposed
+ *   centers      fp32 [D][K]: cluster_weights2[0] (V1) / cluster_centers (V2), the reference's own layout
  *   valid_frames int32 [B] or NULL: frames t >= valid_frames[b] get zero assignment (masked mode)
  *   z            fp16 [B][K][D]  un-normalised cluster-major descriptor V^T
  *   rscale       fp32 [B][K]     vlad[b,k,:] = z[b,k,:]*rscale[b,k]  (intra-norm x global norm)
@@ -123,9 +123,12 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
  * Limits: T <= 256, D % 64 == 0, K % 8 == 0, K <= 256.
  * ------------------------------------------------------------------------------------------- */
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
-                         const float* logit_scale, const float* logit_shift, const float* centers_t,
+                         const float* logit_scale, const float* logit_shift, const float* centers,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
                          float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream);
+/* Profiling aid: when non-NULL, lpm_netvlad_pool_fwd writes 8 clock64 phase stamps per video ([B][8] int64:
+ * start, logits done, softmax done, a_sum done, aggregation done). */
+void lpm_debug_set_pool_clock(long long* buf);
 /* vlad = z * rscale as fp32: d_major!=0 -> [B][D*K] (reference flatten, :2821), else [B][K][D]. */
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
                          lpm_stream_t stream);

@@ -92,6 +92,8 @@ int check_device() {
 
 using namespace lpm;
 
+static long long* g_pool_debug = nullptr;
+
 extern "C" {
 
 int lpm_version(void) { return 100; }
@@ -151,15 +153,18 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
 }
 
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
-                         const float* logit_scale, const float* logit_shift, const float* centers_t,
+                         const float* logit_scale, const float* logit_shift, const float* centers,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
                          float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream) {
   DEVCHK();
-  LPM_REQUIRE(x && centers_t && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
+  LPM_REQUIRE(x && centers && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
   LPM_REQUIRE(assign_in || (wc && logit_scale && logit_shift), "lpm_netvlad_pool_fwd: need cluster weights or assign_in");
-  return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, centers_t,
-                          valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), CH16(assign_in), ST(stream));
+  return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, centers,
+                          valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), CH16(assign_in), g_pool_debug, ST(stream));
 }
+
+/* profiling aid: when set, lpm_netvlad_pool_fwd writes 8 clock64 phase stamps per video into this buffer */
+void lpm_debug_set_pool_clock(long long* buf) { g_pool_debug = buf; }
 
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
                          lpm_stream_t stream) {

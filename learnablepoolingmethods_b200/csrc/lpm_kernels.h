@@ -83,9 +83,9 @@ int adam_clip_step(float* p, const float* g, float* m, float* v, const int* tabl
 
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
-                     const float* logit_scale, const float* logit_shift, const float* centers_t,
+                     const float* logit_scale, const float* logit_shift, const float* centers,
                      const int* valid_frames, int B, int T, int D, int K, __half* z, float* rscale, float* a_sum,
-                     __half* assign, const __half* assign_in, cudaStream_t st);
+                     __half* assign, const __half* assign_in, long long* debug_clock, cudaStream_t st);
 
 // lpm_v2.cu
 int mha_logit_stats(const __half* qkv, long long ld, int B, int L, int Dm, int H, float* partial, cudaStream_t st);

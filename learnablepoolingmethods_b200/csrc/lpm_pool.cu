@@ -10,7 +10,8 @@
 //                                                      UMMA operand), masked for t >= T / invalid frames
 //   phase 2  V^T[k,d] = sum_t A[t,k] X[t,d]            tcgen05.mma, A operand = P^T from smem, X streamed
 //                                                      again by TMA (L2-resident), 64 d-columns per stage
-//   epilogue V^T[k,d] -= a_sum[k] C[d,k];  row norms;  un-normalised fp16 V^T + the combined
+//   epilogue V^T[k,d] -= a_sum[k] C[d,k] (coalesced loads of C[d][.]);  row norms;  fp16 slab in swizzled
+//            smem -> TMA store;  un-normalised fp16 V^T + the combined
 //                                                      intra-/global-L2 row scale are emitted:
 //              vlad[b,k,:] = z[b,k,:] * rscale[b,k]   (consumers apply rscale in their epilogues)
 //
@@ -30,9 +31,11 @@ struct PoolCfg {
   static constexpr int WS_BYTES = KCT * 128;                   // one 64-row slab of Wc: 64 x KCT fp16
   static constexpr int ST1_BYTES = XS_BYTES + WS_BYTES;
   static constexpr int P_BYTES = (KCP / 64) * TP * 128;
+  static constexpr int STG_BYTES = (KCP / 128) * 128 * 128;    // one 128-row x 128-byte output slab per cluster tile
   static constexpr int BUDGET = 224 * 1024;
   static constexpr int NS1 = (BUDGET / ST1_BYTES) > 4 ? 4 : (BUDGET / ST1_BYTES);
-  static constexpr int NS2 = ((BUDGET - P_BYTES) / XS_BYTES) > 4 ? 4 : ((BUDGET - P_BYTES) / XS_BYTES);
+  static constexpr int NS2 = ((BUDGET - P_BYTES - STG_BYTES) / XS_BYTES) > 4 ? 4 : ((BUDGET - P_BYTES - STG_BYTES) / XS_BYTES);
+  static constexpr int STG_OFF = BUDGET - STG_BYTES;
   static constexpr int BAR_OFF = BUDGET;
   static constexpr int AFF_OFF = BAR_OFF + 256;                // float2 (scale, shift) per cluster
   static constexpr int RED_OFF = AFF_OFF + KCT * 8;            // 8 floats for the block reduction
@@ -46,13 +49,14 @@ struct PoolParams {
   int B, T, D, K;                 // K = real cluster count (<= KCT)
   const float* logit_scale;       // [K]  cluster_bn folded scale (1 for the bias branch)
   const float* logit_shift;       // [K]  cluster_bn folded shift (or cluster_biases)
-  const float* centers_t;         // [K][D] fp32: cluster_weights2 transposed
+  const float* centers;           // [D][K] fp32: cluster_weights2[0] / cluster_centers (native layout)
   const int* valid_frames;        // [B] or null: frames t >= valid_frames[b] get zero assignment
   __half* z;                      // [B][K][D]  un-normalised V^T
   float* rscale;                  // [B][K]
   float* a_sum;                   // [B][K] or null
   __half* assign;                 // [B][T][K] or null (saved for backward)
   const __half* assign_in;        // [B][T][K] or null: externally supplied assignments (NetVladV2), phase 1 skipped
+  long long* debug_clock;         // optional [B][8] clock64 phase stamps (profiling aid)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -65,7 +69,7 @@ __device__ __forceinline__ void fence_async_smem() {
 template <int KCT>
 __global__ void __launch_bounds__(320, 1)
 netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const PoolParams p) {
+                        const __grid_constant__ CUtensorMap tmap_z, const PoolParams p) {
   using Cfg = PoolCfg<KCT>;
   // No static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -94,6 +98,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_z);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&full1[i], 1); mbar_init(&empty1[i], 1);
       mbar_init(&full2[i], 1); mbar_init(&empty2[i], 1);
@@ -202,11 +207,14 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int row = quarter * 32 + lane;       // row within the 128-row tile
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
 
+    long long* dbg = (p.debug_clock != nullptr && warp == 2 && lane == 0) ? p.debug_clock + (size_t)b * 8 : nullptr;
+    if (dbg) dbg[0] = clock64();
     // ---------------- softmax over clusters, one thread per frame ----------------
     if (!p.assign_in) {
       mbar_wait(s_full, 0);
       tc_fence_after();
     }
+    if (dbg) dbg[1] = clock64();     // logits complete (phase 1 done)
     {
       const int t = grp * 128 + row;
       int tv = p.T;
@@ -292,6 +300,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     __syncwarp();
     if (lane == 0) mbar_arrive(p_ready);
     named_bar_sync(1, 256);                     // all assignment rows are in smem
+    if (dbg) dbg[2] = clock64();     // softmax done
 
     // ---------------- a_sum[k] = sum_t A[t,k] from the fp16 tile (consistent with the MMA) ---------
     const int k_own = grp * 128 + row;          // cluster row owned in the epilogue
@@ -307,45 +316,61 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const bool k_ok = k_own < p.K;
     if (p.a_sum != nullptr && k_ok) p.a_sum[(size_t)b * p.K + k_own] = a_sum;
 
-    // ---------------- phase-2 epilogue: residual, row norm, fp16 store ----------------
+    if (dbg) dbg[3] = clock64();     // a_sum done
+    // ---------------- phase-2 epilogue: residual, row norm, fp16 slab -> TMA store ----------------
     float sumsq = 0.f;
     if (grp < Cfg::KCP / 128) {
       int buf = 0; uint32_t bphase = 0;
-      const float* crow = p.centers_t + (size_t)(k_ok ? k_own : 0) * p.D;
-      __half* zrow = p.z + ((size_t)b * p.K + (k_ok ? k_own : 0)) * p.D;
+      uint8_t* slab = smem + Cfg::STG_OFF + grp * (128 * 128);
+      const bool leader = quarter == 0 && lane == 0;          // one thread per group issues the TMA stores
+      const int bar_a = 2 + 2 * grp, bar_b = 3 + 2 * grp;
+      const float* ccol = p.centers + (k_ok ? k_own : 0);       // C[d][k]: lanes read consecutive k (coalesced)
       for (int db = 0; db < n_dc; ++db) {
         mbar_wait(&acc_full[buf], bphase);
         tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_addr + buf * 128 + grp * 64 + hh * 32, r);
-          tmem_ld_wait();
-          if (k_ok) {
-            const int d0 = db * 64 + hh * 32;
-            uint32_t o[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 c4 = __ldg(reinterpret_cast<const float4*>(crow + d0 + i));
-              const float v0 = __uint_as_float(r[i]) - a_sum * c4.x;
-              const float v1 = __uint_as_float(r[i + 1]) - a_sum * c4.y;
-              const float v2 = __uint_as_float(r[i + 2]) - a_sum * c4.z;
-              const float v3 = __uint_as_float(r[i + 3]) - a_sum * c4.w;
-              sumsq += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
-              o[i / 2] = pack_half2(v0, v1);
-              o[i / 2 + 1] = pack_half2(v2, v3);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(zrow + d0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
-        }
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + lane_addr + buf * 128 + grp * 64;
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);            // accumulator drained: MMA may reuse it
+        if (leader) bulk_wait_read<0>();                        // previous slab of this group has left smem
+        named_bar_sync(bar_a, 128);
+        const int d0 = db * 64;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t* r = hh == 0 ? r0 : r1;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float c = __ldg(ccol + (size_t)(d0 + hh * 32 + i) * p.K);
+            v[i] = __uint_as_float(r[i]) - a_sum * c;
+            sumsq += v[i] * v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+            w.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+            w.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+            w.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(slab + row * 128 + (((hh * 4 + i) ^ (row & 7)) << 4)) = w;
+          }
+        }
+        fence_async_smem();
+        named_bar_sync(bar_b, 128);
+        if (leader) {
+          tma_store_3d(&tmap_z, slab, d0, grp * 128, b);        // rows k >= K are clipped by the tensor map
+          bulk_commit();
+        }
         if (++buf == 2) { buf = 0; bphase ^= 1; }
       }
+      if (leader) bulk_wait<0>();
+      if (!k_ok) sumsq = 0.f;
     }
+    if (dbg) dbg[4] = clock64();     // phase 2 + epilogue done
     // intra-norm (per cluster row) and global norm (per video): frame_level_models.py:2819-2822
     const float r_intra = rsqrtf(fmaxf(sumsq, 1e-12f));
     float contrib = k_ok ? sumsq * r_intra * r_intra : 0.f;
@@ -368,7 +393,8 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 }
 
 template <int KCT>
-static int launch_pool(const CUtensorMap& tx, const CUtensorMap& tw, const PoolParams& p, cudaStream_t st) {
+static int launch_pool(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tz, const PoolParams& p,
+                       cudaStream_t st) {
   using Cfg = PoolCfg<KCT>;
   auto kern = netvlad_pool_fwd_kernel<KCT>;
   static bool attr_set = false;
@@ -376,31 +402,34 @@ static int launch_pool(const CUtensorMap& tx, const CUtensorMap& tw, const PoolP
     LPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
     attr_set = true;
   }
-  kern<<<p.B, 320, Cfg::TOTAL, st>>>(tx, tw, p);
+  kern<<<p.B, 320, Cfg::TOTAL, st>>>(tx, tw, tz, p);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
-                     const float* logit_scale, const float* logit_shift, const float* centers_t,
+                     const float* logit_scale, const float* logit_shift, const float* centers,
                      const int* valid_frames, int B, int T, int D, int K, __half* z, float* rscale, float* a_sum,
-                     __half* assign, const __half* assign_in, cudaStream_t st) {
+                     __half* assign, const __half* assign_in, long long* debug_clock, cudaStream_t st) {
   LPM_REQUIRE(B > 0 && T > 0 && T <= TP, "netvlad_pool_fwd: frames per video must be in [1,%d] (got %d)", TP, T);
   LPM_REQUIRE(D % 64 == 0 && D >= 64, "netvlad_pool_fwd: feature size must be a multiple of 64 (got %d)", D);
   LPM_REQUIRE(K % 8 == 0 && K >= 8 && K <= 256, "netvlad_pool_fwd: cluster size must be a multiple of 8 in [8,256] (got %d)", K);
   LPM_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && x_batch_stride % 8 == 0, "netvlad_pool_fwd: strides must be multiples of 8");
   PoolParams p{};
   p.B = B; p.T = T; p.D = D; p.K = K;
-  p.logit_scale = logit_scale; p.logit_shift = logit_shift; p.centers_t = centers_t;
+  p.logit_scale = logit_scale; p.logit_shift = logit_shift; p.centers = centers;
   p.valid_frames = valid_frames; p.z = z; p.rscale = rscale; p.a_sum = a_sum; p.assign = assign;
-  p.assign_in = assign_in;
+  p.assign_in = assign_in; p.debug_clock = debug_clock;
   CUtensorMap tx, tw;
   if (int rc = make_tmap_3d(&tx, x, 2, D, T, B, ldx, x_batch_stride, 64, 128)) return rc;
   if (assign_in != nullptr) tw = tx;   // unused in this mode
   else if (int rc = make_tmap_3d(&tw, wc, 2, K, D, 1, ldw, 0, 64, 64)) return rc;
-  if (K <= 64) return launch_pool<64>(tx, tw, p, st);
-  if (K <= 128) return launch_pool<128>(tx, tw, p, st);
-  return launch_pool<256>(tx, tw, p, st);
+  CUtensorMap tz;
+  LPM_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0, "netvlad_pool_fwd: z must be 16-byte aligned");
+  if (int rc = make_tmap_3d(&tz, z, 2, D, K, B, D, (uint64_t)K * D, 64, 128)) return rc;
+  if (K <= 64) return launch_pool<64>(tx, tw, tz, p, st);
+  if (K <= 128) return launch_pool<128>(tx, tw, tz, p, st);
+  return launch_pool<256>(tx, tw, tz, p, st);
 }
 
 }  // namespace lpm

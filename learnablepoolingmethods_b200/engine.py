@@ -266,7 +266,7 @@ class NetVladEngine:
                                 v[bn + "/moving_variance"], training=False, bessel=True, save=save)
         lscale, lshift = r[0], r[1]
         # ---- K1: fused soft-assignment + aggregation + norms -----------------------------------
-        z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, lscale, lshift, sh[vs + "/centers_t"],
+        z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, lscale, lshift, v[vs + "/cluster_weights2"][0],
                                                         save_assign=save)
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
@@ -354,7 +354,7 @@ class NetVladEngine:
         bn = a + "/feed_output_bn"
         ops.batch_norm_cols_f16(A, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
                                 training=training, bessel=False)
-        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, sh[vs + "/centers_t"], assign_in=A)
+        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, v[vs + "/cluster_centers"], assign_in=A)
         ops.netvlad_finalize_f16(z, rscale, out_view, out_view.stride(0))    # d-major flatten, normalised, fp16
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)

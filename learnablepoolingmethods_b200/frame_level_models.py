@@ -100,5 +100,5 @@ class NetVLAD():
                 scale, shift = ops.bn_finalize(None, None, 1, gamma, beta, mm, mv, training=False, bessel=True)
         else:
             scale, shift = torch.ones(K, device=x16.device), bias
-        z, rs, _, _ = ops.netvlad_pool_fwd(x16, B, T, wc16, scale, shift, ops.transpose_f32(c2[0]))
+        z, rs, _, _ = ops.netvlad_pool_fwd(x16, B, T, wc16, scale, shift, c2[0])
         return ops.netvlad_finalize(z, rs, d_major=True)

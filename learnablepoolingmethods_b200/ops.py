@@ -205,9 +205,10 @@ def sample_bn_apply(x, num_frames, T, scale, shift, out=None, split_col=None):
     return ya, yb
 
 
-def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers_t, *, valid_frames=None,
+def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers, *, valid_frames=None,
                      save_assign=False, assign_in=None):
-    """x16: fp16 view [B*T, D] (row stride may exceed D).  Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign.
+    """x16: fp16 view [B*T, D] (row stride may exceed D); centers: fp32 [D, K] contiguous (the TF layout).
+    Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign.
     assign_in (fp16 [B*T, K] contiguous): NetVladV2 mode, the soft-assignment phase is skipped."""
     lib = _lib.load()
     D = x16.shape[1]
@@ -220,7 +221,7 @@ def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers_t, *, va
     ldx = x16.stride(0)
     check(lib.lpm_netvlad_pool_fwd(ptr(x16), C.c_longlong(ldx), C.c_longlong(ldx * T), ptr(wc16),
                                    C.c_longlong(wc16.stride(0) if wc16 is not None else 0), ptr(logit_scale),
-                                   ptr(logit_shift), ptr(centers_t), ptr(valid_frames), B, T, D, K, ptr(z), ptr(rscale),
+                                   ptr(logit_shift), ptr(centers), ptr(valid_frames), B, T, D, K, ptr(z), ptr(rscale),
                                    ptr(a_sum), ptr(assign), ptr(assign_in), stream_ptr()), "lpm_netvlad_pool_fwd")
     return z, rscale, a_sum, assign
 

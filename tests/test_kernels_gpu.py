@@ -59,8 +59,8 @@ def test_netvlad_pool_fwd(cuda, B, T, D, K):
                                    S["v/cluster_bn/moving_mean"].to(dev), S["v/cluster_bn/moving_variance"].to(dev),
                                    training=False, bessel=True)
     wc16 = ops.cast_f16(P["v/cluster_weights"].to(dev))
-    ct = ops.transpose_f32(P["v/cluster_weights2"][0].contiguous().to(dev))
-    z, rs, a_sum, assign = ops.netvlad_pool_fwd(x16.to(dev), B, T, wc16, scale, shift, ct, save_assign=True)
+    z, rs, a_sum, assign = ops.netvlad_pool_fwd(x16.to(dev), B, T, wc16, scale, shift,
+                                                P["v/cluster_weights2"][0].contiguous().to(dev), save_assign=True)
     torch.cuda.synchronize()
     assert rel(assign.float(), A_ref) < 2e-3
     assert rel(a_sum, A_ref.sum(dim=1)) < 1e-3
@@ -85,7 +85,7 @@ def test_netvlad_pool_masked_frames(cuda):
     dev = cuda
     one = torch.ones(K, device=dev)
     z, rs, a_sum, _ = ops.netvlad_pool_fwd(x.to(dev), B, T, ops.cast_f16(P["v/cluster_weights"].to(dev)), one,
-                                           P["v/cluster_biases"].to(dev), ops.transpose_f32(P["v/cluster_weights2"][0].contiguous().to(dev)),
+                                           P["v/cluster_biases"].to(dev), P["v/cluster_weights2"][0].contiguous().to(dev),
                                            valid_frames=valid.to(dev))
     out = ops.netvlad_finalize(z, rs)
     for b in range(B):
