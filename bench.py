@@ -133,14 +133,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    base = {"metric": "NetVladV1 videos/sec (train step; infer reported alongside)", "unit": "videos/s",
+    base = {"metric": f"{args.model} videos/sec (train step; infer reported alongside)", "unit": "videos/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus,
+            "config": {"workload": WORKLOAD.replace("NetVladV1", args.model), "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus,
                        "parallelism": f"dp{args.gpus}", "l2": "working set per step (>=3 GB of weights, moments and "
                        "activations) exceeds the 126 MB L2; no flush needed"}}
 
@@ -168,7 +169,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     store = variables.VariableStore(dev, seed=1810)
-    cfg = NetVladConfig(model="NetVladV1", iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
+    cfg = NetVladConfig(model=args.model, iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
                         hidden_size=CFG["hidden_size"], vocab_size=CFG["vocab"])
     eng = NetVladEngine(cfg, store)
     tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, batch_size=B)

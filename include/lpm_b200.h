@@ -251,8 +251,30 @@ int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int
  * (attention_bn, filter_bn, feed_output_bn: transformer_utils.py:666,747,760). */
 int lpm_colstats_chunks(long long rows);
 int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* partial, lpm_stream_t stream);
-/* x[r][c] = x[r][c]*scale[c] + shift[c] in place (applies a folded batch norm). */
-int lpm_affine_cols_f16(void* x, long long rows, int C, const float* scale, const float* shift, lpm_stream_t stream);
+/* y[r][c] = x[r][c]*scale[c] + shift[c] (applies a folded batch norm; y may alias x). */
+int lpm_affine_cols_f16(const void* x, void* y, long long rows, int C, const float* scale, const float* shift,
+                        lpm_stream_t stream);
+/* slim.batch_norm backward over the rows of an fp16 matrix (training statistics).  stats: partial
+ * [lpm_colstats_chunks(rows)][2][C] = (sum dy | sum dy*xhat), xhat = (x-p0)*p1 (mode 0: x = BN input, p0 = mean,
+ * p1 = rstd) or (x-p0)/p1 (mode 1: x = BN output, p0 = beta, p1 = gamma).  apply: dx = gamma*rstd*(dy - c1/N -
+ * xhat*c2/N) with csum = [2][C] totals, optionally masked by (x > 0) (ReLU in front of the batch norm).
+ * dy is fp16 or fp32 (dy_f32); q (optional fp32 [rows/T][C]) is subtracted on the fly: dy_eff = dy - q[r/T][c]. */
+int lpm_batchnorm_bwd_stats(const void* dy, int dy_f32, long long ld_dy, const float* q, int T, const void* x,
+                            long long ld_x, long long rows, int C, const float* p0, const float* p1, int mode,
+                            float* partial, lpm_stream_t stream);
+int lpm_batchnorm_bwd_apply(const void* dy, int dy_f32, const float* q, int T, void* dx, const void* x, long long rows,
+                            int C, const float* mean, const float* rstd, const float* gamma, const float* csum,
+                            int relu, lpm_stream_t stream);
+/* out[r][k] = fp16(G[r][k] - q[r/T][k]): gradient of the residual aggregation wrt externally supplied assignments. */
+int lpm_sub_q_cast_f16(const float* G, const float* q, long long rows, int T, int K, void* out, lpm_stream_t stream);
+/* out[b][k][d] = in[b*in_stride + d*K + k]: gradient of the d-major flatten back to the cluster-major layout. */
+int lpm_dmajor_to_kmajor_f16(const void* in, long long in_stride, int B, int K, int D, void* out, lpm_stream_t stream);
+/* Attention backward with batch-normed logits (transformer_utils.py:646-664): mode 1 writes per-key partial sums
+ * [B*H][2][L] of (dl' | dl'*lhat); mode 2 takes their means m1/m2 [L] and writes dqkv. */
+int lpm_mha_core_bwd_bn(int mode, const void* qkv, long long ld, const void* o, const void* dout, long long ldo,
+                        const float* lse, int B, int L, int Dm, int H, const float* key_scale, const float* key_shift,
+                        const float* key_mean, const float* key_rstd, const float* m1, const float* m2,
+                        float* stat_partial, void* dqkv, long long ldd, lpm_stream_t stream);
 /* tf.layers.dropout (transformer_utils.py:450): x *= keep/(1-rate); keep from mask_in (fp16 0/1) or a hash of
  * (seed, index); the mask used is written to mask_out when given. */
 int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed, float rate,

@@ -342,10 +342,45 @@ int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* 
   LPM_REQUIRE(x && partial && rows > 0 && C > 0, "lpm_colstats_f16: bad arguments");
   return colstats(CH16(x), ld, rows, C, partial, ST(stream));
 }
-int lpm_affine_cols_f16(void* x, long long rows, int C, const float* scale, const float* shift, lpm_stream_t stream) {
+int lpm_affine_cols_f16(const void* x, void* y, long long rows, int C, const float* scale, const float* shift,
+                        lpm_stream_t stream) {
   DEVCHK();
-  LPM_REQUIRE(x && scale && shift && rows > 0, "lpm_affine_cols_f16: bad arguments");
-  return affine_cols(H16(x), rows, C, scale, shift, ST(stream));
+  LPM_REQUIRE(x && y && scale && shift && rows > 0, "lpm_affine_cols_f16: bad arguments");
+  return affine_cols(CH16(x), H16(y), rows, C, scale, shift, ST(stream));
+}
+int lpm_batchnorm_bwd_stats(const void* dy, int dy_f32, long long ld_dy, const float* q, int T, const void* x,
+                            long long ld_x, long long rows, int C, const float* p0, const float* p1, int mode,
+                            float* partial, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(dy && x && p0 && p1 && partial && rows > 0, "lpm_batchnorm_bwd_stats: bad arguments");
+  return bn_bwd_stats(dy, dy_f32, ld_dy, q, T, CH16(x), ld_x, rows, C, p0, p1, mode, partial, ST(stream));
+}
+int lpm_batchnorm_bwd_apply(const void* dy, int dy_f32, const float* q, int T, void* dx, const void* x, long long rows,
+                            int C, const float* mean, const float* rstd, const float* gamma, const float* csum,
+                            int relu, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(dy && dx && x && mean && rstd && gamma && csum, "lpm_batchnorm_bwd_apply: null pointer");
+  return bn_bwd_apply(dy, dy_f32, q, T, H16(dx), CH16(x), rows, C, mean, rstd, gamma, csum, relu, ST(stream));
+}
+int lpm_sub_q_cast_f16(const float* G, const float* q, long long rows, int T, int K, void* out, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(G && q && out && rows > 0, "lpm_sub_q_cast_f16: bad arguments");
+  return sub_q_cast(G, q, rows, T, K, H16(out), ST(stream));
+}
+int lpm_dmajor_to_kmajor_f16(const void* in, long long in_stride, int B, int K, int D, void* out, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(in && out, "lpm_dmajor_to_kmajor_f16: null pointer");
+  return dmajor_to_kmajor_f16(CH16(in), in_stride, B, K, D, H16(out), ST(stream));
+}
+int lpm_mha_core_bwd_bn(int mode, const void* qkv, long long ld, const void* o, const void* dout, long long ldo,
+                        const float* lse, int B, int L, int Dm, int H, const float* key_scale, const float* key_shift,
+                        const float* key_mean, const float* key_rstd, const float* m1, const float* m2,
+                        float* stat_partial, void* dqkv, long long ldd, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(qkv && o && dout && lse && key_scale && key_shift && key_mean && key_rstd, "lpm_mha_core_bwd_bn: null pointer");
+  LPM_REQUIRE(mode == 1 ? stat_partial != nullptr : (m1 && m2 && dqkv), "lpm_mha_core_bwd_bn: mode 1 needs stat_partial, mode 2 needs m1/m2/dqkv");
+  return mha_bwd_bn(mode, CH16(qkv), ld, CH16(o), CH16(dout), ldo, lse, B, L, Dm, H, key_scale, key_shift, key_mean,
+                    key_rstd, m1, m2, stat_partial, H16(dqkv), ldd, ST(stream));
 }
 int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed, float rate,
                     lpm_stream_t stream) {

@@ -193,11 +193,21 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
 // ------------------------------------------------------------------------------------------------
 constexpr int DS_STRIDE = 264;  // halves per dS row (256 + 8 padding -> conflict-free stores and ldmatrix)
 
-template <int DH>
+// MODE 0: logits = scale * q.k (V1).  MODE 1/2: batch-normed logits l' = l*ks_j + kb_j (V2): MODE 1 only accumulates the
+// per-key sums of dl' and dl'*lhat (lhat = (l - mu_j)*rstd_j) needed by the batch-norm backward; MODE 2 applies
+//   dl = ks_j * (dl' - m1_j - lhat * m2_j)   and produces dQ, dK, dV.
+struct MhaBnArgs {
+  const float* key_scale; const float* key_shift;   // folded BN affine per key (natural-log domain)
+  const float* key_mean; const float* key_rstd;     // batch statistics of the raw logits per key
+  const float* m1; const float* m2;                 // mean(dl'), mean(dl'*lhat) per key (MODE 2)
+  float* stat_partial;                              // [B*H][2][L] (MODE 1)
+};
+
+template <int DH, int MODE>
 __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
                                                       const __half* __restrict__ o, const __half* __restrict__ dout,
                                                       long long ldo, const float* __restrict__ lse, int L, int Dm,
-                                                      int H, float scale, __half* __restrict__ dqkv, long long ldd) {
+                                                      int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn) {
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + L * 32;
@@ -205,7 +215,8 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
   uint8_t* sdO = sV + L * 32;
   float* sLse = reinterpret_cast<float*>(sdO + L * 32);   // lse in log2 units
   float* sDel = sLse + L;
-  __half* sdS = reinterpret_cast<__half*>(sDel + L);       // [L keys][DS_STRIDE]
+  float* sBn = sDel + L;                                   // MODE>0: ks2 | kb2 | mu | rstd | m1 | m2  (6 x L)
+  __half* sdS = reinterpret_cast<__half*>(sBn + (MODE > 0 ? 6 * L : 0));   // [L keys][DS_STRIDE]
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const __half* base = qkv + (long long)b * L * ld + h * DH;
   load_head_tile<DH>(sQ, base, ld, L);
@@ -227,6 +238,14 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
     }
     sDel[r] = d;
     sLse[r] = lse[((long long)b * H + h) * L + r] * 1.4426950408889634f;
+    if (MODE > 0) {
+      sBn[r] = bn.key_scale[r] * 1.4426950408889634f;
+      sBn[L + r] = bn.key_shift[r] * 1.4426950408889634f;
+      sBn[2 * L + r] = bn.key_mean[r];
+      sBn[3 * L + r] = bn.key_rstd[r];
+      sBn[4 * L + r] = MODE == 2 ? bn.m1[r] : 0.f;
+      sBn[5 * L + r] = MODE == 2 ? bn.m2[r] : 0.f;
+    }
   }
   __syncthreads();
 
@@ -246,6 +265,15 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
     float dk[2][4], dv[2][4];
 #pragma unroll
     for (int n = 0; n < 2; ++n) dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+    // per-key (row) constants of the batch-normed logits and the statistics accumulators (MODE 1)
+    const int kr0 = j * 16 + (lane >> 2), kr1 = kr0 + 8;
+    float ks0 = 0.f, ks1 = 0.f, kb0 = 0.f, kb1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
+    float m10 = 0.f, m11 = 0.f, m20 = 0.f, m21 = 0.f, a1r0 = 0.f, a1r1 = 0.f, a2r0 = 0.f, a2r1 = 0.f;
+    if (MODE > 0) {
+      ks0 = sBn[kr0]; ks1 = sBn[kr1]; kb0 = sBn[L + kr0]; kb1 = sBn[L + kr1];
+      mu0 = sBn[2 * L + kr0]; mu1 = sBn[2 * L + kr1]; rs0 = sBn[3 * L + kr0]; rs1 = sBn[3 * L + kr1];
+      m10 = sBn[4 * L + kr0]; m11 = sBn[4 * L + kr1]; m20 = sBn[5 * L + kr0]; m21 = sBn[5 * L + kr1];
+    }
     for (int i = 0; i < nb; ++i) {
       float st[2][4], dp[2][4];
 #pragma unroll
@@ -265,12 +293,31 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
       for (int n = 0; n < 2; ++n) {
         const int qc = i * 16 + n * 8 + (lane & 3) * 2;
         const float l0 = sLse[qc], l1 = sLse[qc + 1], d0 = sDel[qc], d1 = sDel[qc + 1];
-        const float p0 = exp2f(st[n][0] * scale_log2 - l0), p1 = exp2f(st[n][1] * scale_log2 - l1);
-        const float p2 = exp2f(st[n][2] * scale_log2 - l0), p3 = exp2f(st[n][3] * scale_log2 - l1);
+        float p0, p1, p2, p3;
+        if (MODE == 0) {
+          p0 = exp2f(st[n][0] * scale_log2 - l0); p1 = exp2f(st[n][1] * scale_log2 - l1);
+          p2 = exp2f(st[n][2] * scale_log2 - l0); p3 = exp2f(st[n][3] * scale_log2 - l1);
+        } else {
+          p0 = exp2f(st[n][0] * ks0 + kb0 - l0); p1 = exp2f(st[n][1] * ks0 + kb0 - l1);
+          p2 = exp2f(st[n][2] * ks1 + kb1 - l0); p3 = exp2f(st[n][3] * ks1 + kb1 - l1);
+        }
+        float g0 = p0 * (dp[n][0] - d0), g1 = p1 * (dp[n][1] - d1), g2 = p2 * (dp[n][2] - d0), g3 = p3 * (dp[n][3] - d1);
+        if (MODE > 0) {
+          const float h0 = (st[n][0] - mu0) * rs0, h1 = (st[n][1] - mu0) * rs0;
+          const float h2 = (st[n][2] - mu1) * rs1, h3 = (st[n][3] - mu1) * rs1;
+          if (MODE == 1) {
+            a1r0 += g0 + g1; a2r0 += g0 * h0 + g1 * h1;
+            a1r1 += g2 + g3; a2r1 += g2 * h2 + g3 * h3;
+          } else {
+            const float c0 = ks0 * 0.6931471805599453f, c1 = ks1 * 0.6931471805599453f;   // back to natural-log scale
+            g0 = c0 * (g0 - m10 - h0 * m20); g1 = c0 * (g1 - m10 - h1 * m20);
+            g2 = c1 * (g2 - m11 - h2 * m21); g3 = c1 * (g3 - m11 - h3 * m21);
+          }
+        }
         st[n][0] = p0; st[n][1] = p1; st[n][2] = p2; st[n][3] = p3;
-        dp[n][0] = p0 * (dp[n][0] - d0); dp[n][1] = p1 * (dp[n][1] - d1);
-        dp[n][2] = p2 * (dp[n][2] - d0); dp[n][3] = p3 * (dp[n][3] - d1);
+        dp[n][0] = g0; dp[n][1] = g1; dp[n][2] = g2; dp[n][3] = g3;
       }
+      if (MODE == 1) continue;                 // statistics pass: no gradients yet
       // A fragments (rows = keys, k = queries) from the accumulator layout
       const uint32_t pa0 = pack_half2(st[0][0], st[0][1]), pa1 = pack_half2(st[0][2], st[0][3]);
       const uint32_t pa2 = pack_half2(st[1][0], st[1][1]), pa3 = pack_half2(st[1][2], st[1][3]);
@@ -296,6 +343,17 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
         *reinterpret_cast<uint32_t*>(r1 + 8) = sa3;
       }
     }
+    if (MODE == 1) {
+      a1r0 += __shfl_xor_sync(0xffffffffu, a1r0, 1); a1r0 += __shfl_xor_sync(0xffffffffu, a1r0, 2);
+      a2r0 += __shfl_xor_sync(0xffffffffu, a2r0, 1); a2r0 += __shfl_xor_sync(0xffffffffu, a2r0, 2);
+      a1r1 += __shfl_xor_sync(0xffffffffu, a1r1, 1); a1r1 += __shfl_xor_sync(0xffffffffu, a1r1, 2);
+      a2r1 += __shfl_xor_sync(0xffffffffu, a2r1, 1); a2r1 += __shfl_xor_sync(0xffffffffu, a2r1, 2);
+      if ((lane & 3) == 0) {
+        float* sp = bn.stat_partial + (size_t)blockIdx.x * 2 * L;
+        sp[kr0] = a1r0; sp[kr1] = a1r1; sp[L + kr0] = a2r0; sp[L + kr1] = a2r1;
+      }
+      continue;
+    }
     const int r0 = j * 16 + (lane >> 2), r1 = r0 + 8;
     __half* dk0 = dqkv + ((long long)b * L + r0) * ldd + Dm + h * DH + (lane & 3) * 2;
     __half* dk1 = dqkv + ((long long)b * L + r1) * ldd + Dm + h * DH + (lane & 3) * 2;
@@ -307,6 +365,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
       *reinterpret_cast<__half2*>(dk1 + Dm + n * 8) = __floats2half2_rn(dv[n][2], dv[n][3]);
     }
   }
+  if (MODE == 1) return;
   __syncthreads();
 
   // ------------------------------- pass B: dQ -------------------------------
@@ -336,24 +395,43 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
   }
 }
 
-int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
-            int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st) {
+static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo,
+                          const float* lse, int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd,
+                          const MhaBnArgs& bn, cudaStream_t st) {
   const int DH = Dm / H;
   LPM_REQUIRE(DH * H == Dm && (DH == 8 || DH == 16), "mha_bwd: head depth must be 8 or 16 (Dm=%d H=%d)", Dm, H);
   LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 256, "mha_bwd: length must be a multiple of 16 in [16,256] (got %d)", L);
   LPM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0, "mha_bwd: leading dimensions must be multiples of 8");
-  const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (size_t)L * DS_STRIDE * 2;
-  if (DH == 16) {
-    static bool set16 = false;
-    if (!set16) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set16 = true; }
-    mha_bwd_kernel<16><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd);
-  } else {
-    static bool set8 = false;
-    if (!set8) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set8 = true; }
-    mha_bwd_kernel<8><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd);
+  LPM_REQUIRE(mode == 0 || DH == 16, "mha_bwd: batch-normed logits need head depth 16");
+  const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (mode ? (size_t)L * 24 : 0) + (size_t)L * DS_STRIDE * 2;
+#define LPM_MHA_BWD(DHV, MODEV)                                                                                          \
+  {                                                                                                                      \
+    static bool set = false;                                                                                             \
+    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
+    mha_bwd_kernel<DHV, MODEV><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn);    \
   }
+  if (mode == 0) { if (DH == 16) LPM_MHA_BWD(16, 0) else LPM_MHA_BWD(8, 0) }
+  else if (mode == 1) LPM_MHA_BWD(16, 1)
+  else LPM_MHA_BWD(16, 2)
+#undef LPM_MHA_BWD
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
+}
+
+int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
+            int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st) {
+  MhaBnArgs bn{};
+  return mha_bwd_launch(0, qkv, ld, o, dout, ldo, lse, B, L, Dm, H, scale, dqkv, ldd, bn, st);
+}
+
+// Batch-normed-logits attention backward (NetVladV2): mode 1 = per-key statistics partials, mode 2 = gradients.
+int mha_bwd_bn(int mode, const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo,
+               const float* lse, int B, int L, int Dm, int H, const float* key_scale, const float* key_shift,
+               const float* key_mean, const float* key_rstd, const float* m1, const float* m2, float* stat_partial,
+               __half* dqkv, long long ldd, cudaStream_t st) {
+  LPM_REQUIRE(mode == 1 || mode == 2, "mha_bwd_bn: mode must be 1 or 2");
+  MhaBnArgs bn{key_scale, key_shift, key_mean, key_rstd, m1, m2, stat_partial};
+  return mha_bwd_launch(mode, qkv, ld, o, dout, ldo, lse, B, L, Dm, H, 1.0f, dqkv, ldd, bn, st);
 }
 
 }  // namespace lpm

@@ -45,6 +45,11 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
 int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
             int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st);
 
+int mha_bwd_bn(int mode, const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo,
+               const float* lse, int B, int L, int Dm, int H, const float* key_scale, const float* key_shift,
+               const float* key_mean, const float* key_rstd, const float* m1, const float* m2, float* stat_partial,
+               __half* dqkv, long long ldd, cudaStream_t st);
+
 // lpm_backward.cu
 int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred, cudaStream_t st);
 int moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
@@ -91,7 +96,14 @@ int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, c
 int mha_logit_stats(const __half* qkv, long long ld, int B, int L, int Dm, int H, float* partial, cudaStream_t st);
 int colstats_chunks(long long rows);
 int colstats(const __half* x, long long ld, long long rows, int C, float* partial, cudaStream_t st);
-int affine_cols(__half* x, long long rows, int C, const float* scale, const float* shift, cudaStream_t st);
+int affine_cols(const __half* x, __half* y, long long rows, int C, const float* scale, const float* shift,
+                cudaStream_t st);
+int bn_bwd_stats(const void* dy, int dy_f32, long long ld_dy, const float* q, int T, const __half* x, long long ld_x,
+                 long long rows, int C, const float* p0, const float* p1, int mode, float* partial, cudaStream_t st);
+int bn_bwd_apply(const void* dy, int dy_f32, const float* q, int T, __half* dx, const __half* x, long long rows, int C,
+                 const float* mean, const float* rstd, const float* gamma, const float* csum, int relu, cudaStream_t st);
+int sub_q_cast(const float* G, const float* q, long long rows, int T, int K, __half* out, cudaStream_t st);
+int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, int D, __half* out, cudaStream_t st);
 int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed, float rate,
                 cudaStream_t st);
 int vlad_dmajor_f16(const __half* z, const float* rscale, int B, int K, int D, __half* out, long long out_stride,

@@ -72,20 +72,108 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __half* __restrict_
   p[c] = s0; p[c + 1] = s1; p[C + c] = q0; p[C + c + 1] = q1;
 }
 
-// x[r][c] = x[r][c]*scale[c] + shift[c]  (in place, 8 columns per thread)
-__global__ void __launch_bounds__(256) affine_cols_kernel(__half* __restrict__ x, long long rows, int C,
+// y[r][c] = x[r][c]*scale[c] + shift[c]  (y may alias x; 8 columns per thread)
+__global__ void __launch_bounds__(256) affine_cols_kernel(const __half* x, __half* y, long long rows, int C,
                                                           const float* __restrict__ scale, const float* __restrict__ shift) {
   const long long n8 = rows * C / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 8) % C);
-    uint4 v = reinterpret_cast<uint4*>(x)[i];
+    uint4 v = reinterpret_cast<const uint4*>(x)[i];
     __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
       h[j] = __floats2half2_rn(f.x * scale[c + 2 * j] + shift[c + 2 * j], f.y * scale[c + 2 * j + 1] + shift[c + 2 * j + 1]);
     }
-    reinterpret_cast<uint4*>(x)[i] = v;
+    reinterpret_cast<uint4*>(y)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slim.batch_norm backward over the rows of an fp16 matrix (training statistics):
+//   xhat = (x - p0[c]) * p1[c]            mode 0: x = BN input,  p0 = batch mean, p1 = rstd
+//   xhat = (x - p0[c]) / p1[c]            mode 1: x = BN output, p0 = beta,       p1 = gamma
+//   pass 1: partial[chunk][0][c] = sum dy, partial[chunk][1][c] = sum dy*xhat      (= dbeta, dgamma)
+//   pass 2: dx = gamma*rstd*(dy - c1/N - xhat*c2/N), optionally masked by (x > 0) for a preceding ReLU
+// ------------------------------------------------------------------------------------------------
+// dy may be fp16 or fp32 (the batch-norm backward removes a large common-mode part of dy, so the producers that can
+// afford it hand over fp32); `q` (optional, fp32 [rows/T][C]) is subtracted on the fly: dy_eff = dy - q[r/T][c].
+template <typename TD>
+__device__ __forceinline__ float2 ld2(const TD* p);
+template <>
+__device__ __forceinline__ float2 ld2<__half>(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+template <>
+__device__ __forceinline__ float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <typename TD>
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const TD* __restrict__ dy, long long ld_dy,
+                                                           const float* __restrict__ q, int T,
+                                                           const __half* __restrict__ x, long long ld_x, long long rows,
+                                                           int C, const float* __restrict__ p0, const float* __restrict__ p1,
+                                                           int mode, float* __restrict__ partial) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  const float a0 = p0[c], a1 = p0[c + 1];
+  const float b0 = mode ? 1.f / p1[c] : p1[c], b1 = mode ? 1.f / p1[c + 1] : p1[c + 1];
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float2 g = ld2<TD>(dy + r * ld_dy + c);
+    if (q) { const float2 qq = *reinterpret_cast<const float2*>(q + (r / T) * C + c); g.x -= qq.x; g.y -= qq.y; }
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(x + r * ld_x + c));
+    s0 += g.x; s1 += g.y;
+    q0 += g.x * (v.x - a0) * b0; q1 += g.y * (v.y - a1) * b1;
+  }
+  float* p = partial + (size_t)blockIdx.y * 2 * C;
+  p[c] = s0; p[c + 1] = s1; p[C + c] = q0; p[C + c + 1] = q1;
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TD* __restrict__ dy, const float* __restrict__ q, int T,
+                                                           __half* __restrict__ dx, const __half* __restrict__ x,
+                                                           long long rows, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ csum, float inv_n, int relu) {
+  const long long n2 = rows * C / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 2;
+    const long long r = e / C;
+    const int c0 = (int)(e - r * C), c1 = c0 + 1;
+    float2 g = ld2<TD>(dy + e);
+    if (q) { const float2 qq = *reinterpret_cast<const float2*>(q + (r / T) * C + c0); g.x -= qq.x; g.y -= qq.y; }
+    const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + e));
+    float o0 = gamma[c0] * rstd[c0] * (g.x - csum[c0] * inv_n - (xv.x - mean[c0]) * rstd[c0] * csum[C + c0] * inv_n);
+    float o1 = gamma[c1] * rstd[c1] * (g.y - csum[c1] * inv_n - (xv.y - mean[c1]) * rstd[c1] * csum[C + c1] * inv_n);
+    if (relu) { if (!(xv.x > 0.f)) o0 = 0.f; if (!(xv.y > 0.f)) o1 = 0.f; }
+    *reinterpret_cast<__half2*>(dx + e) = __floats2half2_rn(o0, o1);
+  }
+}
+
+// dy16[r][k] = fp16(G[r][k] - q[r / T][k])      (gradient of the aggregation wrt the supplied assignments)
+__global__ void __launch_bounds__(256) sub_q_cast_kernel(const float* __restrict__ G, const float* __restrict__ q,
+                                                         long long rows, int T, int K, __half* __restrict__ out) {
+  const long long n = rows * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K;
+    const int k = (int)(i - r * K);
+    out[i] = __float2half_rn(G[i] - q[(r / T) * K + k]);
+  }
+}
+
+// out[b][k][d] = in[b*in_stride + d*K + k]   (gradient of the d-major flatten back to cluster-major)
+__global__ void dmajor_to_kmajor_f16_kernel(const __half* __restrict__ in, long long in_stride, int K, int D,
+                                            __half* __restrict__ out) {
+  __shared__ __half tile[32][34];
+  const int b = blockIdx.z, d0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int d = d0 + j, k = k0 + threadIdx.x;
+    if (d < D && k < K) tile[j][threadIdx.x] = in[(size_t)b * in_stride + (size_t)d * K + k];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int k = k0 + j, d = d0 + threadIdx.x;
+    if (d < D && k < K) out[((size_t)b * K + k) * D + d] = tile[threadIdx.x][j];
   }
 }
 
@@ -156,9 +244,43 @@ int colstats(const __half* x, long long ld, long long rows, int C, float* partia
   return LPM_OK;
 }
 
-int affine_cols(__half* x, long long rows, int C, const float* scale, const float* shift, cudaStream_t st) {
+int affine_cols(const __half* x, __half* y, long long rows, int C, const float* scale, const float* shift,
+                cudaStream_t st) {
   LPM_REQUIRE(C % 8 == 0, "affine_cols: column count must be a multiple of 8");
-  affine_cols_kernel<<<grid_for_v2(rows * C / 8, 256), 256, 0, st>>>(x, rows, C, scale, shift);
+  affine_cols_kernel<<<grid_for_v2(rows * C / 8, 256), 256, 0, st>>>(x, y, rows, C, scale, shift);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int bn_bwd_stats(const void* dy, int dy_f32, long long ld_dy, const float* q, int T, const __half* x, long long ld_x,
+                 long long rows, int C, const float* p0, const float* p1, int mode, float* partial, cudaStream_t st) {
+  LPM_REQUIRE(C % 2 == 0 && ld_dy % 2 == 0 && ld_x % 2 == 0, "bn_bwd_stats: even column count / pitches required");
+  dim3 grid((C / 2 + 255) / 256, colstats_chunks(rows));
+  if (dy_f32) bn_bwd_stats_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), ld_dy, q, T, x, ld_x, rows, C, p0, p1, mode, partial);
+  else bn_bwd_stats_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(dy), ld_dy, q, T, x, ld_x, rows, C, p0, p1, mode, partial);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int bn_bwd_apply(const void* dy, int dy_f32, const float* q, int T, __half* dx, const __half* x, long long rows, int C,
+                 const float* mean, const float* rstd, const float* gamma, const float* csum, int relu, cudaStream_t st) {
+  LPM_REQUIRE(C % 2 == 0, "bn_bwd_apply: column count must be even");
+  const int grid = grid_for_v2(rows * C / 2, 256);
+  if (dy_f32) bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), q, T, dx, x, rows, C, mean, rstd, gamma, csum, 1.f / (float)rows, relu);
+  else bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(dy), q, T, dx, x, rows, C, mean, rstd, gamma, csum, 1.f / (float)rows, relu);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int sub_q_cast(const float* G, const float* q, long long rows, int T, int K, __half* out, cudaStream_t st) {
+  sub_q_cast_kernel<<<grid_for_v2(rows * K, 256), 256, 0, st>>>(G, q, rows, T, K, out);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, int D, __half* out, cudaStream_t st) {
+  dim3 grid((K + 31) / 32, (D + 31) / 32, B), block(32, 8);
+  dmajor_to_kmajor_f16_kernel<<<grid, block, 0, st>>>(in, in_stride, K, D, out);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -239,10 +239,9 @@ class NetVladEngine:
                 m = self._v1_modality(name, X, B, T, D, K, H, sid, is_training, save, vlad[:, off:off + K * D], ctx,
                                       return_intermediates)
             else:
-                if save:
-                    raise NotImplementedError("NetVladV2 backward (training graph) is not implemented in this round")
                 mask = None if dropout_masks is None else dropout_masks.get(name)
-                m = self._v2_modality(name, X, B, T, D, K, is_training, vlad[:, off:off + K * D], ctx, return_intermediates, mask)
+                m = self._v2_modality(name, X, B, T, D, K, is_training, save, vlad[:, off:off + K * D], ctx,
+                                      return_intermediates, mask)
             if save:
                 ctx[name] = m
             off += K * D
@@ -311,7 +310,7 @@ class NetVladEngine:
                           u3=h2, st3=r3[1]))
         return m
 
-    def _v2_modality(self, name, X, B, T, D, K, training, out_view, ctx, want_inter, dropout_mask):
+    def _v2_modality(self, name, X, B, T, D, K, training, save, out_view, ctx, want_inter, dropout_mask):
         """NetVladAttenCluster.forward (video_pooling_modules.py:1617-1663): cluster similarities from
         TransformerEncoderMod over the frames (transformer_utils.py:443-457, 634-677, 737-767), then the same
         residual aggregation / norms as V1 through the pooling kernel's external-assignment mode."""
@@ -319,47 +318,59 @@ class NetVladEngine:
         vs = name + "_VLAD"
         a = vs + "/cluster_attention"
         H = D // 16                                                   # video_pooling_modules.py:1612
-        if T != c.iterations:
-            raise ValueError("logits_bn is tied to iterations")
+        if K % 8:
+            raise NotImplementedError("cluster sizes that are not multiples of 8")
         qkv = ops.gemm(X, sh[a + "/wqkv16"])                          # [B*T, 3D]; no q scaling (batch-normed logits)
-        bn = a + "/logits_bn"
+
+        def bnv(scope):
+            return (v[scope + "/gamma"], v[scope + "/beta"], v[scope + "/moving_mean"], v[scope + "/moving_variance"])
+
         if training:
             part = ops.mha_logit_stats(qkv, B, T, D, H)
-            ks, kb = ops.bn_finalize(part[:, 0], part[:, 1], B * H * T, v[bn + "/gamma"], v[bn + "/beta"],
-                                     v[bn + "/moving_mean"], v[bn + "/moving_variance"], training=True, bessel=True,
-                                     psum_stride=2 * T)
+            r = ops.bn_finalize(part[:, 0], part[:, 1], B * H * T, *bnv(a + "/logits_bn"), training=True, bessel=True,
+                                psum_stride=2 * T, save=save)
         else:
-            ks, kb = ops.bn_finalize(None, None, 1, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"],
-                                     v[bn + "/moving_variance"], training=False, bessel=True)
-        o = ops.mha_core_fwd(qkv, B, T, D, H, scale=1.0, key_scale=ks, key_shift=kb)
-        bn = a + "/attention_bn"                                      # rank-3 input: biased moving variance
-        ops.batch_norm_cols_f16(o, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
-                                training=training, bessel=False)
-        att = ops.gemm(o, sh[a + "/wo16"], bias=v[a + "/output_transform/bias"])
+            r = ops.bn_finalize(None, None, 1, *bnv(a + "/logits_bn"), training=False, bessel=True, save=save)
+        ks, kb = r[0], r[1]
+        lbn_stats = r[2] if save else None
+        o = ops.mha_core_fwd(qkv, B, T, D, H, scale=1.0, key_scale=ks, key_shift=kb, want_lse=save)
+        lse = None
+        if save:
+            o, lse = o
+        o_bn = torch.empty_like(o) if save else None                  # rank-3 input: biased moving variance
+        r = ops.batch_norm_cols_f16(o, *bnv(a + "/attention_bn"), training=training, bessel=False, save=save, out=o_bn)
+        abn_stats = r[2] if save else None
+        o_in = o_bn if save else o
+        att = ops.gemm(o_in, sh[a + "/wo16"], bias=v[a + "/output_transform/bias"])
+        mask = None
         if training and c.dropout_rate > 0:                           # D7: drop probability 0.9
-            ops.dropout_f16(att, c.dropout_rate, mask_in=dropout_mask, seed=ctx.get("seed", 0) * 2 + (name == "audio"))
-        h1 = ops.layernorm_joint_fwd(att, X, None, B, T, D, v[a + "/LayerNorm/gamma"], v[a + "/LayerNorm/beta"])
+            mask = torch.empty_like(att) if save else None
+            ops.dropout_f16(att, c.dropout_rate, mask_in=dropout_mask, mask_out=mask,
+                            seed=int(ctx.get("seed", 0)) * 2 + (name == "audio"))
+        h1 = ops.layernorm_joint_fwd(att, X, None, B, T, D, v[a + "/LayerNorm/gamma"], v[a + "/LayerNorm/beta"], save=save)
+        st1 = None
+        if save:
+            h1, st1 = h1
         f = ops.gemm(h1.view(B * T, D), sh[a + "/w1_16"], bias=v[a + "/filter_outputencode/bias"], relu=True)
-        bn = a + "/filter_bn"
-        ops.batch_norm_cols_f16(f, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
-                                training=training, bessel=False)
-        k8 = _ceil8(K)
-        b2 = v[a + "/ff_outputencode/bias"]
-        if k8 != K:
-            b2 = torch.zeros(k8, dtype=torch.float32, device=X.device)
-            b2[:K].copy_(v[a + "/ff_outputencode/bias"])
-        A = ops.gemm(f, sh[a + "/w2_16"], bias=b2, relu=True)         # [B*T, ceil8(K)]
-        if k8 != K:
-            raise NotImplementedError("cluster sizes that are not multiples of 8")
-        bn = a + "/feed_output_bn"
-        ops.batch_norm_cols_f16(A, v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"],
-                                training=training, bessel=False)
-        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, v[vs + "/cluster_centers"], assign_in=A)
+        f_bn = torch.empty_like(f) if save else None
+        r = ops.batch_norm_cols_f16(f, *bnv(a + "/filter_bn"), training=training, bessel=False, save=save, out=f_bn)
+        fbn_stats = r[2] if save else None
+        f_in = f_bn if save else f
+        f2 = ops.gemm(f_in, sh[a + "/w2_16"], bias=v[a + "/ff_outputencode/bias"], relu=True)     # [B*T, K]
+        A = torch.empty_like(f2) if save else None
+        r = ops.batch_norm_cols_f16(f2, *bnv(a + "/feed_output_bn"), training=training, bessel=False, save=save, out=A)
+        obn_stats = r[2] if save else None
+        A_in = A if save else f2
+        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, v[vs + "/cluster_centers"], assign_in=A_in)
         ops.netvlad_finalize_f16(z, rscale, out_view, out_view.stride(0))    # d-major flatten, normalised, fp16
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
-            ctx["inter"]["assign_" + name] = A.float().reshape(B, T, K)
-        return {}
+            ctx["inter"]["assign_" + name] = A_in.float().reshape(B, T, K)
+        if not save:
+            return {}
+        return dict(X=X, qkv=qkv, ks=ks, kb=kb, lbn_stats=lbn_stats, o=o, lse=lse, o_bn=o_bn, abn_stats=abn_stats,
+                    mask=mask, u1=att, st1=st1, h1=h1, f=f, fbn_stats=fbn_stats, f_bn=f_bn, f2=f2, obn_stats=obn_stats,
+                    A=A, z=z, rscale=rscale, a_sum=a_sum)
 
     def _head(self, vlad, B, training, save, ctx, want_inter):
         """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""
@@ -393,8 +404,6 @@ class NetVladEngine:
         """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
         Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
-        if c.model != "NetVladV1":
-            raise NotImplementedError("backward is implemented for NetVladV1 in this round")
         if c.remove_diag:
             raise NotImplementedError("gating_remove_diag backward")
         B, hd = ctx["B"], ctx["head"]
@@ -457,7 +466,10 @@ class NetVladEngine:
             offs.append(off)
             off += K * D
         for (name, col0, D, K, H, sid), o0 in reversed(list(zip(mods, offs))):
-            self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put)
+            if c.model == "NetVladV1":
+                self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put)
+            else:
+                self._v2_modality_bwd(ctx, name, col0, D, K, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put)
         put("input_bn/gamma", dgamma_in)
         put("input_bn/beta", dbeta_in)
         return grads
@@ -530,3 +542,81 @@ class NetVladEngine:
         put(vs + "/cluster_weights2", ops.transpose_f32(dCt).view(1, D, K))
         ops.input_bn_grad(v[vs + "/cluster_weights"], dWc, dCt, E, v["input_bn/gamma"][col0:col0 + D],
                           dgamma_in[col0:col0 + D], dbeta_in[col0:col0 + D])
+
+    def _v2_modality_bwd(self, ctx, name, col0, D, K, dv, dgamma_in, dbeta_in, put):
+        """Backward of NetVladAttenCluster + TransformerEncoderMod (video_pooling_modules.py:1617-1663,
+        transformer_utils.py:443-457,634-677,737-767).  Unlike V1 the frames feed the encoder, so dX is formed
+        (three contributions fused into one GEMM epilogue) and reduced into input_bn's gamma / beta."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        S = ctx["loss_scale"]
+        inv = 1.0 / S
+        m, B, T = ctx[name], ctx["B"], c.iterations
+        vs = name + "_VLAD"
+        a = vs + "/cluster_attention"
+        H = D // 16
+        f32 = torch.float32
+        gout = ctx["_gout"]
+        rows = B * T
+        X = m["X"]
+        ct = sh[vs + "/centers_t"]
+        # ---- d-major flatten + norms + residual aggregation ---------------------------------------
+        dvh = ops.dmajor_to_kmajor_f16(dv, B, K, D)
+        dz, q = ops.netvlad_norm_bwd(m["z"], m["rscale"], dvh, ct)
+        X3 = X.view(B, T, D)
+        G = ops.gemm(X3, dz, b_mn=False, out_dtype=f32)                       # [B,T,K] = X dV^T
+        dXpool = ops.gemm(m["A"].view(B, T, K), dz, b_mn=True)                # [B,T,D] = A dV
+        dCt, _ = ops.center_bwd(dz, m["z"], m["a_sum"], ct, v["input_bn/beta"][col0:col0 + D], inv)
+        put(vs + "/cluster_centers", ops.transpose_f32(dCt))
+        # ---- FeedForwardNetworkMod: BN(relu(BN(relu(h1 W1 + b1)) W2 + b2)) -------------------------
+        bn = a + "/feed_output_bn"
+        # grad wrt the BN'd similarities = G - q (kept in fp32: the batch-norm backward cancels its common mode)
+        dpre2, dg, db = ops.batch_norm_cols_bwd(G.view(rows, K), m["f2"], m["obn_stats"], v[bn + "/gamma"], inv_scale=inv,
+                                                relu=True, q=q, T=T)
+        put(bn + "/gamma", dg); put(bn + "/beta", db)
+        put(a + "/ff_outputencode/bias", ops.colsum(dpre2, alpha=inv))
+        put(a + "/ff_outputencode/kernel", ops.gemm(m["f_bn"], dpre2, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                    out=gout(a + "/ff_outputencode/kernel")))
+        df_bn = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, N=4 * D, K=K, out_dtype=f32)
+        bn = a + "/filter_bn"
+        dpre1, dg, db = ops.batch_norm_cols_bwd(df_bn, m["f"], m["fbn_stats"], v[bn + "/gamma"], inv_scale=inv, relu=True)
+        put(bn + "/gamma", dg); put(bn + "/beta", db)
+        put(a + "/filter_outputencode/bias", ops.colsum(dpre1, alpha=inv))
+        h1 = m["h1"].view(rows, D)
+        put(a + "/filter_outputencode/kernel", ops.gemm(h1, dpre1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                        out=gout(a + "/filter_outputencode/kernel")))
+        dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False)
+        # ---- LayerNorm(dropout(att) + X) ---------------------------------------------------------
+        du1, dg, db = ops.layernorm_joint_bwd(m["u1"], dh1, T * D, B, T, D, m["st1"], v[a + "/LayerNorm/gamma"], inv_scale=inv)
+        put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
+        du1 = du1.view(rows, D)
+        datt = du1
+        if m["mask"] is not None:
+            datt = du1.clone()
+            ops.dropout_f16(datt, c.dropout_rate, mask_in=m["mask"])
+        # ---- MultiHeadAttentionBN ------------------------------------------------------------------
+        put(a + "/output_transform/bias", ops.colsum(datt, alpha=inv))
+        put(a + "/output_transform/kernel", ops.gemm(m["o_bn"], datt, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                                     out=gout(a + "/output_transform/kernel")))
+        do_bn = ops.gemm(datt, sh[a + "/wo16"], b_mn=False, out_dtype=f32)
+        bn = a + "/attention_bn"
+        do, dg, db = ops.batch_norm_cols_bwd(do_bn, m["o"], m["abn_stats"], v[bn + "/gamma"], inv_scale=inv, relu=False)
+        put(bn + "/gamma", dg); put(bn + "/beta", db)
+        lmean, lrstd = m["lbn_stats"][0], m["lbn_stats"][1]
+        part = ops.mha_core_bwd_bn(1, m["qkv"], m["o"], do, m["lse"], B, T, D, H, m["ks"], m["kb"], lmean, lrstd)
+        n_l = float(B * H * T)
+        m12 = torch.empty((2, T), dtype=f32, device=X.device)
+        ops.colsum_final(part, B * H, 2 * T, 2 * T, alpha=1.0 / n_l, out=m12.view(-1))
+        bn = a + "/logits_bn"
+        put(bn + "/beta", ops.colsum_final(part, B * H, 2 * T, T, alpha=inv))
+        put(bn + "/gamma", ops.colsum_final(part[:, 1], B * H, 2 * T, T, alpha=inv))
+        dqkv = ops.mha_core_bwd_bn(2, m["qkv"], m["o"], do, m["lse"], B, T, D, H, m["ks"], m["kb"], lmean, lrstd,
+                                   m1=m12[0], m2=m12[1])
+        for i, n in enumerate(("q", "k", "v")):
+            put(f"{a}/{n}/kernel", ops.gemm(X, dqkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                            out=gout(f"{a}/{n}/kernel")))
+        # ---- dX = dqkv Wqkv^T + du1 (residual) + A dV (aggregation); input_bn gamma / beta --------
+        dX = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1, add2=dXpool.view(rows, D))
+        dg, db = ops.bn_output_param_grads(dX, X, v["input_bn/beta"][col0:col0 + D], v["input_bn/gamma"][col0:col0 + D],
+                                           inv_scale=inv)
+        dgamma_in[col0:col0 + D].copy_(dg)
+        dbeta_in[col0:col0 + D].copy_(db)

@@ -477,12 +477,13 @@ def colstats_f16(x, rows=None, cols=None):
     return partial
 
 
-def affine_cols_f16(x, scale, shift):
+def affine_cols_f16(x, scale, shift, out=None):
     lib = _lib.load()
     assert x.is_contiguous()
-    check(lib.lpm_affine_cols_f16(ptr(x), _ll(x.shape[0]), x.shape[1], ptr(scale), ptr(shift), stream_ptr()),
+    out = x if out is None else out
+    check(lib.lpm_affine_cols_f16(ptr(x), ptr(out), _ll(x.shape[0]), x.shape[1], ptr(scale), ptr(shift), stream_ptr()),
           "lpm_affine_cols_f16")
-    return x
+    return out
 
 
 def dropout_f16(x, rate, *, mask_in=None, mask_out=None, seed=0):
@@ -500,8 +501,9 @@ def netvlad_finalize_f16(z, rscale, out, out_stride):
     return out
 
 
-def batch_norm_cols_f16(x, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False):
-    """slim.batch_norm over the rows of an fp16 matrix, applied in place.  Returns (scale, shift[, (mean, rstd)])."""
+def batch_norm_cols_f16(x, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False, out=None):
+    """slim.batch_norm over the rows of an fp16 matrix, applied in place (or into `out`).
+    Returns (scale, shift[, (mean, rstd)])."""
     rows, cols = x.shape
     if training:
         part = colstats_f16(x)
@@ -509,5 +511,69 @@ def batch_norm_cols_f16(x, gamma, beta, moving_mean, moving_var, *, training, be
                         bessel=bessel, save=save, psum_stride=2 * cols)
     else:
         r = bn_finalize(None, None, 1, gamma, beta, moving_mean, moving_var, training=False, bessel=bessel, save=save)
-    affine_cols_f16(x, r[0], r[1])
+    affine_cols_f16(x, r[0], r[1], out=out)
     return r
+
+
+def batch_norm_cols_bwd(dy, x_pre, stats, gamma, *, inv_scale, relu, q=None, T=1):
+    """Backward of batch_norm_cols_f16 in training mode (x_pre = BN input).  dy: fp16 or fp32 [rows, C]; q (fp32
+    [rows/T, C], optional) is subtracted from dy on the fly.  Returns dx (fp16; masked by x_pre > 0 when `relu`),
+    dgamma, dbeta (fp32, unscaled)."""
+    lib = _lib.load()
+    rows, cols = x_pre.shape
+    f32 = int(dy.dtype == torch.float32)
+    assert dy.is_contiguous() and x_pre.is_contiguous()
+    ch = lib.lpm_colstats_chunks(_ll(rows))
+    part = _f32((ch, 2, cols), dy.device)
+    check(lib.lpm_batchnorm_bwd_stats(ptr(dy), f32, _ll(dy.stride(0)), ptr(q), T, ptr(x_pre), _ll(x_pre.stride(0)),
+                                      _ll(rows), cols, ptr(stats[0]), ptr(stats[1]), 0, ptr(part), stream_ptr()),
+          "lpm_batchnorm_bwd_stats")
+    csum = _f32((2, cols), dy.device)
+    colsum_final(part, ch, 2 * cols, 2 * cols, out=csum.view(-1))
+    dbeta = colsum_final(part, ch, 2 * cols, cols, alpha=inv_scale)
+    dgamma = colsum_final(part[:, 1], ch, 2 * cols, cols, alpha=inv_scale)
+    dx = torch.empty_like(x_pre)
+    check(lib.lpm_batchnorm_bwd_apply(ptr(dy), f32, ptr(q), T, ptr(dx), ptr(x_pre), _ll(rows), cols, ptr(stats[0]),
+                                      ptr(stats[1]), ptr(gamma), ptr(csum), int(relu), stream_ptr()),
+          "lpm_batchnorm_bwd_apply")
+    return dx, dgamma, dbeta
+
+
+def bn_output_param_grads(dy, y, beta, gamma, *, inv_scale):
+    """dgamma / dbeta of a batch norm from its OUTPUT y: xhat = (y - beta)/gamma (input_bn, whose input needs no grad)."""
+    lib = _lib.load()
+    rows, cols = y.shape
+    ch = lib.lpm_colstats_chunks(_ll(rows))
+    part = _f32((ch, 2, cols), dy.device)
+    check(lib.lpm_batchnorm_bwd_stats(ptr(dy), int(dy.dtype == torch.float32), _ll(dy.stride(0)), None, 1, ptr(y),
+                                      _ll(y.stride(0)), _ll(rows), cols, ptr(beta), ptr(gamma), 1, ptr(part),
+                                      stream_ptr()), "lpm_batchnorm_bwd_stats")
+    dbeta = colsum_final(part, ch, 2 * cols, cols, alpha=inv_scale)
+    dgamma = colsum_final(part[:, 1], ch, 2 * cols, cols, alpha=inv_scale)
+    return dgamma, dbeta
+
+
+def sub_q_cast_f16(G, q, T):
+    lib = _lib.load()
+    rows, K = G.shape
+    out = _f16((rows, K), G.device)
+    check(lib.lpm_sub_q_cast_f16(ptr(G), ptr(q), _ll(rows), T, K, ptr(out), stream_ptr()), "lpm_sub_q_cast_f16")
+    return out
+
+
+def dmajor_to_kmajor_f16(dv, B, K, D):
+    lib = _lib.load()
+    out = _f16((B, K, D), dv.device)
+    check(lib.lpm_dmajor_to_kmajor_f16(ptr(dv), _ll(dv.stride(0)), B, K, D, ptr(out), stream_ptr()),
+          "lpm_dmajor_to_kmajor_f16")
+    return out
+
+
+def mha_core_bwd_bn(mode, qkv, o, dout, lse, B, L, Dm, H, ks, kb, mean, rstd, m1=None, m2=None):
+    lib = _lib.load()
+    part = _f32((B * H, 2, L), qkv.device) if mode == 1 else None
+    dqkv = torch.empty_like(qkv) if mode == 2 else None
+    check(lib.lpm_mha_core_bwd_bn(mode, ptr(qkv), _ll(qkv.stride(0)), ptr(o), ptr(dout), _ll(o.stride(0)), ptr(lse), B, L,
+                                  Dm, H, ptr(ks), ptr(kb), ptr(mean), ptr(rstd), ptr(m1), ptr(m2), ptr(part), ptr(dqkv),
+                                  _ll(qkv.stride(0)), stream_ptr()), "lpm_mha_core_bwd_bn")
+    return part if mode == 1 else dqkv

@@ -306,7 +306,7 @@ def netvlad_v1(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
 
 def netvlad_v2(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size,
                is_training, num_mixtures=2, rgb_dim=1024, dropout_masks=None, dropout_rate=0.9,
-               remove_diag=False, return_intermediates=False):
+               remove_diag=False, gating=True, return_intermediates=False):
     x, B, T = _shell(model_input, num_frames, iterations, P, S, is_training)
     inter = {}
     outs = []
@@ -317,7 +317,7 @@ def netvlad_v2(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
         inter["vlad_" + name] = v
         outs.append(v)
     vlad = torch.cat(outs, dim=1)
-    pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures,
+    pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
                             remove_diag=remove_diag, return_intermediates=True)
     inter.update(hi)
     return (pred, inter) if return_intermediates else pred

@@ -163,3 +163,75 @@ def test_head_kernels(cuda):
     labels = torch.rand(B, V, generator=g) < 0.1
     loss, _ = ops.xent_fwd(pred, labels.to(torch.uint8).to(cuda))
     assert abs(float(loss) - float(O.cross_entropy_loss(ref, labels))) < 1e-4 * float(O.cross_entropy_loss(ref, labels))
+
+
+def test_batch_norm_cols_backward(cuda):
+    """slim.batch_norm (training statistics) backward over rows, with the ReLU mask of the preceding activation,
+    vs torch autograd in fp64 on the same fp16-rounded inputs."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    rows, C, T = 512, 64, 128
+    x = torch.relu(torch.randn(rows, C, generator=g) + 0.3).half()
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    dy = torch.randn(rows, C, generator=g)
+    q = torch.randn(rows // T, C, generator=g)
+    pre = (x.double() - 0.0).requires_grad_(True)       # treat the post-ReLU value as the BN input
+    xd = pre
+    mean, var = xd.mean(0), xd.var(0, unbiased=False)
+    y = (xd - mean) / torch.sqrt(var + 1e-3) * gamma.double() + beta.double()
+    dy_eff = dy.double() - q.double().repeat_interleave(T, dim=0)
+    (y * dy_eff).sum().backward()
+    ref_dx = pre.grad * (x.double() > 0)
+    xg = x.to(cuda)
+    mm, mv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    out = torch.empty_like(xg)
+    r = ops.batch_norm_cols_f16(xg, gamma.to(cuda), beta.to(cuda), mm, mv, training=True, bessel=False, save=True, out=out)
+    assert rel(out.float(), y.detach()) < 1e-3
+    dx, dgam, dbet = ops.batch_norm_cols_bwd(dy.to(cuda), xg, r[2], gamma.to(cuda), inv_scale=1.0, relu=True, q=q.to(cuda), T=T)
+    assert rel(dx.float(), ref_dx) < 2e-3, rel(dx.float(), ref_dx)
+    xhat = (xd.detach() - mean.detach()) / torch.sqrt(var.detach() + 1e-3)
+    assert rel(dbet, dy_eff.sum(0)) < 1e-4 and rel(dgam, (dy_eff * xhat).sum(0)) < 1e-3
+    # fp16 dy path, no ReLU, no q
+    dx2, _, _ = ops.batch_norm_cols_bwd(dy.half().to(cuda), xg, r[2], gamma.to(cuda), inv_scale=1.0, relu=False)
+    pre.grad = None
+    (y2 := (xd - xd.mean(0)) / torch.sqrt(xd.var(0, unbiased=False) + 1e-3) * gamma.double() + beta.double())
+    (y2 * dy.half().double()).sum().backward()
+    assert rel(dx2.float(), pre.grad) < 2e-3
+
+
+@pytest.mark.parametrize("B,L,Dm,H", [(2, 256, 128, 8), (3, 64, 64, 4)])
+def test_mha_bn_logits_backward(cuda, B, L, Dm, H):
+    """Attention with batch-normed logits (transformer_utils.py:634-664): two-launch backward vs fp64 autograd."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(5 + L)
+    qkv = (torch.randn(B * L, 3 * Dm, generator=g) * 0.7).half()
+    gamma, beta = torch.rand(L, generator=g) + 0.5, torch.randn(L, generator=g) * 0.2
+    dout = torch.randn(B * L, Dm, generator=g).half()
+    t = qkv.double().requires_grad_(True)
+    q, k, v = [u.reshape(B, L, H, 16).permute(0, 2, 1, 3) for u in t.split(Dm, dim=1)]
+    logits = q @ k.transpose(-1, -2)                                  # [B,H,L,L], channel = last axis
+    flat = logits.reshape(-1, L)
+    mean, var = flat.mean(0), flat.var(0, unbiased=False)
+    lb = (logits - mean) / torch.sqrt(var + 1e-3) * gamma.double() + beta.double()
+    out = (torch.softmax(lb, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
+    (out * dout.double()).sum().backward()
+    dgam_ref = torch.autograd.grad((torch.softmax(((logits.detach() - mean.detach()) / torch.sqrt(var.detach() + 1e-3)) * (gm := gamma.double().requires_grad_(True)) + beta.double(), -1) @ v.detach()).permute(0, 2, 1, 3).reshape(B * L, Dm).mul(dout.double()).sum(), gm)[0]
+    dev = cuda
+    qg = qkv.to(dev)
+    part = ops.mha_logit_stats(qg, B, L, Dm, H)
+    mm, mv = torch.zeros(L, device=dev), torch.ones(L, device=dev)
+    ks, kb, st = ops.bn_finalize(part[:, 0], part[:, 1], B * H * L, gamma.to(dev), beta.to(dev), mm, mv, training=True,
+                                 bessel=True, psum_stride=2 * L, save=True)
+    assert rel(st[0], mean.detach()) < 1e-3 and rel(st[1], 1 / torch.sqrt(var.detach() + 1e-3)) < 1e-3
+    o, lse = ops.mha_core_fwd(qg, B, L, Dm, H, scale=1.0, key_scale=ks, key_shift=kb, want_lse=True)
+    assert rel(o.float(), out.detach()) < 2e-3
+    p1 = ops.mha_core_bwd_bn(1, qg, o, dout.to(dev), lse, B, L, Dm, H, ks, kb, st[0], st[1])
+    n = float(B * H * L)
+    m12 = torch.empty(2, L, device=dev)
+    ops.colsum_final(p1, B * H, 2 * L, 2 * L, alpha=1.0 / n, out=m12.view(-1))
+    dgam = ops.colsum_final(p1[:, 1], B * H, 2 * L, L)
+    dqkv = ops.mha_core_bwd_bn(2, qg, o, dout.to(dev), lse, B, L, Dm, H, ks, kb, st[0], st[1], m1=m12[0], m2=m12[1])
+    e = rel(dqkv.float(), t.grad)
+    print(f"\n[mha bn bwd L={L}] dqkv rel-L2 {e:.2e}, dgamma {rel(dgam, dgam_ref):.2e}")
+    assert e < 1e-2
+    assert rel(dgam, dgam_ref) < 1e-2
