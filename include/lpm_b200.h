@@ -241,6 +241,24 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                        const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
                        float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
 
+/* Factored optimiser step for a dense layer whose weight gradient is the rank-R product dW = alpha * A^T G
+ * (hidden1_weights, frame_level_models.py:2314-2319: A = VLAD descriptor fp16 [R][Kd], G = output gradient fp16
+ * [R][N], R = tower batch <= 128).  dW is never materialised: lpm_rank_grad_clip derives the tf.clip_by_norm factor
+ * (utils.py:181-188) from the Gram matrices gram_a = A A^T, gram_g = G G^T (fp32 [R][R]):
+ * ||A^T G||_F^2 = sum_ij gram_a_ij gram_g_ij; lpm_rank_adam_step recomputes 128-row panels of dW on the tensor
+ * cores and applies factor[0], Adam (same formulas as lpm_adam_clip_step, no regulariser) and the fp16 shadow
+ * refresh (w16, row stride ldw16, may be null) in registers (persistent CTAs, cp.async-prefetched panels).  flag: the step is skipped when *flag != 0;
+ * lpm_rank_grad_clip sets it on a non-finite norm. */
+int lpm_rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor,
+                       float* norm, int* flag, lpm_stream_t stream);
+int lpm_rank_adam_step(const void* a16, long long lda, const void* g16, long long ldg, int R, long long Kd, int N,
+                       float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
+                       long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace,
+                       unsigned long long workspace_bytes, lpm_stream_t stream);
+/* bytes of caller-owned device workspace lpm_rank_adam_step needs (the column-permuted copy of G); 0 when the
+ * (R, N) pair is not supported (G must fit in shared memory): callers then keep the dense-gradient path */
+unsigned long long lpm_rank_adam_workspace_bytes(int R, int N);
+
 /* =============================================================================================
  * NetVladV2 (attention-based cluster similarities) helpers
  * ============================================================================================= */

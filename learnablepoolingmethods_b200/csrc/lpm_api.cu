@@ -331,6 +331,25 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                         factor, norms, flag, ST(stream));
 }
 
+int lpm_rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor,
+                       float* norm, int* flag, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(gram_a && gram_g && factor && norm && flag && R > 0, "lpm_rank_grad_clip: bad arguments");
+  return rank_grad_clip(gram_a, gram_g, R, alpha, clip, factor, norm, flag, ST(stream));
+}
+
+int lpm_rank_adam_step(const void* a16, long long lda, const void* g16, long long ldg, int R, long long Kd, int N,
+                       float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
+                       long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace,
+                       unsigned long long workspace_bytes, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(a16 && g16 && factor && flag && w && m && v && Kd > 0, "lpm_rank_adam_step: bad arguments");
+  return rank_adam_step(CH16(a16), lda, CH16(g16), ldg, R, Kd, N, alpha, factor, flag, w, m, v, H16(w16), ldw16, lr_t, b1, b2,
+                        eps, workspace, (size_t)workspace_bytes, ST(stream));
+}
+
+unsigned long long lpm_rank_adam_workspace_bytes(int R, int N) { return rank_adam_workspace_bytes(R, N); }
+
 int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int H, float* partial, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(qkv && partial && B > 0 && L > 0, "lpm_mha_logit_stats: bad arguments");

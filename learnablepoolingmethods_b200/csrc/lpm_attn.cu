@@ -204,10 +204,12 @@ struct MhaBnArgs {
 };
 
 template <int DH, int MODE>
-__global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
-                                                      const __half* __restrict__ o, const __half* __restrict__ dout,
-                                                      long long ldo, const float* __restrict__ lse, int L, int Dm,
-                                                      int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn) {
+__global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
+                                                         const __half* __restrict__ o, const __half* __restrict__ dout,
+                                                         long long ldo, const float* __restrict__ lse, int L, int Dm,
+                                                         int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn) {
+  // 16 warps; one CTA per (sample, head).  The kernel is latency- rather than throughput-bound (one CTA per SM
+  // because dS^T is parked in shared memory), so every warp keeps two independent query blocks in flight.
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + L * 32;
@@ -250,12 +252,13 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
   const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV), do_s = smem_u32(sdO);
   const float scale_log2 = scale * 1.4426950408889634f;
   const int nb = L / 16;
 
   // ------------------------------- pass A: dK, dV, dS -------------------------------
-  for (int j = warp; j < nb; j += 8) {
+  for (int j = warp; j < nb; j += nwarps) {
     uint32_t ka0, ka1, ka2, ka3, va0, va1, va2, va3;
     {
       const int row = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -274,73 +277,89 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
       mu0 = sBn[2 * L + kr0]; mu1 = sBn[2 * L + kr1]; rs0 = sBn[3 * L + kr0]; rs1 = sBn[3 * L + kr1];
       m10 = sBn[4 * L + kr0]; m11 = sBn[4 * L + kr1]; m20 = sBn[5 * L + kr0]; m21 = sBn[5 * L + kr1];
     }
-    for (int i = 0; i < nb; ++i) {
-      float st[2][4], dp[2][4];
+    for (int i = 0; i < nb; i += 2) {
+      // two query blocks per iteration (the second is a masked repeat of the first on an odd tail)
+      const bool two = i + 1 < nb;
+      const int ib[2] = {i, two ? i + 1 : i};
+      float st[2][2][4], dp[2][2][4];
+      uint32_t qf[2][4], of[2][4];
 #pragma unroll
-      for (int n = 0; n < 2; ++n) st[n][0] = st[n][1] = st[n][2] = st[n][3] = dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-      {
-        uint32_t b0, b1, b2, b3;
-        const int qrow = i * 16 + (lane & 7) + (lane >> 4) * 8;
-        ldsm_x4(q_s + tile_off(qrow, (lane >> 3) & 1), b0, b1, b2, b3);
-        mma16816(st[0], ka0, ka1, ka2, ka3, b0, b1);
-        mma16816(st[1], ka0, ka1, ka2, ka3, b2, b3);
-        ldsm_x4(do_s + tile_off(qrow, (lane >> 3) & 1), b0, b1, b2, b3);
-        mma16816(dp[0], va0, va1, va2, va3, b0, b1);
-        mma16816(dp[1], va0, va1, va2, va3, b2, b3);
+      for (int u = 0; u < 2; ++u) {
+        const int qrow = ib[u] * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldsm_x4(q_s + tile_off(qrow, (lane >> 3) & 1), qf[u][0], qf[u][1], qf[u][2], qf[u][3]);
+        ldsm_x4(do_s + tile_off(qrow, (lane >> 3) & 1), of[u][0], of[u][1], of[u][2], of[u][3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+          st[u][n][0] = st[u][n][1] = st[u][n][2] = st[u][n][3] = dp[u][n][0] = dp[u][n][1] = dp[u][n][2] = dp[u][n][3] = 0.f;
+        mma16816(st[u][0], ka0, ka1, ka2, ka3, qf[u][0], qf[u][1]);
+        mma16816(st[u][1], ka0, ka1, ka2, ka3, qf[u][2], qf[u][3]);
+        mma16816(dp[u][0], va0, va1, va2, va3, of[u][0], of[u][1]);
+        mma16816(dp[u][1], va0, va1, va2, va3, of[u][2], of[u][3]);
       }
       // columns of the transposed tiles are queries: n-tile n -> queries i*16 + n*8 + (lane&3)*2 + {0,1}
 #pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const int qc = i * 16 + n * 8 + (lane & 3) * 2;
-        const float l0 = sLse[qc], l1 = sLse[qc + 1], d0 = sDel[qc], d1 = sDel[qc + 1];
-        float p0, p1, p2, p3;
-        if (MODE == 0) {
-          p0 = exp2f(st[n][0] * scale_log2 - l0); p1 = exp2f(st[n][1] * scale_log2 - l1);
-          p2 = exp2f(st[n][2] * scale_log2 - l0); p3 = exp2f(st[n][3] * scale_log2 - l1);
-        } else {
-          p0 = exp2f(st[n][0] * ks0 + kb0 - l0); p1 = exp2f(st[n][1] * ks0 + kb0 - l1);
-          p2 = exp2f(st[n][2] * ks1 + kb1 - l0); p3 = exp2f(st[n][3] * ks1 + kb1 - l1);
-        }
-        float g0 = p0 * (dp[n][0] - d0), g1 = p1 * (dp[n][1] - d1), g2 = p2 * (dp[n][2] - d0), g3 = p3 * (dp[n][3] - d1);
-        if (MODE > 0) {
-          const float h0 = (st[n][0] - mu0) * rs0, h1 = (st[n][1] - mu0) * rs0;
-          const float h2 = (st[n][2] - mu1) * rs1, h3 = (st[n][3] - mu1) * rs1;
-          if (MODE == 1) {
-            a1r0 += g0 + g1; a2r0 += g0 * h0 + g1 * h1;
-            a1r1 += g2 + g3; a2r1 += g2 * h2 + g3 * h3;
+      for (int u = 0; u < 2; ++u) {
+        const float live = (u == 0 || two) ? 1.f : 0.f;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int qc = ib[u] * 16 + n * 8 + (lane & 3) * 2;
+          const float2 l01 = *reinterpret_cast<const float2*>(&sLse[qc]);
+          const float2 d01 = *reinterpret_cast<const float2*>(&sDel[qc]);
+          const float l0 = l01.x, l1 = l01.y, d0 = d01.x, d1 = d01.y;
+          float p0, p1, p2, p3;
+          if (MODE == 0) {
+            p0 = exp2f(st[u][n][0] * scale_log2 - l0); p1 = exp2f(st[u][n][1] * scale_log2 - l1);
+            p2 = exp2f(st[u][n][2] * scale_log2 - l0); p3 = exp2f(st[u][n][3] * scale_log2 - l1);
           } else {
-            const float c0 = ks0 * 0.6931471805599453f, c1 = ks1 * 0.6931471805599453f;   // back to natural-log scale
-            g0 = c0 * (g0 - m10 - h0 * m20); g1 = c0 * (g1 - m10 - h1 * m20);
-            g2 = c1 * (g2 - m11 - h2 * m21); g3 = c1 * (g3 - m11 - h3 * m21);
+            p0 = exp2f(st[u][n][0] * ks0 + kb0 - l0); p1 = exp2f(st[u][n][1] * ks0 + kb0 - l1);
+            p2 = exp2f(st[u][n][2] * ks1 + kb1 - l0); p3 = exp2f(st[u][n][3] * ks1 + kb1 - l1);
           }
+          p0 *= live; p1 *= live; p2 *= live; p3 *= live;
+          float g0 = p0 * (dp[u][n][0] - d0), g1 = p1 * (dp[u][n][1] - d1), g2 = p2 * (dp[u][n][2] - d0), g3 = p3 * (dp[u][n][3] - d1);
+          if (MODE > 0) {
+            const float h0 = (st[u][n][0] - mu0) * rs0, h1 = (st[u][n][1] - mu0) * rs0;
+            const float h2 = (st[u][n][2] - mu1) * rs1, h3 = (st[u][n][3] - mu1) * rs1;
+            if (MODE == 1) {
+              a1r0 += g0 + g1; a2r0 += g0 * h0 + g1 * h1;
+              a1r1 += g2 + g3; a2r1 += g2 * h2 + g3 * h3;
+            } else {
+              const float c0 = ks0 * 0.6931471805599453f * live, c1 = ks1 * 0.6931471805599453f * live;   // natural-log scale
+              g0 = c0 * (g0 - m10 - h0 * m20); g1 = c0 * (g1 - m10 - h1 * m20);
+              g2 = c1 * (g2 - m11 - h2 * m21); g3 = c1 * (g3 - m11 - h3 * m21);
+            }
+          }
+          st[u][n][0] = p0; st[u][n][1] = p1; st[u][n][2] = p2; st[u][n][3] = p3;
+          dp[u][n][0] = g0; dp[u][n][1] = g1; dp[u][n][2] = g2; dp[u][n][3] = g3;
         }
-        st[n][0] = p0; st[n][1] = p1; st[n][2] = p2; st[n][3] = p3;
-        dp[n][0] = g0; dp[n][1] = g1; dp[n][2] = g2; dp[n][3] = g3;
       }
       if (MODE == 1) continue;                 // statistics pass: no gradients yet
-      // A fragments (rows = keys, k = queries) from the accumulator layout
-      const uint32_t pa0 = pack_half2(st[0][0], st[0][1]), pa1 = pack_half2(st[0][2], st[0][3]);
-      const uint32_t pa2 = pack_half2(st[1][0], st[1][1]), pa3 = pack_half2(st[1][2], st[1][3]);
-      const uint32_t sa0 = pack_half2(dp[0][0], dp[0][1]), sa1 = pack_half2(dp[0][2], dp[0][3]);
-      const uint32_t sa2 = pack_half2(dp[1][0], dp[1][1]), sa3 = pack_half2(dp[1][2], dp[1][3]);
-      {
-        uint32_t b0, b1, b2, b3;
-        const int qrow = i * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        // A fragments (rows = keys, k = queries) from the accumulator layout
+        const uint32_t pa0 = pack_half2(st[u][0][0], st[u][0][1]), pa1 = pack_half2(st[u][0][2], st[u][0][3]);
+        const uint32_t pa2 = pack_half2(st[u][1][0], st[u][1][1]), pa3 = pack_half2(st[u][1][2], st[u][1][3]);
+        const uint32_t sa0 = pack_half2(dp[u][0][0], dp[u][0][1]), sa1 = pack_half2(dp[u][0][2], dp[u][0][3]);
+        const uint32_t sa2 = pack_half2(dp[u][1][0], dp[u][1][1]), sa3 = pack_half2(dp[u][1][2], dp[u][1][3]);
+        uint32_t b0, b1, b2, b3, c0, c1, c2, c3;
+        const int qrow = ib[u] * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         ldsm_x4_t(do_s + tile_off(qrow, lane >> 4), b0, b1, b2, b3);
+        ldsm_x4_t(q_s + tile_off(qrow, lane >> 4), c0, c1, c2, c3);
         mma16816(dv[0], pa0, pa1, pa2, pa3, b0, b1);
         if (DH == 16) mma16816(dv[1], pa0, pa1, pa2, pa3, b2, b3);
-        ldsm_x4_t(q_s + tile_off(qrow, lane >> 4), b0, b1, b2, b3);
-        mma16816(dk[0], sa0, sa1, sa2, sa3, b0, b1);
-        if (DH == 16) mma16816(dk[1], sa0, sa1, sa2, sa3, b2, b3);
-      }
-      // park dS^T: element (key = j*16 + lane/4 (+8), query = i*16 + n*8 + (lane&3)*2)
-      {
-        __half* r0 = sdS + (size_t)(j * 16 + (lane >> 2)) * DS_STRIDE + i * 16 + (lane & 3) * 2;
-        __half* r1 = r0 + 8 * DS_STRIDE;
-        *reinterpret_cast<uint32_t*>(r0) = sa0;
-        *reinterpret_cast<uint32_t*>(r1) = sa1;
-        *reinterpret_cast<uint32_t*>(r0 + 8) = sa2;
-        *reinterpret_cast<uint32_t*>(r1 + 8) = sa3;
+        mma16816(dk[0], sa0, sa1, sa2, sa3, c0, c1);
+        if (DH == 16) mma16816(dk[1], sa0, sa1, sa2, sa3, c2, c3);
+        // park dS^T: element (key = j*16 + lane/4 (+8), query = i*16 + n*8 + (lane&3)*2)
+        if (u == 0 || two) {
+          __half* r0 = sdS + (size_t)(j * 16 + (lane >> 2)) * DS_STRIDE + ib[u] * 16 + (lane & 3) * 2;
+          __half* r1 = r0 + 8 * DS_STRIDE;
+          *reinterpret_cast<uint32_t*>(r0) = sa0;
+          *reinterpret_cast<uint32_t*>(r1) = sa1;
+          *reinterpret_cast<uint32_t*>(r0 + 8) = sa2;
+          *reinterpret_cast<uint32_t*>(r1 + 8) = sa3;
+        }
       }
     }
     if (MODE == 1) {
@@ -369,28 +388,36 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const __half* __restrict__
   __syncthreads();
 
   // ------------------------------- pass B: dQ -------------------------------
+  // two independent accumulator sets (even / odd key blocks) break the MMA dependency chain
   const uint32_t ds_s = smem_u32(sdS);
-  for (int i = warp; i < nb; i += 8) {
-    float dq[2][4];
+  for (int i = warp; i < nb; i += nwarps) {
+    float dq[2][2][4];
 #pragma unroll
-    for (int n = 0; n < 2; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
-    for (int j = 0; j < nb; ++j) {
-      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-      const int key = j * 16 + (lane & 7) + (lane >> 4) * 8;
-      const int qcol = i * 16 + ((lane >> 3) & 1) * 8;
-      ldsm_x4_t(ds_s + (uint32_t)(key * DS_STRIDE + qcol) * 2, a0, a1, a2, a3);
-      const int krow = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      ldsm_x4_t(k_s + tile_off(krow, lane >> 4), b0, b1, b2, b3);
-      mma16816(dq[0], a0, a1, a2, a3, b0, b1);
-      if (DH == 16) mma16816(dq[1], a0, a1, a2, a3, b2, b3);
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int n = 0; n < 2; ++n) dq[e][n][0] = dq[e][n][1] = dq[e][n][2] = dq[e][n][3] = 0.f;
+    for (int j = 0; j < nb; j += 2) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (j + e < nb) {
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          const int key = (j + e) * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int qcol = i * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4_t(ds_s + (uint32_t)(key * DS_STRIDE + qcol) * 2, a0, a1, a2, a3);
+          const int krow = (j + e) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          ldsm_x4_t(k_s + tile_off(krow, lane >> 4), b0, b1, b2, b3);
+          mma16816(dq[e][0], a0, a1, a2, a3, b0, b1);
+          if (DH == 16) mma16816(dq[e][1], a0, a1, a2, a3, b2, b3);
+        }
+      }
     }
     const int r0 = i * 16 + (lane >> 2), r1 = r0 + 8;
     __half* q0 = dqkv + ((long long)b * L + r0) * ldd + h * DH + (lane & 3) * 2;
     __half* q1 = dqkv + ((long long)b * L + r1) * ldd + h * DH + (lane & 3) * 2;
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) {
-      *reinterpret_cast<__half2*>(q0 + n * 8) = __floats2half2_rn(dq[n][0] * scale, dq[n][1] * scale);
-      *reinterpret_cast<__half2*>(q1 + n * 8) = __floats2half2_rn(dq[n][2] * scale, dq[n][3] * scale);
+      *reinterpret_cast<__half2*>(q0 + n * 8) = __floats2half2_rn((dq[0][n][0] + dq[1][n][0]) * scale, (dq[0][n][1] + dq[1][n][1]) * scale);
+      *reinterpret_cast<__half2*>(q1 + n * 8) = __floats2half2_rn((dq[0][n][2] + dq[1][n][2]) * scale, (dq[0][n][3] + dq[1][n][3]) * scale);
     }
   }
 }
@@ -408,7 +435,7 @@ static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __hal
   {                                                                                                                      \
     static bool set = false;                                                                                             \
     if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
-    mha_bwd_kernel<DHV, MODEV><<<B * H, 256, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn);    \
+    mha_bwd_kernel<DHV, MODEV><<<B * H, (L >= 256 ? 512 : 256), smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn);    \
   }
   if (mode == 0) { if (DH == 16) LPM_MHA_BWD(16, 0) else LPM_MHA_BWD(8, 0) }
   else if (mode == 1) LPM_MHA_BWD(16, 1)

@@ -86,6 +86,14 @@ int adam_clip_step(float* p, const float* g, float* m, float* v, const int* tabl
                    const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2, float eps,
                    float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
 
+int rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor, float* norm,
+                   int* flag, cudaStream_t st);
+int rank_adam_step(const __half* a16, long long lda, const __half* g16, long long ldg, int R, long long Kd, int N,
+                   float alpha, const float* factor, const int* flag, float* w, float* m, float* v, __half* w16,
+                   long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st);
+size_t rank_adam_workspace_bytes(int R, int N);
+
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const float* centers,

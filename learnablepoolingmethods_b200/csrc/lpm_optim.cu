@@ -10,6 +10,16 @@
 
 namespace lpm {
 
+// p -= lr_t * m / (sqrt(v) + eps) with the approximate MUFU forms (sqrt.approx / rcp.approx, <= 2 ulp each):
+// the update is ~1e-4 of |p|, so the difference from the IEEE sequences is far below one ulp of the parameter,
+// and the dependent-instruction chain per element drops from ~20 to 4.
+__device__ __forceinline__ float adam_update(float m, float v, float lr_t, float eps) {
+  float s, r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s + eps));
+  return lr_t * m * r;
+}
+
 // chunk table entry: {tensor id, start offset / 32, length, element offset inside the tensor / 32}
 __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const float* __restrict__ g, const float* __restrict__ p,
                                                         const int* __restrict__ table, const float* __restrict__ wd,
@@ -89,8 +99,8 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(float* __restrict__ p, con
     mj.z = b1 * mj.z + (1.f - b1) * gz; mj.w = b1 * mj.w + (1.f - b1) * gw;
     vj.x = b2 * vj.x + (1.f - b2) * gx * gx; vj.y = b2 * vj.y + (1.f - b2) * gy * gy;
     vj.z = b2 * vj.z + (1.f - b2) * gz * gz; vj.w = b2 * vj.w + (1.f - b2) * gw * gw;
-    pj.x -= lr_t * mj.x / (sqrtf(vj.x) + eps); pj.y -= lr_t * mj.y / (sqrtf(vj.y) + eps);
-    pj.z -= lr_t * mj.z / (sqrtf(vj.z) + eps); pj.w -= lr_t * mj.w / (sqrtf(vj.w) + eps);
+    pj.x -= adam_update(mj.x, vj.x, lr_t, eps); pj.y -= adam_update(mj.y, vj.y, lr_t, eps);
+    pj.z -= adam_update(mj.z, vj.z, lr_t, eps); pj.w -= adam_update(mj.w, vj.w, lr_t, eps);
     m4[i] = mj; v4[i] = vj; p4[i] = pj;
     if (sdst) {
       const long long e = eoff + 4ll * i;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(float* __restrict__ p, con
     const float gj = (g[j] + w * pj) * f;
     const float mj = b1 * m[j] + (1.f - b1) * gj;
     const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
-    const float pn = pj - lr_t * mj / (sqrtf(vj) + eps);
+    const float pn = pj - adam_update(mj, vj, lr_t, eps);
     m[j] = mj; v[j] = vj; p[j] = pn;
     if (sdst) {
       const long long e = eoff + i;
@@ -115,6 +125,265 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(float* __restrict__ p, con
       sdst[r * ld + (e - r * cols)] = __float2half_rn(pn);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rank-R ("factored") weight-gradient Adam for the hidden projection (frame_level_models.py:2314-2319;
+// train.py:321-336).  The gradient of W[Kd][N] is the rank-R product dW = alpha * A^T G with A = the layer
+// input [R][Kd] (the VLAD descriptor) and G = the output gradient [R][N], R = tower batch.  W is 138 M
+// parameters at config 1, so writing dW (4 B/param), re-reading it for the clip norm and again for Adam
+// is 1.7 GB of HBM traffic per step.  Instead:
+//   * the clip norm comes from two R x R Gram matrices:  ||A^T G||_F^2 = sum_ij (A A^T)_ij (G G^T)_ij
+//   * this kernel recomputes each 128 x N panel of dW on the warp-level tensor path (K = R <= 128: the
+//     product is 2 % of the kernel's time, the rest is the m/v/w stream) and applies clip + Adam +
+//     fp16-shadow refresh in registers.  dW never exists in memory.
+// Column permutation: four m16n8 accumulator tiles are interleaved so that a thread owns two runs of 4 consecutive
+// columns of a row and every 16-byte access of a quad lands in one fully used 64-byte run.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ra_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ra_mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int RA_ROWS = 64;         // rows of W per panel (four 16-row blocks)
+constexpr int RA_MAX_KS = 8;        // R <= 128
+
+__device__ __forceinline__ void ra_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int bytes = valid ? 16 : 0;   // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ra_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ra_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// G [R][N] -> Gp [Rp][N] with the columns of every 32-column group in accumulator order (see rank_adam_kernel) and
+// zero rows beyond R.  Physical column p -> accumulator tile s = 2*(p/16) + (p%4)/2, column n = 2*((p%16)/4) + p%2:
+// a thread then owns columns 4t..4t+3 and 16+4t..16+4t+3 of its row, so every 16-byte access of a quad lands in one
+// contiguous, fully used 64-byte run.
+__global__ void __launch_bounds__(256) rank_permute_kernel(const __half* __restrict__ G, long long ldg, int R, int Rp, int N,
+                                                           __half* __restrict__ Gp) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= Rp * (N / 8)) return;
+  const int r = c / (N / 8), ch = c - r * (N / 8);        // physical columns ch*8 .. ch*8+7
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (r < R) val = __ldg(reinterpret_cast<const uint4*>(G + (long long)r * ldg + ch * 8));
+  const int q = ch >> 2, hi = (ch >> 1) & 1, c2 = ch & 1;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(Gp + (size_t)r * N + q * 32) + 8 * hi + 2 * c2;
+  dst[0] = val.x; dst[4] = val.y; dst[1] = val.z; dst[5] = val.w;
+}
+
+// Persistent: one CTA per SM walks the 64-row panels of W in 16-row blocks; within a block the warps take
+// interleaved 32-column groups, so the CTA streams one contiguous 16 x N block of w / m / v at a time.
+// Gp stays resident in shared memory; the A panel of the next iteration arrives by cp.async while the current one
+// is processed.  The kernel is bound by bytes in flight, not by arithmetic: saturating HBM with this read-modify-
+// write stream needs ~100 KB outstanding per SM, more than the register file can stage next to the MMA fragments.
+// So every thread owns a private 192-byte slot of shared memory into which the w / m / v pieces of its NEXT
+// (block, column group) item are copied asynchronously while it works on the current one.
+__global__ void __launch_bounds__(512, 1) rank_adam_kernel(const __half* __restrict__ A, long long lda,
+                                                           const __half* __restrict__ Gp, int R,
+                                                           long long Kd, int N, float alpha,
+                                                           const float* __restrict__ factor, const int* __restrict__ flag,
+                                                           float* __restrict__ w, float* __restrict__ m,
+                                                           float* __restrict__ v, __half* __restrict__ w16, long long ldw16,
+                                                           float lr_t, float b1, float b2, float eps) {
+  if (*flag) return;   // non-finite gradient norm somewhere: the whole step is skipped
+  extern __shared__ __align__(16) uint8_t ra_sm[];
+  const int Rp = (R + 15) & ~15;
+  const int gs = N + 8, as = RA_ROWS + 8;                 // padded row strides (halves): conflict-free ldmatrix
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
+  uint4* sSlot = reinterpret_cast<uint4*>(ra_sm);         // [12][nthr] 16-byte pieces (thread-private staging)
+  __half* sG = reinterpret_cast<__half*>(ra_sm + (size_t)12 * nthr * 16);   // [Rp][gs], accumulator column order
+  __half* sAbuf = sG + (size_t)Rp * gs;                   // 2 x [Rp][as]
+  const int npanels = (int)((Kd + RA_ROWS - 1) / RA_ROWS);
+  const int nq = N / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nks = Rp / 16;
+  const int j = lane >> 3, i = lane & 7;
+  const int g = lane >> 2, t = lane & 3;
+  auto stage_a = [&](int panel, int buf) {
+    const long long r0 = (long long)panel * RA_ROWS;
+    __half* dst = sAbuf + (size_t)buf * Rp * as;
+    for (int c = threadIdx.x; c < Rp * (RA_ROWS / 8); c += nthr) {
+      const int r = c / (RA_ROWS / 8), ch = c - r * (RA_ROWS / 8);
+      const bool ok = r < R && r0 + ch * 8 < Kd;
+      ra_cp_async16(dst + (size_t)r * as + ch * 8, ok ? A + (long long)r * lda + r0 + ch * 8 : A, ok);
+    }
+  };
+  // this thread's pieces of item (panel, sb, q): rows r_lo / r_lo + 8, columns q*32 + 4t (+16), of w, m, v
+  auto prefetch_item = [&](int panel, int sb, int q) {
+    const long long r_lo = (long long)panel * RA_ROWS + sb * 16 + g;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long r = r_lo + 8 * h;
+      const long long off = (r < Kd ? r : r_lo) * N + q * 32 + t * 4;
+      ra_cp_async16(&sSlot[(h * 6 + 0) * nthr + threadIdx.x], w + off, true);
+      ra_cp_async16(&sSlot[(h * 6 + 1) * nthr + threadIdx.x], w + off + 16, true);
+      ra_cp_async16(&sSlot[(h * 6 + 2) * nthr + threadIdx.x], m + off, true);
+      ra_cp_async16(&sSlot[(h * 6 + 3) * nthr + threadIdx.x], m + off + 16, true);
+      ra_cp_async16(&sSlot[(h * 6 + 4) * nthr + threadIdx.x], v + off, true);
+      ra_cp_async16(&sSlot[(h * 6 + 5) * nthr + threadIdx.x], v + off + 16, true);
+    }
+  };
+  for (int c = threadIdx.x; c < Rp * (N / 8); c += nthr) {
+    const int r = c / (N / 8), ch = c - r * (N / 8);
+    ra_cp_async16(sG + (size_t)r * gs + ch * 8, Gp + (size_t)r * N + ch * 8, true);
+  }
+  if ((int)blockIdx.x < npanels) {
+    stage_a(blockIdx.x, 0);
+    if (warp < nq) prefetch_item(blockIdx.x, 0, warp);
+  }
+  ra_cp_commit();
+  const float f = alpha * factor[0];
+  int buf = 0;
+  for (int panel = blockIdx.x; panel < npanels; panel += gridDim.x, buf ^= 1) {
+    ra_cp_wait<0>();
+    __syncthreads();          // sG / sA[buf] complete for everyone; every warp has left sA[buf ^ 1]
+    const bool more_panels = panel + (int)gridDim.x < npanels;
+    if (more_panels) stage_a(panel + gridDim.x, buf ^ 1);   // committed with the first item's prefetch group
+    const __half* sA = sAbuf + (size_t)buf * Rp * as;
+    const long long row0 = (long long)panel * RA_ROWS;
+    int nsb = RA_ROWS / 16;
+    if (row0 + RA_ROWS > Kd) nsb = (int)((Kd - row0 + 15) / 16);
+    for (int sb = 0; sb < nsb; ++sb) {
+      const long long r_lo = row0 + sb * 16 + g;
+      for (int q = warp; q < nq; q += nwarps) {
+        // ---- this item's w / m / v pieces: private slot -> registers -----------------------------------------
+        ra_cp_wait<0>();
+        uint4 pc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pc[k] = sSlot[k * nthr + threadIdx.x];
+        // ---- next item's pieces -> private slot (asynchronous, lands while this item is processed) -----------
+        {
+          int qn = q + nwarps, sbn = sb, pn = panel;
+          if (qn >= nq) { qn = warp; if (++sbn == nsb) { sbn = 0; pn = panel + gridDim.x; } }
+          if (pn < npanels) prefetch_item(pn, sbn, qn);
+          ra_cp_commit();
+        }
+        // ---- gradient tile on the tensor cores -----------------------------------------------------------------
+        float acc[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < RA_MAX_KS; ++ks) {
+          if (ks < nks) {
+            uint32_t af[4];
+            const __half* asrc = sA + (size_t)(ks * 16 + (j >> 1) * 8 + i) * as + sb * 16 + (j & 1) * 8;
+            ra_ldsm_x4_t(smem_u32(asrc), af[0], af[1], af[2], af[3]);
+#pragma unroll
+            for (int sp = 0; sp < 2; ++sp) {
+              uint32_t b0, b1, b2, b3;
+              const __half* src = sG + (size_t)(ks * 16 + (j & 1) * 8 + i) * gs + q * 32 + 8 * (2 * sp + (j >> 1));
+              ra_ldsm_x4_t(smem_u32(src), b0, b1, b2, b3);
+              ra_mma16816(acc[2 * sp], af, b0, b1);
+              ra_mma16816(acc[2 * sp + 1], af, b2, b3);
+            }
+          }
+        }
+        // ---- clip + Adam + fp16 shadow ------------------------------------------------------------------------
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long r = r_lo + 8 * h;
+          if (r >= Kd) continue;
+          const long long off = r * N + q * 32 + t * 4;
+          float gr[8];
+#pragma unroll
+          for (int s = 0; s < 4; ++s) { gr[2 * s] = acc[s][2 * h] * f; gr[2 * s + 1] = acc[s][2 * h + 1] * f; }
+          float* wv = reinterpret_cast<float*>(&pc[h * 6 + 0]);     // 8 consecutive floats: pieces 0,1 / 2,3 / 4,5
+          float* mv = reinterpret_cast<float*>(&pc[h * 6 + 2]);
+          float* vv = reinterpret_cast<float*>(&pc[h * 6 + 4]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            mv[e] = b1 * mv[e] + (1.f - b1) * gr[e];
+            vv[e] = b2 * vv[e] + (1.f - b2) * gr[e] * gr[e];
+            wv[e] -= adam_update(mv[e], vv[e], lr_t, eps);
+          }
+          *reinterpret_cast<uint4*>(m + off) = pc[h * 6 + 2];
+          *reinterpret_cast<uint4*>(m + off + 16) = pc[h * 6 + 3];
+          *reinterpret_cast<uint4*>(v + off) = pc[h * 6 + 4];
+          *reinterpret_cast<uint4*>(v + off + 16) = pc[h * 6 + 5];
+          *reinterpret_cast<uint4*>(w + off) = pc[h * 6 + 0];
+          *reinterpret_cast<uint4*>(w + off + 16) = pc[h * 6 + 1];
+          if (w16 != nullptr) {
+            __half* dst = w16 + r * ldw16 + q * 32 + t * 4;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_half2(wv[0], wv[1]), pack_half2(wv[2], wv[3]));
+            *reinterpret_cast<uint2*>(dst + 16) = make_uint2(pack_half2(wv[4], wv[5]), pack_half2(wv[6], wv[7]));
+          }
+        }
+      }
+    }
+  }
+  ra_cp_wait<0>();
+}
+
+// norm = alpha * sqrt(sum_ij GA_ij * GG_ij);  factor = clip / max(norm, clip)  (tf.clip_by_norm, utils.py:181-188)
+__global__ void __launch_bounds__(256) rank_grad_clip_kernel(const float* __restrict__ ga, const float* __restrict__ gg, int n,
+                                                             float alpha, float clip, float* __restrict__ factor,
+                                                             float* __restrict__ norm, int* __restrict__ flag) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)ga[i] * (double)gg[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int i = 0; i < 8; ++i) r += red[i];
+    const float nrm = alpha * (float)sqrt(r > 0.0 ? r : 0.0);
+    if (!isfinite(nrm) || !(r == r)) atomicExch(flag, 1);
+    norm[0] = nrm;
+    factor[0] = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;
+  }
+}
+
+int rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor, float* norm,
+                   int* flag, cudaStream_t st) {
+  rank_grad_clip_kernel<<<1, 256, 0, st>>>(gram_a, gram_g, R * R, alpha, clip, factor, norm, flag);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+static size_t rank_adam_smem(int R, int N) {
+  const int Rp = (R + 15) & ~15, nthr = N >= 512 ? 512 : 256;
+  return (size_t)12 * nthr * 16 + (size_t)Rp * (N + 8) * 2 + 2 * (size_t)Rp * (RA_ROWS + 8) * 2;
+}
+// 0 = this (rank, width) is not supported (the caller keeps the dense gradient path)
+size_t rank_adam_workspace_bytes(int R, int N) {
+  if (R < 1 || R > 16 * RA_MAX_KS || N < 32 || N % 32 != 0 || rank_adam_smem(R, N) > 226 * 1024) return 0;
+  return (size_t)((R + 15) & ~15) * N * 2;
+}
+
+int rank_adam_step(const __half* a16, long long lda, const __half* g16, long long ldg, int R, long long Kd, int N,
+                   float alpha, const float* factor, const int* flag, float* w, float* m, float* v, __half* w16,
+                   long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
+  LPM_REQUIRE(R >= 1 && R <= 16 * RA_MAX_KS, "rank_adam_step: rank (tower batch) must be in [1,%d] (got %d)", 16 * RA_MAX_KS, R);
+  LPM_REQUIRE(N % 32 == 0 && N >= 32, "rank_adam_step: output width must be a multiple of 32 (got %d)", N);
+  LPM_REQUIRE(lda % 8 == 0 && ldg % 8 == 0 && ldw16 % 8 == 0 && Kd % 8 == 0, "rank_adam_step: strides must be multiples of 8");
+  LPM_REQUIRE(rank_adam_workspace_bytes(R, N) > 0, "rank_adam_step: R=%d x N=%d does not fit in shared memory", R, N);
+  if (workspace == nullptr || workspace_bytes < rank_adam_workspace_bytes(R, N))
+    return fail(LPM_ERR_WORKSPACE, "rank_adam_step: workspace of %zu bytes required", rank_adam_workspace_bytes(R, N));
+  const int Rp = (R + 15) & ~15;
+  const int nthr = N >= 512 ? 512 : 256;
+  const size_t smem = rank_adam_smem(R, N);
+  static size_t attr = 0;
+  if (smem > attr) {
+    LPM_CUDA_CHECK(cudaFuncSetAttribute(rank_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  __half* gp = reinterpret_cast<__half*>(workspace);
+  rank_permute_kernel<<<(Rp * (N / 8) + 255) / 256, 256, 0, st>>>(g16, ldg, R, Rp, N, gp);
+  const int npanels = (int)((Kd + RA_ROWS - 1) / RA_ROWS);
+  const int grid = npanels < num_sms() ? npanels : num_sms();
+  rank_adam_kernel<<<grid, nthr, smem, st>>>(a16, lda, gp, R, Kd, N, alpha, factor, flag, w, m, v, w16, ldw16, lr_t, b1, b2, eps);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
 }
 
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,

@@ -454,8 +454,12 @@ class NetVladEngine:
         # ---- hidden projection (frame_level_models.py:2314-2334) --------------------------------
         put("hidden1_biases", ops.colsum(dact, alpha=inv))
         dact16 = ops.cast_scaled_f16(dact)
-        put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                        out=gout("hidden1_weights")))
+        if ctx.get("factored_hidden"):
+            # the trainer applies clip + Adam straight from the factors (dW = inv * vlad^T dact16 is never written)
+            ctx["hidden_factors"] = (hd["vlad"], dact16, inv)
+        else:
+            put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
+                                            out=gout("hidden1_weights")))
         dvlad = ops.gemm(dact16, sh["wh16"], b_mn=False)                      # [B, vlad_dim] fp16
         dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
         dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)

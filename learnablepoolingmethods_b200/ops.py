@@ -456,6 +456,48 @@ def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, cl
                                  stream_ptr()), "lpm_adam_clip_step")
 
 
+_WS = {}
+
+
+def _workspace(nbytes, dev):
+    """Caller-owned scratch for the C-ABI calls that ask for one (grown on demand, reused across steps)."""
+    t = _WS.get(dev)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WS[dev] = t
+    return t
+
+
+def rank_adam_supported(R, N) -> bool:
+    lib = _lib.load()
+    lib.lpm_rank_adam_workspace_bytes.restype = C.c_ulonglong
+    return int(lib.lpm_rank_adam_workspace_bytes(int(R), int(N))) > 0
+
+
+def rank_grad_clip(gram_a, gram_g, alpha, clip, factor, norm, flag):
+    """clip_by_norm factor of the rank-R gradient alpha*A^T G from the Gram matrices A A^T and G G^T."""
+    lib = _lib.load()
+    R = gram_a.shape[0]
+    assert gram_a.shape == gram_g.shape == (R, R) and gram_a.is_contiguous() and gram_g.is_contiguous()
+    check(lib.lpm_rank_grad_clip(ptr(gram_a), ptr(gram_g), R, C.c_float(alpha), C.c_float(clip), ptr(factor), ptr(norm),
+                                 ptr(flag), stream_ptr()), "lpm_rank_grad_clip")
+
+
+def rank_adam_step(a16, g16, alpha, factor, flag, w, m, v, w16, *, lr_t, b1=0.9, b2=0.999, eps=1e-8):
+    """Adam on w [Kd, N] (fp32, with moments m, v) for the never-materialised gradient alpha * a16^T g16."""
+    lib = _lib.load()
+    R, Kd = a16.shape
+    N = g16.shape[1]
+    assert g16.shape[0] == R and tuple(w.shape) == (Kd, N) and w.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    lib.lpm_rank_adam_workspace_bytes.restype = C.c_ulonglong
+    ws_bytes = int(lib.lpm_rank_adam_workspace_bytes(R, N))
+    ws = _workspace(ws_bytes, a16.device)
+    check(lib.lpm_rank_adam_step(ptr(a16), _ll(a16.stride(0)), ptr(g16), _ll(g16.stride(0)), R, _ll(Kd), N, C.c_float(alpha),
+                                 ptr(factor), ptr(flag), ptr(w), ptr(m), ptr(v), ptr(w16),
+                                 _ll(w16.stride(0) if w16 is not None else 0), C.c_float(lr_t), C.c_float(b1), C.c_float(b2),
+                                 C.c_float(eps), ptr(ws), C.c_ulonglong(ws_bytes), stream_ptr()), "lpm_rank_adam_step")
+
+
 # ------------------------------------------------------------------------------------------------
 # NetVladV2 helpers
 # ------------------------------------------------------------------------------------------------

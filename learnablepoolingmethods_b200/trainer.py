@@ -24,28 +24,38 @@ ALIGN = 32              # segment alignment inside the flat buffers (elements)
 class FlatState:
     """Parameters, gradients and Adam moments as views of four flat fp32 buffers (fixed addresses)."""
 
-    def __init__(self, store: VariableStore, order: List[str], wd: Dict[str, float]):
-        self.store, self.order = store, list(order)
+    def __init__(self, store: VariableStore, order: List[str], wd: Dict[str, float], factored=()):
+        """`factored`: variables updated by ops.rank_adam_step straight from their gradient factors.  They live at
+        the end of the parameter / moment buffers, have no gradient storage and no optimiser chunks."""
         tr = store.trainable()
-        missing = [n for n in tr if n not in self.order]
-        self.order += missing
+        self.factored = [n for n in factored if n in tr]
+        self.store, self.order = store, [n for n in order if n not in self.factored]
+        missing = [n for n in tr if n not in self.order and n not in self.factored]
+        self.order += missing + self.factored
         dev = store.device
-        offs, off = {}, 0
+        offs, off, g_total = {}, 0, 0
         for n in self.order:
             offs[n] = off
             off += (tr[n].numel() + ALIGN - 1) // ALIGN * ALIGN
-        self.total, self.offsets = off, offs
+            if n not in self.factored:
+                g_total = off
+        self.total, self.offsets, self.g_total = off, offs, g_total
         self.p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(g_total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad_views: Dict[str, torch.Tensor] = {}
+        self.moment_views: Dict[str, tuple] = {}
         table, chunk_begin = [], [0]
         for t, n in enumerate(self.order):
             numel, o = tr[n].numel(), offs[n]
             view = self.p[o:o + numel].view(tr[n].shape)
             view.copy_(tr[n])
             store.vars[n] = view                       # re-home the variable into the flat buffer
+            if n in self.factored:
+                self.moment_views[n] = (self.m[o:o + numel].view(tr[n].shape), self.v[o:o + numel].view(tr[n].shape))
+                chunk_begin.append(len(table))
+                continue
             self.grad_views[n] = self.g[o:o + numel].view(tr[n].shape)
             for c0 in range(0, numel, CHUNK):
                 table.append((t, (o + c0) // ALIGN, min(CHUNK, numel - c0), c0 // ALIGN))
@@ -94,6 +104,35 @@ class Trainer:
         self.flat: Optional[FlatState] = None
         self.bucket_elems = bucket_elems
         self.reducer: Optional[BucketedAllReduce] = None
+        self.rank_scratch = None
+
+    def _factored_hidden(self, batch: int) -> bool:
+        """hidden1_weights (85 % of the parameters) is updated from its gradient factors on a single tower: with
+        several towers the summed gradient is no longer rank-`batch` on this rank, so the dense all-reduce path
+        is kept (DESIGN.md, optimiser)."""
+        c = self.cfg
+        return (self.world == 1 and c.vlad_dim % 8 == 0 and not self.disable_factored_hidden
+                and ops.rank_adam_supported(batch, c.hidden_size))
+
+    disable_factored_hidden = False
+
+    def _factored_hidden_step(self, ctx, lr_t):
+        f = self.flat
+        vlad, dact16, inv = ctx["hidden_factors"]
+        R = vlad.shape[0]
+        a, g = vlad, dact16
+        if R % 8:                                    # tiny test batches: the Gram GEMMs want 16-byte rows
+            Rp = (R + 7) // 8 * 8
+            a = torch.zeros((Rp, vlad.shape[1]), dtype=vlad.dtype, device=vlad.device); a[:R] = vlad
+            g = torch.zeros((Rp, dact16.shape[1]), dtype=dact16.dtype, device=vlad.device); g[:R] = dact16
+        gram_a = ops.gemm(a, a, b_mn=False, out_dtype=torch.float32)
+        gram_g = ops.gemm(g, g, b_mn=False, out_dtype=torch.float32)
+        if self.rank_scratch is None:
+            self.rank_scratch = torch.zeros(2, dtype=torch.float32, device=vlad.device)
+        ops.rank_grad_clip(gram_a, gram_g, inv, self.clip, self.rank_scratch[0:1], self.rank_scratch[1:2], f.scratch[3])
+        return lambda: ops.rank_adam_step(vlad, dact16, inv, self.rank_scratch[0:1], f.scratch[3],
+                                          self.store.vars["hidden1_weights"], *f.moment_views["hidden1_weights"],
+                                          self.store.shadows["wh16"], lr_t=lr_t)
 
     # -- learning rate (train.py:244-249, tf.train.exponential_decay staircase) -------------------
     def learning_rate(self) -> float:
@@ -117,10 +156,12 @@ class Trainer:
         loss, _ = ops.xent_fwd(pred, labels_u8)
         dpred = ops.xent_bwd(pred, labels_u8, 1.0 / B)
         order: List[str] = []
+        factored = self._factored_hidden(B)
+        ctx["factored_hidden"] = factored
         if self.flat is None:
             ctx["grad_hook"] = lambda n, g: order.append(n)
             grads = eng.backward(ctx, dpred)
-            self.flat = FlatState(self.store, order, self._wd())
+            self.flat = FlatState(self.store, order, self._wd(), factored=("hidden1_weights",) if factored else ())
             self.flat.bind_shadows(eng)
             for n, g in grads.items():
                 self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
@@ -140,8 +181,13 @@ class Trainer:
         f = self.flat
         t = self.global_step + 1
         lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        if factored != bool(f.factored):
+            raise RuntimeError("the tower batch size changed across the factored-update limit after the first step")
+        hidden_update = self._factored_hidden_step(ctx, lr_t) if factored else None   # norm first: it may raise the skip flag
         ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=lr_t, scratch=f.scratch,
                            shadow=f.shadow)
+        if hidden_update is not None:
+            hidden_update()
         # the fp16 GEMM operands were refreshed by the Adam kernel; only the two odd layouts remain
         self.store.version += 1
         eng.refresh_small_shadows()

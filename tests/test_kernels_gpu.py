@@ -114,6 +114,26 @@ def test_mha_core_fwd(cuda, B, L, Dm, H):
     assert rel(out2.float(), ref2) < 2e-3
 
 
+@pytest.mark.parametrize("B,L,Dm,H", [(2, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (1, 80, 64, 4), (1, 240, 64, 4)])
+def test_mha_core_bwd(cuda, B, L, Dm, H):
+    """Backward of transformer_utils.py:563-581 against torch autograd (fp64) on the same fp16 inputs."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(7 * L + Dm + H)
+    qkv = torch.randn(B * L, 3 * Dm, generator=g).half()
+    dout = (torch.randn(B * L, Dm, generator=g) * 0.5).half()
+    dh = Dm // H
+    ref_in = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(B, L, H, dh).permute(0, 2, 1, 3) for t in ref_in.split(Dm, dim=1)]
+    out_ref = (torch.softmax((q * dh ** -0.5) @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
+    out_ref.backward(dout.double())
+    qg = qkv.to(cuda)
+    o, lse = ops.mha_core_fwd(qg, B, L, Dm, H, scale=dh ** -0.5, want_lse=True)
+    dqkv = ops.mha_core_bwd(qg, o, dout.to(cuda), lse, B, L, Dm, H, scale=dh ** -0.5)
+    for i, name in enumerate("qkv"):
+        e = rel(dqkv[:, i * Dm:(i + 1) * Dm].float(), ref_in.grad[:, i * Dm:(i + 1) * Dm])
+        assert e < 4e-3, (name, e)       # fp16 P / dS operands, fp32 accumulation
+
+
 def test_layernorm_joint(cuda):
     """tf.contrib.layers.layer_norm (begin_norm_axis=1) + residual (transformer_utils.py:406-407)."""
     from learnablepoolingmethods_b200 import ops
@@ -235,3 +255,44 @@ def test_mha_bn_logits_backward(cuda, B, L, Dm, H):
     print(f"\n[mha bn bwd L={L}] dqkv rel-L2 {e:.2e}, dgamma {rel(dgam, dgam_ref):.2e}")
     assert e < 1e-2
     assert rel(dgam, dgam_ref) < 1e-2
+
+
+@pytest.mark.parametrize("R,Kd,N", [(80, 2048 + 128, 512), (4, 384, 64), (20, 136, 96)])
+def test_rank_adam_step(cuda, R, Kd, N):
+    """Factored hidden-projection update (train.py:321-336 + utils.py:181-188 on hidden1_weights): clip factor from
+    the Gram matrices and Adam from the factors must equal the dense path dW = alpha*A^T G -> clip_by_norm -> Adam."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(R + Kd + N)
+    A = torch.randn(R, Kd, generator=g).half()
+    G = (torch.randn(R, N, generator=g) * 3).half()
+    w = torch.randn(Kd, N, generator=g) * 0.05
+    m, v = torch.randn(Kd, N, generator=g) * 1e-3, torch.rand(Kd, N, generator=g) * 1e-5
+    alpha, clip, lr_t, b1, b2, eps = 1.0 / 64, 1.0, 3e-4, 0.9, 0.999, 1e-8
+    dW = alpha * (A.double().t() @ G.double())
+    norm = float(dW.norm())
+    gr = dW * (clip / max(norm, clip))
+    m_ref = b1 * m.double() + (1 - b1) * gr
+    v_ref = b2 * v.double() + (1 - b2) * gr * gr
+    w_ref = w.double() - lr_t * m_ref / (v_ref.sqrt() + eps)
+    dev = cuda
+    Ad, Gd = A.to(dev), G.to(dev)
+    Rp = (R + 7) // 8 * 8
+    Ap, Gp = torch.zeros(Rp, Kd, dtype=torch.float16, device=dev), torch.zeros(Rp, N, dtype=torch.float16, device=dev)
+    Ap[:R], Gp[:R] = Ad, Gd
+    ga = ops.gemm(Ap, Ap, b_mn=False, out_dtype=torch.float32)
+    gg = ops.gemm(Gp, Gp, b_mn=False, out_dtype=torch.float32)
+    sc = torch.zeros(2, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.rank_grad_clip(ga, gg, alpha, clip, sc[0:1], sc[1:2], flag)
+    assert abs(float(sc[1]) - norm) / norm < 1e-4 and int(flag) == 0
+    wd, md, vd = w.to(dev), m.to(dev), v.to(dev)
+    w16 = torch.zeros(Kd, N, dtype=torch.float16, device=dev)
+    ops.rank_adam_step(Ad, Gd, alpha, sc[0:1], flag, wd, md, vd, w16, lr_t=lr_t, b1=b1, b2=b2, eps=eps)
+    assert rel(md, m_ref) < 1e-5 and rel(vd, v_ref) < 1e-5
+    assert float((wd.double().cpu() - w_ref).abs().max()) < 1e-6
+    assert torch.equal(w16.cpu(), wd.cpu().half())
+    # a raised flag (loss-scale overflow elsewhere) skips the update
+    flag.fill_(1)
+    before = wd.clone()
+    ops.rank_adam_step(Ad, Gd, alpha, sc[0:1], flag, wd, md, vd, w16, lr_t=lr_t)
+    assert torch.equal(before, wd)
