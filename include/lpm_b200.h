@@ -154,6 +154,19 @@ int lpm_layernorm_joint_fwd(void* a, const void* b, const float* b_row_scale, vo
                             float eps, void* y, long long y_stride, float* partial, float* save_mean_rstd,
                             lpm_stream_t stream);
 
+/* One-pass variant for one or two chained joint-axis layer norms sharing the residual b (the tail of the encoder
+ * block, transformer_utils.py:712-713 then :410-411):
+ *   u1 = a + b*b_row_scale ; y1 = LN(u1; gamma1, beta1) ; [u2 = y1 + b ; y2 = LN(u2; gamma2, beta2)]
+ * A thread-block cluster owns a sample, keeps u in shared memory and exchanges the moments over DSMEM, so a and b
+ * are read once and y (= y2 when gamma2 is given, else y1) written once.  u1_out / u2_out (fp16, may be NULL; u1_out
+ * may alias a) and stats1 / stats2 ([B][2] = mean, rstd; may be NULL) are what the backward needs.
+ * lpm_layernorm_chain_supported: 1 when a sample of rows x D fits the cluster's shared memory. */
+int lpm_layernorm_chain_supported(int rows, int D);
+int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,
+                            int B, int rows, int D, float eps, const float* gamma1, const float* beta1, void* u1_out,
+                            long long u1_stride, float* stats1, const float* gamma2, const float* beta2, void* u2_out,
+                            long long u2_stride, float* stats2, void* y, long long y_stride, lpm_stream_t stream);
+
 /* Context gating (frame_level_models.py:2342-2368): act * sigmoid(BN_batch(g - diag*act)). */
 int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
                    const float* beta, float* moving_mean, float* moving_var, float decay, float eps,

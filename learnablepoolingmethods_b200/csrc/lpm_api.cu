@@ -331,6 +331,18 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                         factor, norms, flag, ST(stream));
 }
 
+int lpm_layernorm_chain_supported(int rows, int D) { return layernorm_chain_supported(rows, D); }
+
+int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,
+                            int B, int rows, int D, float eps, const float* gamma1, const float* beta1, void* u1_out,
+                            long long u1_stride, float* stats1, const float* gamma2, const float* beta2, void* u2_out,
+                            long long u2_stride, float* stats2, void* y, long long y_stride, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(a && b && y && gamma1 && beta1 && B > 0, "lpm_layernorm_chain_fwd: bad arguments");
+  return layernorm_chain_fwd(CH16(a), a_stride, CH16(b), b_stride, b_row_scale, B, rows, D, eps, gamma1, beta1, H16(u1_out),
+                             u1_stride, stats1, gamma2, beta2, H16(u2_out), u2_stride, stats2, H16(y), y_stride, ST(stream));
+}
+
 int lpm_rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor,
                        float* norm, int* flag, lpm_stream_t stream) {
   DEVCHK();

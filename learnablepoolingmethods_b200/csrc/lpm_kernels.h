@@ -94,6 +94,13 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
                    cudaStream_t st);
 size_t rank_adam_workspace_bytes(int R, int N);
 
+// lpm_layernorm.cu
+int layernorm_chain_supported(int rows, int D);
+int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, long long b_stride, const float* b_row_scale,
+                        int B, int rows, int D, float eps, const float* gamma1, const float* beta1, __half* u1_out,
+                        long long u1_stride, float* stats1, const float* gamma2, const float* beta2, __half* u2_out,
+                        long long u2_stride, float* stats2, __half* y, long long y_stride, cudaStream_t st);
+
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const float* centers,

@@ -294,20 +294,27 @@ class NetVladEngine:
             h1, st1 = h1
         f1 = ops.gemm(h1.view(B * K, D), sh[a + "/w1_16"], bias=v[f"{a}/filter_output{sid}/bias"], relu=True)
         f2 = ops.gemm(f1, sh[a + "/w2_16"], bias=v[f"{a}/ff_output{sid}/bias"], relu=True)
-        u2 = torch.empty_like(f2) if save else f2
-        h2 = ops.layernorm_joint_fwd(f2, h1, None, B, K, D, v[a + "/LayerNorm_1/gamma"], v[a + "/LayerNorm_1/beta"],
-                                     save=save, u_out=u2)
-        st2 = None
-        if save:
-            h2, st2 = h2
-        r3 = ops.layernorm_joint_fwd(h2, h1, None, B, K, D, v[a + "/LayerNorm_2/gamma"], v[a + "/LayerNorm_2/beta"],
-                                     out=out_view, out_stride=out_view.stride(0), save=save)
+        la, lb = a + "/LayerNorm_1", a + "/LayerNorm_2"
+        if ops.layernorm_chain_supported(K, D):
+            # LN(f2 + h1) (FeedForwardNetwork, :712-713) and LN(. + h1) (TransformerEncoder, :410-411) in one pass
+            rc = ops.layernorm_chain_fwd(f2, h1, B, K, D, v[la + "/gamma"], v[la + "/beta"], v[lb + "/gamma"], v[lb + "/beta"],
+                                         out=out_view, out_stride=out_view.stride(0), save=save)
+            u2, st2, h2, st3 = (rc[1], rc[2], rc[3], rc[4]) if save else (None, None, None, None)
+        else:
+            u2 = torch.empty_like(f2) if save else f2
+            h2 = ops.layernorm_joint_fwd(f2, h1, None, B, K, D, v[la + "/gamma"], v[la + "/beta"], save=save, u_out=u2)
+            st2 = None
+            if save:
+                h2, st2 = h2
+            r3 = ops.layernorm_joint_fwd(h2, h1, None, B, K, D, v[lb + "/gamma"], v[lb + "/beta"],
+                                         out=out_view, out_stride=out_view.stride(0), save=save)
+            st3 = r3[1] if save else None
         if want_inter:
             ctx["inter"]["att_" + name] = out_view.float().reshape(B, K, D)
         if save:
             m.update(dict(X=X, z=z, rscale=rscale, a_sum=a_sum, assign=assign, cluster_bn_stats=r[2], lscale=lscale,
                           zn=zn, qkv=qkv, o=o, lse=lse, u1=att, st1=st1, h1=h1, f1=f1, f2=f2, u2=u2, st2=st2,
-                          u3=h2, st3=r3[1]))
+                          u3=h2, st3=st3))
         return m
 
     def _v2_modality(self, name, X, B, T, D, K, training, save, out_view, ctx, want_inter, dropout_mask):

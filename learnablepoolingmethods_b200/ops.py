@@ -255,19 +255,51 @@ def scale_rows_f16(x, rs):
 
 def layernorm_joint_fwd(a, b, b_row_scale, B, rows, D, gamma, beta, *, out=None, out_stride=None, save=False,
                         eps=LN_EPS, u_out=None):
-    """u = a + b*row_scale (stored over a); returns y = LN_joint(u) (fp16) [, (mean, rstd) [B,2]]."""
+    """u = a + b*row_scale (stored over a, or into u_out); returns y = LN_joint(u) (fp16) [, (mean, rstd) [B,2]]."""
     lib = _lib.load()
     dev = a.device
     if out is None:
         out = _f16((B, rows, D), dev)
         out_stride = rows * D
-    partial = _f32((B, 64), dev)
     sm = _f32((B, 2), dev) if save else None
+    import os
+    if b is not None and lib.lpm_layernorm_chain_supported(rows, D) and not os.environ.get("LPM_NO_LN_FUSED"):
+        # one pass: a thread-block cluster per sample, u kept in shared memory, moments over DSMEM
+        u_dst = (u_out if u_out is not None else a) if save or u_out is not None else None
+        check(lib.lpm_layernorm_chain_fwd(ptr(a), _ll(rows * D), ptr(b), _ll(rows * D), ptr(b_row_scale), B, rows, D,
+                                          C.c_float(eps), ptr(gamma), ptr(beta), ptr(u_dst), _ll(rows * D), ptr(sm),
+                                          None, None, None, _ll(0), None, ptr(out), _ll(out_stride), stream_ptr()),
+              "lpm_layernorm_chain_fwd")
+        return (out, sm) if save else out
+    partial = _f32((B, 64), dev)
     check(lib.lpm_layernorm_joint_fwd(ptr(a), ptr(b), ptr(b_row_scale), ptr(u_out), B, rows, D, C.c_longlong(rows * D),
                                       C.c_longlong(rows * D), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out),
                                       C.c_longlong(out_stride), ptr(partial), ptr(sm), stream_ptr()),
           "lpm_layernorm_joint_fwd")
     return (out, sm) if save else out
+
+
+def layernorm_chain_supported(rows, D) -> bool:
+    import os
+    if os.environ.get("LPM_NO_LN_CHAIN"):
+        return False
+    return bool(_lib.load().lpm_layernorm_chain_supported(int(rows), int(D)))
+
+
+def layernorm_chain_fwd(a, b, B, rows, D, gamma1, beta1, gamma2, beta2, *, out, out_stride, save=False, eps=LN_EPS):
+    """y = LN(LN(a + b; gamma1, beta1) + b; gamma2, beta2) in one pass (transformer_utils.py:712-713 + :410-411).
+    save=True also returns (u1, stats1, u2, stats2) for the backward; a is left untouched."""
+    lib = _lib.load()
+    dev = a.device
+    u1 = _f16((B, rows, D), dev) if save else None
+    u2 = _f16((B, rows, D), dev) if save else None
+    s1 = _f32((B, 2), dev) if save else None
+    s2 = _f32((B, 2), dev) if save else None
+    check(lib.lpm_layernorm_chain_fwd(ptr(a), _ll(rows * D), ptr(b), _ll(rows * D), None, B, rows, D, C.c_float(eps),
+                                      ptr(gamma1), ptr(beta1), ptr(u1), _ll(rows * D), ptr(s1), ptr(gamma2), ptr(beta2),
+                                      ptr(u2), _ll(rows * D), ptr(s2), ptr(out), _ll(out_stride), stream_ptr()),
+          "lpm_layernorm_chain_fwd")
+    return (out, u1, s1, u2, s2) if save else out
 
 
 def gating_fwd(act, g, gamma, beta, moving_mean, moving_var, *, training, wg_diag=None, save=False,

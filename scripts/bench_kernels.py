@@ -57,3 +57,13 @@ if "adam" in which:
     print(f"rank_adam_step {us:8.1f} us  ({gb / us * 1e6:6.0f} GB/s of {gb:.2f} GB algorithmic)")
     us = t(lambda: (ops.gemm(A, A, b_mn=False, out_dtype=torch.float32), ops.gemm(G, G, b_mn=False, out_dtype=torch.float32)), iters=5)
     print(f"gram GEMMs     {us:8.1f} us")
+if "ln" in which:
+    a = torch.randn(B, L, D, device=dev).half(); b = torch.randn(B, L, D, device=dev).half()
+    gm, bt = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    out = torch.empty(B, L * D, dtype=torch.float16, device=dev)
+    us = t(lambda: ops.layernorm_joint_fwd(a, b, None, B, L, D, gm, bt, out=out, out_stride=L * D))
+    print(f"ln single (infer)  {us:8.1f} us  ({3 * a.numel() * 2 / us / 1e3:6.0f} GB/s algorithmic)")
+    us = t(lambda: ops.layernorm_chain_fwd(a, b, B, L, D, gm, bt, gm, bt, out=out, out_stride=L * D))
+    print(f"ln chain  (infer)  {us:8.1f} us  ({3 * a.numel() * 2 / us / 1e3:6.0f} GB/s algorithmic)")
+    us = t(lambda: ops.layernorm_chain_fwd(a, b, B, L, D, gm, bt, gm, bt, out=out, out_stride=L * D, save=True))
+    print(f"ln chain  (train)  {us:8.1f} us  ({5 * a.numel() * 2 / us / 1e3:6.0f} GB/s algorithmic)")

@@ -158,6 +158,40 @@ def test_layernorm_joint(cuda):
     assert float(out[:, :R * D].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B,R,D,save", [(3, 256, 1024, True), (2, 256, 1024, False), (3, 64, 512, True), (2, 64, 128, True),
+                                        (2, 8, 1024, False), (2, 2, 128, True), (1, 512, 1024, True)])
+def test_layernorm_chain(cuda, B, R, D, save):
+    """One-pass cluster kernel for LN(LN(f + h1) + h1) (transformer_utils.py:712-713 + :410-411), every cluster size
+    (1..8 CTAs per sample), against the oracle's layer norm applied twice."""
+    from learnablepoolingmethods_b200 import ops
+    from oracle import netvlad_oracle as O
+    assert ops.layernorm_chain_supported(R, D)
+    g = torch.Generator().manual_seed(R + D)
+    a, b = torch.randn(B, R, D, generator=g).half(), torch.randn(B, R, D, generator=g).half()
+    P = {"l1/gamma": torch.rand(D, generator=g) + 0.5, "l1/beta": torch.randn(D, generator=g) * 0.3,
+         "l2/gamma": torch.rand(D, generator=g) + 0.5, "l2/beta": torch.randn(D, generator=g) * 0.3}
+    u1 = a.float() + b.float()
+    y1 = O.layer_norm_joint(u1, P, "l1")
+    u2 = y1 + b.float()
+    ref = O.layer_norm_joint(u2, P, "l2")
+    dev = cuda
+    out = torch.zeros(B, 2 * R * D, dtype=torch.float16, device=dev)
+    ad = a.to(dev)
+    r = ops.layernorm_chain_fwd(ad, b.to(dev), B, R, D, P["l1/gamma"].to(dev), P["l1/beta"].to(dev), P["l2/gamma"].to(dev),
+                                P["l2/beta"].to(dev), out=out[:, R * D:], out_stride=2 * R * D, save=save)
+    y = out[:, R * D:].float().reshape(B, R, D)
+    assert rel(y, ref) < 2e-3
+    assert float(out[:, :R * D].abs().max()) == 0.0
+    assert torch.equal(ad.cpu(), a)                     # the first operand is preserved (it is the ReLU mask of the backward)
+    if save:
+        _, g1, s1, g2, s2 = r
+        assert rel(g1.float(), u1) < 1e-3 and rel(g2.float(), u2) < 2e-3
+        m1, v1 = u1.reshape(B, -1).mean(1), u1.reshape(B, -1).var(1, unbiased=False)
+        m2, v2 = u2.reshape(B, -1).mean(1), u2.reshape(B, -1).var(1, unbiased=False)
+        assert float((s1[:, 0].cpu() - m1).abs().max()) < 2e-3 and rel(s1[:, 1], (v1 + 1e-12).rsqrt()) < 2e-3
+        assert float((s2[:, 0].cpu() - m2).abs().max()) < 2e-3 and rel(s2[:, 1], (v2 + 1e-12).rsqrt()) < 2e-3
+
+
 def test_head_kernels(cuda):
     """Context gating (frame_level_models.py:2342-2368), MoE mix (video_level_models.py:116-126), xent (losses.py:44-51)."""
     from learnablepoolingmethods_b200 import ops
