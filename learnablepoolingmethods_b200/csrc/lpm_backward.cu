@@ -80,22 +80,30 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   for (long long r = r0; r < r1; ++r) s += to_f<T>(x[r * ld + c]);
   partial[(size_t)blockIdx.y * cols + c] = s;
 }
-// 32 columns x 8 partial-row lanes per block: the partial rows are summed in parallel, then across lanes
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int chunks,
-                                                           long long pstride, int cols, float alpha, int accumulate,
-                                                           float* __restrict__ out) {
-  __shared__ double red[8][33];
+// 32 columns x 32 partial-row lanes per block: the partial rows are summed in parallel (four independent loads in
+// flight per thread: these reductions are pure load latency), then across lanes
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial, int chunks,
+                                                            long long pstride, int cols, float alpha, int accumulate,
+                                                            float* __restrict__ out) {
+  __shared__ double red[32][33];
   const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   double s = 0.0;
-  if (c < cols)
-    for (int k = ky; k < chunks; k += 8) s += partial[(size_t)k * pstride + c];
+  if (c < cols) {
+    int k = ky;
+    for (; k + 96 < chunks; k += 128) {
+      const float v0 = partial[(size_t)k * pstride + c], v1 = partial[(size_t)(k + 32) * pstride + c];
+      const float v2 = partial[(size_t)(k + 64) * pstride + c], v3 = partial[(size_t)(k + 96) * pstride + c];
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; k < chunks; k += 32) s += partial[(size_t)k * pstride + c];
+  }
   red[ky][cx] = s;
   __syncthreads();
   if (ky == 0 && c < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    for (int k = 0; k < 32; ++k) t += red[k][cx];
     const float r = (float)(t * alpha);
     out[c] = accumulate ? out[c] + r : r;
   }
@@ -104,29 +112,44 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 // Context gating backward (frame_level_models.py:2342-2368): out = act * sigmoid(BN_batch(g))
 //   dact (direct path, fp32, still scaled), dg (fp16, scaled), dgamma / dbeta (unscaled)
+// 32 hidden units x 32 batch lanes per block.
 // ------------------------------------------------------------------------------------------------
-__global__ void gating_bwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
+__global__ void __launch_bounds__(1024) gating_bwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                   const float* __restrict__ dout, float inv_scale, float* __restrict__ dact,
                                   __half* __restrict__ dg, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
-  const float mu = mean[c], rs = rstd[c], ga = gamma[c], be = beta[c];
+  __shared__ double red[2][32][33];
+  __shared__ float sm[2][32];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < H;
+  const float mu = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f, ga = ok ? gamma[c] : 0.f, be = ok ? beta[c] : 0.f;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const float xh = (g[(size_t)b * H + c] - mu) * rs;
-    const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
-    const float a = act[(size_t)b * H + c], d = dout[(size_t)b * H + c];
-    const float dv = d * a * sg * (1.f - sg);
-    dact[(size_t)b * H + c] = d * sg;
-    s1 += dv;
-    s2 += (double)dv * xh;
+  if (ok)
+    for (int b = ky; b < B; b += 32) {
+      const float xh = (g[(size_t)b * H + c] - mu) * rs;
+      const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
+      const float a = act[(size_t)b * H + c], d = dout[(size_t)b * H + c];
+      const float dv = d * a * sg * (1.f - sg);
+      dact[(size_t)b * H + c] = d * sg;
+      s1 += dv;
+      s2 += (double)dv * xh;
+    }
+  red[0][ky][cx] = s1; red[1][ky][cx] = s2;
+  __syncthreads();
+  if (ky == 0 && ok) {
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { t1 += red[0][k][cx]; t2 += red[1][k][cx]; }
+    dgamma[c] = (float)t2 * inv_scale;
+    dbeta[c] = (float)t1 * inv_scale;
+    sm[0][cx] = (float)(t1 / B); sm[1][cx] = (float)(t2 / B);
   }
-  dgamma[c] = (float)s2 * inv_scale;
-  dbeta[c] = (float)s1 * inv_scale;
-  const float m1 = (float)(s1 / B), m2 = (float)(s2 / B);
-  for (int b = 0; b < B; ++b) {
+  __syncthreads();
+  if (!ok) return;
+  const float m1 = sm[0][cx], m2 = sm[1][cx];
+  for (int b = ky; b < B; b += 32) {
     const float xh = (g[(size_t)b * H + c] - mu) * rs;
     const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
     const float dv = dout[(size_t)b * H + c] * act[(size_t)b * H + c] * sg * (1.f - sg);
@@ -461,14 +484,14 @@ int colsum(const void* x, int is_f32, long long ld, long long rows, int cols, fl
   dim3 grid((cols + 255) / 256, chunks);
   if (is_f32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), ld, rows, cols, partial);
   else colsum_partial_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), ld, rows, cols, partial);
-  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, chunks, cols, cols, alpha, accumulate, out);
+  colsum_final_kernel<<<(cols + 31) / 32, 1024, 0, st>>>(partial, chunks, cols, cols, alpha, accumulate, out);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
 int colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
                  float* out, cudaStream_t st) {
-  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, chunks, pstride, cols, alpha, accumulate, out);
+  colsum_final_kernel<<<(cols + 31) / 32, 1024, 0, st>>>(partial, chunks, pstride, cols, alpha, accumulate, out);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -476,7 +499,7 @@ int colsum_final(const float* partial, int chunks, long long pstride, int cols, 
 int gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
                const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact, __half* dg,
                float* dgamma, float* dbeta, cudaStream_t st) {
-  gating_bwd_kernel<<<(H + 63) / 64, 64, 0, st>>>(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, dg,
+  gating_bwd_kernel<<<(H + 31) / 32, 1024, 0, st>>>(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, dg,
                                                   dgamma, dbeta);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;

@@ -97,23 +97,31 @@ __global__ void __launch_bounds__(256) sample_apply_kernel(const float* __restri
 // statistics update (decay 0.999; Bessel-corrected variance when `bessel`).  Inference: affine from
 // the moving statistics.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq,
                                                           int P, long long pstride, int C, double count,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                                           float decay, float eps, int bessel, int training,
                                                           float* __restrict__ scale, float* __restrict__ shift,
                                                           float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-  // 32 channels x 8 partial-row lanes per block
-  __shared__ double red[2][8][33];
+  // 32 channels x 32 partial-row lanes per block (the reduction is pure load latency: keep many loads in flight)
+  __shared__ double red[2][32][33];
   const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   double s = 0.0, q = 0.0;
-  if (training && c < C)
-    for (int p = ky; p < P; p += 8) {
+  if (training && c < C) {
+    int p = ky;
+    for (; p + 32 < P; p += 64) {
+      const float s0 = psum[(size_t)p * pstride + c], s1 = psum[(size_t)(p + 32) * pstride + c];
+      const float q0 = psq[(size_t)p * pstride + c], q1 = psq[(size_t)(p + 32) * pstride + c];
+      s += (double)s0 + (double)s1;
+      q += (double)q0 + (double)q1;
+    }
+    for (; p < P; p += 32) {
       s += static_cast<double>(psum[(size_t)p * pstride + c]);
       q += static_cast<double>(psq[(size_t)p * pstride + c]);
     }
+  }
   red[0][ky][cx] = s;
   red[1][ky][cx] = q;
   __syncthreads();
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   if (training) {
     s = 0.0; q = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s += red[0][k][cx]; q += red[1][k][cx]; }
+    for (int k = 0; k < 32; ++k) { s += red[0][k][cx]; q += red[1][k][cx]; }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -255,8 +263,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             int accumulate, float* __restrict__ out32,
                                                             __half* __restrict__ out16) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += part[k * split_stride + i];
+    // four independent partial sums: the loop is load-latency bound (up to 148 splits), order stays fixed
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < splits; k += 4) {
+      s0 += part[k * split_stride + i]; s1 += part[(k + 1) * split_stride + i];
+      s2 += part[(k + 2) * split_stride + i]; s3 += part[(k + 3) * split_stride + i];
+    }
+    for (; k < splits; ++k) s0 += part[k * split_stride + i];
+    float s = (s0 + s1) + (s2 + s3);
     s *= alpha;
     if (bias) s += __ldg(bias + (i % cols));
     if (relu) s = fmaxf(s, 0.f);
@@ -269,36 +284,51 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // Context gating (frame_level_models.py:2342-2368): gates = BN_batch(g [- diag(Wg) * act]) ;
 // act *= sigmoid(gates).  One thread per hidden unit, loops over the (small) batch.
 // ------------------------------------------------------------------------------------------------
-__global__ void gating_fwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
+__global__ void __launch_bounds__(1024) gating_fwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
                                   const float* __restrict__ wg_diag, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
                                   float* __restrict__ moving_var, float decay, float eps, int training,
                                   float* __restrict__ out32, __half* __restrict__ out16,
                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
-  const float dg = wg_diag ? wg_diag[c] : 0.f;
-  float mean, var;
+  // 32 hidden units x 32 batch lanes per block
+  __shared__ double red[2][32][33];
+  __shared__ float sm[2][32];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < H;
+  const float dg = (wg_diag && ok) ? wg_diag[c] : 0.f;
   if (training) {
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < B; ++b) {
-      const float v = g[(size_t)b * H + c] - dg * act[(size_t)b * H + c];
-      s += v; q += (double)v * v;
+    if (ok)
+      for (int b = ky; b < B; b += 32) {
+        const float v = g[(size_t)b * H + c] - dg * act[(size_t)b * H + c];
+        s += v; q += (double)v * v;
+      }
+    red[0][ky][cx] = s; red[1][ky][cx] = q;
+    __syncthreads();
+    if (ky == 0 && ok) {
+      s = 0.0; q = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { s += red[0][k][cx]; q += red[1][k][cx]; }
+      const double m = s / B;
+      double vv = q / B - m * m;
+      if (vv < 0.0) vv = 0.0;
+      const double corr = B > 1 ? (double)B / (B - 1) : 1.0;
+      moving_mean[c] = moving_mean[c] * decay + (float)m * (1.f - decay);
+      moving_var[c] = moving_var[c] * decay + (float)(vv * corr) * (1.f - decay);
+      sm[0][cx] = (float)m; sm[1][cx] = (float)vv;
     }
-    const double m = s / B;
-    double vv = q / B - m * m;
-    if (vv < 0.0) vv = 0.0;
-    mean = (float)m; var = (float)vv;
-    const double corr = B > 1 ? (double)B / (B - 1) : 1.0;
-    moving_mean[c] = moving_mean[c] * decay + mean * (1.f - decay);
-    moving_var[c] = moving_var[c] * decay + (float)(vv * corr) * (1.f - decay);
-  } else {
-    mean = moving_mean[c]; var = moving_var[c];
+    __syncthreads();
+  } else if (ky == 0 && ok) {
+    sm[0][cx] = moving_mean[c]; sm[1][cx] = moving_var[c];
   }
+  if (!training) __syncthreads();
+  if (!ok) return;
+  const float mean = sm[0][cx], var = sm[1][cx];
   const float rstd = rsqrtf(var + eps);
-  if (save_mean) { save_mean[c] = mean; save_rstd[c] = rstd; }
+  if (save_mean && ky == 0) { save_mean[c] = mean; save_rstd[c] = rstd; }
   const float sc = gamma[c] * rstd, sh = beta[c] - mean * sc;
-  for (int b = 0; b < B; ++b) {
+  for (int b = ky; b < B; b += 32) {
     const float a = act[(size_t)b * H + c];
     const float v = (g[(size_t)b * H + c] - dg * a) * sc + sh;
     const float o = a / (1.f + __expf(-v));
@@ -461,7 +491,7 @@ int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, in
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
                 int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(psum, psq, P, pstride, C, count, gamma, beta, mm, mv, decay,
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(psum, psq, P, pstride, C, count, gamma, beta, mm, mv, decay,
                                                       eps, bessel, training, scale, shift, save_mean, save_rstd);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
@@ -497,7 +527,7 @@ int splitk_reduce(const float* part, int splits, long long split_stride, long lo
 int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
                const float* beta, float* mm, float* mv, float decay, float eps, int training, float* out32,
                __half* out16, float* save_mean, float* save_rstd, cudaStream_t st) {
-  gating_fwd_kernel<<<(H + 63) / 64, 64, 0, st>>>(act, g, B, H, wg_diag, gamma, beta, mm, mv, decay, eps, training,
+  gating_fwd_kernel<<<(H + 31) / 32, 1024, 0, st>>>(act, g, B, H, wg_diag, gamma, beta, mm, mv, decay, eps, training,
                                                   out32, out16, save_mean, save_rstd);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;

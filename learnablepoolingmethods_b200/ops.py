@@ -408,8 +408,8 @@ def layernorm_joint_bwd(u, dy, dy_stride, B, rows, D, mean_rstd, gamma, *, inv_s
                                       ptr(du), ptr(dum), ptr(ps), ptr(pc), ptr(pdu), stream_ptr()), "lpm_layernorm_joint_bwd")
     if mask is not None:
         du = (du, dum)
-    dgamma = colsum_final(pc, B * ch, 2 * D, D, alpha=inv_scale)
-    dbeta = colsum_final(pc[:, 1], B * ch, 2 * D, D, alpha=inv_scale)
+    gb = colsum_final(pc, B * ch, 2 * D, 2 * D, alpha=inv_scale)      # [dgamma | dbeta] in one launch
+    dgamma, dbeta = gb[:D], gb[D:]
     if want_du_colsum:
         return du, dgamma, dbeta, colsum_final(pdu, B * ch, D, D, alpha=inv_scale)
     return du, dgamma, dbeta
