@@ -263,7 +263,7 @@ def main():
         T, D, Kc = CFG["iterations"], 1024, CFG["cluster_size"]
         xb = torch.randn(B * T, D, device=dev).half()
         wc = (torch.randn(D, Kc, device=dev) / 32).half()
-        ct = torch.randn(D, Kc, device=dev) / 32
+        ct = ops.transpose_f32_dual(torch.randn(D, Kc, device=dev) / 32, want32=False)[1]   # fp16 [K, D] shadow
         one, zero = torch.ones(Kc, device=dev), torch.zeros(Kc, device=dev)
         p_ms = time_cuda(lambda: ops.netvlad_pool_fwd(xb, B, T, wc, one, zero, ct), 20)
         p_tf = 4.0 * T * D * Kc * B / p_ms / 1e9

@@ -113,17 +113,19 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
  *   x            fp16 [B][T][D] (row stride ldx, video stride x_batch_stride), the batch-normed frames
  *   wc           fp16 [D][K] cluster_weights (row stride ldw)
  *   logit_scale/shift  fp32 [K]: cluster_bn folded affine, or (1, cluster_biases)
- *   centers      fp32 [D][K]: cluster_weights2[0] (V1) / cluster_centers (V2), the reference's own layout
+ *   centers_t16  fp16 [K][D]: cluster_weights2[0] (V1) / cluster_centers (V2) transposed to cluster-major and
+ *                rounded to fp16 (lpm_transpose_f32_dual); TMA-loaded into the output staging slab
  *   valid_frames int32 [B] or NULL: frames t >= valid_frames[b] get zero assignment (masked mode)
  *   z            fp16 [B][K][D]  un-normalised cluster-major descriptor V^T
  *   rscale       fp32 [B][K]     vlad[b,k,:] = z[b,k,:]*rscale[b,k]  (intra-norm x global norm)
  *   a_sum        fp32 [B][K] or NULL;  assign fp16 [B][T][K] or NULL (saved for the backward)
  *   assign_in    fp16 [B][T][K] or NULL: externally supplied cluster similarities (NetVladAttenCluster,
  *                video_pooling_modules.py:1628-1652): the logits/softmax phase is skipped, wc/logit_* unused
- * Limits: T <= 256, D % 64 == 0, K % 8 == 0, K <= 256.
+ * Limits: T <= 256, D % 64 == 0, K % 8 == 0, K <= 512 (K > 256 runs as a 2-CTA cluster per video, each CTA
+ * owning 256 clusters; softmax row statistics and the global norm are exchanged through distributed shared memory).
  * ------------------------------------------------------------------------------------------- */
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
-                         const float* logit_scale, const float* logit_shift, const float* centers,
+                         const float* logit_scale, const float* logit_shift, const void* centers_t16,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
                          float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream);
 /* Profiling aid: when non-NULL, lpm_netvlad_pool_fwd writes 8 clock64 phase stamps per video ([B][8] int64:
@@ -189,6 +191,8 @@ int lpm_scale_rows_f16(const void* x, const float* row_scale, long long rows, in
 int lpm_cast_f32_to_f16(const float* src, long long ld_src, int rows, int cols, void* dst, long long ld_dst,
                         int cols_dst, lpm_stream_t stream);
 int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stream_t stream);
+/* dst32 (fp32) and/or dst16 (fp16) [cols][rows] = src^T; either destination may be NULL. */
+int lpm_transpose_f32_dual(const float* src, int rows, int cols, float* dst32, void* dst16, lpm_stream_t stream);
 
 /* =============================================================================================
  * Backward entry points (autodiff of the reference lines cited by the matching forward call).

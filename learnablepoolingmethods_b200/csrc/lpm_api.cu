@@ -55,10 +55,11 @@ static PFN_encodeTiled get_encode() {
 
 int make_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                  uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,
-                 uint32_t box_cols, uint32_t box_rows) {
+                 uint32_t box_cols, uint32_t box_rows, uint32_t swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(LPM_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  if (box_cols * elem_bytes != 128) return fail(LPM_ERR_ARG, "tmap: box inner extent must be 128 bytes");
+  if ((swizzle_bytes != 128 && swizzle_bytes != 64) || box_cols * elem_bytes != swizzle_bytes)
+    return fail(LPM_ERR_ARG, "tmap: box inner extent must equal the swizzle span (64 or 128 bytes)");
   if (batch_stride_elems == 0) batch_stride_elems = rows * row_stride_elems;  // unused when batch == 1
   cuuint64_t gdim[3] = {cols, rows, batch};
   cuuint64_t gstride[2] = {row_stride_elems * (uint64_t)elem_bytes, batch_stride_elems * (uint64_t)elem_bytes};
@@ -66,7 +67,8 @@ int make_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t co
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(map, dt, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(LPM_ERR_CUDA,
@@ -153,13 +155,13 @@ int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long
 }
 
 int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride, const void* wc, long long ldw,
-                         const float* logit_scale, const float* logit_shift, const float* centers,
+                         const float* logit_scale, const float* logit_shift, const void* centers_t16,
                          const int* valid_frames, int B, int T, int D, int K, void* z, float* rscale,
                          float* a_sum, void* assign, const void* assign_in, lpm_stream_t stream) {
   DEVCHK();
-  LPM_REQUIRE(x && centers && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
+  LPM_REQUIRE(x && centers_t16 && z && rscale, "lpm_netvlad_pool_fwd: null pointer");
   LPM_REQUIRE(assign_in || (wc && logit_scale && logit_shift), "lpm_netvlad_pool_fwd: need cluster weights or assign_in");
-  return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, centers,
+  return netvlad_pool_fwd(CH16(x), ldx, x_batch_stride, CH16(wc), ldw, logit_scale, logit_shift, CH16(centers_t16),
                           valid_frames, B, T, D, K, H16(z), rscale, a_sum, H16(assign), CH16(assign_in), g_pool_debug, ST(stream));
 }
 
@@ -231,7 +233,13 @@ int lpm_cast_f32_to_f16(const float* src, long long ld_src, int rows, int cols, 
 int lpm_transpose_f32(const float* src, int rows, int cols, float* dst, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(src && dst && rows > 0 && cols > 0, "lpm_transpose_f32: bad arguments");
-  return transpose_2d(src, rows, cols, dst, ST(stream));
+  return transpose_2d(src, rows, cols, dst, nullptr, ST(stream));
+}
+
+int lpm_transpose_f32_dual(const float* src, int rows, int cols, float* dst32, void* dst16, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(src && (dst32 || dst16) && rows > 0 && cols > 0, "lpm_transpose_f32_dual: bad arguments");
+  return transpose_2d(src, rows, cols, dst32, H16(dst16), ST(stream));
 }
 
 int lpm_xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred,

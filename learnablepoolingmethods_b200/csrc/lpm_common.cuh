@@ -38,11 +38,11 @@ int fail(int code, const char* fmt, ...);
 int num_sms();
 
 // TMA tensor map over a row-major fp16 (or fp32) tensor viewed as [batch][rows][cols] with `cols`
-// contiguous; box = [box_rows][box_cols] with 128B swizzle (box_cols * elem_bytes must be 128).
+// contiguous; box = [box_rows][box_cols] with 128B (or 64B) swizzle (box_cols * elem_bytes must equal the swizzle span).
 // Out-of-bounds elements are zero-filled.
 int make_tmap_3d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                  uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,
-                 uint32_t box_cols, uint32_t box_rows);
+                 uint32_t box_cols, uint32_t box_rows, uint32_t swizzle_bytes = 128);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers

@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(const __half* __restric
 }
 
 // fp32 2-D transpose (parameter layout preparation, e.g. cluster_weights2 [D][K] -> [K][D])
-__global__ void transpose_2d_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+__global__ void transpose_2d_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst,
+                                    __half* __restrict__ dst16) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -454,7 +455,11 @@ __global__ void transpose_2d_kernel(const float* __restrict__ src, int rows, int
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    if (r < rows && c < cols) {
+      const float v = tile[threadIdx.x][j];
+      if (dst != nullptr) dst[(size_t)c * rows + r] = v;
+      if (dst16 != nullptr) dst16[(size_t)c * rows + r] = __float2half_rn(v);
+    }
   }
 }
 
@@ -565,9 +570,9 @@ int scale_rows(const __half* x, const float* rs, long long rows, int D, __half* 
   return LPM_OK;
 }
 
-int transpose_2d(const float* src, int rows, int cols, float* dst, cudaStream_t st) {
+int transpose_2d(const float* src, int rows, int cols, float* dst, __half* dst16, cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_2d_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst);
+  transpose_2d_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst, dst16);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -35,7 +35,7 @@ int moe_mix(const float* logits, long long ld, int B, int V, int M, int expert_o
 int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss, cudaStream_t st);
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
             cudaStream_t st);
-int transpose_2d(const float* src, int rows, int cols, float* dst, cudaStream_t st);
+int transpose_2d(const float* src, int rows, int cols, float* dst, __half* dst16, cudaStream_t st);
 int vlad_finalize(const __half* z, const float* rscale, int B, int K, int D, int d_major, float* out, cudaStream_t st);
 
 // lpm_attn.cu
@@ -103,7 +103,7 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
 
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
-                     const float* logit_scale, const float* logit_shift, const float* centers,
+                     const float* logit_scale, const float* logit_shift, const __half* centers_t16,
                      const int* valid_frames, int B, int T, int D, int K, __half* z, float* rscale, float* a_sum,
                      __half* assign, const __half* assign_in, long long* debug_clock, cudaStream_t st);
 

@@ -178,7 +178,7 @@ class NetVladEngine:
         for name, _, D, K, H, sid in c.modalities():
             vs = name + "_VLAD"
             src = v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else v[vs + "/cluster_centers"]
-            sh[vs + "/centers_t"] = ops.transpose_f32(src)
+            sh[vs + "/centers_t"], sh[vs + "/centers_t16"] = ops.transpose_f32_dual(src)
         V, M = c.vocab_size, c.num_mixtures
         g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
         bm = self._shadow_buf("bmoe", (g8 + e8,), torch.float32)
@@ -287,7 +287,7 @@ class NetVladEngine:
                                 v[bn + "/moving_variance"], training=False, bessel=True, save=save)
         lscale, lshift = r[0], r[1]
         # ---- K1: fused soft-assignment + aggregation + norms -----------------------------------
-        z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, lscale, lshift, v[vs + "/cluster_weights2"][0],
+        z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, lscale, lshift, sh[vs + "/centers_t16"],
                                                         save_assign=save)
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
@@ -390,7 +390,7 @@ class NetVladEngine:
         r = ops.batch_norm_cols_f16(f2, *bnv(a + "/feed_output_bn"), training=training, bessel=False, save=save, out=A)
         obn_stats = r[2] if save else None
         A_in = A if save else f2
-        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, v[vs + "/cluster_centers"], assign_in=A_in)
+        z, rscale, a_sum, _ = ops.netvlad_pool_fwd(X, B, T, None, None, None, sh[vs + "/centers_t16"], assign_in=A_in)
         ops.netvlad_finalize_f16(z, rscale, out_view, out_view.stride(0))    # d-major flatten, normalised, fp16
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)

@@ -160,6 +160,16 @@ def transpose_f32(src: torch.Tensor):
     return dst
 
 
+def transpose_f32_dual(src: torch.Tensor, want32=True):
+    """(src^T as fp32 or None, src^T as fp16): cluster-major centre layouts of the pooling kernel / backward."""
+    lib = _lib.load()
+    rows, cols = src.shape
+    dst = _f32((cols, rows), src.device) if want32 else None
+    dst16 = _f16((cols, rows), src.device)
+    check(lib.lpm_transpose_f32_dual(ptr(src), rows, cols, ptr(dst), ptr(dst16), stream_ptr()), "lpm_transpose_f32_dual")
+    return dst, dst16
+
+
 def bn_finalize(psum, psq, count, gamma, beta, moving_mean, moving_var, *, training, bessel, save=False,
                 decay=BN_DECAY, eps=BN_EPS, psum_stride=None):
     """Reduce (sum, sumsq) partial rows [P, C] (row stride psum_stride) -> folded affine (scale, shift) [C]."""
@@ -207,13 +217,17 @@ def sample_bn_apply(x, num_frames, T, scale, shift, out=None, split_col=None):
 
 def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers, *, valid_frames=None,
                      save_assign=False, assign_in=None):
-    """x16: fp16 view [B*T, D] (row stride may exceed D); centers: fp32 [D, K] contiguous (the TF layout).
+    """x16: fp16 view [B*T, D] (row stride may exceed D); centers: fp16 [K, D] (cluster-major shadow made by
+    transpose_f32_dual) or fp32 [D, K] (the TF layout; transposed + rounded here, one extra launch).
     Returns z [B,K,D] fp16, rscale [B,K], a_sum, assign.
     assign_in (fp16 [B*T, K] contiguous): NetVladV2 mode, the soft-assignment phase is skipped."""
     lib = _lib.load()
     D = x16.shape[1]
     K = wc16.shape[1] if assign_in is None else assign_in.shape[-1]
     dev = x16.device
+    if centers.dtype == torch.float32:
+        centers = transpose_f32_dual(centers.contiguous(), want32=False)[1]
+    assert centers.dtype == torch.float16 and tuple(centers.shape) == (K, D) and centers.is_contiguous()
     z = _f16((B, K, D), dev)
     rscale = _f32((B, K), dev)
     a_sum = _f32((B, K), dev)

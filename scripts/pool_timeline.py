@@ -4,7 +4,7 @@ from learnablepoolingmethods_b200 import ops, _lib
 dev = torch.device("cuda:0")
 lib = _lib.load()
 T, D, Kc = 256, 1024, 256
-wc = (torch.randn(D, Kc, device=dev) / 32).half(); ct = torch.randn(D, Kc, device=dev) / 32
+wc = (torch.randn(D, Kc, device=dev) / 32).half(); ct = ops.transpose_f32_dual(torch.randn(D, Kc, device=dev) / 32, want32=False)[1]
 one, zero = torch.ones(Kc, device=dev), torch.zeros(Kc, device=dev)
 for B in (80, 148):
     xb = torch.randn(B * T, D, device=dev).half()

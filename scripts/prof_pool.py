@@ -6,7 +6,7 @@ T, D, Kc = 256, 1024, 256
 for B in (80, 1184):
     xb = torch.randn(B * T, D, device=dev).half()
     wc = (torch.randn(D, Kc, device=dev) / 32).half()
-    ct = torch.randn(D, Kc, device=dev) / 32
+    ct = ops.transpose_f32_dual(torch.randn(D, Kc, device=dev) / 32, want32=False)[1]
     one, zero = torch.ones(Kc, device=dev), torch.zeros(Kc, device=dev)
     for _ in range(3):
         ops.netvlad_pool_fwd(xb, B, T, wc, one, zero, ct)
