@@ -128,13 +128,18 @@ def cpu_reference(steps, warmup, sample_batch=8, train=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--cluster-size", type=int, default=CFG["cluster_size"], help="netvlad_cluster_size (512 = wide config)")
+    ap.add_argument("--hidden-size", type=int, default=CFG["hidden_size"], help="netvlad_hidden_size (1024 = wide config)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2"])
     args = ap.parse_args()
+    CFG["cluster_size"], CFG["hidden_size"] = args.cluster_size, args.hidden_size
+    global WORKLOAD
+    WORKLOAD = WORKLOAD.replace("K=256/64, hidden 512", f"K={args.cluster_size}/{args.cluster_size // 4}, hidden {args.hidden_size}")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,7 +265,7 @@ def main():
         g_ms = time_cuda(lambda: ops.gemm(a, w, out=o), 20)
         g_tf = 2.0 * M * N * K / g_ms / 1e9
         # north-star kernel: fused NetVLAD pooling (rgb), 4*T*D*K FLOPs per video
-        T, D, Kc = CFG["iterations"], 1024, CFG["cluster_size"]
+        T, D, Kc = CFG["iterations"], 1024, 256
         xb = torch.randn(B * T, D, device=dev).half()
         wc = (torch.randn(D, Kc, device=dev) / 32).half()
         ct = ops.transpose_f32_dual(torch.randn(D, Kc, device=dev) / 32, want32=False)[1]   # fp16 [K, D] shadow

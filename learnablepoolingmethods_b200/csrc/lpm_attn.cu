@@ -184,14 +184,16 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward of the attention core (V1 scaling mode).  One CTA (8 warps) per (sample, head); L <= 256.
+// Backward of the attention core (V1 scaling mode).  One CTA per (sample, head); L <= 512.  Lengths above 256
+// are processed in query chunks of QC = 128 so that the parked dS^T ([L keys][QC queries]) still fits in
+// shared memory; dK / dV of later chunks are accumulated onto the fp16 results of the earlier ones.
 //   pass A (warp owns a 16-key block j, loops over query blocks i):
 //       S^T = K_j Q_i^T ; P^T = exp2(S^T*scale - lse_i) ; dP^T = V_j dO_i^T ; dS^T = P^T o (dP^T - delta_i)
 //       dV_j += P^T dO_i ; dK_j += dS^T Q_i ; dS^T parked in shared memory (fp16, [key][query])
 //   pass B (warp owns a 16-query block i): dQ_i = sum_j dS_ij K_j with dS read back transposed (ldmatrix.trans)
 // Gradients arrive / leave scaled by the caller's loss scale (the kernel is linear in dO).
 // ------------------------------------------------------------------------------------------------
-constexpr int DS_STRIDE = 264;  // halves per dS row (256 + 8 padding -> conflict-free stores and ldmatrix)
+// halves per dS row = QC + 8 padding (stride = 4 banks mod 32 -> conflict-free stores and ldmatrix)
 
 // MODE 0: logits = scale * q.k (V1).  MODE 1/2: batch-normed logits l' = l*ks_j + kb_j (V2): MODE 1 only accumulates the
 // per-key sums of dl' and dl'*lhat (lhat = (l - mu_j)*rstd_j) needed by the batch-norm backward; MODE 2 applies
@@ -207,7 +209,9 @@ template <int DH, int MODE>
 __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
                                                          const __half* __restrict__ o, const __half* __restrict__ dout,
                                                          long long ldo, const float* __restrict__ lse, int L, int Dm,
-                                                         int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn) {
+                                                         int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn,
+                                                         int QC) {
+  const int DS_STRIDE = QC + 8;
   // 16 warps; one CTA per (sample, head).  The kernel is latency- rather than throughput-bound (one CTA per SM
   // because dS^T is parked in shared memory), so every warp keeps two independent query blocks in flight.
   extern __shared__ __align__(16) uint8_t sm[];
@@ -257,6 +261,8 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
   const float scale_log2 = scale * 1.4426950408889634f;
   const int nb = L / 16;
 
+  for (int q0 = 0; q0 < L; q0 += QC) {
+  const int ib0 = q0 / 16, ib1 = min(nb, (q0 + QC) / 16);
   // ------------------------------- pass A: dK, dV, dS -------------------------------
   for (int j = warp; j < nb; j += nwarps) {
     uint32_t ka0, ka1, ka2, ka3, va0, va1, va2, va3;
@@ -277,9 +283,9 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
       mu0 = sBn[2 * L + kr0]; mu1 = sBn[2 * L + kr1]; rs0 = sBn[3 * L + kr0]; rs1 = sBn[3 * L + kr1];
       m10 = sBn[4 * L + kr0]; m11 = sBn[4 * L + kr1]; m20 = sBn[5 * L + kr0]; m21 = sBn[5 * L + kr1];
     }
-    for (int i = 0; i < nb; i += 2) {
+    for (int i = ib0; i < ib1; i += 2) {
       // two query blocks per iteration (the second is a masked repeat of the first on an odd tail)
-      const bool two = i + 1 < nb;
+      const bool two = i + 1 < ib1;
       const int ib[2] = {i, two ? i + 1 : i};
       float st[2][2][4], dp[2][2][4];
       uint32_t qf[2][4], of[2][4];
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
         if (DH == 16) mma16816(dk[1], sa0, sa1, sa2, sa3, c2, c3);
         // park dS^T: element (key = j*16 + lane/4 (+8), query = i*16 + n*8 + (lane&3)*2)
         if (u == 0 || two) {
-          __half* r0 = sdS + (size_t)(j * 16 + (lane >> 2)) * DS_STRIDE + ib[u] * 16 + (lane & 3) * 2;
+          __half* r0 = sdS + (size_t)(j * 16 + (lane >> 2)) * DS_STRIDE + (ib[u] - ib0) * 16 + (lane & 3) * 2;
           __half* r1 = r0 + 8 * DS_STRIDE;
           *reinterpret_cast<uint32_t*>(r0) = sa0;
           *reinterpret_cast<uint32_t*>(r1) = sa1;
@@ -369,6 +375,7 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
       a2r1 += __shfl_xor_sync(0xffffffffu, a2r1, 1); a2r1 += __shfl_xor_sync(0xffffffffu, a2r1, 2);
       if ((lane & 3) == 0) {
         float* sp = bn.stat_partial + (size_t)blockIdx.x * 2 * L;
+        if (q0 > 0) { a1r0 += sp[kr0]; a1r1 += sp[kr1]; a2r0 += sp[L + kr0]; a2r1 += sp[L + kr1]; }
         sp[kr0] = a1r0; sp[kr1] = a1r1; sp[L + kr0] = a2r0; sp[L + kr1] = a2r1;
       }
       continue;
@@ -378,19 +385,26 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
     __half* dk1 = dqkv + ((long long)b * L + r1) * ldd + Dm + h * DH + (lane & 3) * 2;
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) {
-      *reinterpret_cast<__half2*>(dk0 + n * 8) = __floats2half2_rn(dk[n][0] * scale, dk[n][1] * scale);
-      *reinterpret_cast<__half2*>(dk1 + n * 8) = __floats2half2_rn(dk[n][2] * scale, dk[n][3] * scale);
-      *reinterpret_cast<__half2*>(dk0 + Dm + n * 8) = __floats2half2_rn(dv[n][0], dv[n][1]);
-      *reinterpret_cast<__half2*>(dk1 + Dm + n * 8) = __floats2half2_rn(dv[n][2], dv[n][3]);
+      float2 k0v = make_float2(dk[n][0] * scale, dk[n][1] * scale), k1v = make_float2(dk[n][2] * scale, dk[n][3] * scale);
+      float2 v0v = make_float2(dv[n][0], dv[n][1]), v1v = make_float2(dv[n][2], dv[n][3]);
+      if (q0 > 0) {   // later query chunk: this warp owns these rows, add onto its own earlier result
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(dk0 + n * 8)), c = __half22float2(*reinterpret_cast<__half2*>(dk1 + n * 8));
+        const float2 e = __half22float2(*reinterpret_cast<__half2*>(dk0 + Dm + n * 8)), f = __half22float2(*reinterpret_cast<__half2*>(dk1 + Dm + n * 8));
+        k0v.x += a.x; k0v.y += a.y; k1v.x += c.x; k1v.y += c.y; v0v.x += e.x; v0v.y += e.y; v1v.x += f.x; v1v.y += f.y;
+      }
+      *reinterpret_cast<__half2*>(dk0 + n * 8) = __floats2half2_rn(k0v.x, k0v.y);
+      *reinterpret_cast<__half2*>(dk1 + n * 8) = __floats2half2_rn(k1v.x, k1v.y);
+      *reinterpret_cast<__half2*>(dk0 + Dm + n * 8) = __floats2half2_rn(v0v.x, v0v.y);
+      *reinterpret_cast<__half2*>(dk1 + Dm + n * 8) = __floats2half2_rn(v1v.x, v1v.y);
     }
   }
-  if (MODE == 1) return;
+  if (MODE == 1) continue;
   __syncthreads();
 
   // ------------------------------- pass B: dQ -------------------------------
   // two independent accumulator sets (even / odd key blocks) break the MMA dependency chain
   const uint32_t ds_s = smem_u32(sdS);
-  for (int i = warp; i < nb; i += nwarps) {
+  for (int i = ib0 + warp; i < ib1; i += nwarps) {
     float dq[2][2][4];
 #pragma unroll
     for (int e = 0; e < 2; ++e)
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
         if (j + e < nb) {
           uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
           const int key = (j + e) * 16 + (lane & 7) + (lane >> 4) * 8;
-          const int qcol = i * 16 + ((lane >> 3) & 1) * 8;
+          const int qcol = (i - ib0) * 16 + ((lane >> 3) & 1) * 8;
           ldsm_x4_t(ds_s + (uint32_t)(key * DS_STRIDE + qcol) * 2, a0, a1, a2, a3);
           const int krow = (j + e) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           ldsm_x4_t(k_s + tile_off(krow, lane >> 4), b0, b1, b2, b3);
@@ -420,6 +434,8 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
       *reinterpret_cast<__half2*>(q1 + n * 8) = __floats2half2_rn((dq[0][n][2] + dq[1][n][2]) * scale, (dq[0][n][3] + dq[1][n][3]) * scale);
     }
   }
+  __syncthreads();   // the parked dS^T is rewritten by the next query chunk
+  }
 }
 
 static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo,
@@ -427,15 +443,17 @@ static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __hal
                           const MhaBnArgs& bn, cudaStream_t st) {
   const int DH = Dm / H;
   LPM_REQUIRE(DH * H == Dm && (DH == 8 || DH == 16), "mha_bwd: head depth must be 8 or 16 (Dm=%d H=%d)", Dm, H);
-  LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 256, "mha_bwd: length must be a multiple of 16 in [16,256] (got %d)", L);
+  LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 512, "mha_bwd: length must be a multiple of 16 in [16,512] (got %d)", L);
   LPM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0, "mha_bwd: leading dimensions must be multiples of 8");
   LPM_REQUIRE(mode == 0 || DH == 16, "mha_bwd: batch-normed logits need head depth 16");
-  const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (mode ? (size_t)L * 24 : 0) + (size_t)L * DS_STRIDE * 2;
+  const int QC = L <= 256 ? L : 128;     // query chunk whose dS^T is parked at a time
+  const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (mode ? (size_t)L * 24 : 0) + (size_t)L * (QC + 8) * 2;
+  LPM_REQUIRE(smem <= 227 * 1024, "mha_bwd: shared memory budget exceeded (L=%d)", L);
 #define LPM_MHA_BWD(DHV, MODEV)                                                                                          \
   {                                                                                                                      \
     static bool set = false;                                                                                             \
-    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
-    mha_bwd_kernel<DHV, MODEV><<<B * H, (L >= 256 ? 512 : 256), smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn);    \
+    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; } \
+    mha_bwd_kernel<DHV, MODEV><<<B * H, (L >= 256 ? 512 : 256), smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn, QC);    \
   }
   if (mode == 0) { if (DH == 16) LPM_MHA_BWD(16, 0) else LPM_MHA_BWD(8, 0) }
   else if (mode == 1) LPM_MHA_BWD(16, 1)

@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(256) vlad_norm_bwd_kernel(const __half* __rest
 //          dShat and dShat*shat (shat = (S-mean)*rstd)          G = X dV^T (fp32), S = X Wc (fp16)
 //   pass 2: dS = gamma*rstd*(dShat - c1/N - shat*c2/N)  (training batch norm), in place
 // ------------------------------------------------------------------------------------------------
+template <int J>   // clusters per lane: K <= 32*J
 __global__ void __launch_bounds__(256) assign_bwd1_kernel(const float* __restrict__ G, const __half* __restrict__ A,
                                                           const float* __restrict__ q, const __half* __restrict__ S,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -345,15 +346,15 @@ __global__ void __launch_bounds__(256) assign_bwd1_kernel(const float* __restric
   extern __shared__ float sh[];  // [8 warps][2][K]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * 8 + w, nwarps = (long long)gridDim.x * 8;
-  float c1[8], c2[8];
+  float c1[J], c2[J];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) c1[j] = c2[j] = 0.f;
+  for (int j = 0; j < J; ++j) c1[j] = c2[j] = 0.f;
   for (long long r = warp; r < rows; r += nwarps) {
     const long long b = r / T;
-    float a[8], da[8];
+    float a[J], da[J];
     float inner = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int k = lane + 32 * j;
       if (k < K) {
         a[j] = __half2float(A[r * K + k]);
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) assign_bwd1_kernel(const float* __restric
     }
     inner = warp_sum(inner);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int k = lane + 32 * j;
       if (k < K) {
         const float d = a[j] * (da[j] - inner);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256) assign_bwd1_kernel(const float* __restric
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < J; ++j) {
     const int k = lane + 32 * j;
     if (k < K) { sh[(w * 2 + 0) * K + k] = c1[j]; sh[(w * 2 + 1) * K + k] = c2[j]; }
   }
@@ -544,8 +545,12 @@ int assign_bwd_blocks() { return num_sms() * 2; }
 
 int assign_bwd1(const float* G, const __half* A, const float* q, const __half* S, const float* mean,
                 const float* rstd, long long rows, int T, int K, __half* dsh, float* partial, cudaStream_t st) {
-  LPM_REQUIRE(K <= 256, "assign_bwd1: K must be <= 256");
-  assign_bwd1_kernel<<<assign_bwd_blocks(), 256, (size_t)16 * K * sizeof(float), st>>>(G, A, q, S, mean, rstd, rows, T, K,
+  LPM_REQUIRE(K <= 512, "assign_bwd1: K must be <= 512");
+  if (K > 256)
+    assign_bwd1_kernel<16><<<assign_bwd_blocks(), 256, (size_t)16 * K * sizeof(float), st>>>(G, A, q, S, mean, rstd, rows, T, K,
+                                                                                             dsh, partial);
+  else
+  assign_bwd1_kernel<8><<<assign_bwd_blocks(), 256, (size_t)16 * K * sizeof(float), st>>>(G, A, q, S, mean, rstd, rows, T, K,
                                                                                         dsh, partial);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;

@@ -121,7 +121,8 @@ def test_netvlad_pool_masked_frames(cuda):
         assert rel(out[b], ref[0]) < 1e-3
 
 
-@pytest.mark.parametrize("B,L,Dm,H", [(3, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (2, 256, 128, 8), (1, 80, 64, 4)])
+@pytest.mark.parametrize("B,L,Dm,H", [(3, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (2, 256, 128, 8), (1, 80, 64, 4),
+                                      (2, 512, 128, 8), (1, 128, 128, 16)])
 def test_mha_core_fwd(cuda, B, L, Dm, H):
     """transformer_utils.py:563-581: softmax(q*depth^-0.5 k^T) v per head."""
     from learnablepoolingmethods_b200 import ops
@@ -141,7 +142,8 @@ def test_mha_core_fwd(cuda, B, L, Dm, H):
     assert rel(out2.float(), ref2) < 2e-3
 
 
-@pytest.mark.parametrize("B,L,Dm,H", [(2, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (1, 80, 64, 4), (1, 240, 64, 4)])
+@pytest.mark.parametrize("B,L,Dm,H", [(2, 256, 1024, 64), (2, 64, 128, 16), (2, 16, 128, 16), (1, 80, 64, 4), (1, 240, 64, 4),
+                                      (2, 512, 128, 8), (1, 512, 64, 8), (1, 400, 64, 4)])
 def test_mha_core_bwd(cuda, B, L, Dm, H):
     """Backward of transformer_utils.py:563-581 against torch autograd (fp64) on the same fp16 inputs."""
     from learnablepoolingmethods_b200 import ops
