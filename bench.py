@@ -28,13 +28,16 @@ WORKLOAD = ("NetVladV1 train step (fwd+bwd+allreduce+clip+Adam), batch 80/GPU, 2
             "rgb1024+audio128, K=256/64, hidden 512, vocab 3862, synthetic YT8M-shaped features")
 
 
-def synthetic(batch, seed, device=None, pin=False):
-    """SURVEY 8(d) synthetic batch: uint8 codes from clipped N(0,1), dequantised, L2-normalised frames."""
+def synthetic(batch, seed, device=None, pin=False, codes=False):
+    """SURVEY 8(d) synthetic batch: uint8 codes from clipped N(0,1), dequantised, L2-normalised frames
+    (codes=True: the uint8 codes themselves, as the reader decodes them; the kernels dequantise + normalise)."""
     g = torch.Generator().manual_seed(seed)
     z = torch.randn(batch, CFG["max_frames"], CFG["feat"], generator=g)
     q = torch.clamp(torch.round((z + 2) * 255 / 4), 0, 255)
     x = q * (4.0 / 255.0) + (4.0 / 512.0 - 2.0)
     x = x * torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=1e-12))
+    if codes:
+        x = q.to(torch.uint8)
     nf = torch.full((batch,), CFG["max_frames"], dtype=torch.int32)
     labels = torch.zeros(batch, CFG["vocab"], dtype=torch.uint8)
     w = 1.0 / torch.arange(1, CFG["vocab"] + 1, dtype=torch.float64)
@@ -136,6 +139,9 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2"])
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"],
+                    help="u8: model_input = the reader's uint8 codes (dequantise + L2-normalise fused into the gather kernels); "
+                         "f32: model_input = dequantised, L2-normalised fp32 frames (the reference's create_model contract)")
     args = ap.parse_args()
     CFG["cluster_size"], CFG["hidden_size"] = args.cluster_size, args.hidden_size
     global WORKLOAD
@@ -147,7 +153,9 @@ def main():
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD.replace("NetVladV1", args.model), "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus,
-                       "parallelism": f"dp{args.gpus}", "l2": "working set per step (>=3 GB of weights, moments and "
+                       "parallelism": f"dp{args.gpus}",
+                       "model_input": "uint8 codes [B,300,1152] (readers.py:185-193); dequantise + l2_normalize fused" if args.input == "u8"
+                       else "fp32 frames [B,300,1152], L2-normalised by the caller", "l2": "working set per step (>=3 GB of weights, moments and "
                        "activations) exceeds the 126 MB L2; no flush needed"}}
 
     if args.impl == "reference":
@@ -178,7 +186,7 @@ def main():
                         hidden_size=CFG["hidden_size"], vocab_size=CFG["vocab"])
     eng = NetVladEngine(cfg, store)
     tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, batch_size=B)
-    xh, nfh, lh = synthetic(B, 20181000 + rank, pin=True)
+    xh, nfh, lh = synthetic(B, 20181000 + rank, pin=True, codes=args.input == "u8")
     x, nf, lab = xh.to(dev), nfh.to(dev), lh.to(dev)
 
     def barrier():
@@ -209,7 +217,6 @@ def main():
     barrier()
     train_ms = reduce_max(e0.elapsed_time(e1)) / args.steps
     launches = (_lib.launch_count - l0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
     overflow = tr.overflowed()
 
     # ---------------- training end to end: pinned host inputs, H2D each step, loss read back ----------------
@@ -248,7 +255,8 @@ def main():
     e1.record()
     barrier()
     e2e_ms = reduce_max(e0.elapsed_time(e1)) / args.steps
-    h2d = xh.numel() * 4 + nfh.numel() * 4 + lh.numel()
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident and end-to-end)
+    h2d = xh.numel() * xh.element_size() + nfh.numel() * 4 + lh.numel()
 
     # ---------------- inference: forward only (is_training=False) ----------------
     with torch.no_grad():

@@ -95,6 +95,17 @@ int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_fr
 int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
                         const float* scale, const float* shift, void* y_f16, int split_col, void* y2_f16,
                         lpm_stream_t stream);
+/* Ingest side of the boundary: the same two passes fed with the YT8M uint8 codes
+ * [B][max_frames][F] as the reader decodes them (readers.py:185-193).  Each gathered frame is dequantised
+ * (utils.py:28-43: q*range/255 + range/512 + min, range = max - min) and L2-normalised over all F features
+ * (train.py:264: x*rsqrt(max(sum x^2, 1e-12))) on the fly, so the fp32 [B][300][1152] tensor never exists
+ * and the host->device copy shrinks 4x.  Results equal the fp32 entry points on dequantised+normalised input. */
+int lpm_sample_bn_stats_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
+                           const int* num_frames, int B, int max_frames, int F, int T, float* partial,
+                           lpm_stream_t stream);
+int lpm_sample_bn_apply_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
+                           const int* num_frames, int B, int max_frames, int F, int T, const float* scale,
+                           const float* shift, void* y_f16, int split_col, void* y2_f16, lpm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * slim.batch_norm finalisation (eps 1e-3, decay 0.999 passed by the caller): reduces P partial

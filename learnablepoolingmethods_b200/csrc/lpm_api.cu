@@ -131,7 +131,15 @@ int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_fr
                         float* partial, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && num_frames && partial && B > 0 && T > 0 && max_frames > 0, "lpm_sample_bn_stats: bad arguments");
-  return sample_stats(x, num_frames, B, max_frames, F, T, partial, ST(stream));
+  return sample_stats(x, 0, 0.f, 0.f, num_frames, B, max_frames, F, T, partial, ST(stream));
+}
+
+int lpm_sample_bn_stats_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
+                           const int* num_frames, int B, int max_frames, int F, int T, float* partial,
+                           lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(codes && num_frames && partial && B > 0 && T > 0 && max_frames > 0, "lpm_sample_bn_stats_u8: bad arguments");
+  return sample_stats(codes, 1, max_quantized_value, min_quantized_value, num_frames, B, max_frames, F, T, partial, ST(stream));
 }
 
 int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
@@ -139,7 +147,16 @@ int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_fr
                         lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply: bad arguments");
-  return sample_apply(x, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
+  return sample_apply(x, 0, 0.f, 0.f, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
+}
+
+int lpm_sample_bn_apply_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
+                           const int* num_frames, int B, int max_frames, int F, int T, const float* scale,
+                           const float* shift, void* y_f16, int split_col, void* y2_f16, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(codes && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply_u8: bad arguments");
+  return sample_apply(codes, 1, max_quantized_value, min_quantized_value, num_frames, B, max_frames, F, T, scale, shift,
+                      H16(y_f16), split_col, H16(y2_f16), ST(stream));
 }
 
 int lpm_batchnorm_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,

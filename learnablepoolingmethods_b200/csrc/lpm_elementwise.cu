@@ -31,26 +31,66 @@ __device__ __forceinline__ int sample_index(int i, float step, int nf, int max_f
 }
 
 // partial[blockIdx][0][c] = sum, partial[blockIdx][1][c] = sum of squares over this block's rows
-__global__ void __launch_bounds__(256) sample_stats_kernel(const float* __restrict__ x,
+// CODES: x holds the YT8M uint8 codes; the frame is dequantised (utils.py:28-43, readers.py:185-193) and L2-normalised
+// over all F features (train.py:264) on the fly, i.e. the ingest side of the boundary is fused into the gather.
+// One block per frame row: 256 threads x (4 + 4) columns, F <= 2048.
+struct FrameQuant { float scalar, bias; };
+
+template <bool CODES>
+__device__ __forceinline__ void load_frame(const void* __restrict__ x, size_t frame, int F, FrameQuant qz, float* red,
+                                           int parity, float4 (&v)[2]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = threadIdx.x * 4 + j * 1024;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < F) {
+      if (CODES) {
+        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(static_cast<const uint8_t*>(x) + frame * F + c));
+        v[j] = make_float4(fmaf((float)u.x, qz.scalar, qz.bias), fmaf((float)u.y, qz.scalar, qz.bias),
+                           fmaf((float)u.z, qz.scalar, qz.bias), fmaf((float)u.w, qz.scalar, qz.bias));
+        ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      } else {
+        v[j] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x) + frame * F + c));
+      }
+    }
+  }
+  if (CODES) {
+    // tf.nn.l2_normalize over the feature axis: x * rsqrt(max(sum x^2, 1e-12)); block reduction, one barrier per
+    // frame (the 8 warp partials alternate between two slots)
+    ss = warp_sum(ss);
+    float* slot = red + parity * 8;
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += slot[w];
+    const float rn = rsqrtf(fmaxf(tot, 1e-12f));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { v[j].x *= rn; v[j].y *= rn; v[j].z *= rn; v[j].w *= rn; }
+  }
+}
+
+template <bool CODES>
+__global__ void __launch_bounds__(256) sample_stats_kernel(const void* __restrict__ x,
                                                            const int* __restrict__ num_frames, int B,
-                                                           int max_frames, int F, int T, float step,
+                                                           int max_frames, int F, int T, float step, FrameQuant qz,
                                                            float* __restrict__ partial) {
+  __shared__ float red[16];
   const int rows = B * T;
   float4 s[2], q[2];
 #pragma unroll
   for (int j = 0; j < 2; ++j) { s[j] = make_float4(0, 0, 0, 0); q[j] = make_float4(0, 0, 0, 0); }
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  int parity = 0;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x, parity ^= 1) {
     const int b = r / T, i = r - b * T;
     const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
-    const float* src = x + ((size_t)b * max_frames + idx) * F;
+    float4 v[2];
+    load_frame<CODES>(x, (size_t)b * max_frames + idx, F, qz, red, parity, v);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int c = threadIdx.x * 4 + j * 1024;
-      if (c < F) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
-        s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
-        q[j].x += v.x * v.x; q[j].y += v.y * v.y; q[j].z += v.z * v.z; q[j].w += v.w * v.w;
-      }
+      s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w;
+      q[j].x += v[j].x * v[j].x; q[j].y += v[j].y * v[j].y; q[j].z += v[j].z * v[j].z; q[j].w += v[j].w * v[j].w;
     }
   }
   float* ps = partial + (size_t)blockIdx.x * 2 * F;
@@ -65,23 +105,30 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const float* __restri
 }
 
 // y[r][c] = fp16( x[b, idx(b,i), c] * scale[c] + shift[c] )
-__global__ void __launch_bounds__(256) sample_apply_kernel(const float* __restrict__ x,
+template <bool CODES>
+__global__ void __launch_bounds__(256) sample_apply_kernel(const void* __restrict__ x,
                                                            const int* __restrict__ num_frames, int B,
-                                                           int max_frames, int F, int T, float step,
+                                                           int max_frames, int F, int T, float step, FrameQuant qz,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            __half* __restrict__ y, int split_col,
                                                            __half* __restrict__ y2) {
   // y2 == null: one [rows][F] matrix.  Otherwise columns [0, split_col) go to y ([rows][split_col]) and the rest
   // to y2 ([rows][F - split_col]): contiguous per-modality matrices for NetVladV2's residual / layer norm.
+  __shared__ float red[16];
   const int rows = B * T;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  int parity = 0;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x, parity ^= 1) {
     const int b = r / T, i = r - b * T;
     const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
-    const float* src = x + ((size_t)b * max_frames + idx) * F;
-    for (int c = threadIdx.x * 4; c < F; c += blockDim.x * 4) {
+    float4 vv[2];
+    load_frame<CODES>(x, (size_t)b * max_frames + idx, F, qz, red, parity, vv);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = threadIdx.x * 4 + j * 1024;
+      if (c >= F) continue;
       __half* dst = y2 == nullptr ? y + (size_t)r * F : (c < split_col ? y + (size_t)r * split_col : y2 + (size_t)r * (F - split_col) - split_col);
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+      const float4 v = vv[j];
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
       uint2 o;
@@ -476,19 +523,32 @@ static inline int grid_for(long long n, int threads, int per_sm = 8) {
 
 int sample_stats_blocks() { return num_sms() * 4; }
 
-int sample_stats(const float* x, const int* nf, int B, int max_frames, int F, int T, float* partial, cudaStream_t st) {
+static FrameQuant frame_quant(float qmax, float qmin) {
+  // utils.py:39-43: scalar = range / 255, bias = range / 512 + min
+  const float range = qmax - qmin;
+  return FrameQuant{range / 255.0f, range / 512.0f + qmin};
+}
+
+int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
+                 float* partial, cudaStream_t st) {
   LPM_REQUIRE(F % 4 == 0 && F <= 2048, "sample_stats: feature size must be a multiple of 4 and <= 2048 (got %d)", F);
-  sample_stats_kernel<<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, partial);
+  LPM_REQUIRE(!codes || qmax > qmin, "sample_stats: max_quantized_value must exceed min_quantized_value");
+  const FrameQuant qz = frame_quant(qmax, qmin);
+  if (codes) sample_stats_kernel<true><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, partial);
+  else sample_stats_kernel<false><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, partial);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
-int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, int T, const float* scale,
-                 const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st) {
-  LPM_REQUIRE(F % 4 == 0, "sample_apply: feature size must be a multiple of 4 (got %d)", F);
+int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
+                 const float* scale, const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st) {
+  LPM_REQUIRE(F % 4 == 0 && F <= 2048, "sample_apply: feature size must be a multiple of 4 and <= 2048 (got %d)", F);
+  LPM_REQUIRE(!codes || qmax > qmin, "sample_apply: max_quantized_value must exceed min_quantized_value");
+  const FrameQuant qz = frame_quant(qmax, qmin);
   LPM_REQUIRE(y2 == nullptr || (split_col % 4 == 0 && split_col > 0 && split_col < F), "sample_apply: bad split column");
   int grid = B * T < num_sms() * 8 ? B * T : num_sms() * 8;
-  sample_apply_kernel<<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, scale, shift, y, split_col, y2);
+  if (codes) sample_apply_kernel<true><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, scale, shift, y, split_col, y2);
+  else sample_apply_kernel<false><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, scale, shift, y, split_col, y2);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -16,8 +16,9 @@ int gemm_effective_splits(int K, int splits);
 
 // lpm_elementwise.cu
 int sample_stats_blocks();
-int sample_stats(const float* x, const int* nf, int B, int max_frames, int F, int T, float* partial, cudaStream_t st);
-int sample_apply(const float* x, const int* nf, int B, int max_frames, int F, int T, const float* scale,
+int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
+                 float* partial, cudaStream_t st);
+int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T, const float* scale,
                  const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st);
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,

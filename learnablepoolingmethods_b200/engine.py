@@ -203,7 +203,9 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
                 save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False):
-        """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264);
+        """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264), or the uint8
+        codes [B, max_frames, rgb+audio] as decoded by the reader (readers.py:185-193): those are dequantised
+        (utils.py:28-43) and L2-normalised inside the gather kernels.
         num_frames int [B].  Returns (predictions fp32 [B, vocab], ctx)."""
         c, s = self.cfg, self.store
         v = s.vars
@@ -212,7 +214,7 @@ class NetVladEngine:
             raise ValueError(f"model_input must be [B, frames, {c.feature_size}], got {tuple(model_input.shape)}")
         if not model_input.is_cuda:
             raise RuntimeError("model_input must live on the GPU (there is no CPU path)")
-        x = model_input.contiguous().float()
+        x = model_input.contiguous() if model_input.dtype == torch.uint8 else model_input.contiguous().float()
         nf = num_frames.to(device=x.device, dtype=torch.int32).contiguous()
         B, T, F = x.shape[0], c.iterations, c.feature_size
         ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}}
@@ -486,6 +488,9 @@ class NetVladEngine:
         if ctx.get("factored_hidden"):
             # the trainer applies clip + Adam straight from the factors (dW = inv * vlad^T dact16 is never written)
             ctx["hidden_factors"] = (hd["vlad"], dact16, inv)
+        elif ctx.get("hidden_dw") is not None:
+            # data parallel: the trainer sums this gradient over the ranks from all-gathered factors (dp.FactorGather)
+            put("hidden1_weights", ctx["hidden_dw"](dact16, inv, gout("hidden1_weights")))
         else:
             put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
                                             out=gout("hidden1_weights")))

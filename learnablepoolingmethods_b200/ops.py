@@ -188,30 +188,42 @@ def bn_finalize(psum, psq, count, gamma, beta, moving_mean, moving_var, *, train
     return (scale, shift, sm) if save else (scale, shift)
 
 
+QUANT_MAX, QUANT_MIN = 2.0, -2.0     # readers.py:185-193 / utils.py:28 defaults
+
+
+def _sample_call(name, x, args_after_x):
+    """fp32 frames (already L2-normalised) or uint8 codes (dequantised + normalised inside the kernel)."""
+    lib = _lib.load()
+    if x.dtype == torch.uint8:
+        fn = getattr(lib, name + "_u8")
+        check(fn(ptr(x), C.c_float(QUANT_MAX), C.c_float(QUANT_MIN), *args_after_x), name + "_u8")
+    else:
+        assert x.dtype == torch.float32
+        check(getattr(lib, name)(ptr(x), *args_after_x), name)
+
+
 def sample_bn_stats(x, num_frames, T):
     lib = _lib.load()
     B, Fmax, F = x.shape
     blocks = lib.lpm_sample_stats_blocks()
     partial = _f32((blocks, 2, F), x.device)
-    check(lib.lpm_sample_bn_stats(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(partial), stream_ptr()),
-          "lpm_sample_bn_stats")
+    _sample_call("lpm_sample_bn_stats", x, (ptr(num_frames), B, Fmax, F, T, ptr(partial), stream_ptr()))
     return partial
 
 
 def sample_bn_apply(x, num_frames, T, scale, shift, out=None, split_col=None):
     """Sampled + batch-normed frames as fp16: one [B*T, F] matrix, or (split_col given) two contiguous
-    per-modality matrices ([B*T, split_col], [B*T, F - split_col])."""
-    lib = _lib.load()
+    per-modality matrices ([B*T, split_col], [B*T, F - split_col]).  x: fp32 frames or uint8 codes."""
     B, Fmax, F = x.shape
     if split_col is None:
         if out is None:
             out = _f16((B * T, F), x.device)
-        check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out), 0, None,
-                                      stream_ptr()), "lpm_sample_bn_apply")
+        _sample_call("lpm_sample_bn_apply", x, (ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out), 0, None,
+                                                stream_ptr()))
         return out
     ya, yb = _f16((B * T, split_col), x.device), _f16((B * T, F - split_col), x.device)
-    check(lib.lpm_sample_bn_apply(ptr(x), ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(ya), split_col,
-                                  ptr(yb), stream_ptr()), "lpm_sample_bn_apply")
+    _sample_call("lpm_sample_bn_apply", x, (ptr(num_frames), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(ya), split_col,
+                                            ptr(yb), stream_ptr()))
     return ya, yb
 
 

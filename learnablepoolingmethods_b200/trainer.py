@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .dp import BucketedAllReduce
+from .dp import BucketedAllReduce, FactorGather
 from .engine import NetVladConfig, NetVladEngine
 from .variables import VariableStore
 
@@ -105,6 +105,8 @@ class Trainer:
         self.bucket_elems = bucket_elems
         self.reducer: Optional[BucketedAllReduce] = None
         self.rank_scratch = None
+        # data parallel: hidden1_weights' gradient (85 % of the bytes) is summed from all-gathered factors
+        self.gather = FactorGather(process_group) if self.world > 1 and self.gather_hidden_factors else None
 
     def _factored_hidden(self, batch: int) -> bool:
         """hidden1_weights (85 % of the parameters) is updated from its gradient factors on a single tower: with
@@ -115,6 +117,14 @@ class Trainer:
                 and ops.rank_adam_supported(batch, c.hidden_size))
 
     disable_factored_hidden = False
+    gather_hidden_factors = True
+
+    def _hidden_dw(self, dact16, inv, out):
+        """sum over ranks of inv * vlad_r^T dact_r from the gathered factors (one GEMM over world*B rows)."""
+        g_all = self.gather.start("dact", dact16)
+        a_all = self.gather.wait("vlad")
+        g_all = self.gather.wait("dact")
+        return ops.gemm(a_all, g_all, a_mn=True, b_mn=True, out_dtype=torch.float32, alpha=inv, out=out)
 
     def _factored_hidden_step(self, ctx, lr_t):
         f = self.flat
@@ -153,6 +163,9 @@ class Trainer:
         eng = self.engine
         pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True)
         B = pred.shape[0]
+        if self.gather is not None:
+            self.gather.start("vlad", ctx["head"]["vlad"])       # rides under the whole backward
+            ctx["hidden_dw"] = self._hidden_dw
         loss, _ = ops.xent_fwd(pred, labels_u8)
         dpred = ops.xent_bwd(pred, labels_u8, 1.0 / B)
         order: List[str] = []
@@ -166,7 +179,11 @@ class Trainer:
             for n, g in grads.items():
                 self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
             if self.world > 1:
-                self.reducer = BucketedAllReduce(self.flat.g, self.bucket_elems, self.pg)
+                skip = ()
+                if self.gather is not None:
+                    o = self.flat.offsets["hidden1_weights"]
+                    skip = ((o, self.flat.end_offset("hidden1_weights")),)
+                self.reducer = BucketedAllReduce(self.flat.g, self.bucket_elems, self.pg, skip=skip)
                 self.reducer.flush()
         else:
             ctx["grad_views"] = self.flat.grad_views

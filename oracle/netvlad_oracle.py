@@ -478,8 +478,17 @@ def init_params(specs, seed=1810, dtype=torch.float32, perturb=0.0):
     return P, S
 
 
+def dequantize(feat_vector, max_quantized_value=2, min_quantized_value=-2):
+    """utils.py:28-43 Dequantize: byte codes -> floats."""
+    assert max_quantized_value > min_quantized_value
+    quantized_range = max_quantized_value - min_quantized_value
+    scalar = quantized_range / 255.0
+    bias = (quantized_range / 512.0) + min_quantized_value
+    return feat_vector * scalar + bias
+
+
 def synthetic_batch(batch, *, seed, max_frames=300, feat=1152, vocab=3862, fixed_num_frames=None,
-                    dtype=torch.float32):
+                    dtype=torch.float32, return_codes=False):
     """uint8 codes from clipped N(0,1), dequantised (utils.py:28-43),
     zero-padded to max_frames (readers.py:193), per-frame L2 normalised (train.py:264)."""
     g = torch.Generator().manual_seed(seed)
@@ -489,7 +498,7 @@ def synthetic_batch(batch, *, seed, max_frames=300, feat=1152, vocab=3862, fixed
         nf = torch.full((batch,), fixed_num_frames, dtype=torch.int32)
     z = torch.randn(batch, max_frames, feat, generator=g)
     q = torch.clamp(torch.round((z + 2) * 255 / 4), 0, 255)
-    x = q * (4.0 / 255.0) + (4.0 / 512.0 - 2.0)
+    x = dequantize(q)
     mask = (torch.arange(max_frames)[None, :] < nf[:, None]).to(x.dtype)
     x = x * mask[:, :, None]
     x = l2_normalize(x, 2)
@@ -500,4 +509,8 @@ def synthetic_batch(batch, *, seed, max_frames=300, feat=1152, vocab=3862, fixed
     for b in range(batch):
         cls = torch.multinomial(w, int(npos[b]), replacement=False, generator=g)
         labels[b, cls] = True
+    if return_codes:
+        # what the reader holds before Dequantize (readers.py:185-193); padded frames carry arbitrary codes here
+        # (they are never sampled: model_utils.py:101-122 draws indices < num_frames)
+        return x.to(dtype), nf, labels, q.to(torch.uint8)
     return x.to(dtype), nf, labels

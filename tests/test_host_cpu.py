@@ -120,6 +120,16 @@ def _dp_worker(rank, world, port, q):
     red.wait()
     expect = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
     ok = torch.equal(g, expect)
+    # a skipped range (summed another way, dp.FactorGather) is left untouched and never crosses a bucket
+    g2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    red2 = BucketedAllReduce(g2, bucket_elems=256, skip=((100, 600),))
+    red2.mark_done(650)
+    n_early = len(red2.launched)
+    red2.flush()
+    red2.wait()
+    expect2 = expect.clone()
+    expect2[100:600] = torch.arange(100, 600, dtype=torch.float32) * (rank + 1)
+    ok = ok and torch.equal(g2, expect2) and n_early == 1 and red2.launched == [(0, 100), (600, 856), (856, 1000)]
     q.put((rank, ok, launched_at, list(red.launched)))
     dist.destroy_process_group()
 

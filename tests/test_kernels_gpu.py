@@ -41,6 +41,33 @@ def test_sample_and_input_bn(cuda):
             assert rel(mv, Sref["input_bn/moving_variance"]) < 1e-5
 
 
+def test_sample_from_uint8_codes(cuda):
+    """Ingest side: gather kernels fed with the reader's uint8 codes (readers.py:185-193) dequantise
+    (utils.py:28-43) and L2-normalise (train.py:264) on the fly; same statistics / frames as the fp32 entry points fed
+    with the oracle's dequantised + normalised tensor, and the model output follows."""
+    from learnablepoolingmethods_b200 import ops, variables
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from oracle import netvlad_oracle as O
+    B, T, F = 5, 256, 1152
+    x, nf, _, codes = O.synthetic_batch(B, seed=11, return_codes=True)
+    nf[0] = 1          # (only shrink: the fp32 tensor is zero beyond the generated num_frames, the codes are not)
+    xd, cd, nfd = x.to(cuda), codes.to(cuda), nf.to(cuda)
+    p32, p8 = ops.sample_bn_stats(xd, nfd, T), ops.sample_bn_stats(cd, nfd, T)
+    assert rel(p8.sum(0), p32.sum(0)) < 1e-6
+    g = torch.Generator().manual_seed(0)
+    scale, shift = (torch.rand(F, generator=g) + 0.5).to(cuda), torch.randn(F, generator=g).to(cuda)
+    y32, y8 = ops.sample_bn_apply(xd, nfd, T, scale, shift), ops.sample_bn_apply(cd, nfd, T, scale, shift)
+    assert float((y32.float() - y8.float()).abs().max()) <= 2e-3 and rel(y8.float(), y32.float()) < 2e-4   # fp16 ulp flips only
+    ya, yb = ops.sample_bn_apply(cd, nfd, T, scale, shift, split_col=1024)
+    assert torch.equal(ya, y8[:, :1024]) and torch.equal(yb, y8[:, 1024:])
+    store = variables.VariableStore(cuda, seed=1810)
+    eng = NetVladEngine(NetVladConfig(iterations=T, cluster_size=64, hidden_size=64, vocab_size=100), store)
+    for training in (False, True):
+        pa, _ = eng.forward(xd, nfd, training)
+        pb, _ = eng.forward(cd, nfd, training)
+        assert float((pa - pb).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("B,T,D,K", [(3, 256, 1024, 256), (2, 256, 128, 64), (2, 200, 256, 128), (2, 96, 128, 32), (1, 30, 64, 8),
                                      (3, 256, 1024, 512), (2, 100, 256, 384), (2, 256, 128, 264), (5, 256, 1024, 192)])
 def test_netvlad_pool_fwd(cuda, B, T, D, K):
