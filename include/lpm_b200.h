@@ -142,6 +142,8 @@ int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride,
 /* Profiling aid: when non-NULL, lpm_netvlad_pool_fwd writes 8 clock64 phase stamps per video ([B][8] int64:
  * start, logits done, softmax done, a_sum done, aggregation done). */
 void lpm_debug_set_pool_clock(long long* buf);
+/* Measurement aid: 0 = lpm_gemm_f16 never uses 2-CTA (cta_group::2) tiles, 1 = automatic (default). */
+void lpm_debug_set_gemm_pair_mode(int mode);
 /* vlad = z * rscale as fp32: d_major!=0 -> [B][D*K] (reference flatten, :2821), else [B][K][D]. */
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
                          lpm_stream_t stream);

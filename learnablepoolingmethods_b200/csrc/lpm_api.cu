@@ -111,6 +111,7 @@ int lpm_gemm_f16(const lpm_gemm_desc* desc, lpm_stream_t stream) {
 int lpm_gemm_tile_n(int N) { return gemm_pick_bn(N); }
 
 int lpm_gemm_splits(int K, int requested_splits) { return gemm_effective_splits(K, requested_splits); }
+void lpm_debug_set_gemm_pair_mode(int mode) { gemm_set_pair_mode(mode); }
 
 #define ST(s) static_cast<cudaStream_t>(s)
 #define H16(p) reinterpret_cast<__half*>(p)

@@ -7,6 +7,12 @@
 // Either operand may be K-major or MN-major in memory, so NN / NT / TN products (forward, dX, dW)
 // need no transposes.  Batched (3-D tensor maps) and split-K (fp32 partials) variants included.
 //
+// TWO = 1 (large products): a 2-CTA cluster works on a 256 x 256 tile with tcgen05.mma.cta_group::2.  Each CTA
+// loads its own 128 rows of A and HALF of the B tile (128 columns), so the L2 -> shared-memory feed per CTA drops
+// from 48 KB to 32 KB per k-block (the 1-CTA kernel is bound by that feed), and the ring holds 6 stages.  The
+// leader CTA issues every MMA; completion is multicast to both CTAs' barriers; each CTA runs the unchanged
+// epilogue on its own 128 x 256 accumulator.
+//
 // Replaces the tf.matmul / tf.layers.dense / slim.fully_connected call sites of the hot path:
 //   frame_level_models.py:2319,2347  transformer_utils.py:559-561,583-585,701-711
 //   video_level_models.py:86-114 and their autodiff transposes.
@@ -46,7 +52,7 @@ struct GemmKernelParams {
   int tma_store;        // 1: epilogue stages 128-byte-row slabs in smem and writes them with TMA
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES>     // BN = B columns staged by ONE CTA per k-block
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
@@ -172,11 +178,83 @@ __device__ __forceinline__ void epi_store_direct(const float* v, const GemmKerne
   }
 }
 
-template <int BN, int STAGES, int A_MN, int B_MN>
+// ---- 2-CTA (cta_group::2) primitives ----
+__device__ __forceinline__ uint32_t g2_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t g2_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void g2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory, completion bytes signalled on a barrier of the CTA pair (cluster address)
+__device__ __forceinline__ void g2_tma_load_3d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                               int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr),
+        "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void g2_umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the issued MMAs retire
+__device__ __forceinline__ void g2_umma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void g2_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void g2_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) {
+      printf("lpm: gemm pair mbarrier timeout block=%d thread=%d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void g2_tmem_alloc(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void g2_tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(kCols) : "memory");
+}
+
+template <int BN, int STAGES, int A_MN, int B_MN, int TWO>
 __global__ void __launch_bounds__(320, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_c, const GemmKernelParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  constexpr int BNL = TWO ? BN / 2 : BN;      // B columns staged by this CTA
+  constexpr int MT = TWO ? 2 : 1;             // 128-row tiles per work item (one per CTA of the pair)
+  using L = GemmSmem<BNL, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -199,17 +277,24 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 8 * MT);       // the leader's barrier also collects the peer's epilogue warps
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (TWO) g2_tmem_alloc<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (TWO) g2_cluster_sync();                  // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = TWO ? (int)g2_ctarank() : 0;
+  const int work_id = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int m_units = (p.m_tiles + MT - 1) / MT;
+  const int tiles_per_batch = m_units * p.n_tiles;
   const int total_tiles = tiles_per_batch * p.batch * p.splits;
 
   if (warp == 0) {
@@ -217,34 +302,54 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = work_id; tile < total_tiles; tile += work_stride) {
         int t = tile;
-        const int mt = t % p.m_tiles; t /= p.m_tiles;
+        const int mt = t % m_units;   t /= m_units;
         const int nt = t % p.n_tiles; t /= p.n_tiles;
         const int bz = t % p.batch;   t /= p.batch;
         const int sp = t;
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = mt * BM, n0 = nt * BN;
+        const int m0 = (mt * MT + crank) * BM, n0 = nt * BN + crank * BNL;
         const int za = p.a_batched ? bz : 0, zb = p.b_batched ? bz : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if (A_MN == 0) {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, za);
-          } else {
+          if (!TWO) {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if (A_MN == 0) {
+              tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, za);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_3d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, za);
-          }
-          if (B_MN == 0) {
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * BK, n0, zb);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_3d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * BK, za);
+            }
+            if (B_MN == 0) {
+              tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * BK, n0, zb);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK, zb);
+              for (int j = 0; j < BNL / 64; ++j)
+                tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * BK, zb);
+            }
+          } else {
+            // both CTAs' bytes complete on the LEADER's barrier, which expects the whole pair's stage
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            const uint32_t fb = g2_mapa(smem_u32(&full_bar[stage]), 0);
+            if (A_MN == 0) {
+              g2_tma_load_3d(sa, &tmap_a, fb, kb * BK, m0, za);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                g2_tma_load_3d(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, kb * BK, za);
+            }
+            if (B_MN == 0) {
+              g2_tma_load_3d(sb, &tmap_b, fb, kb * BK, n0, zb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BNL / 64; ++j)
+                g2_tma_load_3d(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, kb * BK, zb);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -252,17 +357,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * MT, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = work_id; tile < total_tiles; tile += work_stride) {
         const int sp = tile / (tiles_per_batch * p.batch);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (TWO) g2_wait_cluster(&tempty_bar[acc], acc_phase ^ 1); else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -276,12 +381,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                         : umma_smem_desc(sa + ks * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc(sb + ks * 2048, 8192, 1024)
                                         : umma_smem_desc(sb + ks * 32, 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+            if (TWO) g2_umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+            else umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (TWO) g2_umma_commit(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (TWO) g2_umma_commit(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -296,12 +404,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int trow = quarter * 32 + lane;    // row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tempty_leader[2] = {TWO ? g2_mapa(smem_u32(&tempty_bar[0]), 0) : 0u,
+                                       TWO ? g2_mapa(smem_u32(&tempty_bar[1]), 0) : 0u};
+    for (int tile = work_id; tile < total_tiles; tile += work_stride) {
       int t = tile;
-      const int mt = t % p.m_tiles; t /= p.m_tiles;
+      const int mu = t % m_units;   t /= m_units;
       const int nt = t % p.n_tiles; t /= p.n_tiles;
       const int bz = t % p.batch;   t /= p.batch;
       const int sp = t;
+      const int mt = mu * MT + crank;          // this CTA's 128-row tile
       const int row = mt * BM + trow;
       const bool row_ok = row < p.M;
       const float rs = (p.row_scale != nullptr && row_ok)
@@ -320,7 +431,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if (my_last < 0) {                      // this group has no slab in a narrow tail tile
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) { if (TWO) g2_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]); }
       }
 #pragma unroll 1
       for (int sl = grp; sl < n_slabs; sl += 2) {
@@ -335,7 +446,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           // accumulator fully read by this warp: hand the TMEM buffer back before finishing the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) { if (TWO) g2_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]); }
         }
         if (p.tma_store) {
           if (leader) bulk_wait_read<0>();                   // this group's previous slab has left smem
@@ -394,40 +505,60 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) g2_cluster_sync();                  // no CTA of the pair leaves (or frees TMEM) while the other still works
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (TWO) g2_tmem_dealloc<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
 // ----------------------------------------------------------------------------------------------
 // host launcher
 // ----------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int A_MN, int B_MN>
+template <int BN, int STAGES, int A_MN, int B_MN, int TWO>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKernelParams& p,
                        cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_f16_kernel<BN, STAGES, A_MN, B_MN>;
+  using L = GemmSmem<TWO ? BN / 2 : BN, STAGES>;
+  auto kern = gemm_f16_kernel<BN, STAGES, A_MN, B_MN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
     LPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.batch * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 320, L::TOTAL, st>>>(ta, tb, tc, p);
-  LPM_CUDA_CHECK(cudaGetLastError());
+  const int m_units = TWO ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total = m_units * p.n_tiles * p.batch * p.splits;
+  if (!TWO) {
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, 320, L::TOTAL, st>>>(ta, tb, tc, p);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
+  const int pairs = total < num_sms() / 2 ? total : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return LPM_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TWO>
 static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                           const GemmKernelParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, 0, 0>(ta, tb, tc, p, st);
-  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, 0, 1>(ta, tb, tc, p, st);
-  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, 1, 0>(ta, tb, tc, p, st);
-  return launch_gemm<BN, STAGES, 1, 1>(ta, tb, tc, p, st);
+  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, 0, 0, TWO>(ta, tb, tc, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, 0, 1, TWO>(ta, tb, tc, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, 1, 0, TWO>(ta, tb, tc, p, st);
+  return launch_gemm<BN, STAGES, 1, 1, TWO>(ta, tb, tc, p, st);
 }
+
+static int g_gemm_pair_mode = 1;   // 0: never use CTA pairs, 1: automatic
+void gemm_set_pair_mode(int mode) { g_gemm_pair_mode = mode; }
 
 int gemm_pick_bn(int N) {
   if (N >= 256 || N > 192) return 256;
@@ -473,7 +604,10 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
   if (!g.a_mn) rc = make_tmap_3d(&ta, g.A, 2, g.K, g.M, p.a_batched ? g.batch : 1, g.lda, g.a_batch_stride, BK, BM);
   else         rc = make_tmap_3d(&ta, g.A, 2, g.M, g.K, p.a_batched ? g.batch : 1, g.lda, g.a_batch_stride, 64, BK);
   if (rc) return rc;
-  if (!g.b_mn) rc = make_tmap_3d(&tb, g.B, 2, g.K, g.N, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, BK, BN);
+  // 2-CTA pairs for products with at least one full wave of 256 x 256 tiles (each CTA then stages half of the B tile)
+  const bool two = g_gemm_pair_mode != 0 && BN == 256 &&
+                   (long long)((p.m_tiles + 1) / 2) * p.n_tiles * p.batch * p.splits >= num_sms() / 2 && p.m_tiles >= 2;
+  if (!g.b_mn) rc = make_tmap_3d(&tb, g.B, 2, g.K, g.N, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, BK, two ? BN / 2 : BN);
   else         rc = make_tmap_3d(&tb, g.B, 2, g.N, g.K, p.b_batched ? g.batch : 1, g.ldb, g.b_batch_stride, 64, BK);
   if (rc) return rc;
 
@@ -492,9 +626,10 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
     rc = make_tmap_3d(&tc, g.out, es, g.N, g.M, (uint64_t)p.splits * p.batch, g.ldc, zstride, g.out_f32 ? 32 : 64, BM);
     if (rc) return rc;
   }
-  if (BN == 256) return dispatch_major<256, 4>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
-  if (BN == 128) return dispatch_major<128, 6>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
-  return dispatch_major<64, 8>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  if (two) return dispatch_major<256, 6, 1>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  if (BN == 256) return dispatch_major<256, 4, 0>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  if (BN == 128) return dispatch_major<128, 6, 0>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
+  return dispatch_major<64, 8, 0>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
 }
 
 int gemm_effective_splits(int K, int splits) {

@@ -13,6 +13,7 @@ using GemmArgs = lpm_gemm_desc;
 int gemm_f16(const GemmArgs& g, cudaStream_t st);
 int gemm_pick_bn(int N);
 int gemm_effective_splits(int K, int splits);
+void gemm_set_pair_mode(int mode);
 
 // lpm_elementwise.cu
 int sample_stats_blocks();

@@ -36,6 +36,48 @@ def test_gemm_layouts(cuda, M, N, K, a_mn, b_mn):
     _check(out16, ref, 1e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(4900, 1024, 200), (9728, 512, 136), (2560, 1000, 72)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (False, False), (True, True), (True, False)])
+def test_gemm_cta_pairs(cuda, M, N, K, a_mn, b_mn):
+    """Products with at least 74 tiles of 256 x 256 run on 2-CTA clusters (tcgen05.mma.cta_group::2): odd numbers of
+    128-row tiles (4900 -> 39, the peer CTA's last tile is all padding), ragged N / K, every operand layout, fused
+    epilogue; identical to the 1-CTA kernel's result (the accumulation order per element is the same)."""
+    import ctypes as C
+    from learnablepoolingmethods_b200 import ops, _lib
+    lib = _lib.load()
+    torch.manual_seed(M + N + K)
+    def alloc(r, c):
+        cp = (c + 7) // 8 * 8
+        return _rand((r, cp), cuda)[:, :c]
+    A = alloc(K, M) if a_mn else alloc(M, K)
+    B = alloc(K, N) if b_mn else alloc(N, K)
+    bias = torch.randn(N, device=cuda)
+    ref = torch.relu((A.t() if a_mn else A).float() @ (B if b_mn else B.t()).float() + bias)
+    out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True, out_dtype=torch.float32)
+    out16 = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True)
+    lib.lpm_debug_set_gemm_pair_mode(0)
+    try:
+        single = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True, out_dtype=torch.float32)
+    finally:
+        lib.lpm_debug_set_gemm_pair_mode(1)
+    torch.cuda.synchronize()
+    _check(out, ref, 1e-5)
+    _check(out16, ref, 1e-3)
+    assert torch.equal(out, single)
+
+
+def test_gemm_cta_pairs_batched_stats(cuda):
+    from learnablepoolingmethods_b200 import ops
+    torch.manual_seed(3)
+    Bt, M, N, K = 20, 512, 512, 192
+    A, B = _rand((Bt, M, K), cuda), _rand((K, N), cuda, 0.1)
+    rs = torch.rand(Bt, M, device=cuda) + 0.5
+    ref = rs[:, :, None] * torch.matmul(A.float(), B.float())
+    out, st = ops.gemm(A, B, row_scale=rs, out_dtype=torch.float32, stats=True)
+    _check(out, ref, 1e-5)
+    _check(st[0].sum(dim=1), ref.sum(dim=2), 1e-4)
+
+
 def test_gemm_epilogue_bias_relu_rowscale_stats(cuda):
     from learnablepoolingmethods_b200 import ops
     torch.manual_seed(0)
