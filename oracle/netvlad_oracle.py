@@ -488,7 +488,7 @@ def dequantize(feat_vector, max_quantized_value=2, min_quantized_value=-2):
 
 
 def synthetic_batch(batch, *, seed, max_frames=300, feat=1152, vocab=3862, fixed_num_frames=None,
-                    dtype=torch.float32, return_codes=False):
+                    dtype=torch.float32, return_codes=False, video_scale=0.0):
     """uint8 codes from clipped N(0,1), dequantised (utils.py:28-43),
     zero-padded to max_frames (readers.py:193), per-frame L2 normalised (train.py:264)."""
     g = torch.Generator().manual_seed(seed)
@@ -497,6 +497,10 @@ def synthetic_batch(batch, *, seed, max_frames=300, feat=1152, vocab=3862, fixed
     else:
         nf = torch.full((batch,), fixed_num_frames, dtype=torch.int32)
     z = torch.randn(batch, max_frames, feat, generator=g)
+    if video_scale > 0:
+        # videos that differ from each other (a per-video offset in feature space): i.i.d. noise videos are nearly
+        # identical after pooling, which makes every batch statistic downstream degenerate
+        z = (z + video_scale * torch.randn(batch, 1, feat, generator=g)) / math.sqrt(1.0 + video_scale ** 2)
     q = torch.clamp(torch.round((z + 2) * 255 / 4), 0, 255)
     x = dequantize(q)
     mask = (torch.arange(max_frames)[None, :] < nf[:, None]).to(x.dtype)
