@@ -21,6 +21,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: keep a private handle to it and send everything else that writes to fd 1
+# (NCCL prints its version banner there from C) to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 import torch  # noqa: E402
 
 CFG = dict(batch=80, max_frames=300, iterations=256, cluster_size=256, hidden_size=512, vocab=3862, feat=1152)
@@ -168,7 +173,7 @@ def main():
                    cpu_baseline={"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample},
                    e2e={"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
-        print(json.dumps(out))
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
         return
 
     import torch.distributed as dist
@@ -301,7 +306,7 @@ def main():
         if args.gpus == 1 and not args.no_cpu_baseline:
             v, sec, cores, sample = cpu_reference(2, 1)
             out["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(out))
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -271,6 +271,19 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                        const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
                        float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
 
+/* Split-phase variant for ONE tensor whose rows are sharded over data-parallel ranks (hidden1_weights under DP:
+ * every rank owns rows [r*Kd/W, (r+1)*Kd/W), updates them, and the fp16 operand shards are all-gathered).
+ * p/g/m/v point at the shard; table = chunk table of the shard ({0, start/32, len, start/32}); wd1 = [1] regulariser.
+ *   lpm_shard_sqnorm: sumsq[0] = sum (g + wd p)^2 over the shard   -> the caller all-reduces sumsq over the ranks
+ *   lpm_shard_adam  : factor = clip / max(sqrt(sumsq), clip) (tf.clip_by_norm over the whole tensor), then Adam and
+ *                     the fp16 shadow of the shard (sh_* as in lpm_adam_clip_step, one entry). */
+int lpm_shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
+                     float* sumsq, lpm_stream_t stream);
+int lpm_shard_adam(float* p, const float* g, float* m, float* v, const int* table, int n_chunks, const float* wd1,
+                   const float* sumsq, float clip, float* factor, float* norm, int* flag,
+                   const unsigned long long* sh_ptr, const int* sh_cols, const long long* sh_ld, float lr_t, float b1,
+                   float b2, float eps, lpm_stream_t stream);
+
 /* Factored optimiser step for a dense layer whose weight gradient is the rank-R product dW = alpha * A^T G
  * (hidden1_weights, frame_level_models.py:2314-2319: A = VLAD descriptor fp16 [R][Kd], G = output gradient fp16
  * [R][N], R = tower batch <= 128).  dW is never materialised: lpm_rank_grad_clip derives the tf.clip_by_norm factor

@@ -357,6 +357,23 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                         factor, norms, flag, ST(stream));
 }
 
+int lpm_shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
+                     float* sumsq, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(g && p && table && wd1 && partial && sumsq && n_chunks > 0, "lpm_shard_sqnorm: bad arguments");
+  return shard_sqnorm(g, p, table, n_chunks, wd1, partial, sumsq, ST(stream));
+}
+
+int lpm_shard_adam(float* p, const float* g, float* m, float* v, const int* table, int n_chunks, const float* wd1,
+                   const float* sumsq, float clip, float* factor, float* norm, int* flag,
+                   const unsigned long long* sh_ptr, const int* sh_cols, const long long* sh_ld, float lr_t, float b1,
+                   float b2, float eps, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(p && g && m && v && table && wd1 && sumsq && factor && norm && flag && n_chunks > 0, "lpm_shard_adam: bad arguments");
+  return shard_adam(p, g, m, v, table, n_chunks, wd1, sumsq, clip, factor, norm, flag, sh_ptr, sh_cols, sh_ld, lr_t, b1, b2,
+                    eps, ST(stream));
+}
+
 int lpm_layernorm_chain_supported(int rows, int D) { return layernorm_chain_supported(rows, D); }
 
 int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,

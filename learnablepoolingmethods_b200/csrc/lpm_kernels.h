@@ -95,6 +95,11 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
                    long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace, size_t workspace_bytes,
                    cudaStream_t st);
 size_t rank_adam_workspace_bytes(int R, int N);
+int shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
+                 float* sumsq, cudaStream_t st);
+int shard_adam(float* p, const float* g, float* m, float* v, const int* table, int n_chunks, const float* wd1,
+               const float* sumsq, float clip, float* factor, float* norm, int* flag, const unsigned long long* sh_ptr,
+               const int* sh_cols, const long long* sh_ld, float lr_t, float b1, float b2, float eps, cudaStream_t st);
 
 // lpm_layernorm.cu
 int layernorm_chain_supported(int rows, int D);

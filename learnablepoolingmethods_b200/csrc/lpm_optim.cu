@@ -386,6 +386,52 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
   return LPM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-phase clip + Adam for a tensor whose rows are SHARDED over the data-parallel ranks (hidden1_weights):
+//   shard_sqnorm : sum of squares of this rank's gradient shard -> sumsq[0]      (then all-reduced by the caller)
+//   shard_adam   : factor = clip / max(sqrt(sumsq), clip) (tf.clip_by_norm over the WHOLE tensor, utils.py:181-188),
+//                  Adam + fp16 shadow on the shard with the multi-tensor kernel (table of one tensor)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shard_sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int i = 0; i < 8; ++i) r += red[i];
+    out[0] = (float)r;
+  }
+}
+
+__global__ void shard_clip_kernel(const float* __restrict__ sumsq, float clip, float* __restrict__ factor,
+                                  float* __restrict__ norm, int* __restrict__ flag) {
+  const float n = sqrtf(fmaxf(sumsq[0], 0.f));
+  if (!isfinite(n) || !(sumsq[0] == sumsq[0])) atomicExch(flag, 1);
+  norm[0] = n;
+  factor[0] = clip > 0.f ? clip / fmaxf(n, clip) : 1.f;
+}
+
+int shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
+                 float* sumsq, cudaStream_t st) {
+  mt_sqnorm_kernel<<<n_chunks, 256, 0, st>>>(g, p, table, wd1, partial);
+  shard_sumsq_final_kernel<<<1, 256, 0, st>>>(partial, n_chunks, sumsq);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+int shard_adam(float* p, const float* g, float* m, float* v, const int* table, int n_chunks, const float* wd1,
+               const float* sumsq, float clip, float* factor, float* norm, int* flag, const unsigned long long* sh_ptr,
+               const int* sh_cols, const long long* sh_ld, float lr_t, float b1, float b2, float eps, cudaStream_t st) {
+  shard_clip_kernel<<<1, 1, 0, st>>>(sumsq, clip, factor, norm, flag);
+  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd1, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, b1, b2, eps);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
                    const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                    const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2, float eps,

@@ -71,6 +71,7 @@ class NetVladEngine:
             raise NotImplementedError("netvlad_add_batch_norm=False is unreachable in the reference (D7)")
         self.build_variables()
         self._side = None          # second CUDA stream + fork / join events (created on first use)
+        self.pre_head_hook = None  # callable run right before the hidden projection reads its fp16 weights
 
     def _side_stream(self):
         if self._side is None:
@@ -407,6 +408,8 @@ class NetVladEngine:
         """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         Hn = c.hidden_size
+        if self.pre_head_hook is not None:
+            self.pre_head_hook()    # data parallel: the all-gather of the updated fp16 weight shards lands here
         parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
         act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
         act16 = torch.empty((B, Hn), dtype=torch.float16, device=vlad.device)
@@ -448,6 +451,7 @@ class NetVladEngine:
         f32 = torch.float32
         grads: Dict[str, torch.Tensor] = {}
         hook = ctx.get("grad_hook")
+        deferred_hidden = None
         views = ctx.get("grad_views")       # optional {name: preallocated fp32 view} (flat gradient buffer)
         ctx["_gout"] = (lambda n: views.get(n) if views is not None else None)
         gout = ctx["_gout"]
@@ -489,8 +493,10 @@ class NetVladEngine:
             # the trainer applies clip + Adam straight from the factors (dW = inv * vlad^T dact16 is never written)
             ctx["hidden_factors"] = (hd["vlad"], dact16, inv)
         elif ctx.get("hidden_dw") is not None:
-            # data parallel: the trainer sums this gradient over the ranks from all-gathered factors (dp.FactorGather)
-            put("hidden1_weights", ctx["hidden_dw"](dact16, inv, gout("hidden1_weights")))
+            # data parallel: the trainer sums this gradient over the ranks from all-gathered factors (dp.FactorGather).
+            # The product is formed at the END of the backward so that the gather of the 43 MB-per-rank descriptors
+            # (started right after the forward) has the whole backward to hide under.
+            deferred_hidden = (dact16, inv)
         else:
             put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
                                             out=gout("hidden1_weights")))
@@ -526,6 +532,8 @@ class NetVladEngine:
             put(n, g)
         put("input_bn/gamma", dgamma_in)
         put("input_bn/beta", dbeta_in)
+        if deferred_hidden is not None:
+            put("hidden1_weights", ctx["hidden_dw"](deferred_hidden[0], deferred_hidden[1], gout("hidden1_weights")))
         return grads
 
     def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):

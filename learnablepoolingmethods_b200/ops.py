@@ -514,6 +514,20 @@ def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, cl
                                  stream_ptr()), "lpm_adam_clip_step")
 
 
+def shard_sqnorm(p, g, table, wd1, partial, sumsq):
+    lib = _lib.load()
+    check(lib.lpm_shard_sqnorm(ptr(g), ptr(p), ptr(table), table.shape[0], ptr(wd1), ptr(partial), ptr(sumsq), stream_ptr()),
+          "lpm_shard_sqnorm")
+
+
+def shard_adam(p, g, m, v, table, wd1, sumsq, *, clip, lr_t, factor, norm, flag, shadow=None, b1=0.9, b2=0.999, eps=1e-8):
+    lib = _lib.load()
+    sp, sc, sl = shadow if shadow is not None else (None, None, None)
+    check(lib.lpm_shard_adam(ptr(p), ptr(g), ptr(m), ptr(v), ptr(table), table.shape[0], ptr(wd1), ptr(sumsq), C.c_float(clip),
+                             ptr(factor), ptr(norm), ptr(flag), ptr(sp), ptr(sc), ptr(sl), C.c_float(lr_t), C.c_float(b1),
+                             C.c_float(b2), C.c_float(eps), stream_ptr()), "lpm_shard_adam")
+
+
 _WS = {}
 
 

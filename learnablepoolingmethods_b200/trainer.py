@@ -89,6 +89,93 @@ class FlatState:
         return self.offsets[name] + self.store.vars[name].numel()
 
 
+class ShardedHiddenUpdate:
+    """Data-parallel update of hidden1_weights (85 % of the parameters) without moving its gradient or repeating its
+    optimiser step on every rank.  Rank r owns rows [r*Kd/W, (r+1)*Kd/W) of W_h [Kd, H]:
+
+      * after the forward the ranks exchange descriptor COLUMN slices (all-to-all, 43 MB/W received per peer): rank r
+        ends up with A_all[:, rows_r] for every video of the global batch;  dLoss/dhidden (80 KB) is all-gathered;
+      * dW[rows_r] = inv * A_all[:, rows_r]^T G_all  -- the tower-summed gradient (utils.py:205-211) of the shard, one
+        tcgen05 GEMM;  tf.clip_by_norm (utils.py:181-188) needs the norm of the whole tensor: a scalar all-reduce;
+      * clip + Adam run on the shard only (1/W of the 3.6 GB optimiser stream) and refresh the fp16 operand shard;
+      * the fp16 shards are all-gathered in place into the GEMM operand; the gather rides under the next forward
+        (the engine waits for it right before the hidden projection).
+
+    fp32 master rows of other ranks go stale on purpose; `sync_master()` all-gathers them (checkpointing)."""
+
+    def __init__(self, trainer, flat):
+        import torch.distributed as dist
+        self.dist, self.pg = dist, trainer.pg
+        self.world, self.rank = dist.get_world_size(trainer.pg), dist.get_rank(trainer.pg)
+        store, c = trainer.store, trainer.cfg
+        Kd, H = c.vlad_dim, c.hidden_size
+        self.rows, self.H = Kd // self.world, H
+        r0 = self.rank * self.rows
+        dev = store.device
+        w = store.vars["hidden1_weights"]
+        m, v = flat.moment_views["hidden1_weights"]
+        self.w, self.m_full, self.v_full = w, m, v
+        self.w_s, self.m_s, self.v_s = w[r0:r0 + self.rows], m[r0:r0 + self.rows], v[r0:r0 + self.rows]
+        self.wh16 = store.shadows["wh16"]
+        assert self.wh16.is_contiguous() and tuple(self.wh16.shape) == (Kd, H)
+        self.wh16_s = self.wh16[r0:r0 + self.rows]
+        n = self.rows * H
+        table = [(0, c0 // ALIGN, min(CHUNK, n - c0), c0 // ALIGN) for c0 in range(0, n, CHUNK)]
+        self.table = torch.tensor(table, dtype=torch.int32, device=dev)
+        self.wd1 = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.partial = torch.zeros(len(table), dtype=torch.float32, device=dev)
+        self.sumsq, self.factor, self.norm = (torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3))
+        self.flag = flat.scratch[3]
+        ptrs = torch.tensor([self.wh16_s.data_ptr()], dtype=torch.int64, device=dev)
+        self.shadow = (ptrs.view(torch.uint64) if hasattr(torch, "uint64") else ptrs,
+                       torch.tensor([H], dtype=torch.int32, device=dev),
+                       torch.tensor([self.wh16.stride(0)], dtype=torch.int64, device=dev))
+        self.dw = torch.empty((self.rows, H), dtype=torch.float32, device=dev)
+        self.send = self.recv = self.g_all = None
+        self.h_a2a = self.h_gather = None
+
+    @staticmethod
+    def supported(cfg, world) -> bool:
+        return world > 1 and cfg.vlad_dim % world == 0 and (cfg.vlad_dim // world) % 64 == 0 and cfg.hidden_size % 8 == 0
+
+    def start_exchange(self, vlad):
+        """vlad fp16 [B, Kd] of this tower -> every rank receives its row slice of every tower's descriptor."""
+        B = vlad.shape[0]
+        if self.send is None or self.send.shape[1] != B:
+            self.send = torch.empty((self.world, B, self.rows), dtype=vlad.dtype, device=vlad.device)
+            self.recv = torch.empty_like(self.send)
+            self.g_all = torch.empty((self.world * B, self.H), dtype=torch.float16, device=vlad.device)
+        self.send.copy_(vlad.view(B, self.world, self.rows).transpose(0, 1))      # pack (plumbing for the collective)
+        self.h_a2a = self.dist.all_to_all_single(self.recv, self.send, group=self.pg, async_op=True)
+
+    def wait_weights(self):
+        if self.h_gather is not None:
+            self.h_gather.wait()
+            self.h_gather = None
+
+    def step(self, dact16, inv, clip, lr_t):
+        d = self.dist
+        d.all_gather_into_tensor(self.g_all, dact16.contiguous(), group=self.pg)
+        self.h_a2a.wait()
+        a_s = self.recv.view(-1, self.rows)                                        # [W*B, rows] = A_all[:, my rows]
+        ops.gemm(a_s, self.g_all, a_mn=True, b_mn=True, out_dtype=torch.float32, alpha=inv, out=self.dw)
+        ops.shard_sqnorm(self.w_s, self.dw, self.table, self.wd1, self.partial, self.sumsq)
+        d.all_reduce(self.sumsq, op=d.ReduceOp.SUM, group=self.pg)
+        return lambda: self._apply(clip, lr_t)
+
+    def _apply(self, clip, lr_t):
+        ops.shard_adam(self.w_s, self.dw, self.m_s, self.v_s, self.table, self.wd1, self.sumsq, clip=clip, lr_t=lr_t,
+                       factor=self.factor, norm=self.norm, flag=self.flag, shadow=self.shadow)
+        self.h_gather = self.dist.all_gather_into_tensor(self.wh16, self.wh16_s, group=self.pg, async_op=True)
+
+    def sync_master(self):
+        """All-gather the fp32 master rows (and Adam moments) so that every rank holds the full tensors again."""
+        self.wait_weights()
+        r0 = self.rank * self.rows
+        for full in (self.w, self.m_full, self.v_full):
+            self.dist.all_gather_into_tensor(full, full[r0:r0 + self.rows], group=self.pg)
+
+
 class Trainer:
     def __init__(self, engine: NetVladEngine, *, base_learning_rate=0.0002, learning_rate_decay=0.85,
                  learning_rate_decay_examples=4000000, clip_gradient_norm=1.0, regularization_penalty=1.0,
@@ -107,6 +194,9 @@ class Trainer:
         self.rank_scratch = None
         # data parallel: hidden1_weights' gradient (85 % of the bytes) is summed from all-gathered factors
         self.gather = FactorGather(process_group) if self.world > 1 and self.gather_hidden_factors else None
+        self.shard: Optional[ShardedHiddenUpdate] = None      # created with the flat state (first step)
+        self.use_shard = (self.world > 1 and self.shard_hidden_update and self.gather_hidden_factors
+                          and ShardedHiddenUpdate.supported(self.cfg, self.world))
 
     def _factored_hidden(self, batch: int) -> bool:
         """hidden1_weights (85 % of the parameters) is updated from its gradient factors on a single tower: with
@@ -118,10 +208,11 @@ class Trainer:
 
     disable_factored_hidden = False
     gather_hidden_factors = True
+    shard_hidden_update = True
 
     def _hidden_dw(self, dact16, inv, out):
         """sum over ranks of inv * vlad_r^T dact_r from the gathered factors (one GEMM over world*B rows)."""
-        g_all = self.gather.start("dact", dact16)
+        self.gather.start("dact", dact16)
         a_all = self.gather.wait("vlad")
         g_all = self.gather.wait("dact")
         return ops.gemm(a_all, g_all, a_mn=True, b_mn=True, out_dtype=torch.float32, alpha=inv, out=out)
@@ -163,13 +254,15 @@ class Trainer:
         eng = self.engine
         pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True)
         B = pred.shape[0]
-        if self.gather is not None:
-            self.gather.start("vlad", ctx["head"]["vlad"])       # rides under the whole backward
+        if self.use_shard and self.shard is not None:
+            self.shard.start_exchange(ctx["head"]["vlad"])       # rides under the whole backward
+        elif self.gather is not None and not self.use_shard:
+            self.gather.start("vlad", ctx["head"]["vlad"])
             ctx["hidden_dw"] = self._hidden_dw
         loss, _ = ops.xent_fwd(pred, labels_u8)
         dpred = ops.xent_bwd(pred, labels_u8, 1.0 / B)
         order: List[str] = []
-        factored = self._factored_hidden(B)
+        factored = self._factored_hidden(B) or self.use_shard
         ctx["factored_hidden"] = factored
         if self.flat is None:
             ctx["grad_hook"] = lambda n, g: order.append(n)
@@ -178,9 +271,13 @@ class Trainer:
             self.flat.bind_shadows(eng)
             for n, g in grads.items():
                 self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
+            if self.use_shard:
+                self.shard = ShardedHiddenUpdate(self, self.flat)
+                eng.pre_head_hook = self.shard.wait_weights
+                self.shard.start_exchange(ctx["head"]["vlad"])
             if self.world > 1:
                 skip = ()
-                if self.gather is not None:
+                if self.gather is not None and not self.use_shard:
                     o = self.flat.offsets["hidden1_weights"]
                     skip = ((o, self.flat.end_offset("hidden1_weights")),)
                 self.reducer = BucketedAllReduce(self.flat.g, self.bucket_elems, self.pg, skip=skip)
@@ -200,7 +297,12 @@ class Trainer:
         lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
         if factored != bool(f.factored):
             raise RuntimeError("the tower batch size changed across the factored-update limit after the first step")
-        hidden_update = self._factored_hidden_step(ctx, lr_t) if factored else None   # norm first: it may raise the skip flag
+        # norm first: it may raise the skip flag
+        if self.use_shard:
+            _, dact16, inv = ctx["hidden_factors"]
+            hidden_update = self.shard.step(dact16, inv, self.clip, lr_t)
+        else:
+            hidden_update = self._factored_hidden_step(ctx, lr_t) if factored else None
         ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=lr_t, scratch=f.scratch,
                            shadow=f.shadow)
         if hidden_update is not None:
@@ -221,3 +323,9 @@ class Trainer:
         if r:
             flag.zero_()
         return r
+
+    def sync_parameters(self):
+        """Data parallel: make every rank's fp32 copy of hidden1_weights (and its Adam moments) complete again
+        (rows owned by other ranks are only refreshed as fp16 GEMM operands during training).  Call before saving."""
+        if self.shard is not None:
+            self.shard.sync_master()
