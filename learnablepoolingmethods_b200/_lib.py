@@ -67,9 +67,18 @@ def check(rc: int, what: str = "") -> None:
         raise LpmError(f"{what} failed (code {rc}): {msg}")
 
 
+_DEVICE_INDEX = None
+
+
 def stream_ptr() -> C.c_void_p:
+    """cudaStream_t of torch's current stream on this process's device (one process per GPU: the device index is
+    read once).  torch.cuda.current_stream() costs ~14 us per call, a third of the host time of a training step;
+    the raw getter is ~0.3 us."""
+    global _DEVICE_INDEX
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if _DEVICE_INDEX is None:
+        _DEVICE_INDEX = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(_DEVICE_INDEX))
 
 
 def ptr(t) -> C.c_void_p:
