@@ -284,6 +284,24 @@ int lpm_shard_adam(float* p, const float* g, float* m, float* v, const int* tabl
                    const unsigned long long* sh_ptr, const int* sh_cols, const long long* sh_ld, float lr_t, float b1,
                    float b2, float eps, lpm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (the reference computes them with numpy on a host copy of the
+ * predictions every logged step, train.py:448-449).
+ *   lpm_eval_topk    : per video the k largest predictions, descending (ties -> lower class index):
+ *                      eval_util.top_k_triplets (eval_util.py:128-135) as top_val/top_idx/top_lab [B][k]
+ *                      (unused slots when V < k: -inf / -1 / 0), and row_stats [B][3] =
+ *                      { hit@1 (eval_util.py:27-42), PERR (eval_util.py:45-70; 0 for a video without labels),
+ *                        number of labels }.  pred fp32 [B][V] (row stride ld), labels uint8 [B][V] (stride ldl).
+ *   lpm_eval_metrics : metrics[3] = { mean hit@1, mean PERR, GAP } with GAP = eval_util.calculate_gap
+ *                      (eval_util.py:73-91 -> average_precision_calculator.py:203-262: all B*k triplets ranked by
+ *                      score, average precision against the number of positives of the whole batch).
+ * Limits: V <= 8192, B*k <= 16384.
+ * ------------------------------------------------------------------------------------------- */
+int lpm_eval_topk(const float* pred, long long ld, const unsigned char* labels, long long ldl, int B, int V, int k,
+                  float* top_val, int* top_idx, unsigned char* top_lab, float* row_stats, lpm_stream_t stream);
+int lpm_eval_metrics(const float* top_val, const unsigned char* top_lab, int B, int k, const float* row_stats,
+                     float* metrics, lpm_stream_t stream);
+
 /* Factored optimiser step for a dense layer whose weight gradient is the rank-R product dW = alpha * A^T G
  * (hidden1_weights, frame_level_models.py:2314-2319: A = VLAD descriptor fp16 [R][Kd], G = output gradient fp16
  * [R][N], R = tower batch <= 128).  dW is never materialised: lpm_rank_grad_clip derives the tf.clip_by_norm factor

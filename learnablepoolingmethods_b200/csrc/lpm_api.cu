@@ -374,6 +374,20 @@ int lpm_shard_adam(float* p, const float* g, float* m, float* v, const int* tabl
                     eps, ST(stream));
 }
 
+int lpm_eval_topk(const float* pred, long long ld, const unsigned char* labels, long long ldl, int B, int V, int k,
+                  float* top_val, int* top_idx, unsigned char* top_lab, float* row_stats, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(pred && labels && top_val && top_idx && top_lab && row_stats, "lpm_eval_topk: null pointer");
+  return eval_topk(pred, ld, labels, ldl, B, V, k, top_val, top_idx, top_lab, row_stats, ST(stream));
+}
+
+int lpm_eval_metrics(const float* top_val, const unsigned char* top_lab, int B, int k, const float* row_stats,
+                     float* metrics, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(top_val && top_lab && row_stats && metrics, "lpm_eval_metrics: null pointer");
+  return eval_metrics(top_val, top_lab, B, k, row_stats, metrics, ST(stream));
+}
+
 int lpm_layernorm_chain_supported(int rows, int D) { return layernorm_chain_supported(rows, D); }
 
 int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,

@@ -108,6 +108,12 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
                         long long u1_stride, float* stats1, const float* gamma2, const float* beta2, __half* u2_out,
                         long long u2_stride, float* stats2, __half* y, long long y_stride, cudaStream_t st);
 
+// lpm_eval.cu
+int eval_topk(const float* pred, long long ld, const unsigned char* labels, long long ldl, int B, int V, int k,
+              float* top_val, int* top_idx, unsigned char* top_lab, float* row_stats, cudaStream_t st);
+int eval_metrics(const float* top_val, const unsigned char* top_lab, int B, int k, const float* row_stats, float* metrics,
+                 cudaStream_t st);
+
 // lpm_pool.cu
 int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, const __half* wc, long long ldw,
                      const float* logit_scale, const float* logit_shift, const __half* centers_t16,

@@ -528,6 +528,28 @@ def shard_adam(p, g, m, v, table, wd1, sumsq, *, clip, lr_t, factor, norm, flag,
                              C.c_float(b2), C.c_float(eps), stream_ptr()), "lpm_shard_adam")
 
 
+def eval_topk(pred, labels_u8, k=20):
+    """(top_val [B,k] fp32, top_idx [B,k] int32, top_lab [B,k] uint8, row_stats [B,3] = hit@1 | PERR | #labels)."""
+    lib = _lib.load()
+    B, V = pred.shape
+    dev = pred.device
+    assert pred.dtype == torch.float32 and labels_u8.dtype == torch.uint8 and pred.stride(1) == 1 and labels_u8.stride(1) == 1
+    tv, ti = _f32((B, k), dev), torch.empty((B, k), dtype=torch.int32, device=dev)
+    tl, rs = torch.empty((B, k), dtype=torch.uint8, device=dev), _f32((B, 3), dev)
+    check(lib.lpm_eval_topk(ptr(pred), _ll(pred.stride(0)), ptr(labels_u8), _ll(labels_u8.stride(0)), B, V, k, ptr(tv), ptr(ti),
+                            ptr(tl), ptr(rs), stream_ptr()), "lpm_eval_topk")
+    return tv, ti, tl, rs
+
+
+def eval_metrics(top_val, top_lab, row_stats):
+    """Device tensor [3] = (hit@1, PERR, GAP) of the batch."""
+    lib = _lib.load()
+    B, k = top_val.shape
+    out = _f32((3,), top_val.device)
+    check(lib.lpm_eval_metrics(ptr(top_val), ptr(top_lab), B, k, ptr(row_stats), ptr(out), stream_ptr()), "lpm_eval_metrics")
+    return out
+
+
 _WS = {}
 
 

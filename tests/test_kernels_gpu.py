@@ -388,3 +388,30 @@ def test_rank_adam_step(cuda, R, Kd, N):
     before = wd.clone()
     ops.rank_adam_step(Ad, Gd, alpha, sc[0:1], flag, wd, md, vd, w16, lr_t=lr_t)
     assert torch.equal(before, wd)
+
+
+def test_eval_metrics_against_reference_golden(cuda):
+    """lpm_eval_topk / lpm_eval_metrics against the frozen outputs of the reference's own
+    eval_util.py (tests/golden/eval_golden.npz) and the numpy oracle: top-20 class sets identical, hit@1 / PERR exact to
+    fp32, GAP to 1e-6; videos without labels, V < k and a full 80 x 3862 batch included."""
+    import os
+    from learnablepoolingmethods_b200 import eval_util as GE
+    from oracle import eval_oracle as E
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_golden.npz"))
+    for seed in sorted(int(k[4:]) for k in G.files if k.startswith("case")):
+        meta = G[f"case{seed}"]
+        pred, labels = E.synthetic_eval_batch(int(meta[0]), int(meta[1]), int(meta[2]), tuple(int(z) for z in meta[3:]))
+        p, a = torch.from_numpy(pred).to(cuda), torch.from_numpy(labels).to(cuda)
+        idx, val, lab = GE.top_k_triplets(p, a, 20)
+        k = min(20, pred.shape[1])
+        got = [sorted(r[:k]) for r in idx.cpu().tolist()]
+        assert got == [sorted(r.tolist()) for r in G[f"topk{seed}"]]
+        v = val.cpu().numpy()[:, :k]
+        assert (np.diff(v, axis=1) <= 0).all()                                     # ranked
+        assert np.array_equal(v, np.take_along_axis(pred, idx.cpu().numpy()[:, :k].astype(np.int64), 1))
+        assert np.array_equal(lab.cpu().numpy()[:, :k], np.take_along_axis(labels, idx.cpu().numpy()[:, :k].astype(np.int64), 1))
+        m = GE.batch_metrics(p, a).cpu().double().numpy()
+        assert abs(m[0] - float(G[f"hit{seed}"])) < 1e-6 and abs(m[1] - float(G[f"perr{seed}"])) < 1e-6
+        assert abs(m[2] - float(G[f"gap{seed}"])) < 1e-6
+        assert abs(m[2] - E.gap(pred, labels)) < 1e-6
+    assert abs(GE.calculate_gap(p, a) - float(G[f"gap{seed}"])) < 1e-6

@@ -137,3 +137,34 @@ def test_topk_and_gap_with_reference_eval_util():
         assert ref_set == mine
     gap = eval_util.calculate_gap(pred, labels)
     assert 0.0 <= gap <= 1.0
+
+
+def test_eval_oracle_matches_reference_golden():
+    """tests/golden/eval_golden.npz holds the outputs of the REFERENCE's eval_util.py / average_precision_calculator.py
+    (oracle/make_eval_golden.py, run where /root/reference is mounted): hit@1, PERR, GAP and the top-20 class sets
+    of seeded batches.  The numpy restatement in oracle/eval_oracle.py must reproduce them."""
+    import numpy as np
+    from oracle import eval_oracle as E
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_golden.npz"))
+    seeds = sorted(int(k[4:]) for k in G.files if k.startswith("case"))
+    assert len(seeds) >= 4
+    for seed in seeds:
+        meta = G[f"case{seed}"]
+        pred, labels = E.synthetic_eval_batch(int(meta[0]), int(meta[1]), int(meta[2]), tuple(int(z) for z in meta[3:]))
+        assert abs(E.hit_at_one(pred, labels) - float(G[f"hit{seed}"])) < 1e-12
+        assert abs(E.perr(pred, labels) - float(G[f"perr{seed}"])) < 1e-12
+        assert abs(E.gap(pred, labels) - float(G[f"gap{seed}"])) < 1e-9
+        assert E.top_k_sets(pred, 20) == [sorted(r.tolist()) for r in G[f"topk{seed}"]]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/eval_util.py"), reason="reference tree not mounted")
+def test_eval_golden_is_current():
+    """The committed golden file equals what the reference's module returns today (guards the generator script)."""
+    import numpy as np
+    sys.path.insert(0, "/root/reference")
+    import eval_util
+    from oracle import eval_oracle as E
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_golden.npz"))
+    pred, labels = E.synthetic_eval_batch(102, 7, 50, (3,))
+    assert abs(eval_util.calculate_gap(pred, labels) - float(G["gap102"])) < 1e-12
+    assert abs(eval_util.calculate_precision_at_equal_recall_rate(pred, labels) - float(G["perr102"])) < 1e-12
