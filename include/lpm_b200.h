@@ -326,9 +326,9 @@ unsigned long long lpm_rank_adam_workspace_bytes(int R, int N);
 /* Batch-norm statistics of the attention logits q.k^T per key channel without materialising them
  * (transformer_utils.py:646-654): partial [B*H][2][L] = (sum_i q_i.k_j | sum_i (q_i.k_j)^2); head depth 16. */
 int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int H, float* partial, lpm_stream_t stream);
-/* Per-column (sum | sum of squares) partials of an fp16 matrix: partial [lpm_colstats_chunks(rows)][2][C]
+/* Per-column (sum | sum of squares) partials of an fp16 matrix: partial [lpm_colstats_chunks(rows, C)][2][C]
  * (attention_bn, filter_bn, feed_output_bn: transformer_utils.py:666,747,760). */
-int lpm_colstats_chunks(long long rows);
+int lpm_colstats_chunks(long long rows, int C);
 int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* partial, lpm_stream_t stream);
 /* y[r][c] = x[r][c]*scale[c] + shift[c] (applies a folded batch norm; y may alias x). */
 int lpm_affine_cols_f16(const void* x, void* y, long long rows, int C, const float* scale, const float* shift,

@@ -424,7 +424,7 @@ int lpm_mha_logit_stats(const void* qkv, long long ld, int B, int L, int Dm, int
   LPM_REQUIRE(qkv && partial && B > 0 && L > 0, "lpm_mha_logit_stats: bad arguments");
   return mha_logit_stats(CH16(qkv), ld, B, L, Dm, H, partial, ST(stream));
 }
-int lpm_colstats_chunks(long long rows) { return colstats_chunks(rows); }
+int lpm_colstats_chunks(long long rows, int C) { return colstats_chunks(rows, C); }
 int lpm_colstats_f16(const void* x, long long ld, long long rows, int C, float* partial, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && partial && rows > 0 && C > 0, "lpm_colstats_f16: bad arguments");

@@ -122,7 +122,7 @@ int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, c
 
 // lpm_v2.cu
 int mha_logit_stats(const __half* qkv, long long ld, int B, int L, int Dm, int H, float* partial, cudaStream_t st);
-int colstats_chunks(long long rows);
+int colstats_chunks(long long rows, int C);
 int colstats(const __half* x, long long ld, long long rows, int C, float* partial, cudaStream_t st);
 int affine_cols(const __half* x, __half* y, long long rows, int C, const float* scale, const float* shift,
                 cudaStream_t st);

@@ -56,20 +56,42 @@ __global__ void __launch_bounds__(256) mha_logit_stats_kernel(const __half* __re
   }
 }
 
-// partial[chunk][0][c] = sum_r x[r][c], partial[chunk][1][c] = sum_r x[r][c]^2   (thread = 2 columns)
+// Column-statistic kernels: a CTA owns 128 columns (64 threads x 2) and one chunk of rows; its four row lanes walk the
+// chunk with a stride of 4 rows, four rows per lane in flight, and are combined through shared memory.  The grid is
+// (C/128, chunks) with chunks chosen so that ~8 CTAs per SM are resident (colstats_chunks).
+constexpr int CS_COLS = 128, CS_LANES = 4, CS_UNROLL = 4;
+
+// partial[chunk][0][c] = sum_r x[r][c], partial[chunk][1][c] = sum_r x[r][c]^2
 __global__ void __launch_bounds__(256) colstats_kernel(const __half* __restrict__ x, long long ld, long long rows, int C,
                                                        float* __restrict__ partial) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-  if (c >= C) return;
+  __shared__ float4 sh[CS_LANES][CS_COLS / 2];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = blockIdx.x * CS_COLS + tx * 2;
+  const bool ok = c < C;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(x + r * ld + c));
-    s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
+  if (ok) {
+    for (long long r = r0 + ty; r < r1; r += CS_LANES * CS_UNROLL) {
+      float2 v[CS_UNROLL];
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) {
+        const long long rr = r + u * CS_LANES;
+        v[u] = rr < r1 ? __half22float2(*reinterpret_cast<const __half2*>(x + rr * ld + c)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) { s0 += v[u].x; s1 += v[u].y; q0 += v[u].x * v[u].x; q1 += v[u].y * v[u].y; }
+    }
   }
-  float* p = partial + (size_t)blockIdx.y * 2 * C;
-  p[c] = s0; p[c + 1] = s1; p[C + c] = q0; p[C + c + 1] = q1;
+  sh[ty][tx] = make_float4(s0, s1, q0, q1);
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float4 t = sh[0][tx];
+#pragma unroll
+    for (int l = 1; l < CS_LANES; ++l) { const float4 o = sh[l][tx]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+    float* p = partial + (size_t)blockIdx.y * 2 * C;
+    p[c] = t.x; p[c + 1] = t.y; p[C + c] = t.z; p[C + c + 1] = t.w;
+  }
 }
 
 // y[r][c] = x[r][c]*scale[c] + shift[c]  (y may alias x; 8 columns per thread)
@@ -111,22 +133,46 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const TD* __restrict_
                                                            const __half* __restrict__ x, long long ld_x, long long rows,
                                                            int C, const float* __restrict__ p0, const float* __restrict__ p1,
                                                            int mode, float* __restrict__ partial) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-  if (c >= C) return;
+  __shared__ float4 sh[CS_LANES][CS_COLS / 2];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = blockIdx.x * CS_COLS + tx * 2;
+  const bool ok = c < C;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  const float a0 = p0[c], a1 = p0[c + 1];
-  const float b0 = mode ? 1.f / p1[c] : p1[c], b1 = mode ? 1.f / p1[c + 1] : p1[c + 1];
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float2 g = ld2<TD>(dy + r * ld_dy + c);
-    if (q) { const float2 qq = *reinterpret_cast<const float2*>(q + (r / T) * C + c); g.x -= qq.x; g.y -= qq.y; }
-    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(x + r * ld_x + c));
-    s0 += g.x; s1 += g.y;
-    q0 += g.x * (v.x - a0) * b0; q1 += g.y * (v.y - a1) * b1;
+  if (ok) {
+    const float a0 = p0[c], a1 = p0[c + 1];
+    const float b0 = mode ? 1.f / p1[c] : p1[c], b1 = mode ? 1.f / p1[c + 1] : p1[c + 1];
+    for (long long r = r0 + ty; r < r1; r += CS_LANES * CS_UNROLL) {
+      float2 g[CS_UNROLL], v[CS_UNROLL];
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) {
+        const long long rr = r + u * CS_LANES;
+        if (rr < r1) {
+          g[u] = ld2<TD>(dy + rr * ld_dy + c);
+          if (q) { const float2 qq = *reinterpret_cast<const float2*>(q + (rr / T) * C + c); g[u].x -= qq.x; g[u].y -= qq.y; }
+          v[u] = __half22float2(*reinterpret_cast<const __half2*>(x + rr * ld_x + c));
+        } else {
+          g[u] = make_float2(0.f, 0.f);
+          v[u] = make_float2(a0, a1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) {
+        s0 += g[u].x; s1 += g[u].y;
+        q0 += g[u].x * (v[u].x - a0) * b0; q1 += g[u].y * (v[u].y - a1) * b1;
+      }
+    }
   }
-  float* p = partial + (size_t)blockIdx.y * 2 * C;
-  p[c] = s0; p[c + 1] = s1; p[C + c] = q0; p[C + c + 1] = q1;
+  sh[ty][tx] = make_float4(s0, s1, q0, q1);
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float4 t = sh[0][tx];
+#pragma unroll
+    for (int l = 1; l < CS_LANES; ++l) { const float4 o = sh[l][tx]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+    float* p = partial + (size_t)blockIdx.y * 2 * C;
+    p[c] = t.x; p[c + 1] = t.y; p[C + c] = t.z; p[C + c + 1] = t.w;
+  }
 }
 
 template <typename TD>
@@ -231,14 +277,19 @@ int mha_logit_stats(const __half* qkv, long long ld, int B, int L, int Dm, int H
   return LPM_OK;
 }
 
-int colstats_chunks(long long rows) {
-  long long c = (rows + 127) / 128;
-  return (int)(c > 64 ? 64 : (c < 1 ? 1 : c));
+int colstats_chunks(long long rows, int C) {
+  // ~8 CTAs per SM in total, at least 16 rows per chunk, at most 512 chunks (the partials are reduced by colsum_final)
+  const long long gx = (C + CS_COLS - 1) / CS_COLS;
+  long long c = (8ll * num_sms() + gx - 1) / gx;
+  const long long by_rows = (rows + 15) / 16;
+  if (c > by_rows) c = by_rows;
+  if (c > 512) c = 512;
+  return (int)(c < 1 ? 1 : c);
 }
 
 int colstats(const __half* x, long long ld, long long rows, int C, float* partial, cudaStream_t st) {
   LPM_REQUIRE(C % 2 == 0 && ld % 2 == 0, "colstats: column count and pitch must be even");
-  dim3 grid((C / 2 + 255) / 256, colstats_chunks(rows));
+  dim3 grid((C + CS_COLS - 1) / CS_COLS, colstats_chunks(rows, C));
   colstats_kernel<<<grid, 256, 0, st>>>(x, ld, rows, C, partial);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
@@ -255,7 +306,7 @@ int affine_cols(const __half* x, __half* y, long long rows, int C, const float* 
 int bn_bwd_stats(const void* dy, int dy_f32, long long ld_dy, const float* q, int T, const __half* x, long long ld_x,
                  long long rows, int C, const float* p0, const float* p1, int mode, float* partial, cudaStream_t st) {
   LPM_REQUIRE(C % 2 == 0 && ld_dy % 2 == 0 && ld_x % 2 == 0, "bn_bwd_stats: even column count / pitches required");
-  dim3 grid((C / 2 + 255) / 256, colstats_chunks(rows));
+  dim3 grid((C + CS_COLS - 1) / CS_COLS, colstats_chunks(rows, C));
   if (dy_f32) bn_bwd_stats_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), ld_dy, q, T, x, ld_x, rows, C, p0, p1, mode, partial);
   else bn_bwd_stats_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(dy), ld_dy, q, T, x, ld_x, rows, C, p0, p1, mode, partial);
   LPM_CUDA_CHECK(cudaGetLastError());

@@ -608,7 +608,7 @@ def colstats_f16(x, rows=None, cols=None):
     lib = _lib.load()
     rows = rows or x.shape[0]
     cols = cols or x.shape[1]
-    partial = _f32((lib.lpm_colstats_chunks(_ll(rows)), 2, cols), x.device)
+    partial = _f32((lib.lpm_colstats_chunks(_ll(rows), int(cols)), 2, cols), x.device)
     check(lib.lpm_colstats_f16(ptr(x), _ll(x.stride(0)), _ll(rows), cols, ptr(partial), stream_ptr()), "lpm_colstats_f16")
     return partial
 
@@ -659,7 +659,7 @@ def batch_norm_cols_bwd(dy, x_pre, stats, gamma, *, inv_scale, relu, q=None, T=1
     rows, cols = x_pre.shape
     f32 = int(dy.dtype == torch.float32)
     assert dy.is_contiguous() and x_pre.is_contiguous()
-    ch = lib.lpm_colstats_chunks(_ll(rows))
+    ch = lib.lpm_colstats_chunks(_ll(rows), int(cols))
     part = _f32((ch, 2, cols), dy.device)
     check(lib.lpm_batchnorm_bwd_stats(ptr(dy), f32, _ll(dy.stride(0)), ptr(q), T, ptr(x_pre), _ll(x_pre.stride(0)),
                                       _ll(rows), cols, ptr(stats[0]), ptr(stats[1]), 0, ptr(part), stream_ptr()),
@@ -679,7 +679,7 @@ def bn_output_param_grads(dy, y, beta, gamma, *, inv_scale):
     """dgamma / dbeta of a batch norm from its OUTPUT y: xhat = (y - beta)/gamma (input_bn, whose input needs no grad)."""
     lib = _lib.load()
     rows, cols = y.shape
-    ch = lib.lpm_colstats_chunks(_ll(rows))
+    ch = lib.lpm_colstats_chunks(_ll(rows), int(cols))
     part = _f32((ch, 2, cols), dy.device)
     check(lib.lpm_batchnorm_bwd_stats(ptr(dy), int(dy.dtype == torch.float32), _ll(dy.stride(0)), None, 1, ptr(y),
                                       _ll(y.stride(0)), _ll(rows), cols, ptr(beta), ptr(gamma), 1, ptr(part),
