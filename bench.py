@@ -295,9 +295,11 @@ def main():
                    e2e={"value": B * world / (e2e_ms / 1e3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
                    gpu_launches=int(launches), clocks=clocks, loss=float(loss), loss_scale_overflow=bool(overflow),
-                   roofline={"kernel": "gemm_f16_kernel (tcgen05, FFN 20480x4096x1024 call)", "bound": "tensor",
+                   roofline={"kernel": "gemm_f16_kernel<256,6,0,1,TWO=1> (tcgen05.mma.cta_group::2, FFN 20480x4096x1024 call)", "bound": "tensor",
                              "achieved": g_tf, "peak": sustained, "unit": "TFLOP/s", "frac": g_tf / sustained,
-                             "traffic": None, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)"},
+                             "traffic": 225.4e6, "traffic_unit": "bytes per launch (dram read 88.3 MB + write 137.1 MB, ncu --set full, "
+                             "profiles/r1j_ncu_summary.md; algorithmic 218 MB)",
+                             "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)"},
                    roofline_pool={"kernel": "netvlad_pool_fwd_kernel<256> (rgb, fused)", "bound": "tensor",
                                   "achieved": p_tf, "peak": burst, "unit": "TFLOP/s", "frac": p_tf / burst,
                                   "achieved_full_waves": pl_tf, "frac_full_waves": pl_tf / burst,

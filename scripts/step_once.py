@@ -10,7 +10,7 @@ C = bench.CFG
 store = variables.VariableStore(dev, seed=1810)
 eng = NetVladEngine(NetVladConfig(iterations=C["iterations"], cluster_size=C["cluster_size"], hidden_size=C["hidden_size"], vocab_size=C["vocab"]), store)
 tr = Trainer(eng, batch_size=C["batch"])
-x, nf, lab = bench.synthetic(C["batch"], 20181000, device=dev)
+x, nf, lab = bench.synthetic(C["batch"], 20181000, device=dev, codes=True)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 for _ in range(n):
     tr.train_step(x, nf, lab)
