@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
       m0 = mn0; m1 = mn1;
       l0 *= c0; l1 *= c1;
 #pragma unroll
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j < 2 * nb) {
-          s[j][0] = exp2f(s[j][0] - m0); s[j][1] = exp2f(s[j][1] - m0);
-          s[j][2] = exp2f(s[j][2] - m1); s[j][3] = exp2f(s[j][3] - m1);
+          s[j][0] = fast_exp2(s[j][0] - m0); s[j][1] = fast_exp2(s[j][1] - m0);
+          s[j][2] = fast_exp2(s[j][2] - m1); s[j][3] = fast_exp2(s[j][3] - m1);
           l0 += s[j][0] + s[j][1];
           l1 += s[j][2] + s[j][3];
         }
@@ -317,11 +317,11 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
           const float l0 = l01.x, l1 = l01.y, d0 = d01.x, d1 = d01.y;
           float p0, p1, p2, p3;
           if (MODE == 0) {
-            p0 = exp2f(st[u][n][0] * scale_log2 - l0); p1 = exp2f(st[u][n][1] * scale_log2 - l1);
-            p2 = exp2f(st[u][n][2] * scale_log2 - l0); p3 = exp2f(st[u][n][3] * scale_log2 - l1);
+            p0 = fast_exp2(st[u][n][0] * scale_log2 - l0); p1 = fast_exp2(st[u][n][1] * scale_log2 - l1);
+            p2 = fast_exp2(st[u][n][2] * scale_log2 - l0); p3 = fast_exp2(st[u][n][3] * scale_log2 - l1);
           } else {
-            p0 = exp2f(st[u][n][0] * ks0 + kb0 - l0); p1 = exp2f(st[u][n][1] * ks0 + kb0 - l1);
-            p2 = exp2f(st[u][n][2] * ks1 + kb1 - l0); p3 = exp2f(st[u][n][3] * ks1 + kb1 - l1);
+            p0 = fast_exp2(st[u][n][0] * ks0 + kb0 - l0); p1 = fast_exp2(st[u][n][1] * ks0 + kb0 - l1);
+            p2 = fast_exp2(st[u][n][2] * ks1 + kb1 - l0); p3 = fast_exp2(st[u][n][3] * ks1 + kb1 - l1);
           }
           p0 *= live; p1 *= live; p2 *= live; p3 *= live;
           float g0 = p0 * (dp[u][n][0] - d0), g1 = p1 * (dp[u][n][1] - d1), g2 = p2 * (dp[u][n][2] - d0), g3 = p3 * (dp[u][n][3] - d1);

@@ -227,6 +227,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, ui
 }
 
 // ---- misc math ----
+// 2^x on the MUFU (ex2.approx.ftz, rel. error 2^-22, -inf -> 0): exp2f() without -use_fast_math wraps the same
+// instruction in a denormal-range rescale (4 extra instructions per call), which shows in the softmax-bound kernels
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
