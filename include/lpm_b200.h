@@ -362,6 +362,32 @@ int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, u
 int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, int D, void* out, long long out_stride,
                              lpm_stream_t stream);
 
+/* =============================================================================================
+ * Baseline NetVLAD (WillowModelReg / NetVladOrthoReg / LightVLAD)
+ * ============================================================================================= */
+/* Random frame sampling indices, int32 [B][T] (consumed by lpm_gather_bn_*):
+ *   mode 0  SampleRandomFrames   (model_utils.py:54-73): idx = int32(u[b][i] * fl32(num_frames[b]))
+ *   mode 1  SampleRandomSequence (model_utils.py:26-51): start = int32(u[b] * fl32(max(nf-T,0)+1)), idx = min(start+i, nf-1)
+ * uniform: device fp32 [B][T] (mode 0) / [B] (mode 1) in [0,1), or NULL: a counter-based generator keyed by seed. */
+int lpm_random_frame_index(const int* num_frames, const float* uniform, unsigned long long seed, int B, int T,
+                           int max_frames, int mode, int* frame_index, lpm_stream_t stream);
+/* lpm_sample_bn_stats / lpm_sample_bn_apply with explicit gather indices frame_index int32 [B*T] (tf.gather_nd,
+ * model_utils.py:50-51,72-73).  x: fp32 frames (is_codes = 0) or the reader's uint8 codes (is_codes = 1:
+ * dequantised with the given range and L2-normalised per frame, as in the *_u8 entry points). */
+int lpm_gather_bn_stats(const void* x, int is_codes, float max_quantized_value, float min_quantized_value,
+                        const int* frame_index, int B, int max_frames, int F, int T, float* partial,
+                        lpm_stream_t stream);
+int lpm_gather_bn_apply(const void* x, int is_codes, float max_quantized_value, float min_quantized_value,
+                        const int* frame_index, int B, int max_frames, int F, int T, const float* scale,
+                        const float* shift, void* y_f16, int split_col, void* y2_f16, lpm_stream_t stream);
+/* Orthogonal regulariser on the cluster centres (module_utils.py:55-90; video_pooling_modules.py:1560-1568):
+ *   value[0] = scale * sum_ij |(N^T N - I)_ij|,  N = l2_normalize(w [D][K], axis=1)   (fp32 throughout)
+ *   dw [D][K] (optional) = (accumulate ? dw : 0) + grad_scale * d value / d w         (sign(0) = 0, as tf.abs)
+ * workspace: lpm_ortho_reg_workspace_bytes(D, K) bytes of device memory. */
+unsigned long long lpm_ortho_reg_workspace_bytes(int D, int K);
+int lpm_ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value,
+                  float* dw, void* workspace, unsigned long long workspace_bytes, lpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,9 +9,9 @@ import torch
 
 class NetVladFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, model_input, num_frames, dropout_masks, names, *params):
+    def forward(ctx, engine, model_input, num_frames, dropout_masks, frame_index, names, *params):
         pred, ectx = engine.forward(model_input, num_frames, True, save_for_backward=True,
-                                    dropout_masks=dropout_masks)
+                                    dropout_masks=dropout_masks, frame_index=frame_index)
         ctx.engine, ctx.ectx, ctx.names = engine, ectx, names
         return pred
 
@@ -20,13 +20,13 @@ class NetVladFunction(torch.autograd.Function):
         grads = ctx.engine.backward(ctx.ectx, dpred.contiguous())
         out = tuple(grads.get(n) for n in ctx.names)
         ctx.ectx = None
-        return (None, None, None, None, None) + out
+        return (None, None, None, None, None, None) + out
 
 
-def netvlad_apply(engine, model_input, num_frames, is_training, dropout_masks=None):
+def netvlad_apply(engine, model_input, num_frames, is_training, dropout_masks=None, frame_index=None):
     train_graph = is_training and torch.is_grad_enabled()
     if not train_graph:
-        pred, _ = engine.forward(model_input, num_frames, is_training, dropout_masks=dropout_masks)
+        pred, _ = engine.forward(model_input, num_frames, is_training, dropout_masks=dropout_masks, frame_index=frame_index)
         return pred
     tr = engine.store.trainable()
     names = tuple(tr.keys())
@@ -34,4 +34,4 @@ def netvlad_apply(engine, model_input, num_frames, is_training, dropout_masks=No
     for p in params:
         if not p.requires_grad:
             p.requires_grad_(True)
-    return NetVladFunction.apply(engine, model_input, num_frames, dropout_masks, names, *params)
+    return NetVladFunction.apply(engine, model_input, num_frames, dropout_masks, frame_index, names, *params)

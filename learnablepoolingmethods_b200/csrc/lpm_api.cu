@@ -132,7 +132,7 @@ int lpm_sample_bn_stats(const float* x, const int* num_frames, int B, int max_fr
                         float* partial, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && num_frames && partial && B > 0 && T > 0 && max_frames > 0, "lpm_sample_bn_stats: bad arguments");
-  return sample_stats(x, 0, 0.f, 0.f, num_frames, B, max_frames, F, T, partial, ST(stream));
+  return sample_stats(x, 0, 0.f, 0.f, num_frames, nullptr, B, max_frames, F, T, partial, ST(stream));
 }
 
 int lpm_sample_bn_stats_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
@@ -140,7 +140,7 @@ int lpm_sample_bn_stats_u8(const unsigned char* codes, float max_quantized_value
                            lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(codes && num_frames && partial && B > 0 && T > 0 && max_frames > 0, "lpm_sample_bn_stats_u8: bad arguments");
-  return sample_stats(codes, 1, max_quantized_value, min_quantized_value, num_frames, B, max_frames, F, T, partial, ST(stream));
+  return sample_stats(codes, 1, max_quantized_value, min_quantized_value, num_frames, nullptr, B, max_frames, F, T, partial, ST(stream));
 }
 
 int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_frames, int F, int T,
@@ -148,7 +148,7 @@ int lpm_sample_bn_apply(const float* x, const int* num_frames, int B, int max_fr
                         lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply: bad arguments");
-  return sample_apply(x, 0, 0.f, 0.f, num_frames, B, max_frames, F, T, scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
+  return sample_apply(x, 0, 0.f, 0.f, num_frames, nullptr, B, max_frames, F, T, scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
 }
 
 int lpm_sample_bn_apply_u8(const unsigned char* codes, float max_quantized_value, float min_quantized_value,
@@ -156,7 +156,7 @@ int lpm_sample_bn_apply_u8(const unsigned char* codes, float max_quantized_value
                            const float* shift, void* y_f16, int split_col, void* y2_f16, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(codes && num_frames && scale && shift && y_f16 && B > 0 && T > 0, "lpm_sample_bn_apply_u8: bad arguments");
-  return sample_apply(codes, 1, max_quantized_value, min_quantized_value, num_frames, B, max_frames, F, T, scale, shift,
+  return sample_apply(codes, 1, max_quantized_value, min_quantized_value, num_frames, nullptr, B, max_frames, F, T, scale, shift,
                       H16(y_f16), split_col, H16(y2_f16), ST(stream));
 }
 
@@ -481,6 +481,37 @@ int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, i
   DEVCHK();
   LPM_REQUIRE(z && rscale && out, "lpm_netvlad_finalize_f16: null pointer");
   return vlad_dmajor_f16(CH16(z), rscale, B, K, D, H16(out), out_stride, ST(stream));
+}
+
+int lpm_random_frame_index(const int* num_frames, const float* uniform, unsigned long long seed, int B, int T,
+                           int max_frames, int mode, int* frame_index, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(num_frames && frame_index && B > 0 && T > 0 && max_frames > 0, "lpm_random_frame_index: bad arguments");
+  return random_frame_index(num_frames, uniform, seed, B, T, max_frames, mode, frame_index, ST(stream));
+}
+int lpm_gather_bn_stats(const void* x, int is_codes, float max_quantized_value, float min_quantized_value,
+                        const int* frame_index, int B, int max_frames, int F, int T, float* partial,
+                        lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && frame_index && partial && B > 0 && T > 0 && max_frames > 0, "lpm_gather_bn_stats: bad arguments");
+  return sample_stats(x, is_codes != 0, max_quantized_value, min_quantized_value, nullptr, frame_index, B, max_frames, F, T,
+                      partial, ST(stream));
+}
+int lpm_gather_bn_apply(const void* x, int is_codes, float max_quantized_value, float min_quantized_value,
+                        const int* frame_index, int B, int max_frames, int F, int T, const float* scale,
+                        const float* shift, void* y_f16, int split_col, void* y2_f16, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && frame_index && scale && shift && y_f16 && B > 0 && T > 0, "lpm_gather_bn_apply: bad arguments");
+  return sample_apply(x, is_codes != 0, max_quantized_value, min_quantized_value, nullptr, frame_index, B, max_frames, F, T,
+                      scale, shift, H16(y_f16), split_col, H16(y2_f16), ST(stream));
+}
+unsigned long long lpm_ortho_reg_workspace_bytes(int D, int K) { return ortho_reg_workspace_bytes(D, K); }
+int lpm_ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value,
+                  float* dw, void* workspace, unsigned long long workspace_bytes, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(w && workspace && (value || dw), "lpm_ortho_reg: null pointer");
+  return ortho_reg(w, D, K, scale, grad_scale, accumulate, value, dw, static_cast<float*>(workspace), workspace_bytes,
+                   ST(stream));
 }
 
 }  // extern "C"

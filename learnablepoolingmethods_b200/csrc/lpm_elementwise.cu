@@ -75,6 +75,7 @@ template <bool CODES>
 __global__ void __launch_bounds__(256) sample_stats_kernel(const void* __restrict__ x,
                                                            const int* __restrict__ num_frames, int B,
                                                            int max_frames, int F, int T, float step, FrameQuant qz,
+                                                           const int* __restrict__ frame_index,
                                                            float* __restrict__ partial) {
   __shared__ float red[16];
   const int rows = B * T;
@@ -84,7 +85,9 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const void* __restric
   int parity = 0;
   for (int r = blockIdx.x; r < rows; r += gridDim.x, parity ^= 1) {
     const int b = r / T, i = r - b * T;
-    const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
+    // explicit indices (random frame sampling, model_utils.py:26-73) or the uniform rule (model_utils.py:101-122)
+    const int idx = frame_index ? min(max(__ldg(frame_index + r), 0), max_frames - 1)
+                                : sample_index(i, step, __ldg(num_frames + b), max_frames);
     float4 v[2];
     load_frame<CODES>(x, (size_t)b * max_frames + idx, F, qz, red, parity, v);
 #pragma unroll
@@ -109,6 +112,7 @@ template <bool CODES>
 __global__ void __launch_bounds__(256) sample_apply_kernel(const void* __restrict__ x,
                                                            const int* __restrict__ num_frames, int B,
                                                            int max_frames, int F, int T, float step, FrameQuant qz,
+                                                           const int* __restrict__ frame_index,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            __half* __restrict__ y, int split_col,
@@ -120,7 +124,9 @@ __global__ void __launch_bounds__(256) sample_apply_kernel(const void* __restric
   int parity = 0;
   for (int r = blockIdx.x; r < rows; r += gridDim.x, parity ^= 1) {
     const int b = r / T, i = r - b * T;
-    const int idx = sample_index(i, step, __ldg(num_frames + b), max_frames);
+    // explicit indices (random frame sampling, model_utils.py:26-73) or the uniform rule (model_utils.py:101-122)
+    const int idx = frame_index ? min(max(__ldg(frame_index + r), 0), max_frames - 1)
+                                : sample_index(i, step, __ldg(num_frames + b), max_frames);
     float4 vv[2];
     load_frame<CODES>(x, (size_t)b * max_frames + idx, F, qz, red, parity, vv);
 #pragma unroll
@@ -529,26 +535,27 @@ static FrameQuant frame_quant(float qmax, float qmin) {
   return FrameQuant{range / 255.0f, range / 512.0f + qmin};
 }
 
-int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
-                 float* partial, cudaStream_t st) {
+int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, const int* frame_index, int B,
+                 int max_frames, int F, int T, float* partial, cudaStream_t st) {
   LPM_REQUIRE(F % 4 == 0 && F <= 2048, "sample_stats: feature size must be a multiple of 4 and <= 2048 (got %d)", F);
   LPM_REQUIRE(!codes || qmax > qmin, "sample_stats: max_quantized_value must exceed min_quantized_value");
   const FrameQuant qz = frame_quant(qmax, qmin);
-  if (codes) sample_stats_kernel<true><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, partial);
-  else sample_stats_kernel<false><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, partial);
+  if (codes) sample_stats_kernel<true><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, frame_index, partial);
+  else sample_stats_kernel<false><<<sample_stats_blocks(), 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, frame_index, partial);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
-int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
-                 const float* scale, const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st) {
+int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, const int* frame_index, int B,
+                 int max_frames, int F, int T, const float* scale, const float* shift, __half* y, int split_col,
+                 __half* y2, cudaStream_t st) {
   LPM_REQUIRE(F % 4 == 0 && F <= 2048, "sample_apply: feature size must be a multiple of 4 and <= 2048 (got %d)", F);
   LPM_REQUIRE(!codes || qmax > qmin, "sample_apply: max_quantized_value must exceed min_quantized_value");
   const FrameQuant qz = frame_quant(qmax, qmin);
   LPM_REQUIRE(y2 == nullptr || (split_col % 4 == 0 && split_col > 0 && split_col < F), "sample_apply: bad split column");
   int grid = B * T < num_sms() * 8 ? B * T : num_sms() * 8;
-  if (codes) sample_apply_kernel<true><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, scale, shift, y, split_col, y2);
-  else sample_apply_kernel<false><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, scale, shift, y, split_col, y2);
+  if (codes) sample_apply_kernel<true><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, frame_index, scale, shift, y, split_col, y2);
+  else sample_apply_kernel<false><<<grid, 256, 0, st>>>(x, nf, B, max_frames, F, T, 1.0f / (float)T, qz, frame_index, scale, shift, y, split_col, y2);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

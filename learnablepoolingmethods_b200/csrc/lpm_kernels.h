@@ -17,10 +17,12 @@ void gemm_set_pair_mode(int mode);
 
 // lpm_elementwise.cu
 int sample_stats_blocks();
-int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T,
-                 float* partial, cudaStream_t st);
-int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, int B, int max_frames, int F, int T, const float* scale,
-                 const float* shift, __half* y, int split_col, __half* y2, cudaStream_t st);
+// frame_index: null = SampleUniformFrames rule from nf; else explicit int32 [B*T] gather indices (nf unused)
+int sample_stats(const void* x, int codes, float qmax, float qmin, const int* nf, const int* frame_index, int B,
+                 int max_frames, int F, int T, float* partial, cudaStream_t st);
+int sample_apply(const void* x, int codes, float qmax, float qmin, const int* nf, const int* frame_index, int B,
+                 int max_frames, int F, int T, const float* scale, const float* shift, __half* y, int split_col,
+                 __half* y2, cudaStream_t st);
 int bn_finalize(const float* psum, const float* psq, int P, long long pstride, int C, double count,
                 const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps, int bessel,
                 int training, float* scale, float* shift, float* save_mean, float* save_rstd, cudaStream_t st);
@@ -136,5 +138,12 @@ int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out,
                 cudaStream_t st);
 int vlad_dmajor_f16(const __half* z, const float* rscale, int B, int K, int D, __half* out, long long out_stride,
                     cudaStream_t st);
+
+// lpm_willow.cu
+int random_frame_index(const int* nf, const float* uniform, unsigned long long seed, int B, int T, int max_frames,
+                       int mode, int* idx, cudaStream_t st);
+unsigned long long ortho_reg_workspace_bytes(int D, int K);
+int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value, float* dw,
+              float* ws, unsigned long long ws_bytes, cudaStream_t st);
 
 }  // namespace lpm

@@ -1,0 +1,168 @@
+// Baseline NetVLAD (WillowModelReg / NetVladOrthoReg) pieces that the NetVladV1/V2 path lacks:
+//   * random frame sampling indices (model_utils.py:26-73), consumed by the gather kernels through `frame_index`
+//   * the orthogonal regulariser on the cluster centres (module_utils.py:55-90): value and gradient, fp32 on the
+//     CUDA cores (K x K x D = 67 MFLOP for rgb: launch-bound, the tensor cores would only add rounding to a sign())
+#include "lpm_common.cuh"
+#include "lpm_kernels.h"
+
+namespace lpm {
+
+// ------------------------------------------------------------------------------------------------
+// counter-based uniform [0,1): splitmix64 of (seed, counter) -> 24 random mantissa bits
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// mode 0: SampleRandomFrames   idx[b,i] = int32( u[b,i] * fl32(nf[b]) )                        (model_utils.py:54-73)
+// mode 1: SampleRandomSequence start = int32( u[b] * fl32(max(nf-T,0)+1) ); idx = min(start+i, nf-1)    (:26-51)
+__global__ void __launch_bounds__(256) random_index_kernel(const int* __restrict__ nf, const float* __restrict__ uniform,
+                                                           unsigned long long seed, int B, int T, int max_frames,
+                                                           int mode, int* __restrict__ idx) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B * T) return;
+  const int b = r / T, i = r - b * T;
+  const int n = __ldg(nf + b);
+  int v;
+  if (mode == 0) {
+    const float u = uniform ? __ldg(uniform + r) : uniform01(seed, (unsigned long long)r);
+    v = __float2int_rz(__fmul_rn(u, (float)n));
+  } else {
+    const float u = uniform ? __ldg(uniform + b) : uniform01(seed, (unsigned long long)b);
+    const float span = fmaxf((float)n - (float)T, 0.f) + 1.f;
+    v = min(__float2int_rz(__fmul_rn(u, span)) + i, n - 1);
+  }
+  idx[r] = min(max(v, 0), max_frames - 1);   // tf.gather_nd would fault on nf = 0; frame 0 (zero padding) is read instead
+}
+
+int random_frame_index(const int* nf, const float* uniform, unsigned long long seed, int B, int T, int max_frames,
+                       int mode, int* idx, cudaStream_t st) {
+  LPM_REQUIRE(mode == 0 || mode == 1, "random_frame_index: mode must be 0 (frames) or 1 (sequence)");
+  random_index_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(nf, uniform, seed, B, T, max_frames, mode, idx);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// orthogonal regulariser  R(W) = scale * sum_ij | (N^T N - I)_ij |,  N = l2_normalize(W [D][K], axis=1)
+//   dR/dN = scale * N (S + S^T),  S = sign(N^T N - I);   dW_d = (dN_d - N_d (N_d . dN_d)) * rn_d
+// workspace (floats): N [D*K] | dN [D*K] | M [K*K] | rn [D] | partial [tiles]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ortho_rownorm_kernel(const float* __restrict__ w, int D, int K, float* __restrict__ n,
+                                                            float* __restrict__ rn) {
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (d >= D) return;
+  float ss = 0.f;
+  for (int k = lane; k < K; k += 32) { const float v = w[(size_t)d * K + k]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(fmaxf(ss, 1e-12f));
+  if (lane == 0) rn[d] = ss >= 1e-12f ? r : -r;          // sign bit marks the clamped branch (constant scale)
+  for (int k = lane; k < K; k += 32) n[(size_t)d * K + k] = w[(size_t)d * K + k] * r;
+}
+
+// G tile = N^T N (contraction over d); writes S = sign(G - I) and the tile's sum |G - I|
+__global__ void __launch_bounds__(1024) ortho_gram_kernel(const float* __restrict__ n, int D, int K, float* __restrict__ S,
+                                                          float* __restrict__ partial) {
+  __shared__ float sa[32][33], sb[32][33];
+  __shared__ float red[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + ty;
+    sa[ty][tx] = (d < D && blockIdx.y * 32 + tx < K) ? n[(size_t)d * K + blockIdx.y * 32 + tx] : 0.f;
+    sb[ty][tx] = (d < D && j < K) ? n[(size_t)d * K + j] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int dd = 0; dd < 32; ++dd) acc = fmaf(sa[dd][ty], sb[dd][tx], acc);
+    __syncthreads();
+  }
+  float a = 0.f;
+  if (i < K && j < K) {
+    const float g = acc - (i == j ? 1.f : 0.f);
+    a = fabsf(g);
+    S[(size_t)i * K + j] = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
+  }
+  a = warp_sum(a);
+  if (tx == 0) red[ty] = a;
+  __syncthreads();
+  if (ty == 0) {
+    float t = warp_sum(red[tx]);
+    if (tx == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// dN tile = N (S + S^T)   [D x K]
+__global__ void __launch_bounds__(1024) ortho_dn_kernel(const float* __restrict__ n, const float* __restrict__ S, int D, int K,
+                                                        float* __restrict__ dn) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int d = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  for (int i0 = 0; i0 < K; i0 += 32) {
+    sa[ty][tx] = (d < D && i0 + tx < K) ? n[(size_t)d * K + i0 + tx] : 0.f;
+    const int i = i0 + ty;
+    sb[ty][tx] = (i < K && j < K) ? S[(size_t)i * K + j] + S[(size_t)j * K + i] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 32; ++ii) acc = fmaf(sa[ty][ii], sb[ii][tx], acc);
+    __syncthreads();
+  }
+  if (d < D && j < K) dn[(size_t)d * K + j] = acc;
+}
+
+// back through the row normalisation; accumulates grad_scale * dW into dw and writes the regulariser value
+__global__ void __launch_bounds__(256) ortho_finish_kernel(const float* __restrict__ n, const float* __restrict__ dn,
+                                                           const float* __restrict__ rn, int D, int K, float scale,
+                                                           float grad_scale, int accumulate, float* __restrict__ dw,
+                                                           const float* __restrict__ partial, int n_partial,
+                                                           float* __restrict__ value) {
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && value != nullptr) {
+    double t = 0.0;
+    for (int i = 0; i < n_partial; ++i) t += partial[i];
+    *value = scale * (float)t;
+  }
+  if (d >= D || dw == nullptr) return;
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) dot = fmaf(n[(size_t)d * K + k], dn[(size_t)d * K + k], dot);
+  dot = warp_sum(dot);
+  const float r = rn[d];
+  const float rr = fabsf(r);
+  if (r < 0.f) dot = 0.f;                                // clamped norm: N = W * const
+  for (int k = lane; k < K; k += 32) {
+    const size_t o = (size_t)d * K + k;
+    const float g = scale * grad_scale * (dn[o] - n[o] * dot) * rr;
+    dw[o] = accumulate ? dw[o] + g : g;
+  }
+}
+
+unsigned long long ortho_reg_workspace_bytes(int D, int K) {
+  const unsigned long long tiles = (unsigned long long)((K + 31) / 32) * ((K + 31) / 32);
+  return sizeof(float) * (2ull * D * K + (unsigned long long)K * K + D + tiles);
+}
+
+int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value, float* dw,
+              float* ws, unsigned long long ws_bytes, cudaStream_t st) {
+  LPM_REQUIRE(D > 0 && K > 0, "ortho_reg: bad shape %d x %d", D, K);
+  if (ws_bytes < ortho_reg_workspace_bytes(D, K))
+    return fail(LPM_ERR_WORKSPACE, "ortho_reg: workspace too small (%llu < %llu bytes)", ws_bytes, ortho_reg_workspace_bytes(D, K));
+  float* n = ws;
+  float* dn = n + (size_t)D * K;
+  float* S = dn + (size_t)D * K;
+  float* rn = S + (size_t)K * K;
+  float* partial = rn + D;
+  const int kt = (K + 31) / 32;
+  ortho_rownorm_kernel<<<(D + 7) / 8, 256, 0, st>>>(w, D, K, n, rn);
+  ortho_gram_kernel<<<dim3(kt, kt), 1024, 0, st>>>(n, D, K, S, partial);
+  if (dw != nullptr) ortho_dn_kernel<<<dim3(kt, (D + 31) / 32), 1024, 0, st>>>(n, S, D, K, dn);
+  ortho_finish_kernel<<<(D + 7) / 8, 256, 0, st>>>(n, dn, rn, D, K, scale, grad_scale, accumulate, dw, partial, kt * kt, value);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
+}  // namespace lpm

@@ -5,7 +5,9 @@ the hand-written backward needs.  torch owns memory and the autograd edge at the
 (`NetVladFunction`); all arithmetic runs in the CUDA kernels.  There is no fallback path.
 
 Reference lines mirrored: frame_level_models.py:2222-2377 (V1), :2383-2513 (V2), :2765-2824 (NetVLAD),
-transformer_utils.py:374-457,507-767, video_level_models.py:48-159, model_utils.py:101-122.
+transformer_utils.py:374-457,507-767, video_level_models.py:48-159, model_utils.py:101-122; baseline NetVLAD
+(SURVEY 8f row 4): frame_level_models.py:2516-2635 (WillowModelReg), video_pooling_modules.py:1499-1586
+(NetVladOrthoReg), module_utils.py:55-90 (orthogonal regulariser), model_utils.py:26-73 (random frame sampling).
 """
 from __future__ import annotations
 
@@ -44,6 +46,10 @@ class NetVladConfig:
     loss_scale: float = 0.0        # fp16 activation-gradient scale inside the backward; 0 = auto (8 x batch)
     hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
     overlap_audio: bool = True     # run the audio modality (0.4 % of the FLOPs, ~1/3 of the launches) on a second stream
+    # WillowModelReg only (frame_level_models.py:2209-2216, 2535-2544)
+    rgb_det_reg: float = 1e-4      # --rgb_det_reg: orthogonal-regulariser scale of the rgb cluster centres
+    audio_det_reg: float = 1e-4    # --audio_det_reg
+    random_frames: bool = True     # SampleRandomFrames (True) or SampleRandomSequence (False)
 
     def modalities(self):
         ka = self.cluster_size // 4          # D7: integer division (frame_level_models.py:2263)
@@ -63,7 +69,7 @@ class NetVladEngine:
     def __init__(self, cfg: NetVladConfig, store: VariableStore):
         self.cfg = cfg
         self.store = store
-        if cfg.model not in ("NetVladV1", "NetVladV2"):
+        if cfg.model not in ("NetVladV1", "NetVladV2", "WillowModelReg"):
             raise ValueError(f"unknown model {cfg.model}")
         if not cfg.add_batch_norm:
             # frame_level_models.py:2236 `add_batch_norm or FLAGS...` can never be False and the no-BN
@@ -71,6 +77,7 @@ class NetVladEngine:
             raise NotImplementedError("netvlad_add_batch_norm=False is unreachable in the reference (D7)")
         self.build_variables()
         self._side = None          # second CUDA stream + fork / join events (created on first use)
+        self.draws = 0             # training/eval forwards so far: keys the dropout / frame-sampling generators
         self.pre_head_hook = None  # callable run right before the hidden projection reads its fp16 weights
 
     def _side_stream(self):
@@ -86,7 +93,12 @@ class NetVladEngine:
         s.batch_norm_vars("input_bn", c.feature_size)
         for name, _, D, K, H, sid in c.modalities():
             with s.variable_scope(name + "_VLAD"):
-                if c.model == "NetVladV1":
+                if c.model == "WillowModelReg":
+                    # NetVladOrthoReg: the scope id is glued to the variable name (video_pooling_modules.py:1527-1531)
+                    s.get_variable("cluster_weights" + self.wc_suffix(name), (D, K), "normal", 1 / math.sqrt(D))
+                    s.batch_norm_vars("cluster_bn", K)
+                    s.get_variable("cluster_weights2", (D, K), "normal", 1 / math.sqrt(D))
+                elif c.model == "NetVladV1":
                     s.get_variable("cluster_weights", (D, K), "normal", 1 / math.sqrt(D))
                     s.batch_norm_vars("cluster_bn", K)
                     s.get_variable("cluster_weights2", (1, D, K), "normal", 1 / math.sqrt(D))
@@ -121,6 +133,12 @@ class NetVladEngine:
             s.get_variable("weights", (c.hidden_size, V * M), "glorot")
             s.get_variable("biases", (V * M,), "zeros")
 
+    def wc_suffix(self, name: str) -> str:
+        """frame_level_models.py:2552-2557: scope ids "netvlad_rgb_scope" / "netvlad_audio_scope"."""
+        if self.cfg.model != "WillowModelReg":
+            return ""
+        return "netvlad_rgb_scope" if name == "video" else "netvlad_audio_scope"
+
     def _dense_vars(self, scope, i, o, bias):
         s = self.store
         with s.variable_scope(scope):
@@ -144,6 +162,9 @@ class NetVladEngine:
         specs = []
         for name, _, D, K, H, sid in c.modalities():
             vs = name + "_VLAD"
+            if c.model == "WillowModelReg":
+                specs.append((vs + "/cluster_weights" + self.wc_suffix(name), vs + "/wc16", (D, K), 0))
+                continue
             if c.model == "NetVladV1":
                 specs.append((vs + "/cluster_weights", vs + "/wc16", (D, K), 0))
                 a = name + "_attention"
@@ -178,7 +199,8 @@ class NetVladEngine:
         v, sh = s.vars, s.shadows
         for name, _, D, K, H, sid in c.modalities():
             vs = name + "_VLAD"
-            src = v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else v[vs + "/cluster_centers"]
+            src = (v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else
+                   v[vs + "/cluster_weights2"] if c.model == "WillowModelReg" else v[vs + "/cluster_centers"])
             sh[vs + "/centers_t"], sh[vs + "/centers_t16"] = ops.transpose_f32_dual(src)
         V, M = c.vocab_size, c.num_mixtures
         g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
@@ -203,11 +225,13 @@ class NetVladEngine:
     # forward
     # ------------------------------------------------------------------------------------------
     def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
-                save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False):
+                save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False,
+                frame_index=None):
         """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264), or the uint8
         codes [B, max_frames, rgb+audio] as decoded by the reader (readers.py:185-193): those are dequantised
         (utils.py:28-43) and L2-normalised inside the gather kernels.
-        num_frames int [B].  Returns (predictions fp32 [B, vocab], ctx)."""
+        num_frames int [B].  frame_index (WillowModelReg only): int32 [B, iterations] gather indices replacing the
+        random draw of model_utils.py:26-73.  Returns (predictions fp32 [B, vocab], ctx)."""
         c, s = self.cfg, self.store
         v = s.vars
         sh = self.refresh_shadows()
@@ -218,8 +242,13 @@ class NetVladEngine:
         x = model_input.contiguous() if model_input.dtype == torch.uint8 else model_input.contiguous().float()
         nf = num_frames.to(device=x.device, dtype=torch.int32).contiguous()
         B, T, F = x.shape[0], c.iterations, c.feature_size
-        ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}}
+        ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}, "seed": self.draws}
+        self.draws += 1
         save = save_for_backward
+        if c.model == "WillowModelReg":
+            return self._willow_forward(x, nf, B, T, is_training, save, ctx, return_intermediates, frame_index)
+        if frame_index is not None:
+            raise ValueError("frame_index applies to WillowModelReg only (NetVladV1/V2 sample uniformly)")
 
         # ---- a2 + a3: uniform frame sampling + input_bn -> fp16 frames [B*T, F] -----------------
         if is_training:
@@ -404,6 +433,105 @@ class NetVladEngine:
                     mask=mask, u1=att, st1=st1, h1=h1, f=f, fbn_stats=fbn_stats, f_bn=f_bn, f2=f2, obn_stats=obn_stats,
                     A=A, z=z, rscale=rscale, a_sum=a_sum)
 
+    # ------------------------------------------------------------------------------------------
+    # WillowModelReg: baseline NetVLAD + context gating + orthogonal regulariser
+    # ------------------------------------------------------------------------------------------
+    def _willow_forward(self, x, nf, B, T, training, save, ctx, want_inter, frame_index):
+        """frame_level_models.py:2516-2635: random frames -> input_bn -> NetVladOrthoReg per modality (K1 + d-major
+        flatten, no attention block) -> shared head."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        F = c.feature_size
+        if frame_index is None:
+            # tf.random_uniform is redrawn on every session.run (training and evaluation alike)
+            frame_index = ops.random_frame_index(nf, T, x.shape[1], mode=0 if c.random_frames else 1,
+                                                 seed=0x5EED0000 + int(ctx["seed"]))
+        else:
+            frame_index = frame_index.to(device=x.device, dtype=torch.int32).contiguous()
+            if tuple(frame_index.shape) != (B, T):
+                raise ValueError(f"frame_index must be [{B}, {T}], got {tuple(frame_index.shape)}")
+        bnv = (v["input_bn/gamma"], v["input_bn/beta"], v["input_bn/moving_mean"], v["input_bn/moving_variance"])
+        if training:
+            part = ops.gather_bn_stats(x, frame_index, T)
+            r = ops.bn_finalize(part[:, 0], part[:, 1], B * T, *bnv, training=True, bessel=True, save=save, psum_stride=2 * F)
+        else:
+            r = ops.bn_finalize(None, None, 1, *bnv, training=False, bessel=True, save=save)
+        xb = ops.gather_bn_apply(x, frame_index, T, r[0], r[1])
+        if save:
+            ctx["xb"], ctx["input_bn_stats"], ctx["frame_index"] = xb, r[2], frame_index
+        vlad = torch.empty((B, c.vlad_dim), dtype=torch.float16, device=x.device)
+        off = 0
+        for name, col0, D, K, _, _ in c.modalities():
+            vs = name + "_VLAD"
+            X = xb[:, col0:col0 + D]
+            wc16, bn = sh[vs + "/wc16"], vs + "/cluster_bn"
+            bv = (v[bn + "/gamma"], v[bn + "/beta"], v[bn + "/moving_mean"], v[bn + "/moving_variance"])
+            if training:
+                _, st = ops.gemm(wc16, X, a_mn=True, b_mn=False, out="none", stats=True)
+                rb = ops.bn_finalize(st[0].reshape(-1, K), st[1].reshape(-1, K), B * T, *bv, training=True, bessel=True, save=save)
+            else:
+                rb = ops.bn_finalize(None, None, 1, *bv, training=False, bessel=True, save=save)
+            z, rscale, a_sum, assign = ops.netvlad_pool_fwd(X, B, T, wc16, rb[0], rb[1], sh[vs + "/centers_t16"],
+                                                            save_assign=save)
+            out_view = vlad[:, off:off + K * D]
+            ops.netvlad_finalize_f16(z, rscale, out_view, out_view.stride(0))      # d-major flatten (:1583)
+            if want_inter:
+                ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
+            if save:
+                ctx[name] = dict(X=X, z=z, rscale=rscale, a_sum=a_sum, assign=assign, cluster_bn_stats=rb[2])
+            off += K * D
+        pred = self._head(vlad, B, training, save, ctx, want_inter)
+        return pred, ctx
+
+    def regularization_loss(self):
+        """REGULARIZATION_LOSSES of the model beyond the MoE weight decay (device scalar, fp32): the orthogonal
+        regulariser of the two NetVladOrthoReg modules (module_utils.py:55-90), zero for NetVladV1/V2."""
+        c, v = self.cfg, self.store.vars
+        tot = torch.zeros(1, dtype=torch.float32, device=self.store.device)
+        if c.model == "WillowModelReg":
+            for name, scale in (("video", c.rgb_det_reg), ("audio", c.audio_det_reg)):
+                if scale > 0:
+                    tot += ops.ortho_reg(v[name + "_VLAD/cluster_weights2"], scale)
+        return tot[0]
+
+    def _willow_modality_bwd(self, ctx, name, col0, D, K, dv, dgamma_in, dbeta_in, put):
+        """Backward of NetVladOrthoReg (same residual aggregation / soft-assignment backward as NetVladV1, entered from
+        the d-major flatten) + the regulariser's gradient on cluster_weights2."""
+        c, v, sh = self.cfg, self.store.vars, self.store.shadows
+        inv = 1.0 / ctx["loss_scale"]
+        m, B, T = ctx[name], ctx["B"], c.iterations
+        vs = name + "_VLAD"
+        f32 = torch.float32
+        gout = ctx["_gout"]
+        ct = sh[vs + "/centers_t"]
+        dvh = ops.dmajor_to_kmajor_f16(dv, B, K, D)
+        dz, q = ops.netvlad_norm_bwd(m["z"], m["rscale"], dvh, ct)
+        X, wc16 = m["X"], sh[vs + "/wc16"]
+        S16 = ops.gemm(X, wc16)                                               # logits recomputed: [B*T, K]
+        X3 = ctx["xb"].view(B, T, -1)[:, :, col0:col0 + D]
+        G = ops.gemm(X3, dz, b_mn=False, out_dtype=f32)                       # [B, T, K] = X dV^T per video
+        bn = vs + "/cluster_bn"
+        dS, dg, db = ops.assign_bwd(G.view(B * T, K), m["assign"].view(B * T, K), q, S16, m["cluster_bn_stats"],
+                                    v[bn + "/gamma"], T, inv_scale=inv)
+        put(bn + "/gamma", dg); put(bn + "/beta", db)
+        wname = vs + "/cluster_weights" + self.wc_suffix(name)
+        m_tiles = (D + 127) // 128
+        parts = ops.gemm(X, dS, a_mn=True, b_mn=True, splits=max(2, min(64, 148 // max(1, m_tiles))))
+        dWc = gout(wname)
+        if dWc is None:
+            dWc = torch.empty((D, K), dtype=f32, device=X.device)
+        ops.splitk_reduce(parts, alpha=inv, out32=dWc)
+        put(wname, dWc)
+        dCt, E = ops.center_bwd(dz, m["z"], m["a_sum"], ct, v["input_bn/beta"][col0:col0 + D], inv)
+        ops.input_bn_grad(v[wname], dWc, dCt, E, v["input_bn/gamma"][col0:col0 + D],
+                          dgamma_in[col0:col0 + D], dbeta_in[col0:col0 + D])
+        dC = ops.transpose_f32(dCt)                                           # [D, K]
+        scale = c.rgb_det_reg if name == "video" else c.audio_det_reg
+        if scale > 0:
+            # loss = label_loss + regularization_penalty * reg_loss (train.py:301-303, 323-324)
+            ops.ortho_reg(v[vs + "/cluster_weights2"], scale, dw=dC, grad_scale=float(ctx.get("reg_penalty", 1.0)),
+                          want_value=False)
+        put(vs + "/cluster_weights2", dC)
+
     def _head(self, vlad, B, training, save, ctx, want_inter):
         """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
@@ -522,6 +650,8 @@ class NetVladEngine:
             with torch.cuda.stream(side if on_side else main):
                 if c.model == "NetVladV1":
                     self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m)
+                elif c.model == "WillowModelReg":
+                    self._willow_modality_bwd(ctx, name, col0, D, K, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m)
                 else:
                     self._v2_modality_bwd(ctx, name, col0, D, K, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m)
             if on_side:

@@ -16,7 +16,7 @@ def _define(fn, name, default, help_):
 # frame_level_models.py:35-42
 _define(flags.DEFINE_integer, "iterations", 30, "Number of frames per batch for DBoF.")
 _define(flags.DEFINE_bool, "sample_random_frames", True,
-        "If true samples random frames (for frame level models). Unused by NetVladV1/V2.")
+        "If true samples random frames (for frame level models). Unused by NetVladV1/V2; read by WillowModelReg.")
 # frame_level_models.py:2197-2216
 _define(flags.DEFINE_bool, "netvlad_add_batch_norm", True, "Adds batch normalization to the DBoF model.")
 _define(flags.DEFINE_integer, "netvlad_cluster_size", 256, "Number of units in the NetVLAD cluster layer.")
@@ -24,6 +24,12 @@ _define(flags.DEFINE_integer, "netvlad_hidden_size", 1024, "Number of units in t
 _define(flags.DEFINE_bool, "netvlad_relu", False, "add ReLU to hidden layer")
 _define(flags.DEFINE_bool, "gating", True, "Gating for NetVLAD")
 _define(flags.DEFINE_bool, "gating_remove_diag", False, "Remove diag for self gating")
+_define(flags.DEFINE_float, "audio_det_reg", 1e-4,
+        "The coefficient that determines the strength of the determinant regularization penalty "
+        "(of the VLAD cluster centres, for audio features).")
+_define(flags.DEFINE_float, "rgb_det_reg", 1e-4,
+        "The coefficient that determines the strength of the determinant regularization penalty "
+        "(of the VLAD cluster centres, for rgb features).")
 # video_level_models.py:26-45
 _define(flags.DEFINE_integer, "moe_num_mixtures", 2,
         "The number of mixtures (excluding the dummy 'expert') used for MoeModel.")

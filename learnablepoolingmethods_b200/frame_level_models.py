@@ -1,7 +1,8 @@
 """Frame-level models of the hot path with the reference's registry names and call signatures.
 
-Drop-in for `frame_level_models.NetVladV1` / `NetVladV2` (frame_level_models.py:2222-2377, 2383-2513)
-and the `NetVLAD` pooling module (:2765-2824).  `create_model` executes eagerly on the GPU (there is no
+Drop-in for `frame_level_models.NetVladV1` / `NetVladV2` (frame_level_models.py:2222-2377, 2383-2513),
+the `NetVLAD` pooling module (:2765-2824) and -- SURVEY 8f row 4 -- the baseline `WillowModelReg` (:2516-2635)
+and the `LightVLAD` module (:2827-2877).  `create_model` executes eagerly on the GPU (there is no
 graph): it returns `{"predictions": tensor [B, vocab]}`; when called with `is_training=True` under
 torch autograd the tensor carries the backward of the whole path (hand-written CUDA).
 """
@@ -14,7 +15,7 @@ from .engine import NetVladConfig, NetVladEngine
 from .flags import FLAGS, ensure_parsed
 
 
-def _resolve(cls_name, model_input, vocab_size, iterations, cluster_size, hidden_size, unused):
+def _resolve(cls_name, model_input, vocab_size, iterations, cluster_size, hidden_size, unused, sample_random_frames=None):
     ensure_parsed()
     # kwargs resolve as `kw or FLAGS.<name>` (frame_level_models.py:2235-2242)
     iterations = iterations or FLAGS.iterations
@@ -28,7 +29,9 @@ def _resolve(cls_name, model_input, vocab_size, iterations, cluster_size, hidden
                          rgb_dim=rgb_dim, audio_dim=feat - rgb_dim,
                          rgb_heads=int(unused.get("rgb_heads", 64)), audio_heads=int(unused.get("audio_heads", 16)),
                          add_batch_norm=True, gating=FLAGS.gating, remove_diag=FLAGS.gating_remove_diag,
-                         moe_l2=FLAGS.moe_l2)
+                         moe_l2=FLAGS.moe_l2, rgb_det_reg=float(FLAGS.rgb_det_reg), audio_det_reg=float(FLAGS.audio_det_reg),
+                         # `sample_random_frames or FLAGS.sample_random_frames` (frame_level_models.py:2531)
+                         random_frames=bool(sample_random_frames or FLAGS.sample_random_frames))
 
 
 def get_engine(cfg: NetVladConfig, store=None) -> NetVladEngine:
@@ -47,12 +50,18 @@ class _NetVladBase(models.BaseModel):
     def create_model(self, model_input, vocab_size, num_frames, iterations=None, add_batch_norm=None,
                      sample_random_frames=None, cluster_size=None, hidden_size=None, is_training=True,
                      **unused_params):
-        cfg = _resolve(self._NAME, model_input, vocab_size, iterations, cluster_size, hidden_size, unused_params)
+        cfg = _resolve(self._NAME, model_input, vocab_size, iterations, cluster_size, hidden_size, unused_params,
+                       sample_random_frames)
         engine = get_engine(cfg, unused_params.get("store"))
         from .autograd import netvlad_apply
         pred = netvlad_apply(engine, model_input, num_frames, is_training,
-                             dropout_masks=unused_params.get("dropout_masks"))
-        return {"predictions": pred}
+                             dropout_masks=unused_params.get("dropout_masks"), frame_index=unused_params.get("frame_index"))
+        result = {"predictions": pred}
+        if self._NAME == "WillowModelReg":
+            # TF collects the orthogonal regulariser through REGULARIZATION_LOSSES (train.py:301-303); the eager
+            # mirror hands it back under the key train.py:296-297 already honours
+            result["regularization_loss"] = engine.regularization_loss()
+        return result
 
 
 class NetVladV1(_NetVladBase):
@@ -63,6 +72,13 @@ class NetVladV1(_NetVladBase):
 class NetVladV2(_NetVladBase):
     """ NetVlad with attention-based cluster similarities (paper 3.2). """
     _NAME = "NetVladV2"
+
+
+class WillowModelReg(_NetVladBase):
+    """ WILLOW model with orthogonal regularization for robust features (frame_level_models.py:2516-2635):
+    random frame sampling, NetVladOrthoReg pooling per modality, context gating, MoE.  `frame_index=` (int32
+    [B, iterations]) in **unused_params replaces the random draw (deterministic evaluation / parity tests). """
+    _NAME = "WillowModelReg"
 
 
 class NetVLAD():
@@ -101,4 +117,40 @@ class NetVLAD():
         else:
             scale, shift = torch.ones(K, device=x16.device), bias
         z, rs, _, _ = ops.netvlad_pool_fwd(x16, B, T, wc16, scale, shift, c2[0])
+        return ops.netvlad_finalize(z, rs, d_major=True)
+
+
+class LightVLAD():
+    """frame_level_models.py:2827-2877: NetVLAD without the cluster-centre residual.  Runs the same fused pooling
+    kernel with zero centres."""
+
+    def __init__(self, feature_size, max_frames, cluster_size, add_batch_norm, is_training):
+        self.feature_size = feature_size
+        self.max_frames = max_frames
+        self.is_training = is_training
+        self.add_batch_norm = add_batch_norm
+        self.cluster_size = int(cluster_size)
+
+    def forward(self, reshaped_input, store=None):
+        """reshaped_input: [(B*max_frames), feature_size] -> [B, cluster_size*feature_size] fp32 (d-major flatten)."""
+        import math
+        s = store or variables.default_store()
+        D, K, T = self.feature_size, self.cluster_size, self.max_frames
+        wc = s.get_variable("cluster_weights", (D, K), "normal", 1 / math.sqrt(D))
+        x16 = reshaped_input if reshaped_input.dtype == torch.float16 else ops.cast_f16(reshaped_input.contiguous())
+        B = x16.shape[0] // T
+        wc16 = ops.cast_f16(wc)
+        if self.add_batch_norm:
+            beta, gamma, mm, mv = s.batch_norm_vars("cluster_bn", K)
+            if self.is_training:
+                _, st = ops.gemm(wc16, x16, a_mn=True, b_mn=False, out="none", stats=True)
+                scale, shift = ops.bn_finalize(st[0].reshape(-1, K), st[1].reshape(-1, K), B * T, gamma, beta, mm, mv,
+                                               training=True, bessel=True)
+            else:
+                scale, shift = ops.bn_finalize(None, None, 1, gamma, beta, mm, mv, training=False, bessel=True)
+        else:
+            scale = torch.ones(K, device=x16.device)
+            shift = s.get_variable("cluster_biases", (K,), "normal", 1 / math.sqrt(D))
+        zero_centers = torch.zeros((K, D), dtype=torch.float16, device=x16.device)
+        z, rs, _, _ = ops.netvlad_pool_fwd(x16, B, T, wc16, scale, shift, zero_centers)
         return ops.netvlad_finalize(z, rs, d_major=True)

@@ -227,6 +227,56 @@ def sample_bn_apply(x, num_frames, T, scale, shift, out=None, split_col=None):
     return ya, yb
 
 
+def random_frame_index(num_frames, T, max_frames, *, mode=0, uniform=None, seed=0):
+    """int32 [B, T] gather indices of SampleRandomFrames (mode 0) / SampleRandomSequence (mode 1), model_utils.py:26-73.
+    uniform: optional fp32 [B, T] / [B] draws in [0,1) (parity tests inject tf.random_uniform's values)."""
+    lib = _lib.load()
+    B = num_frames.shape[0]
+    idx = torch.empty((B, T), dtype=torch.int32, device=num_frames.device)
+    if uniform is not None:
+        uniform = uniform.to(device=num_frames.device, dtype=torch.float32).contiguous()
+        assert uniform.numel() == (B * T if mode == 0 else B)
+    check(lib.lpm_random_frame_index(ptr(num_frames), ptr(uniform), C.c_ulonglong(seed & (2 ** 64 - 1)), B, T, max_frames,
+                                     mode, ptr(idx), stream_ptr()), "lpm_random_frame_index")
+    return idx
+
+
+def gather_bn_stats(x, frame_index, T):
+    """sample_bn_stats with explicit gather indices (int32 [B, T])."""
+    lib = _lib.load()
+    B, Fmax, F = x.shape
+    blocks = lib.lpm_sample_stats_blocks()
+    partial = _f32((blocks, 2, F), x.device)
+    check(lib.lpm_gather_bn_stats(ptr(x), int(x.dtype == torch.uint8), C.c_float(QUANT_MAX), C.c_float(QUANT_MIN),
+                                  ptr(frame_index), B, Fmax, F, T, ptr(partial), stream_ptr()), "lpm_gather_bn_stats")
+    return partial
+
+
+def gather_bn_apply(x, frame_index, T, scale, shift):
+    """sample_bn_apply with explicit gather indices: fp16 [B*T, F]."""
+    lib = _lib.load()
+    B, Fmax, F = x.shape
+    out = _f16((B * T, F), x.device)
+    check(lib.lpm_gather_bn_apply(ptr(x), int(x.dtype == torch.uint8), C.c_float(QUANT_MAX), C.c_float(QUANT_MIN),
+                                  ptr(frame_index), B, Fmax, F, T, ptr(scale), ptr(shift), ptr(out), 0, None, stream_ptr()),
+          "lpm_gather_bn_apply")
+    return out
+
+
+def ortho_reg(w, scale, *, dw=None, grad_scale=1.0, accumulate=True, want_value=True):
+    """Orthogonal regulariser of module_utils.py:55-90 on w fp32 [D, K]: returns the value (device scalar) and adds
+    grad_scale * gradient into dw (fp32 [D, K]) when given."""
+    lib = _lib.load()
+    D, K = w.shape
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    nbytes = lib.lpm_ortho_reg_workspace_bytes(D, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=w.device)    # not the shared scratch: modalities run on two streams
+    value = _f32((1,), w.device) if want_value else None
+    check(lib.lpm_ortho_reg(ptr(w), D, K, C.c_float(scale), C.c_float(grad_scale), int(accumulate), ptr(value), ptr(dw),
+                            ptr(ws), C.c_ulonglong(nbytes), stream_ptr()), "lpm_ortho_reg")
+    return value
+
+
 def netvlad_pool_fwd(x16, B, T, wc16, logit_scale, logit_shift, centers, *, valid_frames=None,
                      save_assign=False, assign_in=None):
     """x16: fp16 view [B*T, D] (row stride may exceed D); centers: fp16 [K, D] (cluster-major shadow made by

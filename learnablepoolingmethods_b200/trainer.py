@@ -249,10 +249,12 @@ class Trainer:
         if self.reducer is not None:
             self.reducer.mark_done(self.flat.end_offset(name))
 
-    def train_step(self, model_input, num_frames, labels_u8):
-        """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32)."""
+    def train_step(self, model_input, num_frames, labels_u8, frame_index=None):
+        """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32).
+        frame_index: optional int32 [B, iterations] (WillowModelReg: replaces the random frame draw)."""
         eng = self.engine
-        pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True)
+        pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True, frame_index=frame_index)
+        ctx["reg_penalty"] = self.reg_penalty
         B = pred.shape[0]
         if self.use_shard and self.shard is not None:
             self.shard.start_exchange(ctx["head"]["vlad"])       # rides under the whole backward

@@ -27,6 +27,11 @@ Reference lines followed (all relative to /root/reference):
   video_level_models.py:48-159      MoeModel
   losses.py:41-51                   CrossEntropyLoss
   utils.py:170-213, train.py:244-252,321-336  combine / clip / Adam / LR decay
+  model_utils.py:26-73              SampleRandomSequence / SampleRandomFrames      
+  frame_level_models.py:2516-2635   WillowModelReg.create_model
+  video_pooling_modules.py:1499-1586 NetVladOrthoReg.forward
+  frame_level_models.py:2827-2877   LightVLAD.forward
+  module_utils.py:55-90             orthogonal_regularizer
 Decisions D1-D7 of SURVEY.md section 0 are applied (see the `D5`/`D6`/`D7` notes inline).
 """
 from __future__ import annotations
@@ -118,6 +123,30 @@ def sample_uniform_frames(model_input: torch.Tensor, num_frames, num_samples: in
 
 
 # --------------------------------------------------------------------------- #
+# model_utils.py:26-73  SampleRandomSequence / SampleRandomFrames (uniform draws injected)
+# --------------------------------------------------------------------------- #
+def sample_random_frame_indices(num_frames: np.ndarray, uniform: np.ndarray) -> np.ndarray:
+    """frame_index = int32( uniform[B,S] * tile(float32(num_frames)) ), fp32 product, truncation (:66-69)."""
+    nf = np.asarray(num_frames).astype(np.float32)[:, None]
+    return (np.asarray(uniform, dtype=np.float32) * nf).astype(np.float32).astype(np.int32)
+
+
+def sample_random_sequence_indices(num_frames: np.ndarray, num_samples: int, uniform: np.ndarray) -> np.ndarray:
+    """start = int32(uniform[B,1] * float32(max(nf - S, 0) + 1)); index = min(start + range(S), int32(nf - 1)) (:38-47)."""
+    nf = np.asarray(num_frames).astype(np.float32)[:, None]
+    max_start = np.maximum(nf - np.float32(num_samples), np.float32(0))
+    start = (np.asarray(uniform, dtype=np.float32).reshape(-1, 1) * (max_start + np.float32(1))).astype(np.float32).astype(np.int32)
+    return np.minimum(start + np.arange(num_samples, dtype=np.int32)[None, :], (nf - 1).astype(np.int32))
+
+
+def gather_frames(model_input: torch.Tensor, frame_index: np.ndarray) -> torch.Tensor:
+    """tf.gather_nd(model_input, stack([batch_index, frame_index], 2)) (:48-51, 70-73).  Indices are clamped to the
+    padded frame range: TF's CPU kernel raises on an out-of-range index (only reachable with num_frames = 0)."""
+    idx = torch.from_numpy(np.clip(np.asarray(frame_index), 0, model_input.shape[1] - 1)).long()
+    return model_input[torch.arange(model_input.shape[0])[:, None], idx]
+
+
+# --------------------------------------------------------------------------- #
 # frame_level_models.py:2765-2824  NetVLAD.forward
 # --------------------------------------------------------------------------- #
 def netvlad_forward(x, P, S, scope, max_frames, add_batch_norm, is_training, return_assign=False):
@@ -140,6 +169,60 @@ def netvlad_forward(x, P, S, scope, max_frames, add_batch_norm, is_training, ret
     vlad = vlad.reshape(-1, K * D)                                  # :2821 d-major flatten
     vlad = l2_normalize(vlad, 1)                                    # :2822
     return (vlad, act) if return_assign else vlad
+
+
+# --------------------------------------------------------------------------- #
+# module_utils.py:55-90  orthogonal_regularizer
+# --------------------------------------------------------------------------- #
+def orthogonal_regularizer(weights: torch.Tensor, scale: float) -> torch.Tensor:
+    """scale * sum | l2n(W, axis=1)^T l2n(W, axis=1) - I |   (W is [feature_size, cluster_size]: ROWS are normalised)."""
+    n = l2_normalize(weights, 1)                                    # :78
+    det = n.transpose(0, 1) @ n                                     # :79-80
+    det = det - torch.eye(det.shape[0], dtype=det.dtype)            # :81-82
+    return scale * det.abs().sum()                                  # :83, 88
+
+
+# --------------------------------------------------------------------------- #
+# video_pooling_modules.py:1499-1586  NetVladOrthoReg.forward
+# --------------------------------------------------------------------------- #
+def netvlad_ortho_reg_forward(x, P, S, scope, max_frames, batch_norm_, is_training, scope_id=None):
+    """Same arithmetic as NetVLAD.forward; `cluster_weights<scope_id>` is the variable name (:1527-1531) and
+    `cluster_weights2` is [D, K] (no leading 1, :1558-1568).  The regulariser is collected separately
+    (`willow_regularization`): TF attaches it to the variable, train.py:301-303 adds it to the loss."""
+    sid = "" if scope_id is None else str(scope_id)
+    Wc = P[scope + "/cluster_weights" + sid]
+    D, K = Wc.shape
+    act = x @ Wc                                                    # :1536
+    if batch_norm_:
+        act = batch_norm(act, P, S, scope + "/cluster_bn", is_training)   # :1538-1544
+    else:
+        act = act + P[scope + "/cluster_biases" + sid]              # :1545-1552
+    act = torch.softmax(act, dim=-1)                                # :1554
+    act = act.reshape(-1, max_frames, K)                            # :1557
+    a_sum = act.sum(dim=-2, keepdim=True)                           # :1559
+    a = a_sum * P[scope + "/cluster_weights2"].unsqueeze(0)         # :1573-1574
+    xr = x.reshape(-1, max_frames, D)
+    vlad = torch.matmul(act.transpose(1, 2), xr).transpose(1, 2) - a      # :1576-1581
+    vlad = l2_normalize(vlad, 1)                                    # :1582
+    vlad = vlad.reshape(-1, K * D)                                  # :1583
+    return l2_normalize(vlad, 1)                                    # :1584
+
+
+# --------------------------------------------------------------------------- #
+# frame_level_models.py:2827-2877  LightVLAD.forward (no cluster centres)
+# --------------------------------------------------------------------------- #
+def light_vlad_forward(x, P, S, scope, max_frames, add_batch_norm, is_training):
+    Wc = P[scope + "/cluster_weights"]
+    D, K = Wc.shape
+    act = x @ Wc                                                    # :2841
+    if add_batch_norm:
+        act = batch_norm(act, P, S, scope + "/cluster_bn", is_training)   # :2843-2849
+    else:
+        act = act + P[scope + "/cluster_biases"]
+    act = torch.softmax(act, dim=-1).reshape(-1, max_frames, K)     # :2858-2860
+    vlad = torch.matmul(act.transpose(1, 2), x.reshape(-1, max_frames, D)).transpose(1, 2)   # :2862-2869
+    vlad = l2_normalize(vlad, 1)                                    # :2871
+    return l2_normalize(vlad.reshape(-1, K * D), 1)                 # :2873-2874
 
 
 # --------------------------------------------------------------------------- #
@@ -323,6 +406,35 @@ def netvlad_v2(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
     return (pred, inter) if return_intermediates else pred
 
 
+WILLOW_SCOPES = (("video", "netvlad_rgb_scope"), ("audio", "netvlad_audio_scope"))   # frame_level_models.py:2552-2557
+
+
+def willow_model_reg(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size, is_training,
+                     frame_index, num_mixtures=2, rgb_dim=1024, remove_diag=False, gating=True,
+                     return_intermediates=False):
+    """WillowModelReg.create_model forward (frame_level_models.py:2516-2635; netvlad_relu False).
+    `frame_index` int [B, iterations]: the indices SampleRandomFrames / SampleRandomSequence drew (:2539-2544)."""
+    x = gather_frames(model_input, frame_index)
+    B, T, F = x.shape
+    x = batch_norm(x.reshape(-1, F), P, S, "input_bn", is_training)  # :2558-2564
+    inter, outs = {}, []
+    for (name, sid), sl in zip(WILLOW_SCOPES, (slice(0, rgb_dim), slice(rgb_dim, None))):
+        v = netvlad_ortho_reg_forward(x[:, sl], P, S, name + "_VLAD", T, True, is_training, scope_id=sid)
+        inter["vlad_" + name] = v
+        outs.append(v)
+    vlad = torch.cat(outs, dim=1)                                   # :2573
+    pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
+                            remove_diag=remove_diag, return_intermediates=True)
+    inter.update(hi)
+    return (pred, inter) if return_intermediates else pred
+
+
+def willow_regularization(P, rgb_det_reg=1e-4, audio_det_reg=1e-4):
+    """REGULARIZATION_LOSSES contributed by the two NetVladOrthoReg modules (flags :2209-2216)."""
+    return (orthogonal_regularizer(P["video_VLAD/cluster_weights2"], rgb_det_reg)
+            + orthogonal_regularizer(P["audio_VLAD/cluster_weights2"], audio_det_reg))
+
+
 # --------------------------------------------------------------------------- #
 # losses.py:41-51, regulariser, utils.py:170-213, Adam
 # --------------------------------------------------------------------------- #
@@ -360,7 +472,7 @@ TRAINABLE_EXCLUDE = ("moving_mean", "moving_variance")
 
 
 def train_step(model_fn, P, S, opt_state, batches, labels_list, *, step, lr, clip_norm=1.0,
-               reg_penalty=1.0, l2_penalty=1e-8):
+               reg_penalty=1.0, l2_penalty=1e-8, extra_reg=None):
     """One reference training step over `len(batches)` towers: per-tower loss/grads
     (per-tower BN statistics), SUM over towers (utils.py:205-211), per-tensor clip
     (utils.py:170-189), Adam.  `model_fn(batch, P, S) -> pred`.  Returns (losses, grads)."""
@@ -372,7 +484,10 @@ def train_step(model_fn, P, S, opt_state, batches, labels_list, *, step, lr, cli
             P[n].grad = None
         pred = model_fn(batch, P, S)
         label_loss = cross_entropy_loss(pred, labels)
-        loss = label_loss + reg_penalty * moe_regularization(P, l2_penalty)
+        reg = moe_regularization(P, l2_penalty)
+        if extra_reg is not None:                                   # e.g. willow_regularization (train.py:301-303)
+            reg = reg + extra_reg(P)
+        loss = label_loss + reg_penalty * reg
         loss.backward()
         losses.append(float(label_loss))
         for n in names:
@@ -414,7 +529,12 @@ def param_specs(model: str, *, iterations, cluster_size, hidden_size, vocab_size
     for name, D, K, sid in (("video", rgb_dim, cluster_size, "encode1"),
                             ("audio", audio_dim, cluster_size // 4, "encode2")):
         vs = name + "_VLAD"
-        if model == "NetVladV1":
+        if model == "WillowModelReg":
+            sid = dict(WILLOW_SCOPES)[name]
+            sp[vs + "/cluster_weights" + sid] = ((D, K), "normal", 1 / math.sqrt(D))
+            bn(vs + "/cluster_bn", K)
+            sp[vs + "/cluster_weights2"] = ((D, K), "normal", 1 / math.sqrt(D))
+        elif model == "NetVladV1":
             sp[vs + "/cluster_weights"] = ((D, K), "normal", 1 / math.sqrt(D))
             bn(vs + "/cluster_bn", K)
             sp[vs + "/cluster_weights2"] = ((1, D, K), "normal", 1 / math.sqrt(D))

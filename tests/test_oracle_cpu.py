@@ -18,7 +18,7 @@ def _run(model, is_training, dtype):
     return make_golden.run(model, is_training, dtype)
 
 
-@pytest.mark.parametrize("model", ["NetVladV1", "NetVladV2"])
+@pytest.mark.parametrize("model", ["NetVladV1", "NetVladV2", "WillowModelReg"])
 @pytest.mark.parametrize("is_training", [False, True])
 def test_oracle_matches_golden(model, is_training):
     gold = np.load(os.path.join(GOLD, f"{model}_{'train' if is_training else 'infer'}_tiny_f64.npz"))
@@ -168,3 +168,81 @@ def test_eval_golden_is_current():
     pred, labels = E.synthetic_eval_batch(102, 7, 50, (3,))
     assert abs(eval_util.calculate_gap(pred, labels) - float(G["gap102"])) < 1e-12
     assert abs(eval_util.calculate_precision_at_equal_recall_rate(pred, labels) - float(G["perr102"])) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# baseline NetVLAD (WillowModelReg / NetVladOrthoReg / LightVLAD), random sampling, regulariser
+# ------------------------------------------------------------------------------------------------------------------
+def test_random_sampling_rules():
+    """model_utils.py:54-73: int32(u*nf) in [0, nf); :26-51: a contiguous window clipped to nf-1."""
+    rng = np.random.RandomState(0)
+    nf = np.concatenate([[1, 2, 300, 299], rng.randint(1, 301, size=60)]).astype(np.int32)
+    u = rng.rand(len(nf), 256).astype(np.float32)
+    u[0, 0], u[2, 0] = 0.0, np.float32(1.0) - np.float32(2.0 ** -24)
+    idx = O.sample_random_frame_indices(nf, u)
+    assert idx.dtype == np.int32 and (idx >= 0).all() and (idx < nf[:, None]).all()
+    np.testing.assert_array_equal(idx, np.floor(u.astype(np.float64) * nf[:, None]).clip(max=nf[:, None] - 1).astype(np.int32))
+    seq = O.sample_random_sequence_indices(nf, 30, u[:, 0])
+    assert (seq >= 0).all() and (seq < nf[:, None]).all()
+    d = np.diff(seq, axis=1)
+    assert ((d == 1) | (d == 0)).all()                      # consecutive frames, then stuck at the last frame
+    long = nf >= 30
+    assert (d[long] == 1).all() and (seq[long, -1] <= nf[long] - 1).all()
+    assert (seq[~long, 0] == 0).all()                       # max_start = 0 -> start = int(u*1) = 0
+
+
+def test_orthogonal_regularizer_closed_forms():
+    """module_utils.py:55-90: rows of W are normalised (axis=1), the Gram matrix is K x K."""
+    eye = torch.eye(6, dtype=torch.float64)
+    assert float(O.orthogonal_regularizer(eye, 0.5)) == 0.0
+    assert float(O.orthogonal_regularizer(3.0 * eye, 0.5)) == 0.0               # scale invariance of the rows
+    D, K = 10, 4
+    ones = torch.ones(D, K, dtype=torch.float64)                               # N = 1/sqrt(K): N^T N = D/K everywhere
+    want = 0.25 * (K * abs(D / K - 1.0) + K * (K - 1) * D / K)
+    assert abs(float(O.orthogonal_regularizer(ones, 0.25)) - want) < 1e-12
+    # brute force against explicit loops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 3, generator=g, dtype=torch.float64)
+    n = w / w.norm(dim=1, keepdim=True)
+    tot = 0.0
+    for i in range(3):
+        for j in range(3):
+            tot += abs(float((n[:, i] * n[:, j]).sum()) - (1.0 if i == j else 0.0))
+    assert abs(float(O.orthogonal_regularizer(w, 2.0)) - 2.0 * tot) < 1e-12
+
+
+def test_ortho_reg_pooling_equals_netvlad_and_light_drops_centres():
+    """NetVladOrthoReg.forward (video_pooling_modules.py:1522-1586) is NetVLAD.forward with renamed variables;
+    LightVLAD (frame_level_models.py:2827-2877) is the same with zero centres."""
+    g = torch.Generator().manual_seed(3)
+    B, T, D, K = 2, 6, 8, 4
+    x = torch.randn(B * T, D, generator=g, dtype=torch.float64)
+    Wc, C, b = (torch.randn(D, K, generator=g, dtype=torch.float64), torch.randn(D, K, generator=g, dtype=torch.float64),
+                torch.randn(K, generator=g, dtype=torch.float64))
+    ref = O.netvlad_forward(x, {"s/cluster_weights": Wc, "s/cluster_biases": b, "s/cluster_weights2": C[None]}, None, "s", T, False, False)
+    got = O.netvlad_ortho_reg_forward(x, {"s/cluster_weightsnetvlad_rgb_scope": Wc, "s/cluster_biasesnetvlad_rgb_scope": b,
+                                          "s/cluster_weights2": C}, None, "s", T, False, False, scope_id="netvlad_rgb_scope")
+    torch.testing.assert_close(got, ref, rtol=1e-12, atol=1e-14)
+    light = O.light_vlad_forward(x, {"s/cluster_weights": Wc, "s/cluster_biases": b}, None, "s", T, False, False)
+    zero = O.netvlad_forward(x, {"s/cluster_weights": Wc, "s/cluster_biases": b, "s/cluster_weights2": torch.zeros(1, D, K, dtype=torch.float64)},
+                             None, "s", T, False, False)
+    torch.testing.assert_close(light, zero, rtol=1e-12, atol=1e-14)
+
+
+def test_willow_train_step_adds_the_regulariser_gradient():
+    sp = O.param_specs("WillowModelReg", iterations=8, cluster_size=8, hidden_size=16, vocab_size=10, rgb_dim=16, audio_dim=8)
+    assert sp["video_VLAD/cluster_weights2"][0] == (16, 8) and "audio_VLAD/cluster_weightsnetvlad_audio_scope" in sp
+    x, nf, labels = O.synthetic_batch(3, seed=1, max_frames=12, feat=24, vocab=10)
+    idx = O.sample_random_frame_indices(nf.numpy(), np.random.RandomState(0).rand(3, 8).astype(np.float32))
+    fn = lambda b, P, S: O.willow_model_reg(b[0], b[1], P, S, vocab_size=10, iterations=8, cluster_size=8, is_training=True,
+                                            frame_index=idx, rgb_dim=16)
+    grads = []
+    for extra in (None, lambda P: O.willow_regularization(P, 0.5, 0.5)):
+        P, S = O.init_params(sp, seed=3)
+        _, g = O.train_step(fn, P, S, {}, [(x, nf)], [labels], step=1, lr=1e-3, extra_reg=extra)
+        grads.append(g)
+    P, _ = O.init_params(sp, seed=3)
+    O.willow_regularization(P, 0.5, 0.5).backward()
+    for k in ("video_VLAD/cluster_weights2", "audio_VLAD/cluster_weights2"):
+        torch.testing.assert_close(grads[1][k] - grads[0][k], P[k].grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(grads[1]["hidden1_weights"], grads[0]["hidden1_weights"])
