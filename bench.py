@@ -111,22 +111,30 @@ def time_cuda(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
-def cpu_reference(steps, warmup, sample_batch=8, train=True):
+def cpu_reference(steps, warmup, sample_batch=8, train=True, model="NetVladV1"):
     """The CPU oracle (torch-CPU port of the TF reference) on all host cores; one step = a train step on
     `sample_batch` videos of the config-1 shape (a bounded sample of the 80-video tower batch)."""
     from oracle import netvlad_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    sp = O.param_specs("NetVladV1", iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
+    sp = O.param_specs(model, iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
                        hidden_size=CFG["hidden_size"], vocab_size=CFG["vocab"])
     P, S = O.init_params(sp)
     x, nf, labels = synthetic(sample_batch, 20181000)
     opt = {}
-    fn = lambda xx, Pp, Ss: O.netvlad_v1(xx[0], xx[1], Pp, Ss, vocab_size=CFG["vocab"], iterations=CFG["iterations"],
-                                         cluster_size=CFG["cluster_size"], is_training=True)
+    kw = dict(vocab_size=CFG["vocab"], iterations=CFG["iterations"], cluster_size=CFG["cluster_size"], is_training=True)
+    extra = None
+    if model == "WillowModelReg":
+        import numpy as np
+        rng = np.random.RandomState(0)
+        fn = lambda xx, Pp, Ss: O.willow_model_reg(xx[0], xx[1], Pp, Ss, frame_index=O.sample_random_frame_indices(
+            xx[1].numpy(), rng.rand(sample_batch, CFG["iterations"]).astype(np.float32)), **kw)
+        extra = O.willow_regularization
+    else:
+        fn = lambda xx, Pp, Ss: getattr(O, {"NetVladV1": "netvlad_v1", "NetVladV2": "netvlad_v2"}[model])(xx[0], xx[1], Pp, Ss, **kw)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(fn, P, S, opt, [(x, nf)], [labels.bool()], step=i + 1, lr=2e-4)
+        O.train_step(fn, P, S, opt, [(x, nf)], [labels.bool()], step=i + 1, lr=2e-4, extra_reg=extra)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
@@ -143,7 +151,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2"])
+    ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2", "WillowModelReg"])
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: model_input = the reader's uint8 codes (dequantise + L2-normalise fused into the gather kernels); "
                          "f32: model_input = dequantised, L2-normalised fp32 frames (the reference's create_model contract)")
@@ -167,7 +175,7 @@ def main():
         if rank != 0:
             return
         steps = max(1, min(args.steps, 3))
-        v, sec, cores, sample = cpu_reference(steps, min(args.warmup, 1))
+        v, sec, cores, sample = cpu_reference(steps, min(args.warmup, 1), model=args.model)
         out = dict(base, impl="reference", value=v, ms_per_step=sec * 1e3, steps=steps, warmup=min(args.warmup, 1),
                    dtype="f32", n_gpus=args.gpus,
                    cpu_baseline={"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample},
@@ -306,7 +314,7 @@ def main():
                                   "note": "B=80 fills 80 of 148 SMs (one CTA per video); full-wave figure at B=1184",
                                   "peak_source": f"{src} bf16 burst (kernel timed alone)"})
         if args.gpus == 1 and not args.no_cpu_baseline:
-            v, sec, cores, sample = cpu_reference(2, 1)
+            v, sec, cores, sample = cpu_reference(2, 1, model=args.model)
             out["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:

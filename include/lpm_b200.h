@@ -388,6 +388,11 @@ unsigned long long lpm_ortho_reg_workspace_bytes(int D, int K);
 int lpm_ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value,
                   float* dw, void* workspace, unsigned long long workspace_bytes, lpm_stream_t stream);
 
+/* Host utility (no GPU work): CRC-32C (Castagnoli, reflected, init/xorout 0xFFFFFFFF) continued from `crc` (0 to start).
+ * TensorFlow's tensor-bundle checkpoints store it (masked) per tensor and per index block; used by the checkpoint
+ * reader/writer of learnablepoolingmethods_b200/checkpoint.py (train.py:415-423 saver, :390-411). */
+unsigned int lpm_crc32c(unsigned int crc, const void* data, unsigned long long n);
+
 #ifdef __cplusplus
 }
 #endif

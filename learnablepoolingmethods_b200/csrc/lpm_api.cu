@@ -514,4 +514,33 @@ int lpm_ortho_reg(const float* w, int D, int K, float scale, float grad_scale, i
                    ST(stream));
 }
 
+// ---- host utility for checkpoint interchange: CRC-32C (Castagnoli), slicing-by-8 ----
+static uint32_t g_crc_tab[8][256];
+static std::once_flag g_crc_once;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xff];
+}
+unsigned int lpm_crc32c(unsigned int crc, const void* data, unsigned long long n) {
+  std::call_once(g_crc_once, crc_init);
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8); --n; }
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = g_crc_tab[7][w & 0xff] ^ g_crc_tab[6][(w >> 8) & 0xff] ^ g_crc_tab[5][(w >> 16) & 0xff] ^ g_crc_tab[4][(w >> 24) & 0xff] ^
+        g_crc_tab[3][(w >> 32) & 0xff] ^ g_crc_tab[2][(w >> 40) & 0xff] ^ g_crc_tab[1][(w >> 48) & 0xff] ^ g_crc_tab[0][w >> 56];
+    p += 8; n -= 8;
+  }
+  while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return ~c;
+}
+
 }  // extern "C"

@@ -206,6 +206,7 @@ class Trainer:
         return (self.world == 1 and c.vlad_dim % 8 == 0 and not self.disable_factored_hidden
                 and ops.rank_adam_supported(batch, c.hidden_size))
 
+    on_flat_created = None
     disable_factored_hidden = False
     gather_hidden_factors = True
     shard_hidden_update = True
@@ -271,6 +272,9 @@ class Trainer:
             grads = eng.backward(ctx, dpred)
             self.flat = FlatState(self.store, order, self._wd(), factored=("hidden1_weights",) if factored else ())
             self.flat.bind_shadows(eng)
+            if self.on_flat_created is not None:        # checkpoint.load_into_store: restored Adam moments
+                self.on_flat_created(self.flat)
+                self.on_flat_created = None
             for n, g in grads.items():
                 self.flat.grad_views[n].copy_(g.reshape(self.flat.grad_views[n].shape))
             if self.use_shard:

@@ -62,3 +62,14 @@ def synthetic_eval_batch(seed, B, V, zero_label_rows=()):
         labels[b, cls] = 1
         pred[b, cls[: max(1, len(cls) // 2)]] += 0.5           # some positives score high
     return np.clip(pred, 0.0, 1.0).astype(np.float32), labels
+
+
+def format_lines(video_ids, predictions, top_k):
+    """inference.py:88-96 restated (numpy only; the reference module imports tensorflow at the top and cannot be
+    imported here): argpartition for the top_k classes, sorted by descending score, "%i %g" pairs."""
+    batch_size = len(video_ids)
+    for video_index in range(batch_size):
+        top_indices = np.argpartition(predictions[video_index], -top_k)[-top_k:]
+        line = [(class_index, predictions[video_index][class_index]) for class_index in top_indices]
+        line = sorted(line, key=lambda p: -p[1])
+        yield video_ids[video_index].decode('utf-8') + "," + " ".join("%i %g" % (label, score) for (label, score) in line) + "\n"
