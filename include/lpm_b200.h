@@ -225,9 +225,22 @@ int lpm_colsum(const void* x, int is_f32, long long ld, long long rows, int cols
 int lpm_colsum_final(const float* partial, int chunks, long long pstride, int cols, float alpha, int accumulate,
                      float* out, lpm_stream_t stream);
 /* frame_level_models.py:2342-2368 backward. */
+/* wg_diag / ddiag (both or neither; --gating_remove_diag, :2349-2352): the batch norm saw g - diag*act; dact then also
+ * carries -diag*dv and ddiag[c] = -sum_b dv*act (unscaled) is the extra gradient of gating_weights_2's diagonal. */
 int lpm_gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
                    const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact,
-                   void* dg_f16, float* dgamma, float* dbeta, lpm_stream_t stream);
+                   void* dg_f16, float* dgamma, float* dbeta, const float* wg_diag, float* ddiag, lpm_stream_t stream);
+/* m[i][i] += alpha*d[i], i < n (fp32, row stride ld). */
+int lpm_add_diag(float* m, int n, long long ld, const float* d, float alpha, lpm_stream_t stream);
+/* --netvlad_relu head (frame_level_models.py:2321-2327, 2339-2340): y = relu6(slim.batch_norm(x)) over the batch rows of
+ * x fp32 [B][H] (relu6 = 0: batch norm only).  Training updates the moving statistics (decay, Bessel-corrected variance)
+ * and saves (mean, rstd); backward: dy at y (fp32, loss-scaled) -> dx (may alias dy), dgamma / dbeta (x inv_scale). */
+int lpm_hidden_bn_relu6_fwd(const float* x, int B, int H, const float* gamma, const float* beta, float* moving_mean,
+                            float* moving_var, float decay, float eps, int training, int relu6, float* out_f32,
+                            void* out_f16, float* save_mean, float* save_rstd, lpm_stream_t stream);
+int lpm_hidden_bn_relu6_bwd(const float* x, const float* y, const float* dy, int B, int H, const float* gamma,
+                            const float* mean, const float* rstd, int relu6, float inv_scale, float* dx, float* dgamma,
+                            float* dbeta, lpm_stream_t stream);
 /* Joint layer norm backward: du = rstd*(dy*gamma - c1/N - xhat*c2/N); with `mask`, du_masked = du o (mask>0)
  * (ReLU backward of the pre-residual branch).  part_sample: B*chunks*2, part_cols: B*chunks*2*D (sum dy*xhat |
  * sum dy per column), part_cols_du (optional): B*chunks*D column sums of du_masked (du without mask);

@@ -287,10 +287,11 @@ int lpm_colsum_final(const float* partial, int chunks, long long pstride, int co
 }
 int lpm_gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
                    const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact,
-                   void* dg_f16, float* dgamma, float* dbeta, lpm_stream_t stream) {
+                   void* dg_f16, float* dgamma, float* dbeta, const float* wg_diag, float* ddiag, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(act && g && gamma && beta && mean && rstd && dout && dact && dg_f16 && dgamma && dbeta, "lpm_gating_bwd: null pointer");
-  return gating_bwd(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, H16(dg_f16), dgamma, dbeta, ST(stream));
+  return gating_bwd(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, H16(dg_f16), dgamma, dbeta, wg_diag, ddiag,
+                    ST(stream));
 }
 int lpm_layernorm_bwd_chunks(void) { return ln_bwd_chunks(); }
 int lpm_layernorm_joint_bwd(const void* u, const void* dy, long long dy_stride, int B, int rows, int D,
@@ -541,6 +542,27 @@ unsigned int lpm_crc32c(unsigned int crc, const void* data, unsigned long long n
   }
   while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8);
   return ~c;
+}
+
+int lpm_hidden_bn_relu6_fwd(const float* x, int B, int H, const float* gamma, const float* beta, float* moving_mean,
+                            float* moving_var, float decay, float eps, int training, int relu6, float* out_f32,
+                            void* out_f16, float* save_mean, float* save_rstd, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && gamma && beta && moving_mean && moving_var && out_f32 && B > 0 && H > 0, "lpm_hidden_bn_relu6_fwd: bad arguments");
+  return hidden_bn_relu6_fwd(x, B, H, gamma, beta, moving_mean, moving_var, decay, eps, training, relu6, out_f32, H16(out_f16),
+                             save_mean, save_rstd, ST(stream));
+}
+int lpm_hidden_bn_relu6_bwd(const float* x, const float* y, const float* dy, int B, int H, const float* gamma,
+                            const float* mean, const float* rstd, int relu6, float inv_scale, float* dx, float* dgamma,
+                            float* dbeta, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && y && dy && gamma && mean && rstd && dx && dgamma && dbeta, "lpm_hidden_bn_relu6_bwd: null pointer");
+  return hidden_bn_relu6_bwd(x, y, dy, B, H, gamma, mean, rstd, relu6, inv_scale, dx, dgamma, dbeta, ST(stream));
+}
+int lpm_add_diag(float* m, int n, long long ld, const float* d, float alpha, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(m && d && n > 0 && ld >= n, "lpm_add_diag: bad arguments");
+  return add_diag(m, n, ld, d, alpha, ST(stream));
 }
 
 }  // extern "C"

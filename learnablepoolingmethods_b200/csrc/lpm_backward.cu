@@ -118,17 +118,21 @@ __global__ void __launch_bounds__(1024) gating_bwd_kernel(const float* __restric
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                   const float* __restrict__ dout, float inv_scale, float* __restrict__ dact,
-                                  __half* __restrict__ dg, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                  __half* __restrict__ dg, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                  const float* __restrict__ wg_diag, float* __restrict__ ddiag) {
+  // wg_diag != null (--gating_remove_diag, :2349-2352): the batch norm saw g - diag*act; then additionally
+  //   dact -= diag * dv   and   ddiag[c] = -sum_b dv[b,c] * act[b,c]   (dv = gradient at the batch-norm input)
   __shared__ double red[2][32][33];
   __shared__ float sm[2][32];
   const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const bool ok = c < H;
   const float mu = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f, ga = ok ? gamma[c] : 0.f, be = ok ? beta[c] : 0.f;
+  const float dgc = (wg_diag && ok) ? wg_diag[c] : 0.f;
   double s1 = 0.0, s2 = 0.0;
   if (ok)
     for (int b = ky; b < B; b += 32) {
-      const float xh = (g[(size_t)b * H + c] - mu) * rs;
+      const float xh = (g[(size_t)b * H + c] - dgc * act[(size_t)b * H + c] - mu) * rs;
       const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
       const float a = act[(size_t)b * H + c], d = dout[(size_t)b * H + c];
       const float dv = d * a * sg * (1.f - sg);
@@ -147,13 +151,30 @@ __global__ void __launch_bounds__(1024) gating_bwd_kernel(const float* __restric
     sm[0][cx] = (float)(t1 / B); sm[1][cx] = (float)(t2 / B);
   }
   __syncthreads();
-  if (!ok) return;
   const float m1 = sm[0][cx], m2 = sm[1][cx];
-  for (int b = ky; b < B; b += 32) {
-    const float xh = (g[(size_t)b * H + c] - mu) * rs;
-    const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
-    const float dv = dout[(size_t)b * H + c] * act[(size_t)b * H + c] * sg * (1.f - sg);
-    dg[(size_t)b * H + c] = __float2half_rn(ga * rs * (dv - m1 - xh * m2));
+  double sd = 0.0;
+  if (ok)
+    for (int b = ky; b < B; b += 32) {
+      const float a = act[(size_t)b * H + c];
+      const float xh = (g[(size_t)b * H + c] - dgc * a - mu) * rs;
+      const float sg = 1.f / (1.f + __expf(-(xh * ga + be)));
+      const float dv = dout[(size_t)b * H + c] * a * sg * (1.f - sg);
+      const float gv = ga * rs * (dv - m1 - xh * m2);
+      dg[(size_t)b * H + c] = __float2half_rn(gv);
+      if (wg_diag) {
+        dact[(size_t)b * H + c] -= dgc * gv;       // written by this same thread in the first loop
+        sd += (double)gv * a;
+      }
+    }
+  if (ddiag == nullptr) return;
+  __syncthreads();
+  red[0][ky][cx] = sd;
+  __syncthreads();
+  if (ky == 0 && ok) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[0][k][cx];
+    ddiag[c] = -(float)t * inv_scale;
   }
 }
 
@@ -499,9 +520,10 @@ int colsum_final(const float* partial, int chunks, long long pstride, int cols, 
 
 int gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
                const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact, __half* dg,
-               float* dgamma, float* dbeta, cudaStream_t st) {
+               float* dgamma, float* dbeta, const float* wg_diag, float* ddiag, cudaStream_t st) {
+  LPM_REQUIRE((wg_diag == nullptr) == (ddiag == nullptr), "gating_bwd: wg_diag and ddiag go together");
   gating_bwd_kernel<<<(H + 31) / 32, 1024, 0, st>>>(act, g, B, H, gamma, beta, mean, rstd, dout, inv_scale, dact, dg,
-                                                  dgamma, dbeta);
+                                                  dgamma, dbeta, wg_diag, ddiag);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -65,7 +65,7 @@ int colsum_final(const float* partial, int chunks, long long pstride, int cols, 
                  float* out, cudaStream_t st);
 int gating_bwd(const float* act, const float* g, int B, int H, const float* gamma, const float* beta,
                const float* mean, const float* rstd, const float* dout, float inv_scale, float* dact, __half* dg,
-               float* dgamma, float* dbeta, cudaStream_t st);
+               float* dgamma, float* dbeta, const float* wg_diag, float* ddiag, cudaStream_t st);
 int ln_bwd_chunks();
 int layernorm_joint_bwd(const __half* u, const __half* dy, long long dy_stride, int B, int rows, int D,
                         const float* mean_rstd, const float* gamma, const __half* mask, __half* du,
@@ -145,5 +145,13 @@ int random_frame_index(const int* nf, const float* uniform, unsigned long long s
 unsigned long long ortho_reg_workspace_bytes(int D, int K);
 int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value, float* dw,
               float* ws, unsigned long long ws_bytes, cudaStream_t st);
+
+// lpm_head.cu
+int hidden_bn_relu6_fwd(const float* x, int B, int H, const float* gamma, const float* beta, float* mm, float* mv,
+                        float decay, float eps, int training, int relu6, float* out32, __half* out16, float* save_mean,
+                        float* save_rstd, cudaStream_t st);
+int hidden_bn_relu6_bwd(const float* x, const float* y, const float* dy, int B, int H, const float* gamma, const float* mean,
+                        const float* rstd, int relu6, float inv_scale, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+int add_diag(float* m, int n, long long ld, const float* d, float alpha, cudaStream_t st);
 
 }  // namespace lpm

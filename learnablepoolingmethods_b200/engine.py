@@ -40,6 +40,7 @@ class NetVladConfig:
     add_batch_norm: bool = True
     gating: bool = True
     remove_diag: bool = False
+    netvlad_relu: bool = False     # --netvlad_relu: hidden1_bn instead of hidden1_biases, then relu6 (:2321-2340)
     moe_l2: float = 1e-8
     d5_raw_reshape: bool = False   # SURVEY.md defect D5 switch (raw reinterpret instead of transpose)
     dropout_rate: float = 0.9      # D7: tf.layers.dropout(rate=1-0.1) in TransformerEncoderMod
@@ -123,7 +124,10 @@ class NetVladEngine:
                     self._dense_vars("filter_output" + sid, D, 4 * D, True)
                     self._dense_vars("ff_output" + sid, 4 * D, D, True)
         s.get_variable("hidden1_weights", (c.vlad_dim, c.hidden_size), "normal", 1 / math.sqrt(c.cluster_size))
-        s.get_variable("hidden1_biases", (c.hidden_size,), "normal", 0.01)
+        if c.netvlad_relu:
+            s.batch_norm_vars("hidden1_bn", c.hidden_size)        # `add_batch_norm and relu` (:2321-2327)
+        else:
+            s.get_variable("hidden1_biases", (c.hidden_size,), "normal", 0.01)
         s.get_variable("gating_weights_2", (c.hidden_size, c.hidden_size), "normal", 1 / math.sqrt(c.hidden_size))
         s.batch_norm_vars("gating_bn", c.hidden_size)
         V, M = c.vocab_size, c.num_mixtures
@@ -541,7 +545,16 @@ class NetVladEngine:
         parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
         act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
         act16 = torch.empty((B, Hn), dtype=torch.float16, device=vlad.device)
-        ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=act16)
+        hpre, hstats = None, None
+        if c.netvlad_relu:
+            hpre = act32
+            ops.splitk_reduce(parts, out32=hpre)
+            r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
+                                        v["hidden1_bn/moving_variance"], training=training, save=save)
+            act32, act16 = r[0], r[1]
+            hstats = r[2] if save else None
+        else:
+            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=act16)
         if c.gating:
             gates = ops.gemm(act16, sh["wg16"], out_dtype=torch.float32)
             diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
@@ -556,7 +569,7 @@ class NetVladEngine:
             ctx["inter"].update(hidden=act32, gated=gated32)
         if save:
             ctx["head"] = dict(vlad=vlad, act32=act32, act16=act16, gates=gates, gating_stats=r[2] if c.gating else None,
-                               gated32=gated32, gated16=gated16, logits=logits, pred=pred)
+                               gated32=gated32, gated16=gated16, logits=logits, pred=pred, hpre=hpre, hstats=hstats)
         return pred
 
     # ------------------------------------------------------------------------------------------
@@ -566,8 +579,6 @@ class NetVladEngine:
         """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
         Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
-        if c.remove_diag:
-            raise NotImplementedError("gating_remove_diag backward")
         B, hd = ctx["B"], ctx["head"]
         # dLoss/dpred scales as 1/B; LayerNorm over the L2-normalised descriptor has rstd ~ 200, so the scale
         # is kept modest (see DESIGN.md "numerics"): auto = 8*B clamped to [8, 4096]
@@ -605,17 +616,27 @@ class NetVladEngine:
         dgated = ops.gemm(dl16, sh["wmoe16"], b_mn=False, out_dtype=f32)
         # ---- context gating (frame_level_models.py:2342-2368) -----------------------------------
         if c.gating:
-            dact, dg16, dgam, dbet = ops.gating_bwd(hd["act32"], hd["gates"], v["gating_bn/gamma"], v["gating_bn/beta"],
-                                                    hd["gating_stats"], dgated, inv)
+            diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
+            gb = ops.gating_bwd(hd["act32"], hd["gates"], v["gating_bn/gamma"], v["gating_bn/beta"],
+                                hd["gating_stats"], dgated, inv, wg_diag=diag)
+            dact, dg16, dgam, dbet = gb[:4]
             put("gating_bn/gamma", dgam)
             put("gating_bn/beta", dbet)
-            put("gating_weights_2", ops.gemm(hd["act16"], dg16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                             out=gout("gating_weights_2")))
+            dwg = ops.gemm(hd["act16"], dg16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv, out=gout("gating_weights_2"))
+            if c.remove_diag:
+                ops.add_diag(dwg, gb[4])              # -sum_b dv*act on the diagonal (:2349-2352)
+            put("gating_weights_2", dwg)
             ops.gemm(dg16, sh["wg16"], b_mn=False, out=dact, accumulate=True)
         else:
             dact = dgated
         # ---- hidden projection (frame_level_models.py:2314-2334) --------------------------------
-        put("hidden1_biases", ops.colsum(dact, alpha=inv))
+        if c.netvlad_relu:
+            dact, dgam, dbet = ops.hidden_bn_relu6_bwd(hd["hpre"], hd["act32"], dact, v["hidden1_bn/gamma"], hd["hstats"],
+                                                       inv_scale=inv)
+            put("hidden1_bn/gamma", dgam)
+            put("hidden1_bn/beta", dbet)
+        else:
+            put("hidden1_biases", ops.colsum(dact, alpha=inv))
         dact16 = ops.cast_scaled_f16(dact)
         if ctx.get("factored_hidden"):
             # the trainer applies clip + Adam straight from the factors (dW = inv * vlad^T dact16 is never written)

@@ -29,6 +29,7 @@ def _resolve(cls_name, model_input, vocab_size, iterations, cluster_size, hidden
                          rgb_dim=rgb_dim, audio_dim=feat - rgb_dim,
                          rgb_heads=int(unused.get("rgb_heads", 64)), audio_heads=int(unused.get("audio_heads", 16)),
                          add_batch_norm=True, gating=FLAGS.gating, remove_diag=FLAGS.gating_remove_diag,
+                         netvlad_relu=FLAGS.netvlad_relu,
                          moe_l2=FLAGS.moe_l2, rgb_det_reg=float(FLAGS.rgb_det_reg), audio_det_reg=float(FLAGS.audio_det_reg),
                          # `sample_random_frames or FLAGS.sample_random_frames` (frame_level_models.py:2531)
                          random_frames=bool(sample_random_frames or FLAGS.sample_random_frames))

@@ -457,16 +457,53 @@ def colsum_final(partial, chunks, pstride, cols, *, alpha=1.0, out=None, accumul
     return out
 
 
-def gating_bwd(act, g, gamma, beta, stats, dout, inv_scale):
+def gating_bwd(act, g, gamma, beta, stats, dout, inv_scale, wg_diag=None):
+    """Returns dact, dg16, dgamma, dbeta[, ddiag] (ddiag: unscaled extra gradient of diag(gating_weights_2) when the
+    forward removed the diagonal, frame_level_models.py:2349-2352)."""
     lib = _lib.load()
     B, H = act.shape
     dev = act.device
     dact, dg = _f32((B, H), dev), _f16((B, H), dev)
     dgamma, dbeta = _f32((H,), dev), _f32((H,), dev)
+    ddiag = _f32((H,), dev) if wg_diag is not None else None
     check(lib.lpm_gating_bwd(ptr(act), ptr(g), B, H, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]), ptr(dout),
-                             C.c_float(inv_scale), ptr(dact), ptr(dg), ptr(dgamma), ptr(dbeta), stream_ptr()),
-          "lpm_gating_bwd")
-    return dact, dg, dgamma, dbeta
+                             C.c_float(inv_scale), ptr(dact), ptr(dg), ptr(dgamma), ptr(dbeta), ptr(wg_diag), ptr(ddiag),
+                             stream_ptr()), "lpm_gating_bwd")
+    return (dact, dg, dgamma, dbeta) if wg_diag is None else (dact, dg, dgamma, dbeta, ddiag)
+
+
+def add_diag(m, d, alpha=1.0):
+    lib = _lib.load()
+    n = d.numel()
+    check(lib.lpm_add_diag(ptr(m), n, _ll(m.stride(0)), ptr(d), C.c_float(alpha), stream_ptr()), "lpm_add_diag")
+    return m
+
+
+def hidden_bn_relu6_fwd(x, gamma, beta, moving_mean, moving_var, *, training, relu6=True, save=False,
+                        decay=BN_DECAY, eps=BN_EPS):
+    """relu6(slim.batch_norm(x)) over the batch rows of x fp32 [B, H] (--netvlad_relu, frame_level_models.py:2321-2340).
+    Returns (out32, out16[, (mean, rstd)])."""
+    lib = _lib.load()
+    B, H = x.shape
+    dev = x.device
+    out32, out16 = _f32((B, H), dev), _f16((B, H), dev)
+    sm = _f32((2, H), dev) if save else None
+    check(lib.lpm_hidden_bn_relu6_fwd(ptr(x), B, H, ptr(gamma), ptr(beta), ptr(moving_mean), ptr(moving_var), C.c_float(decay),
+                                      C.c_float(eps), int(training), int(relu6), ptr(out32), ptr(out16),
+                                      ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
+          "lpm_hidden_bn_relu6_fwd")
+    return (out32, out16, sm) if save else (out32, out16)
+
+
+def hidden_bn_relu6_bwd(x, y, dy, gamma, stats, *, inv_scale, relu6=True):
+    """dy (fp32, loss-scaled, gradient at y) -> dx in place; returns (dx, dgamma, dbeta) (parameter gradients unscaled)."""
+    lib = _lib.load()
+    B, H = x.shape
+    dgamma, dbeta = _f32((H,), x.device), _f32((H,), x.device)
+    check(lib.lpm_hidden_bn_relu6_bwd(ptr(x), ptr(y), ptr(dy), B, H, ptr(gamma), ptr(stats[0]), ptr(stats[1]), int(relu6),
+                                      C.c_float(inv_scale), ptr(dy), ptr(dgamma), ptr(dbeta), stream_ptr()),
+          "lpm_hidden_bn_relu6_bwd")
+    return dy, dgamma, dbeta
 
 
 def layernorm_joint_bwd(u, dy, dy_stride, B, rows, D, mean_rstd, gamma, *, inv_scale, mask=None, want_du_colsum=False):

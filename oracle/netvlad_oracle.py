@@ -332,8 +332,13 @@ def moe_forward(act, P, vocab_size, num_mixtures):
 # frame_level_models.py:2309-2377  shared head
 # --------------------------------------------------------------------------- #
 def head_forward(vlad, P, S, vocab_size, is_training, num_mixtures=2, gating=True,
-                 remove_diag=False, return_intermediates=False):
-    act = vlad @ P["hidden1_weights"] + P["hidden1_biases"]         # :2319,2329-2334 (netvlad_relu False)
+                 remove_diag=False, return_intermediates=False, relu=False):
+    act = vlad @ P["hidden1_weights"]                               # :2319
+    if relu:                                                        # `add_batch_norm and relu` (:2321-2327)
+        act = batch_norm(act, P, S, "hidden1_bn", is_training)
+        act = torch.clamp(act, 0.0, 6.0)                            # tf.nn.relu6 (:2339-2340)
+    else:
+        act = act + P["hidden1_biases"]                             # :2329-2334 (netvlad_relu False)
     hidden = act
     if gating:
         Wg = P["gating_weights_2"]
@@ -361,7 +366,7 @@ def _shell(model_input, num_frames, iterations, P, S, is_training):
 
 def netvlad_v1(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size,
                is_training, num_mixtures=2, rgb_dim=1024, rgb_heads=64, audio_heads=16,
-               d5_raw_reshape=False, remove_diag=False, gating=True, return_intermediates=False):
+               d5_raw_reshape=False, remove_diag=False, gating=True, return_intermediates=False, relu=False):
     """NetVladV1.create_model forward.  model_input [B, max_frames, rgb+audio] is
     already L2-normalised by the caller (train.py:264)."""
     x, B, T = _shell(model_input, num_frames, iterations, P, S, is_training)
@@ -382,14 +387,14 @@ def netvlad_v1(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
         outs.append(z.reshape(B, K * D))                            # :2292, :2304 k-major flatten
     vlad = torch.cat(outs, dim=1)                                   # :2309
     pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
-                            remove_diag=remove_diag, return_intermediates=True)
+                            remove_diag=remove_diag, return_intermediates=True, relu=relu)
     inter.update(hi)
     return (pred, inter) if return_intermediates else pred
 
 
 def netvlad_v2(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size,
                is_training, num_mixtures=2, rgb_dim=1024, dropout_masks=None, dropout_rate=0.9,
-               remove_diag=False, gating=True, return_intermediates=False):
+               remove_diag=False, gating=True, return_intermediates=False, relu=False):
     x, B, T = _shell(model_input, num_frames, iterations, P, S, is_training)
     inter = {}
     outs = []
@@ -401,7 +406,7 @@ def netvlad_v2(model_input, num_frames, P, S, *, vocab_size, iterations, cluster
         outs.append(v)
     vlad = torch.cat(outs, dim=1)
     pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
-                            remove_diag=remove_diag, return_intermediates=True)
+                            remove_diag=remove_diag, return_intermediates=True, relu=relu)
     inter.update(hi)
     return (pred, inter) if return_intermediates else pred
 
@@ -411,7 +416,7 @@ WILLOW_SCOPES = (("video", "netvlad_rgb_scope"), ("audio", "netvlad_audio_scope"
 
 def willow_model_reg(model_input, num_frames, P, S, *, vocab_size, iterations, cluster_size, is_training,
                      frame_index, num_mixtures=2, rgb_dim=1024, remove_diag=False, gating=True,
-                     return_intermediates=False):
+                     return_intermediates=False, relu=False):
     """WillowModelReg.create_model forward (frame_level_models.py:2516-2635; netvlad_relu False).
     `frame_index` int [B, iterations]: the indices SampleRandomFrames / SampleRandomSequence drew (:2539-2544)."""
     x = gather_frames(model_input, frame_index)
@@ -424,7 +429,7 @@ def willow_model_reg(model_input, num_frames, P, S, *, vocab_size, iterations, c
         outs.append(v)
     vlad = torch.cat(outs, dim=1)                                   # :2573
     pred, hi = head_forward(vlad, P, S, vocab_size, is_training, num_mixtures, gating=gating,
-                            remove_diag=remove_diag, return_intermediates=True)
+                            remove_diag=remove_diag, return_intermediates=True, relu=relu)
     inter.update(hi)
     return (pred, inter) if return_intermediates else pred
 
