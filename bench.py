@@ -275,6 +275,16 @@ def main():
     with torch.no_grad():
         infer_ms = reduce_max(time_cuda(lambda: eng.forward(x, nf, False), max(5, args.steps)))
 
+    # the same forward replayed from a CUDA graph (one launch instead of ~28 from Python)
+    graph_ms = None
+    try:
+        from learnablepoolingmethods_b200.engine import InferenceGraph
+        ig = InferenceGraph(eng, B, CFG["max_frames"], input_dtype=x.dtype)
+        ig(x, nf)
+        graph_ms = reduce_max(time_cuda(lambda: ig(x, nf), max(5, args.steps)))
+    except Exception as e:                                     # reported, never fatal for the headline numbers
+        print(f"inference graph unavailable: {e!r}", file=sys.stderr)
+
     out = None
     if rank == 0:
         burst, sustained, hbm, src = peaks()
@@ -300,6 +310,7 @@ def main():
         del xbl
         out = dict(base, value=B * world / (train_ms / 1e3), ms_per_step=train_ms,
                    infer_value=B * world / (infer_ms / 1e3), infer_ms_per_step=infer_ms,
+                   infer_graph_ms_per_step=graph_ms,
                    e2e={"value": B * world / (e2e_ms / 1e3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
                    gpu_launches=int(launches), clocks=clocks, loss=float(loss), loss_scale_overflow=bool(overflow),

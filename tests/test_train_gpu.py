@@ -71,3 +71,31 @@ def test_netvlad_v2_training_steps(cuda):
     assert not tr.overflowed()
     moved = [k for k in before if not torch.equal(before[k], store.vars[k])]
     assert len(moved) == len(before), sorted(set(before) - set(moved))
+
+
+@pytest.mark.parametrize("model", ["NetVladV1", "NetVladV2", "WillowModelReg"])
+def test_inference_graph_equals_eager(cuda, model):
+    """The CUDA-graph replay of the inference forward (two streams captured) returns exactly the eager result, for
+    changing inputs, and re-captures after the parameters change."""
+    from learnablepoolingmethods_b200 import ops, variables
+    from learnablepoolingmethods_b200.engine import InferenceGraph, NetVladConfig, NetVladEngine
+    from learnablepoolingmethods_b200.trainer import Trainer
+    from oracle import netvlad_oracle as O
+    B, K, Hd, V, T = 4, 64, 64, 100, 128
+    store = variables.VariableStore(cuda, seed=3)
+    eng = NetVladEngine(NetVladConfig(model=model, iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V), store)
+    g = InferenceGraph(eng, B, 300)
+    for seed in (1, 2):
+        x, nf, labels = O.synthetic_batch(B, seed=seed, vocab=V)
+        idx = ops.random_frame_index(nf.to(cuda), T, 300, seed=seed) if model == "WillowModelReg" else None
+        want, _ = eng.forward(x.to(cuda), nf.to(cuda), False, frame_index=idx)
+        got = g(x.to(cuda), nf.to(cuda), frame_index=idx)
+        assert torch.equal(got, want), seed
+    first = g.graph
+    tr = Trainer(eng, base_learning_rate=1e-3, batch_size=B)
+    tr.train_step(x.to(cuda), nf.to(cuda), labels.to(torch.uint8).to(cuda), frame_index=idx)
+    want, _ = eng.forward(x.to(cuda), nf.to(cuda), False, frame_index=idx)
+    got = g(x.to(cuda), nf.to(cuda), frame_index=idx)
+    assert g.graph is not first and torch.equal(got, want)
+    with pytest.raises(ValueError):
+        g(x[:2].to(cuda), nf[:2].to(cuda))
