@@ -406,6 +406,11 @@ int lpm_ortho_reg(const float* w, int D, int K, float scale, float grad_scale, i
  * reader/writer of learnablepoolingmethods_b200/checkpoint.py (train.py:415-423 saver, :390-411). */
 unsigned int lpm_crc32c(unsigned int crc, const void* data, unsigned long long n);
 
+/* Caller prelude of the model (train.py:262-264, eval.py:140-143, export_model.py:91-92): tf.nn.l2_normalize(model_input,
+ * 2) on fp32 frames, y[r][:] = x[r][:] * rsqrt(max(sum x^2, 1e-12)); rows = B*max_frames; y may alias x.  (With uint8
+ * input the *_u8 / lpm_gather_bn_* entry points do this on the fly.) */
+int lpm_l2_normalize_rows(const float* x, long long rows, int F, float* y, lpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

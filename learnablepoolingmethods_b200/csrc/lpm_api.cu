@@ -565,4 +565,10 @@ int lpm_add_diag(float* m, int n, long long ld, const float* d, float alpha, lpm
   return add_diag(m, n, ld, d, alpha, ST(stream));
 }
 
+int lpm_l2_normalize_rows(const float* x, long long rows, int F, float* y, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(x && y && rows > 0, "lpm_l2_normalize_rows: bad arguments");
+  return l2_normalize_rows(x, rows, F, y, ST(stream));
+}
+
 }  // extern "C"

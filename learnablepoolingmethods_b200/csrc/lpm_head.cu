@@ -101,6 +101,40 @@ __global__ void add_diag_kernel(float* __restrict__ m, int n, long long ld, cons
   if (i < n) m[(size_t)i * ld + i] += alpha * d[i];
 }
 
+// caller prelude (train.py:262-264, eval.py:140-143, export_model.py:91-92): tf.nn.l2_normalize(model_input, 2) on fp32
+// frames; one warp per frame row, two passes over the row (the second one hits L1/L2).  y may alias x.
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, long long rows, int F,
+                                                                float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * F);
+    float ss = 0.f;
+    for (int i = lane; i < F / 4; i += 32) {
+      const float4 v = xr[i];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float rn = rsqrtf(fmaxf(ss, 1e-12f));
+    float4* yr = reinterpret_cast<float4*>(y + r * F);
+    for (int i = lane; i < F / 4; i += 32) {
+      float4 v = xr[i];
+      v.x *= rn; v.y *= rn; v.z *= rn; v.w *= rn;
+      yr[i] = v;
+    }
+  }
+}
+
+int l2_normalize_rows(const float* x, long long rows, int F, float* y, cudaStream_t st) {
+  LPM_REQUIRE(F % 4 == 0 && F > 0, "l2_normalize_rows: feature size must be a multiple of 4 (got %d)", F);
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  l2_normalize_rows_kernel<<<(int)blocks, 256, 0, st>>>(x, rows, F, y);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
 int hidden_bn_relu6_fwd(const float* x, int B, int H, const float* gamma, const float* beta, float* mm, float* mv,
                         float decay, float eps, int training, int relu6, float* out32, __half* out16, float* save_mean,
                         float* save_rstd, cudaStream_t st) {

@@ -153,5 +153,6 @@ int hidden_bn_relu6_fwd(const float* x, int B, int H, const float* gamma, const 
 int hidden_bn_relu6_bwd(const float* x, const float* y, const float* dy, int B, int H, const float* gamma, const float* mean,
                         const float* rstd, int relu6, float inv_scale, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
 int add_diag(float* m, int n, long long ld, const float* d, float alpha, cudaStream_t st);
+int l2_normalize_rows(const float* x, long long rows, int F, float* y, cudaStream_t st);
 
 }  // namespace lpm

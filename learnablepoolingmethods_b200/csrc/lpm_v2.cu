@@ -259,6 +259,45 @@ __global__ void vlad_dmajor_f16_kernel(const __half* __restrict__ z, const float
   }
 }
 
+
+// 64 x 64 fp16 tile transpose with 16-byte global accesses on both sides: dst[c][r] = src[r][c] * (row_scale ? row_scale[r] : 1).
+// src: [R][C] (row stride lds), dst: [C][R] (row stride ldd); R, C multiples of 8, 16-byte aligned rows.  blockIdx.z = batch.
+__global__ void __launch_bounds__(256) transpose64_f16_kernel(const __half* __restrict__ src, long long lds, long long src_batch,
+                                                              const float* __restrict__ row_scale, long long scale_batch,
+                                                              int R, int C, __half* __restrict__ dst, long long ldd,
+                                                              long long dst_batch) {
+  __shared__ __half tile[64][64 + 8];
+  const int b = blockIdx.z, r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const __half* s = src + (size_t)b * src_batch;
+  __half* d = dst + (size_t)b * dst_batch;
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int r = i >> 3, ch = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + r < R && c0 + ch * 8 < C) {
+      v = __ldg(reinterpret_cast<const uint4*>(s + (size_t)(r0 + r) * lds + c0 + ch * 8));
+      if (row_scale) {
+        const float f = __ldg(row_scale + (size_t)b * scale_batch + r0 + r);
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h[j]); h[j] = __floats2half2_rn(t.x * f, t.y * f); }
+      }
+    }
+    *reinterpret_cast<uint4*>(&tile[r][ch * 8]) = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int c = i & 63, ch = i >> 6;            // consecutive threads -> consecutive tile columns: conflict-free reads
+    if (c0 + c < C && r0 + ch * 8 < R) {
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = tile[ch * 8 + j][c];
+      *reinterpret_cast<uint4*>(d + (size_t)(c0 + c) * ldd + r0 + ch * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
+static inline bool vec16_ok(const void* p, long long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0; }
+
 // ----------------------------------------------------------------------------------------------
 static inline int grid_for_v2(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
@@ -330,6 +369,13 @@ int sub_q_cast(const float* G, const float* q, long long rows, int T, int K, __h
 }
 
 int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, int D, __half* out, cudaStream_t st) {
+  if (K % 8 == 0 && D % 8 == 0 && vec16_ok(in, in_stride) && vec16_ok(out, D)) {
+    // src = in[b] viewed as [D][K], dst = out[b] as [K][D]
+    transpose64_f16_kernel<<<dim3((K + 63) / 64, (D + 63) / 64, B), 256, 0, st>>>(in, K, in_stride, nullptr, 0, D, K, out, D,
+                                                                                  (long long)K * D);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
   dim3 grid((K + 31) / 32, (D + 31) / 32, B), block(32, 8);
   dmajor_to_kmajor_f16_kernel<<<grid, block, 0, st>>>(in, in_stride, K, D, out);
   LPM_CUDA_CHECK(cudaGetLastError());
@@ -346,6 +392,13 @@ int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out,
 
 int vlad_dmajor_f16(const __half* z, const float* rscale, int B, int K, int D, __half* out, long long out_stride,
                     cudaStream_t st) {
+  if (K % 8 == 0 && D % 8 == 0 && vec16_ok(z, D) && vec16_ok(out, out_stride)) {
+    // src = z[b] as [K][D] scaled per row by rscale[b][k], dst = out[b] viewed as [D][K]
+    transpose64_f16_kernel<<<dim3((D + 63) / 64, (K + 63) / 64, B), 256, 0, st>>>(z, D, (long long)K * D, rscale, K, K, D, out, K,
+                                                                                  out_stride);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
   dim3 grid((D + 31) / 32, (K + 31) / 32, B), block(32, 8);
   vlad_dmajor_f16_kernel<<<grid, block, 0, st>>>(z, rscale, K, D, out, out_stride);
   LPM_CUDA_CHECK(cudaGetLastError());

@@ -64,55 +64,95 @@ __global__ void __launch_bounds__(256) ortho_rownorm_kernel(const float* __restr
   for (int k = lane; k < K; k += 32) n[(size_t)d * K + k] = w[(size_t)d * K + k] * r;
 }
 
+// 64 x 64 output tile per block, 4 x 4 outputs per thread, 16-deep slices through shared memory (fp32 FMA)
+struct Tile64 {
+  float a[16][64 + 4];
+  float b[16][64 + 4];
+};
+
 // G tile = N^T N (contraction over d); writes S = sign(G - I) and the tile's sum |G - I|
-__global__ void __launch_bounds__(1024) ortho_gram_kernel(const float* __restrict__ n, int D, int K, float* __restrict__ S,
-                                                          float* __restrict__ partial) {
-  __shared__ float sa[32][33], sb[32][33];
-  __shared__ float red[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int i = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  for (int d0 = 0; d0 < D; d0 += 32) {
-    const int d = d0 + ty;
-    sa[ty][tx] = (d < D && blockIdx.y * 32 + tx < K) ? n[(size_t)d * K + blockIdx.y * 32 + tx] : 0.f;
-    sb[ty][tx] = (d < D && j < K) ? n[(size_t)d * K + j] : 0.f;
+__global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict__ n, int D, int K, float* __restrict__ S,
+                                                         float* __restrict__ partial) {
+  __shared__ Tile64 t;
+  __shared__ float red[8];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int dd = e >> 6, c = e & 63, d = d0 + dd;
+      t.a[dd][c] = (d < D && i0 + c < K) ? n[(size_t)d * K + i0 + c] : 0.f;
+      t.b[dd][c] = (d < D && j0 + c < K) ? n[(size_t)d * K + j0 + c] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int dd = 0; dd < 32; ++dd) acc = fmaf(sa[dd][ty], sb[dd][tx], acc);
+    for (int dd = 0; dd < 16; ++dd) {
+      const float4 av = *reinterpret_cast<const float4*>(&t.a[dd][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&t.b[dd][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a4[p], b4[q], acc[p][q]);
+    }
     __syncthreads();
   }
   float a = 0.f;
-  if (i < K && j < K) {
-    const float g = acc - (i == j ? 1.f : 0.f);
-    a = fabsf(g);
-    S[(size_t)i * K + j] = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
-  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + ty * 4 + p, j = j0 + tx * 4 + q;
+      if (i < K && j < K) {
+        const float g = acc[p][q] - (i == j ? 1.f : 0.f);
+        a += fabsf(g);
+        S[(size_t)i * K + j] = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
+      }
+    }
   a = warp_sum(a);
-  if (tx == 0) red[ty] = a;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
   __syncthreads();
-  if (ty == 0) {
-    float t = warp_sum(red[tx]);
-    if (tx == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
   }
 }
 
 // dN tile = N (S + S^T)   [D x K]
-__global__ void __launch_bounds__(1024) ortho_dn_kernel(const float* __restrict__ n, const float* __restrict__ S, int D, int K,
-                                                        float* __restrict__ dn) {
-  __shared__ float sa[32][33], sb[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int d = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  for (int i0 = 0; i0 < K; i0 += 32) {
-    sa[ty][tx] = (d < D && i0 + tx < K) ? n[(size_t)d * K + i0 + tx] : 0.f;
-    const int i = i0 + ty;
-    sb[ty][tx] = (i < K && j < K) ? S[(size_t)i * K + j] + S[(size_t)j * K + i] : 0.f;
+__global__ void __launch_bounds__(256) ortho_dn_kernel(const float* __restrict__ n, const float* __restrict__ S, int D, int K,
+                                                       float* __restrict__ dn) {
+  __shared__ Tile64 t;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int i0 = 0; i0 < K; i0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int c = e >> 4, ii = e & 15;                 // a: N[r0 + c][i0 + ii] (coalesced along i), stored [ii][c]
+      t.a[ii][c] = (r0 + c < D && i0 + ii < K) ? n[(size_t)(r0 + c) * K + i0 + ii] : 0.f;
+      const int i2 = e >> 6, c2 = e & 63, i = i0 + i2, j = j0 + c2;
+      t.b[i2][c2] = (i < K && j < K) ? S[(size_t)i * K + j] + S[(size_t)j * K + i] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int ii = 0; ii < 32; ++ii) acc = fmaf(sa[ty][ii], sb[ii][tx], acc);
+    for (int ii = 0; ii < 16; ++ii) {
+      const float4 av = *reinterpret_cast<const float4*>(&t.a[ii][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&t.b[ii][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a4[p], b4[q], acc[p][q]);
+    }
     __syncthreads();
   }
-  if (d < D && j < K) dn[(size_t)d * K + j] = acc;
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = r0 + ty * 4 + p, j = j0 + tx * 4 + q;
+      if (d < D && j < K) dn[(size_t)d * K + j] = acc[p][q];
+    }
 }
 
 // back through the row normalisation; accumulates grad_scale * dW into dw and writes the regulariser value
@@ -142,7 +182,7 @@ __global__ void __launch_bounds__(256) ortho_finish_kernel(const float* __restri
 }
 
 unsigned long long ortho_reg_workspace_bytes(int D, int K) {
-  const unsigned long long tiles = (unsigned long long)((K + 31) / 32) * ((K + 31) / 32);
+  const unsigned long long tiles = (unsigned long long)((K + 63) / 64) * ((K + 63) / 64);
   return sizeof(float) * (2ull * D * K + (unsigned long long)K * K + D + tiles);
 }
 
@@ -156,10 +196,10 @@ int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int a
   float* S = dn + (size_t)D * K;
   float* rn = S + (size_t)K * K;
   float* partial = rn + D;
-  const int kt = (K + 31) / 32;
+  const int kt = (K + 63) / 64;
   ortho_rownorm_kernel<<<(D + 7) / 8, 256, 0, st>>>(w, D, K, n, rn);
-  ortho_gram_kernel<<<dim3(kt, kt), 1024, 0, st>>>(n, D, K, S, partial);
-  if (dw != nullptr) ortho_dn_kernel<<<dim3(kt, (D + 31) / 32), 1024, 0, st>>>(n, S, D, K, dn);
+  ortho_gram_kernel<<<dim3(kt, kt), 256, 0, st>>>(n, D, K, S, partial);
+  if (dw != nullptr) ortho_dn_kernel<<<dim3(kt, (D + 63) / 64), 256, 0, st>>>(n, S, D, K, dn);
   ortho_finish_kernel<<<(D + 7) / 8, 256, 0, st>>>(n, dn, rn, D, K, scale, grad_scale, accumulate, dw, partial, kt * kt, value);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;

@@ -472,6 +472,17 @@ def gating_bwd(act, g, gamma, beta, stats, dout, inv_scale, wg_diag=None):
     return (dact, dg, dgamma, dbeta) if wg_diag is None else (dact, dg, dgamma, dbeta, ddiag)
 
 
+def l2_normalize_frames(x, out=None):
+    """tf.nn.l2_normalize(model_input, 2) (train.py:262-264) on fp32 frames [B, max_frames, F]; out may be x itself."""
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    F = x.shape[-1]
+    check(lib.lpm_l2_normalize_rows(ptr(x), _ll(x.numel() // F), F, ptr(out), stream_ptr()), "lpm_l2_normalize_rows")
+    return out
+
+
 def add_diag(m, d, alpha=1.0):
     lib = _lib.load()
     n = d.numel()

@@ -1,4 +1,4 @@
-"""A few NetVladV1 train + infer steps at config 1 (for ncu launch lists)."""
+"""A few train + infer steps at config 1 (for ncu launch lists): step_once.py [steps] [model]."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -8,7 +8,8 @@ from learnablepoolingmethods_b200.trainer import Trainer
 dev = torch.device("cuda:0")
 C = bench.CFG
 store = variables.VariableStore(dev, seed=1810)
-eng = NetVladEngine(NetVladConfig(iterations=C["iterations"], cluster_size=C["cluster_size"], hidden_size=C["hidden_size"], vocab_size=C["vocab"]), store)
+model = sys.argv[2] if len(sys.argv) > 2 else "NetVladV1"
+eng = NetVladEngine(NetVladConfig(model=model, iterations=C["iterations"], cluster_size=C["cluster_size"], hidden_size=C["hidden_size"], vocab_size=C["vocab"]), store)
 tr = Trainer(eng, batch_size=C["batch"])
 x, nf, lab = bench.synthetic(C["batch"], 20181000, device=dev, codes=True)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3

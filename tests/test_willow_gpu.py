@@ -278,3 +278,19 @@ def test_netvlad_atten_cluster_module(cuda, is_training):
         ref = O.netvlad_atten_cluster_forward(x, P, S, "audio_VLAD", T, is_training, dropout_mask=mask)
     assert tuple(out.shape) == (B, K * D)
     assert rel(out, ref) < 8e-3
+
+
+def test_l2_normalize_prelude(cuda):
+    """train.py:262-264: per-frame l2_normalize over rgb|audio jointly; zero-padded frames stay zero; in place allowed."""
+    from learnablepoolingmethods_b200 import model_utils, ops
+    from oracle import netvlad_oracle as O
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 300, 1152, generator=g) * 3
+    x[1, 100:] = 0
+    x[2] = 0
+    want = O.l2_normalize(x.double(), 2)
+    got = model_utils.l2_normalize_frames(x.to(cuda))
+    assert float((got.cpu().double() - want).abs().max()) < 1e-6 and float(got[2].abs().max()) == 0.0
+    xi = x.to(cuda).clone()
+    ops.l2_normalize_frames(xi, out=xi)
+    assert torch.equal(xi, got)
