@@ -57,7 +57,7 @@ launch_count = 0   # kernels launched through the C-ABI by this process (bench.p
 
 # kernels per C-ABI call (everything not listed launches exactly one)
 _LAUNCHES = {"lpm_layernorm_joint_fwd": 2, "lpm_layernorm_joint_bwd": 2, "lpm_colsum": 2, "lpm_xent_fwd": 2,
-             "lpm_adam_clip_step": 3, "lpm_rank_adam_step": 2, "lpm_shard_sqnorm": 2, "lpm_shard_adam": 2, "lpm_ortho_reg": 4}
+             "lpm_adam_clip_step": 3, "lpm_rank_adam_step": 2, "lpm_shard_sqnorm": 2, "lpm_shard_adam": 2, "lpm_ortho_reg": 5}
 
 
 def check(rc: int, what: str = "") -> None:

@@ -70,19 +70,21 @@ struct Tile64 {
   float b[16][64 + 4];
 };
 
-// G tile = N^T N (contraction over d); writes S = sign(G - I) and the tile's sum |G - I|
-__global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict__ n, int D, int K, float* __restrict__ S,
-                                                         float* __restrict__ partial) {
+// Partial Gram tile over one slice of the contraction: Gp[z] = N[d in slice z]^T N[d in slice z].  The contraction is
+// split over gridDim.z so that the (K/64)^2 output tiles still fill the GPU (16 tiles for K = 256) and no block walks
+// more than a few global-load round trips (a single-block-per-tile version was load-latency bound: 160 us).
+__global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict__ n, int D, int K, int d_per_split,
+                                                         float* __restrict__ Gp) {
   __shared__ Tile64 t;
-  __shared__ float red[8];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int d_begin = blockIdx.z * d_per_split, d_end = min(D, d_begin + d_per_split);
   float acc[4][4] = {};
-  for (int d0 = 0; d0 < D; d0 += 16) {
+  for (int d0 = d_begin; d0 < d_end; d0 += 16) {
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
       const int dd = e >> 6, c = e & 63, d = d0 + dd;
-      t.a[dd][c] = (d < D && i0 + c < K) ? n[(size_t)d * K + i0 + c] : 0.f;
-      t.b[dd][c] = (d < D && j0 + c < K) ? n[(size_t)d * K + j0 + c] : 0.f;
+      t.a[dd][c] = (d < d_end && i0 + c < K) ? n[(size_t)d * K + i0 + c] : 0.f;
+      t.b[dd][c] = (d < d_end && j0 + c < K) ? n[(size_t)d * K + j0 + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -97,29 +99,42 @@ __global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict
     }
     __syncthreads();
   }
-  float a = 0.f;
+  float* g = Gp + (size_t)blockIdx.z * K * K;
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = i0 + ty * 4 + p, j = j0 + tx * 4 + q;
-      if (i < K && j < K) {
-        const float g = acc[p][q] - (i == j ? 1.f : 0.f);
-        a += fabsf(g);
-        S[(size_t)i * K + j] = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
-      }
+      if (i < K && j < K) g[(size_t)i * K + j] = acc[p][q];
     }
+}
+
+// G = sum of the slices (fixed order); S = sign(G - I); per-block sums of |G - I|
+__global__ void __launch_bounds__(256) ortho_sign_kernel(const float* __restrict__ Gp, int splits, int K, float* __restrict__ S,
+                                                         float* __restrict__ partial) {
+  __shared__ float red[8];
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  float a = 0.f;
+  if (e < (long long)K * K) {
+    float g = 0.f;
+    for (int z = 0; z < splits; ++z) g += Gp[(size_t)z * K * K + e];
+    const int i = (int)(e / K), j = (int)(e - (long long)i * K);
+    g -= (i == j ? 1.f : 0.f);
+    a = fabsf(g);
+    S[e] = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
+  }
   a = warp_sum(a);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
   }
 }
 
-// dN tile = N (S + S^T)   [D x K]
+// dN tile = N (S + S^T) = 2 N S   [D x K]   (G[i][j] and G[j][i] are the same products summed in the same order, so S is
+// exactly symmetric and the transposed, uncoalesced read of S is not needed)
 __global__ void __launch_bounds__(256) ortho_dn_kernel(const float* __restrict__ n, const float* __restrict__ S, int D, int K,
                                                        float* __restrict__ dn) {
   __shared__ Tile64 t;
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(256) ortho_dn_kernel(const float* __restrict__
       const int c = e >> 4, ii = e & 15;                 // a: N[r0 + c][i0 + ii] (coalesced along i), stored [ii][c]
       t.a[ii][c] = (r0 + c < D && i0 + ii < K) ? n[(size_t)(r0 + c) * K + i0 + ii] : 0.f;
       const int i2 = e >> 6, c2 = e & 63, i = i0 + i2, j = j0 + c2;
-      t.b[i2][c2] = (i < K && j < K) ? S[(size_t)i * K + j] + S[(size_t)j * K + i] : 0.f;
+      t.b[i2][c2] = (i < K && j < K) ? 2.f * S[(size_t)i * K + j] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -181,9 +196,11 @@ __global__ void __launch_bounds__(256) ortho_finish_kernel(const float* __restri
   }
 }
 
+static int ortho_splits(int D) { int sp = (D + 63) / 64; return sp > 16 ? 16 : (sp < 1 ? 1 : sp); }
+
 unsigned long long ortho_reg_workspace_bytes(int D, int K) {
-  const unsigned long long tiles = (unsigned long long)((K + 63) / 64) * ((K + 63) / 64);
-  return sizeof(float) * (2ull * D * K + (unsigned long long)K * K + D + tiles);
+  const unsigned long long nb = ((unsigned long long)K * K + 255) / 256;
+  return sizeof(float) * (2ull * D * K + (unsigned long long)K * K + D + nb + (unsigned long long)ortho_splits(D) * K * K);
 }
 
 int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int accumulate, float* value, float* dw,
@@ -191,16 +208,20 @@ int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int a
   LPM_REQUIRE(D > 0 && K > 0, "ortho_reg: bad shape %d x %d", D, K);
   if (ws_bytes < ortho_reg_workspace_bytes(D, K))
     return fail(LPM_ERR_WORKSPACE, "ortho_reg: workspace too small (%llu < %llu bytes)", ws_bytes, ortho_reg_workspace_bytes(D, K));
+  const int nb = (int)(((long long)K * K + 255) / 256), splits = ortho_splits(D);
   float* n = ws;
   float* dn = n + (size_t)D * K;
   float* S = dn + (size_t)D * K;
   float* rn = S + (size_t)K * K;
   float* partial = rn + D;
+  float* Gp = partial + nb;
   const int kt = (K + 63) / 64;
+  const int d_per_split = ((D + splits - 1) / splits + 15) / 16 * 16;
   ortho_rownorm_kernel<<<(D + 7) / 8, 256, 0, st>>>(w, D, K, n, rn);
-  ortho_gram_kernel<<<dim3(kt, kt), 256, 0, st>>>(n, D, K, S, partial);
+  ortho_gram_kernel<<<dim3(kt, kt, splits), 256, 0, st>>>(n, D, K, d_per_split, Gp);
+  ortho_sign_kernel<<<nb, 256, 0, st>>>(Gp, splits, K, S, partial);
   if (dw != nullptr) ortho_dn_kernel<<<dim3(kt, (D + 63) / 64), 256, 0, st>>>(n, S, D, K, dn);
-  ortho_finish_kernel<<<(D + 7) / 8, 256, 0, st>>>(n, dn, rn, D, K, scale, grad_scale, accumulate, dw, partial, kt * kt, value);
+  ortho_finish_kernel<<<(D + 7) / 8, 256, 0, st>>>(n, dn, rn, D, K, scale, grad_scale, accumulate, dw, partial, nb, value);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
