@@ -205,7 +205,11 @@ class NetVladEngine:
             vs = name + "_VLAD"
             src = (v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else
                    v[vs + "/cluster_weights2"] if c.model == "WillowModelReg" else v[vs + "/cluster_centers"])
-            sh[vs + "/centers_t"], sh[vs + "/centers_t16"] = ops.transpose_f32_dual(src)
+            o32, o16 = sh.get(vs + "/centers_t"), sh.get(vs + "/centers_t16")
+            if o32 is not None and tuple(o32.shape) != (K, D):
+                o32 = o16 = None
+            # refreshed IN PLACE once they exist: a captured training / inference graph holds their addresses
+            sh[vs + "/centers_t"], sh[vs + "/centers_t16"] = ops.transpose_f32_dual(src, out32=o32, out16=o16)
         V, M = c.vocab_size, c.num_mixtures
         g8, e8 = _ceil8(V * (M + 1)), _ceil8(V * M)
         bm = self._shadow_buf("bmoe", (g8 + e8,), torch.float32)
@@ -865,8 +869,12 @@ class InferenceGraph:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.launch_count
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.pred, _ = eng.forward(self.x, self.nf, False, frame_index=self.idx)
+        self.launches = _lib.launch_count - n0       # kernels one replay launches (bench.py's gpu_launches)
+        _lib.launch_count = n0
         self.version = eng.store.version
 
     def __call__(self, model_input, num_frames, frame_index=None):
@@ -884,5 +892,7 @@ class InferenceGraph:
         if self.graph is None or self.version != eng.store.version:
             self._capture()
         self.graph.replay()
+        from . import _lib
+        _lib.launch_count += self.launches
         self.calls += 1
         return self.pred

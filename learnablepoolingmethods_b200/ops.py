@@ -160,12 +160,13 @@ def transpose_f32(src: torch.Tensor):
     return dst
 
 
-def transpose_f32_dual(src: torch.Tensor, want32=True):
-    """(src^T as fp32 or None, src^T as fp16): cluster-major centre layouts of the pooling kernel / backward."""
+def transpose_f32_dual(src: torch.Tensor, want32=True, out32=None, out16=None):
+    """(src^T as fp32 or None, src^T as fp16): cluster-major centre layouts of the pooling kernel / backward.
+    out32 / out16: refresh existing buffers in place (their addresses may be baked into a captured CUDA graph)."""
     lib = _lib.load()
     rows, cols = src.shape
-    dst = _f32((cols, rows), src.device) if want32 else None
-    dst16 = _f16((cols, rows), src.device)
+    dst = (out32 if out32 is not None else _f32((cols, rows), src.device)) if want32 else None
+    dst16 = out16 if out16 is not None else _f16((cols, rows), src.device)
     check(lib.lpm_transpose_f32_dual(ptr(src), rows, cols, ptr(dst), ptr(dst16), stream_ptr()), "lpm_transpose_f32_dual")
     return dst, dst16
 

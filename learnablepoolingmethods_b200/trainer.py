@@ -197,6 +197,10 @@ class Trainer:
         self.shard: Optional[ShardedHiddenUpdate] = None      # created with the flat state (first step)
         self.use_shard = (self.world > 1 and self.shard_hidden_update and self.gather_hidden_factors
                           and ShardedHiddenUpdate.supported(self.cfg, self.world))
+        # single tower: forward + loss + backward (~130 launches) are captured in a CUDA graph after the first steps and
+        # replayed with one launch; the optimiser (learning rate changes every step) stays outside the graph
+        self.graph = None
+        self.graph_after = 2           # eager steps before the capture (flat optimiser state, workspaces, attributes)
 
     def _factored_hidden(self, batch: int) -> bool:
         """hidden1_weights (85 % of the parameters) is updated from its gradient factors on a single tower: with
@@ -250,10 +254,77 @@ class Trainer:
         if self.reducer is not None:
             self.reducer.mark_done(self.flat.end_offset(name))
 
+    use_graph = True
+
+    def _graph_ok(self, model_input) -> bool:
+        # NetVladV2 draws its dropout masks from a host-side seed per launch: it stays eager
+        return (self.use_graph and self.world == 1 and self.flat is not None and self.cfg.model in ("NetVladV1", "WillowModelReg")
+                and self.global_step >= self.graph_after and model_input.is_cuda)
+
+    def _graph_step(self, model_input, num_frames, labels_u8, frame_index):
+        """Replay (capture on first use) forward + cross-entropy + backward on static input buffers; then the eager
+        optimiser.  Same arithmetic as the eager step: the kernels and their order are identical."""
+        eng, f = self.engine, self.flat
+        g = self.graph
+        key = (tuple(model_input.shape), model_input.dtype)
+        if g is not None and g["key"] != key:
+            g = self.graph = None                                   # batch shape changed: capture again
+        willow = self.cfg.model == "WillowModelReg"
+        if g is None:
+            dev = model_input.device
+            g = {"key": key, "x": torch.empty_like(model_input), "nf": torch.empty(num_frames.shape, dtype=torch.int32, device=dev),
+                 "lab": torch.empty_like(labels_u8),
+                 "idx": torch.zeros((model_input.shape[0], self.cfg.iterations), dtype=torch.int32, device=dev) if willow else None}
+        g["x"].copy_(model_input, non_blocking=True)
+        g["nf"].copy_(num_frames.to(torch.int32), non_blocking=True)
+        g["lab"].copy_(labels_u8, non_blocking=True)
+        if willow:
+            if frame_index is None:      # tf.random_uniform: a fresh draw per step, made outside the graph
+                frame_index = ops.random_frame_index(g["nf"], self.cfg.iterations, model_input.shape[1],
+                                                     mode=0 if self.cfg.random_frames else 1, seed=0x5EED0000 + eng.draws)
+                eng.draws += 1
+            g["idx"].copy_(frame_index.to(torch.int32), non_blocking=True)
+        if "graph" not in g:
+            def body():
+                pred, ctx = eng.forward(g["x"], g["nf"], True, save_for_backward=True, frame_index=g["idx"])
+                ctx["reg_penalty"] = self.reg_penalty
+                loss, _ = ops.xent_fwd(pred, g["lab"])
+                dpred = ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
+                ctx["factored_hidden"] = bool(f.factored)
+                ctx["grad_views"] = f.grad_views
+                eng.backward(ctx, dpred)
+                return loss, ctx
+            side = torch.cuda.Stream(device=model_input.device)
+            side.wait_stream(torch.cuda.current_stream())
+            snap = {k: v.clone() for k, v in self.store.vars.items() if k.endswith(("moving_mean", "moving_variance"))}
+            with torch.cuda.stream(side):
+                body()                                               # warm-up on a side stream (allocator, attributes)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for k, v in snap.items():                                # the warm-up pass must not count as a training step
+                self.store.vars[k].copy_(v)
+            graph = torch.cuda.CUDAGraph()
+            from . import _lib
+            n0 = _lib.launch_count
+            with torch.cuda.graph(graph):
+                g["loss"], g["ctx"] = body()
+            g["graph"], g["launches"] = graph, _lib.launch_count - n0     # kernels one replay launches
+            _lib.launch_count = n0
+            for k, v in snap.items():                                # capture does not execute, but keep the invariant explicit
+                self.store.vars[k].copy_(v)
+            self.graph = g
+        g["graph"].replay()
+        from . import _lib
+        _lib.launch_count += g["launches"]
+        return g["loss"], g["ctx"]
+
     def train_step(self, model_input, num_frames, labels_u8, frame_index=None):
         """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32).
         frame_index: optional int32 [B, iterations] (WillowModelReg: replaces the random frame draw)."""
         eng = self.engine
+        if self._graph_ok(model_input):
+            loss, ctx = self._graph_step(model_input, num_frames, labels_u8, frame_index)
+            return self._optimizer_step(ctx, bool(self.flat.factored), loss)
         pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True, frame_index=frame_index)
         ctx["reg_penalty"] = self.reg_penalty
         B = pred.shape[0]
@@ -298,6 +369,10 @@ class Trainer:
                 self.reducer.flush()
         if self.reducer is not None:
             self.reducer.wait()
+        return self._optimizer_step(ctx, factored, loss)
+
+    def _optimizer_step(self, ctx, factored, loss):
+        eng = self.engine
         f = self.flat
         t = self.global_step + 1
         lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
