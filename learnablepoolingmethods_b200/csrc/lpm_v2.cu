@@ -232,7 +232,10 @@ __device__ __forceinline__ uint32_t hash32(uint64_t z) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 __global__ void __launch_bounds__(256) dropout_kernel(__half* __restrict__ x, long long n, const __half* __restrict__ mask_in,
-                                                      __half* __restrict__ mask_out, unsigned long long seed, float rate) {
+                                                      __half* __restrict__ mask_out, unsigned long long seed,
+                                                      const unsigned long long* __restrict__ seed_dev, float rate) {
+  // effective seed = seed + *seed_dev: the device part lets a captured CUDA graph draw a fresh mask on every replay
+  if (seed_dev) seed += *seed_dev;
   const float inv_keep = 1.f / (1.f - rate);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float keep;
@@ -382,10 +385,10 @@ int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, in
   return LPM_OK;
 }
 
-int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed, float rate,
-                cudaStream_t st) {
+int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed,
+                const unsigned long long* seed_dev, float rate, cudaStream_t st) {
   LPM_REQUIRE(rate >= 0.f && rate < 1.f, "dropout: rate must be in [0,1)");
-  dropout_kernel<<<grid_for_v2(n, 256), 256, 0, st>>>(x, n, mask_in, mask_out, seed, rate);
+  dropout_kernel<<<grid_for_v2(n, 256), 256, 0, st>>>(x, n, mask_in, mask_out, seed, seed_dev, rate);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

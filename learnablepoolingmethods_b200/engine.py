@@ -79,6 +79,7 @@ class NetVladEngine:
         self.build_variables()
         self._side = None          # second CUDA stream + fork / join events (created on first use)
         self.draws = 0             # training/eval forwards so far: keys the dropout / frame-sampling generators
+        self.seed_dev = None       # device copy of 2 * draws for graph-captured steps (NetVladV2 dropout)
         self.pre_head_hook = None  # callable run right before the hidden projection reads its fp16 weights
 
     def _side_stream(self):
@@ -234,7 +235,7 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
                 save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False,
-                frame_index=None):
+                frame_index=None, device_seed: bool = False):
         """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264), or the uint8
         codes [B, max_frames, rgb+audio] as decoded by the reader (readers.py:185-193): those are dequantised
         (utils.py:28-43) and L2-normalised inside the gather kernels.
@@ -252,6 +253,12 @@ class NetVladEngine:
         B, T, F = x.shape[0], c.iterations, c.feature_size
         ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}, "seed": self.draws}
         self.draws += 1
+        if device_seed:
+            # captured in a CUDA graph: the per-call part of the dropout seed lives in device memory (2 * draw counter,
+            # written by the caller before each replay), so that eager and replayed steps draw the same masks
+            if self.seed_dev is None:
+                self.seed_dev = torch.zeros(1, dtype=torch.int64, device=x.device)
+            ctx["seed"], ctx["seed_dev"] = 0, self.seed_dev
         save = save_for_backward
         if c.model == "WillowModelReg":
             return self._willow_forward(x, nf, B, T, is_training, save, ctx, return_intermediates, frame_index)
@@ -415,7 +422,7 @@ class NetVladEngine:
         if training and c.dropout_rate > 0:                           # D7: drop probability 0.9
             mask = torch.empty_like(att) if save else None
             ops.dropout_f16(att, c.dropout_rate, mask_in=dropout_mask, mask_out=mask,
-                            seed=int(ctx.get("seed", 0)) * 2 + (name == "audio"))
+                            seed=int(ctx.get("seed", 0)) * 2 + (name == "audio"), seed_dev=ctx.get("seed_dev"))
         h1 = ops.layernorm_joint_fwd(att, X, None, B, T, D, v[a + "/LayerNorm/gamma"], v[a + "/LayerNorm/beta"], save=save)
         st1 = None
         if save:

@@ -198,7 +198,8 @@ class Trainer:
         self.use_shard = (self.world > 1 and self.shard_hidden_update and self.gather_hidden_factors
                           and ShardedHiddenUpdate.supported(self.cfg, self.world))
         # single tower: forward + loss + backward (~130 launches) are captured in a CUDA graph after the first steps and
-        # replayed with one launch; the optimiser (learning rate changes every step) stays outside the graph
+        # replayed with one launch; the optimiser (learning rate changes every step) stays outside the graph, and so do the per-step random draws
+        # (WillowModelReg frame indices: a static buffer filled before the replay; NetVladV2 dropout: a device-side seed)
         self.graph = None
         self.graph_after = 2           # eager steps before the capture (flat optimiser state, workspaces, attributes)
 
@@ -257,9 +258,8 @@ class Trainer:
     use_graph = True
 
     def _graph_ok(self, model_input) -> bool:
-        # NetVladV2 draws its dropout masks from a host-side seed per launch: it stays eager
-        return (self.use_graph and self.world == 1 and self.flat is not None and self.cfg.model in ("NetVladV1", "WillowModelReg")
-                and self.global_step >= self.graph_after and model_input.is_cuda)
+        return (self.use_graph and self.world == 1 and self.flat is not None and self.global_step >= self.graph_after
+                and model_input.is_cuda)
 
     def _graph_step(self, model_input, num_frames, labels_u8, frame_index):
         """Replay (capture on first use) forward + cross-entropy + backward on static input buffers; then the eager
@@ -286,7 +286,8 @@ class Trainer:
             g["idx"].copy_(frame_index.to(torch.int32), non_blocking=True)
         if "graph" not in g:
             def body():
-                pred, ctx = eng.forward(g["x"], g["nf"], True, save_for_backward=True, frame_index=g["idx"])
+                pred, ctx = eng.forward(g["x"], g["nf"], True, save_for_backward=True, frame_index=g["idx"],
+                                        device_seed=self.cfg.model == "NetVladV2")
                 ctx["reg_penalty"] = self.reg_penalty
                 loss, _ = ops.xent_fwd(pred, g["lab"])
                 dpred = ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
@@ -297,6 +298,7 @@ class Trainer:
             side = torch.cuda.Stream(device=model_input.device)
             side.wait_stream(torch.cuda.current_stream())
             snap = {k: v.clone() for k, v in self.store.vars.items() if k.endswith(("moving_mean", "moving_variance"))}
+            draws0 = eng.draws                                       # warm-up / capture passes do not consume random draws
             with torch.cuda.stream(side):
                 body()                                               # warm-up on a side stream (allocator, attributes)
             torch.cuda.current_stream().wait_stream(side)
@@ -313,6 +315,10 @@ class Trainer:
             for k, v in snap.items():                                # capture does not execute, but keep the invariant explicit
                 self.store.vars[k].copy_(v)
             self.graph = g
+            eng.draws = draws0
+        if self.cfg.model == "NetVladV2":
+            eng.seed_dev.fill_(2 * eng.draws)        # NetVladV2's dropout: a fresh mask per replay (engine.forward, device_seed)
+            eng.draws += 1
         g["graph"].replay()
         from . import _lib
         _lib.launch_count += g["launches"]
