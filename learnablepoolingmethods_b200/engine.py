@@ -235,12 +235,14 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
                 save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False,
-                frame_index=None, device_seed: bool = False):
+                frame_index=None, device_seed: bool = False, head: bool = True):
         """model_input fp32 [B, max_frames, rgb+audio] (L2-normalised by the caller, train.py:264), or the uint8
         codes [B, max_frames, rgb+audio] as decoded by the reader (readers.py:185-193): those are dequantised
         (utils.py:28-43) and L2-normalised inside the gather kernels.
         num_frames int [B].  frame_index (WillowModelReg only): int32 [B, iterations] gather indices replacing the
-        random draw of model_utils.py:26-73.  Returns (predictions fp32 [B, vocab], ctx)."""
+        random draw of model_utils.py:26-73.  Returns (predictions fp32 [B, vocab], ctx).
+        head=False stops after the concatenated descriptor (returns (None, ctx)); `forward_head(ctx)` finishes the pass:
+        the data-parallel trainer replays the two halves as separate CUDA graphs around the wait for the weight shards."""
         c, s = self.cfg, self.store
         v = s.vars
         sh = self.refresh_shadows()
@@ -251,7 +253,8 @@ class NetVladEngine:
         x = model_input.contiguous() if model_input.dtype == torch.uint8 else model_input.contiguous().float()
         nf = num_frames.to(device=x.device, dtype=torch.int32).contiguous()
         B, T, F = x.shape[0], c.iterations, c.feature_size
-        ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}, "seed": self.draws}
+        ctx: Dict[str, object] = {"B": B, "training": is_training, "inter": {}, "seed": self.draws, "_head": head,
+                                  "_save": save_for_backward, "_want_inter": return_intermediates}
         self.draws += 1
         if device_seed:
             # captured in a CUDA graph: the per-call part of the dropout seed lives in device memory (2 * draw counter,
@@ -315,8 +318,17 @@ class NetVladEngine:
         if side is not None:
             main.wait_event(ev_join)
 
-        pred = self._head(vlad, B, is_training, save, ctx, return_intermediates)
-        return pred, ctx
+        return self._finish(vlad, ctx)
+
+    def _finish(self, vlad, ctx):
+        if not ctx["_head"]:
+            ctx["_vlad"] = vlad
+            return None, ctx
+        return self._head(vlad, ctx["B"], ctx["training"], ctx["_save"], ctx, ctx["_want_inter"]), ctx
+
+    def forward_head(self, ctx):
+        """Second half of a forward started with head=False: hidden projection, gating, MoE -> predictions."""
+        return self._head(ctx.pop("_vlad"), ctx["B"], ctx["training"], ctx["_save"], ctx, ctx["_want_inter"])
 
     def _v1_modality(self, name, X, B, T, D, K, H, sid, training, save, out_view, ctx, want_inter):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
@@ -494,8 +506,7 @@ class NetVladEngine:
             if save:
                 ctx[name] = dict(X=X, z=z, rscale=rscale, a_sum=a_sum, assign=assign, cluster_bn_stats=rb[2])
             off += K * D
-        pred = self._head(vlad, B, training, save, ctx, want_inter)
-        return pred, ctx
+        return self._finish(vlad, ctx)
 
     def regularization_loss(self):
         """REGULARIZATION_LOSSES of the model beyond the MoE weight decay (device scalar, fp32): the orthogonal

@@ -258,18 +258,24 @@ class Trainer:
     use_graph = True
 
     def _graph_ok(self, model_input) -> bool:
-        return (self.use_graph and self.world == 1 and self.flat is not None and self.global_step >= self.graph_after
-                and model_input.is_cuda)
+        if not (self.use_graph and self.flat is not None and self.global_step >= self.graph_after and model_input.is_cuda):
+            return False
+        # several towers: only the sharded hidden update has all of its collectives outside forward / backward
+        return self.world == 1 or (self.use_shard and self.shard is not None)
 
     def _graph_step(self, model_input, num_frames, labels_u8, frame_index):
         """Replay (capture on first use) forward + cross-entropy + backward on static input buffers; then the eager
-        optimiser.  Same arithmetic as the eager step: the kernels and their order are identical."""
+        optimiser.  Same arithmetic as the eager step: the kernels and their order are identical.
+        Single tower: one graph.  Data parallel: three graphs -- (A) frames -> descriptor, (B) head + loss, (C) backward --
+        with the collectives in between, exactly where the eager step has them: the wait for the all-gathered fp16 weight
+        shards before the hidden projection, the all-to-all of descriptor slices after the forward, the gradient all-reduce
+        after the backward."""
         eng, f = self.engine, self.flat
         g = self.graph
         key = (tuple(model_input.shape), model_input.dtype)
         if g is not None and g["key"] != key:
             g = self.graph = None                                   # batch shape changed: capture again
-        willow = self.cfg.model == "WillowModelReg"
+        willow, dp = self.cfg.model == "WillowModelReg", self.world > 1
         if g is None:
             dev = model_input.device
             g = {"key": key, "x": torch.empty_like(model_input), "nf": torch.empty(num_frames.shape, dtype=torch.int32, device=dev),
@@ -284,43 +290,71 @@ class Trainer:
                                                      mode=0 if self.cfg.random_frames else 1, seed=0x5EED0000 + eng.draws)
                 eng.draws += 1
             g["idx"].copy_(frame_index.to(torch.int32), non_blocking=True)
-        if "graph" not in g:
-            def body():
-                pred, ctx = eng.forward(g["x"], g["nf"], True, save_for_backward=True, frame_index=g["idx"],
-                                        device_seed=self.cfg.model == "NetVladV2")
+        from . import _lib
+        if "graphs" not in g:
+            def seg_a():
+                _, ctx = eng.forward(g["x"], g["nf"], True, save_for_backward=True, frame_index=g["idx"],
+                                     device_seed=self.cfg.model == "NetVladV2", head=False)
                 ctx["reg_penalty"] = self.reg_penalty
+                return ctx
+
+            def seg_b(ctx):
+                pred = eng.forward_head(ctx)
                 loss, _ = ops.xent_fwd(pred, g["lab"])
-                dpred = ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
+                return loss, ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
+
+            def seg_c(ctx, dpred):
                 ctx["factored_hidden"] = bool(f.factored)
                 ctx["grad_views"] = f.grad_views
                 eng.backward(ctx, dpred)
-                return loss, ctx
+
+            eng.pre_head_hook = None                                 # the wait for the weight shards happens between graphs
+            if self.shard is not None:
+                self.shard.wait_weights()
             side = torch.cuda.Stream(device=model_input.device)
             side.wait_stream(torch.cuda.current_stream())
             snap = {k: v.clone() for k, v in self.store.vars.items() if k.endswith(("moving_mean", "moving_variance"))}
             draws0 = eng.draws                                       # warm-up / capture passes do not consume random draws
-            with torch.cuda.stream(side):
-                body()                                               # warm-up on a side stream (allocator, attributes)
+            with torch.cuda.stream(side):                            # warm-up on a side stream (allocator, attributes)
+                c0 = seg_a()
+                seg_c(c0, seg_b(c0)[1])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             for k, v in snap.items():                                # the warm-up pass must not count as a training step
                 self.store.vars[k].copy_(v)
-            graph = torch.cuda.CUDAGraph()
-            from . import _lib
             n0 = _lib.launch_count
-            with torch.cuda.graph(graph):
-                g["loss"], g["ctx"] = body()
-            g["graph"], g["launches"] = graph, _lib.launch_count - n0     # kernels one replay launches
+            graphs = [torch.cuda.CUDAGraph()]
+            if not dp:
+                with torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
+                    g["ctx"] = seg_a()
+                    g["loss"], dpred = seg_b(g["ctx"])
+                    seg_c(g["ctx"], dpred)
+            else:
+                with torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
+                    g["ctx"] = seg_a()
+                graphs.append(torch.cuda.CUDAGraph())
+                with torch.cuda.graph(graphs[1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
+                    g["loss"], g["dpred"] = seg_b(g["ctx"])
+                graphs.append(torch.cuda.CUDAGraph())
+                with torch.cuda.graph(graphs[2], pool=graphs[0].pool(), capture_error_mode="thread_local"):
+                    seg_c(g["ctx"], g["dpred"])
+            g["graphs"], g["launches"] = graphs, _lib.launch_count - n0     # kernels one replay launches
             _lib.launch_count = n0
-            for k, v in snap.items():                                # capture does not execute, but keep the invariant explicit
-                self.store.vars[k].copy_(v)
             self.graph = g
             eng.draws = draws0
         if self.cfg.model == "NetVladV2":
             eng.seed_dev.fill_(2 * eng.draws)        # NetVladV2's dropout: a fresh mask per replay (engine.forward, device_seed)
             eng.draws += 1
-        g["graph"].replay()
-        from . import _lib
+        graphs = g["graphs"]
+        graphs[0].replay()
+        if dp:
+            self.shard.wait_weights()                # the fp16 weight shards gathered under the forward
+            graphs[1].replay()
+            self.shard.start_exchange(g["ctx"]["head"]["vlad"])      # rides under the backward
+            graphs[2].replay()
+            self.reducer.reset()
+            self.reducer.flush()
+            self.reducer.wait()
         _lib.launch_count += g["launches"]
         return g["loss"], g["ctx"]
 

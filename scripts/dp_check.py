@@ -1,7 +1,7 @@
 """torchrun --nproc-per-node 2 scripts/dp_check.py: (zero-initialised biases move by ~lr*sign(g) per Adam step, so fp32 summation-order differences show up as ~5e-3 of their tiny norm)
 data-parallel training with the hidden1_weights gradient summed
 from all-gathered factors (dp.FactorGather) against the plain bucketed all-reduce of the dense gradient: same weights
-after 3 steps (up to fp32 summation order), identical on every rank."""
+after 5 steps (the sharded mode replays its last three steps from CUDA graphs) (up to fp32 summation order), identical on every rank."""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from learnablepoolingmethods_b200 import variables
@@ -24,7 +24,7 @@ for mode in (True, "gather", False):
         tr.use_shard = False
     if mode is False:
         tr.gather = None
-    for step in range(3):
+    for step in range(5):
         x, nf, lab = O.synthetic_batch(B, seed=100 + step * world + rank, vocab=V)
         loss = tr.train_step(x.to(dev), nf.to(dev), lab.to(torch.uint8).to(dev))
     assert (tr.shard is not None) == (mode is True)
