@@ -597,9 +597,14 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     # backward (NetVladV1): hand-written autodiff of the forward above
     # ------------------------------------------------------------------------------------------
-    def backward(self, ctx, dpred: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def backward(self, ctx, dpred: torch.Tensor, stage: Optional[str] = None) -> Dict[str, torch.Tensor]:
         """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
-        Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled."""
+        Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled.
+        stage: None = the whole backward; "head" = MoE, gating and hidden projection only (stops once dLoss/dvlad exists);
+        "body" = the rest (after a "head" call on the same ctx).  The data-parallel trainer replays the two stages as
+        separate CUDA graphs and starts the all-reduce of the head's gradients in between."""
+        if stage == "body":
+            return self._backward_body(ctx, *ctx.pop("_bwd_state"))
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         B, hd = ctx["B"], ctx["head"]
         # dLoss/dpred scales as 1/B; LayerNorm over the L2-normalised descriptor has rstd ~ 200, so the scale
@@ -672,8 +677,17 @@ class NetVladEngine:
             put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
                                             out=gout("hidden1_weights")))
         dvlad = ops.gemm(dact16, sh["wh16"], b_mn=False)                      # [B, vlad_dim] fp16
-        dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
-        dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dpred.device)
+        if stage == "head":
+            ctx["_bwd_state"] = (dvlad, grads, put, deferred_hidden)
+            return grads
+        return self._backward_body(ctx, dvlad, grads, put, deferred_hidden)
+
+    def _backward_body(self, ctx, dvlad, grads, put, deferred_hidden):
+        c, v = self.cfg, self.store.vars
+        f32 = torch.float32
+        gout = ctx["_gout"]
+        dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dvlad.device)
+        dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dvlad.device)
         off = 0
         mods = list(c.modalities())
         offs = []

@@ -269,7 +269,8 @@ class Trainer:
         Single tower: one graph.  Data parallel: three graphs -- (A) frames -> descriptor, (B) head + loss, (C) backward --
         with the collectives in between, exactly where the eager step has them: the wait for the all-gathered fp16 weight
         shards before the hidden projection, the all-to-all of descriptor slices after the forward, the gradient all-reduce
-        after the backward."""
+        (the backward is itself split after the head so that the MoE / gating gradients travel under the modalities'
+        backward)."""
         eng, f = self.engine, self.flat
         g = self.graph
         key = (tuple(model_input.shape), model_input.dtype)
@@ -303,10 +304,18 @@ class Trainer:
                 loss, _ = ops.xent_fwd(pred, g["lab"])
                 return loss, ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
 
-            def seg_c(ctx, dpred):
-                ctx["factored_hidden"] = bool(f.factored)
-                ctx["grad_views"] = f.grad_views
-                eng.backward(ctx, dpred)
+            def seg_c(ctx, dpred, stage=None):
+                if stage != "body":
+                    ctx["factored_hidden"] = bool(f.factored)
+                    ctx["grad_views"] = f.grad_views
+                eng.backward(ctx, dpred, stage=stage)
+
+            # data parallel: the head's gradients (MoE, gating: the first ~40 % of the flat buffer) are all-reduced while
+            # the modalities' backward runs; valid when the flat layout really has them in front
+            body = [n for n in f.order if n not in f.factored and n.startswith(("video_", "audio_", "input_bn"))]
+            head = [n for n in f.order if n not in f.factored and n not in body]
+            g["head_end"] = max(f.end_offset(n) for n in head)
+            g["split"] = dp and all(f.offsets[n] >= g["head_end"] for n in body)
 
             eng.pre_head_hook = None                                 # the wait for the weight shards happens between graphs
             if self.shard is not None:
@@ -335,9 +344,10 @@ class Trainer:
                 graphs.append(torch.cuda.CUDAGraph())
                 with torch.cuda.graph(graphs[1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
                     g["loss"], g["dpred"] = seg_b(g["ctx"])
-                graphs.append(torch.cuda.CUDAGraph())
-                with torch.cuda.graph(graphs[2], pool=graphs[0].pool(), capture_error_mode="thread_local"):
-                    seg_c(g["ctx"], g["dpred"])
+                for stage in (("head", "body") if g["split"] else (None,)):
+                    graphs.append(torch.cuda.CUDAGraph())
+                    with torch.cuda.graph(graphs[-1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
+                        seg_c(g["ctx"], g["dpred"], stage)
             g["graphs"], g["launches"] = graphs, _lib.launch_count - n0     # kernels one replay launches
             _lib.launch_count = n0
             self.graph = g
@@ -352,9 +362,15 @@ class Trainer:
             graphs[1].replay()
             self.shard.start_exchange(g["ctx"]["head"]["vlad"])      # rides under the backward
             graphs[2].replay()
-            self.reducer.reset()
-            self.reducer.flush()
-            self.reducer.wait()
+            d = torch.distributed
+            if g["split"]:
+                h0 = d.all_reduce(f.g[:g["head_end"]], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
+                graphs[3].replay()
+                h1 = d.all_reduce(f.g[g["head_end"]:], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
+                h0.wait()
+                h1.wait()
+            else:
+                d.all_reduce(f.g, op=d.ReduceOp.SUM, group=self.pg)
         _lib.launch_count += g["launches"]
         return g["loss"], g["ctx"]
 
