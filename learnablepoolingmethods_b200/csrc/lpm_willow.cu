@@ -64,10 +64,12 @@ __global__ void __launch_bounds__(256) ortho_rownorm_kernel(const float* __restr
   for (int k = lane; k < K; k += 32) n[(size_t)d * K + k] = w[(size_t)d * K + k] * r;
 }
 
-// 64 x 64 output tile per block, 4 x 4 outputs per thread, 16-deep slices through shared memory (fp32 FMA)
+// 64 x 64 output tile per block, 4 x 4 outputs per thread, BK-deep slices through shared memory (fp32 FMA).  These
+// products are small and latency-bound (one global round trip per slice), hence the deep slices.
+constexpr int BK = 32;
 struct Tile64 {
-  float a[16][64 + 4];
-  float b[16][64 + 4];
+  float a[BK][64 + 4];
+  float b[BK][64 + 4];
 };
 
 // Partial Gram tile over one slice of the contraction: Gp[z] = N[d in slice z]^T N[d in slice z].  The contraction is
@@ -80,15 +82,15 @@ __global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const int d_begin = blockIdx.z * d_per_split, d_end = min(D, d_begin + d_per_split);
   float acc[4][4] = {};
-  for (int d0 = d_begin; d0 < d_end; d0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+  for (int d0 = d_begin; d0 < d_end; d0 += BK) {
+    for (int e = threadIdx.x; e < BK * 64; e += 256) {
       const int dd = e >> 6, c = e & 63, d = d0 + dd;
       t.a[dd][c] = (d < d_end && i0 + c < K) ? n[(size_t)d * K + i0 + c] : 0.f;
       t.b[dd][c] = (d < d_end && j0 + c < K) ? n[(size_t)d * K + j0 + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int dd = 0; dd < 16; ++dd) {
+    for (int dd = 0; dd < BK; ++dd) {
       const float4 av = *reinterpret_cast<const float4*>(&t.a[dd][ty * 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&t.b[dd][tx * 4]);
       const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -141,16 +143,16 @@ __global__ void __launch_bounds__(256) ortho_dn_kernel(const float* __restrict__
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int r0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   float acc[4][4] = {};
-  for (int i0 = 0; i0 < K; i0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      const int c = e >> 4, ii = e & 15;                 // a: N[r0 + c][i0 + ii] (coalesced along i), stored [ii][c]
+  for (int i0 = 0; i0 < K; i0 += BK) {
+    for (int e = threadIdx.x; e < BK * 64; e += 256) {
+      const int c = e / BK, ii = e % BK;                 // a: N[r0 + c][i0 + ii] (coalesced along i), stored [ii][c]
       t.a[ii][c] = (r0 + c < D && i0 + ii < K) ? n[(size_t)(r0 + c) * K + i0 + ii] : 0.f;
       const int i2 = e >> 6, c2 = e & 63, i = i0 + i2, j = j0 + c2;
       t.b[i2][c2] = (i < K && j < K) ? 2.f * S[(size_t)i * K + j] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int ii = 0; ii < 16; ++ii) {
+    for (int ii = 0; ii < BK; ++ii) {
       const float4 av = *reinterpret_cast<const float4*>(&t.a[ii][ty * 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&t.b[ii][tx * 4]);
       const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -216,7 +218,7 @@ int ortho_reg(const float* w, int D, int K, float scale, float grad_scale, int a
   float* partial = rn + D;
   float* Gp = partial + nb;
   const int kt = (K + 63) / 64;
-  const int d_per_split = ((D + splits - 1) / splits + 15) / 16 * 16;
+  const int d_per_split = ((D + splits - 1) / splits + BK - 1) / BK * BK;
   ortho_rownorm_kernel<<<(D + 7) / 8, 256, 0, st>>>(w, D, K, n, rn);
   ortho_gram_kernel<<<dim3(kt, kt, splits), 256, 0, st>>>(n, D, K, d_per_split, Gp);
   ortho_sign_kernel<<<nb, 256, 0, st>>>(Gp, splits, K, S, partial);

@@ -196,6 +196,7 @@ class NetVladEngine:
         if t is None or tuple(t.shape) != tuple(shape):
             t = torch.zeros(shape, dtype=dtype, device=self.store.device)
             sh[key] = t
+            self.store.layout_version += 1
         return t
 
     def refresh_small_shadows(self):
@@ -207,8 +208,9 @@ class NetVladEngine:
             src = (v[vs + "/cluster_weights2"][0] if c.model == "NetVladV1" else
                    v[vs + "/cluster_weights2"] if c.model == "WillowModelReg" else v[vs + "/cluster_centers"])
             o32, o16 = sh.get(vs + "/centers_t"), sh.get(vs + "/centers_t16")
-            if o32 is not None and tuple(o32.shape) != (K, D):
+            if o32 is None or tuple(o32.shape) != (K, D):
                 o32 = o16 = None
+                s.layout_version += 1
             # refreshed IN PLACE once they exist: a captured training / inference graph holds their addresses
             sh[vs + "/centers_t"], sh[vs + "/centers_t16"] = ops.transpose_f32_dual(src, out32=o32, out16=o16)
         V, M = c.vocab_size, c.num_mixtures
@@ -877,8 +879,9 @@ class InferenceGraph:
     The forward is 28 launches at config 1 (15 for WillowModelReg) issued from Python; at small batches the ~10 us of host
     work per launch, not the GPU, sets the latency.  Capturing the whole sequence -- both streams: the audio modality
     forks onto the side stream and joins before the head -- replays it with one launch.  Inputs are copied into static
-    buffers; the returned predictions tensor is static too (clone it to keep it past the next call).  The capture is
-    redone automatically when the parameters change (the fp16 operand shadows are then rebuilt)."""
+    buffers; the returned predictions tensor is static too (clone it to keep it past the next call).  Parameter VALUES may
+    change between calls (training steps refresh the fp16 operand shadows in place); the capture is redone only when a
+    variable or shadow buffer moves (`VariableStore.layout_version`: first trainer step, load of new variables)."""
 
     def __init__(self, engine: NetVladEngine, batch: int, max_frames: int, input_dtype=torch.float32):
         self.engine = engine
@@ -907,7 +910,7 @@ class InferenceGraph:
             self.pred, _ = eng.forward(self.x, self.nf, False, frame_index=self.idx)
         self.launches = _lib.launch_count - n0       # kernels one replay launches (bench.py's gpu_launches)
         _lib.launch_count = n0
-        self.version = eng.store.version
+        self.version = eng.store.layout_version
 
     def __call__(self, model_input, num_frames, frame_index=None):
         eng = self.engine
@@ -921,7 +924,8 @@ class InferenceGraph:
                                                      mode=0 if eng.cfg.random_frames else 1, seed=0x5EED0000 + eng.draws)
                 eng.draws += 1
             self.idx.copy_(frame_index.to(torch.int32), non_blocking=True)
-        if self.graph is None or self.version != eng.store.version:
+        eng.refresh_shadows()                          # in place; a no-op unless values changed outside the trainer
+        if self.graph is None or self.version != eng.store.layout_version:
             self._capture()
         self.graph.replay()
         from . import _lib

@@ -68,6 +68,7 @@ class FlatState:
                         torch.zeros(nt, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
         self.shadow = None
         store.mark_dirty()
+        store.layout_version += 1                      # every trainable variable now lives at a new address
 
     def bind_shadows(self, engine):
         """Per-tensor fp16 shadow destinations so the Adam kernel refreshes the GEMM operands in the same pass."""
@@ -274,8 +275,9 @@ class Trainer:
         eng, f = self.engine, self.flat
         g = self.graph
         key = (tuple(model_input.shape), model_input.dtype)
-        if g is not None and g["key"] != key:
-            g = self.graph = None                                   # batch shape changed: capture again
+        eng.refresh_shadows()                                       # no-op unless values changed outside train_step
+        if g is not None and (g["key"] != key or g["layout"] != self.store.layout_version):
+            g = self.graph = None                                   # batch shape or buffer addresses changed: capture again
         willow, dp = self.cfg.model == "WillowModelReg", self.world > 1
         if g is None:
             dev = model_input.device
@@ -349,6 +351,7 @@ class Trainer:
                     with torch.cuda.graph(graphs[-1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
                         seg_c(g["ctx"], g["dpred"], stage)
             g["graphs"], g["launches"] = graphs, _lib.launch_count - n0     # kernels one replay launches
+            g["layout"] = self.store.layout_version
             _lib.launch_count = n0
             self.graph = g
             eng.draws = draws0

@@ -23,6 +23,8 @@ class VariableStore:
         self._gen = torch.Generator().manual_seed(seed)   # CPU generator: identical on every rank
         self._scope = []
         self.version = 0          # bumped whenever parameter values change
+        self.layout_version = 0   # bumped whenever a variable or shadow buffer is (re)allocated: captured CUDA graphs hold
+                                  # raw addresses and are re-captured only then (values are refreshed in place)
         self.shadows: Dict[str, torch.Tensor] = {}
         self.shadow_version = -1
 
@@ -62,6 +64,7 @@ class VariableStore:
         t = t.to(self.device)
         self.vars[full] = t
         self.version += 1
+        self.layout_version += 1
         return t
 
     def batch_norm_vars(self, scope: str, c: int):
@@ -89,6 +92,7 @@ class VariableStore:
                 self.vars[k].copy_(t)
             else:
                 self.vars[k] = t.to(self.device).clone()
+                self.layout_version += 1
         self.mark_dirty()
 
     def num_parameters(self) -> int:

@@ -57,3 +57,11 @@ def test_checkpoint_round_trip_continues_training(cuda, tmp_path):
     assert la == lb
     for k in a.vars:
         assert torch.equal(a.vars[k], b.vars[k]), k
+    # restoring INTO a trainer whose step is already replayed from a CUDA graph: values land in place (same addresses),
+    # the fp16 operand shadows are refreshed before the next replay, and the step repeats exactly
+    step(tra, 0)                                          # move away from the checkpointed state (graph replay)
+    assert tra.graph is not None
+    ck.load_into_store(a, prefix, trainer=tra)
+    assert tra.global_step == 2 and step(tra, 2) == la
+    for k in a.vars:
+        assert torch.equal(a.vars[k], b.vars[k]), k

@@ -96,7 +96,12 @@ def test_inference_graph_equals_eager(cuda, model):
     tr.train_step(x.to(cuda), nf.to(cuda), labels.to(torch.uint8).to(cuda), frame_index=idx)
     want, _ = eng.forward(x.to(cuda), nf.to(cuda), False, frame_index=idx)
     got = g(x.to(cuda), nf.to(cuda), frame_index=idx)
-    assert g.graph is not first and torch.equal(got, want)
+    assert g.graph is not first and torch.equal(got, want)          # the trainer re-homed the variables: captured again
+    second = g.graph
+    tr.train_step(x.to(cuda), nf.to(cuda), labels.to(torch.uint8).to(cuda), frame_index=idx)
+    want, _ = eng.forward(x.to(cuda), nf.to(cuda), False, frame_index=idx)
+    got = g(x.to(cuda), nf.to(cuda), frame_index=idx)
+    assert g.graph is second and torch.equal(got, want)             # values changed in place: same graph, new result
     with pytest.raises(ValueError):
         g(x[:2].to(cuda), nf[:2].to(cuda))
 
