@@ -47,6 +47,8 @@ class NetVladConfig:
     loss_scale: float = 0.0        # fp16 activation-gradient scale inside the backward; 0 = auto (8 x batch)
     hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
     overlap_audio: bool = True     # run the audio modality (0.4 % of the FLOPs, ~1/3 of the launches) on a second stream
+    overlap_wgrad: bool = True     # rgb weight-gradient GEMMs on a third stream: they have no consumer before the optimiser
+                                   # and fill the SMs the data-gradient GEMMs leave idle (partial last waves, 128-tile grids)
     # WillowModelReg only (frame_level_models.py:2209-2216, 2535-2544)
     rgb_det_reg: float = 1e-4      # --rgb_det_reg: orthogonal-regulariser scale of the rgb cluster centres
     audio_det_reg: float = 1e-4    # --audio_det_reg
@@ -78,9 +80,15 @@ class NetVladEngine:
             raise NotImplementedError("netvlad_add_batch_norm=False is unreachable in the reference (D7)")
         self.build_variables()
         self._side = None          # second CUDA stream + fork / join events (created on first use)
+        self._wside = None         # third stream for the rgb weight-gradient GEMMs of the backward
         self.draws = 0             # training/eval forwards so far: keys the dropout / frame-sampling generators
         self.seed_dev = None       # device copy of 2 * draws for graph-captured steps (NetVladV2 dropout)
         self.pre_head_hook = None  # callable run right before the hidden projection reads its fp16 weights
+
+    def _wgrad_stream(self):
+        if self._wside is None:
+            self._wside = (torch.cuda.Stream(device=self.store.device), torch.cuda.Event(), torch.cuda.Event())
+        return self._wside
 
     def _side_stream(self):
         if self._side is None:
@@ -701,6 +709,11 @@ class NetVladEngine:
         if side is not None:
             ev_fork.record(main)
         deferred = []                       # audio gradients are announced after the join (hooks may start an all-reduce)
+        # weight gradients of the rgb attention block on their own stream -- only when nobody listens for finished
+        # gradients while the backward runs (the eager data-parallel path starts all-reduces from `put`)
+        ctx["_wgrad"] = None
+        if c.overlap_wgrad and c.model == "NetVladV1" and ctx.get("grad_hook") is None:
+            ctx["_wgrad"] = self._wgrad_stream() + ([],)
         for (name, col0, D, K, H, sid), o0 in reversed(list(zip(mods, offs))):
             on_side = side is not None and name == "audio"
             put_m = (lambda n, g: deferred.append((n, g))) if on_side else put
@@ -717,6 +730,12 @@ class NetVladEngine:
                 ev_join.record(side)
         if side is not None:
             main.wait_event(ev_join)
+        if ctx["_wgrad"] is not None:
+            wstream, _, wjoin, keep = ctx["_wgrad"]
+            wjoin.record(wstream)
+            main.wait_event(wjoin)
+            keep.clear()                    # operands of the side-stream products may be recycled from here on
+            ctx["_wgrad"] = None
         for n, g in deferred:
             put(n, g)
         put("input_bn/gamma", dgamma_in)
@@ -724,6 +743,21 @@ class NetVladEngine:
         if deferred_hidden is not None:
             put("hidden1_weights", ctx["hidden_dw"](deferred_hidden[0], deferred_hidden[1], gout("hidden1_weights")))
         return grads
+
+    def _wgrad_gemm(self, ctx, name, a, b, **kw):
+        """Weight-gradient product dW = a^T b.  For the rgb modality it runs on the wgrad stream as a parallel branch (forked
+        after its operands exist on the main stream, joined at the end of the backward); operands stay referenced until
+        the join so that their memory cannot be recycled underneath the product."""
+        w = ctx.get("_wgrad")
+        if w is None or name != "video":
+            return ops.gemm(a, b, a_mn=True, b_mn=True, **kw)
+        wstream, wfork, _, keep = w
+        main = torch.cuda.current_stream()
+        wfork.record(main)
+        wstream.wait_event(wfork)
+        keep.extend((a, b))
+        with torch.cuda.stream(wstream):
+            return ops.gemm(a, b, a_mn=True, b_mn=True, **kw)
 
     def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
@@ -747,12 +781,12 @@ class NetVladEngine:
         h1 = m["h1"].view(rows, D)
         f1 = m["f1"]
         dpre2 = dpre2.view(rows, D)
-        put(f"{a}/ff_output{sid}/kernel", ops.gemm(f1, dpre2, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                                   out=gout(f"{a}/ff_output{sid}/kernel")))
+        put(f"{a}/ff_output{sid}/kernel", self._wgrad_gemm(ctx, name, f1, dpre2, out_dtype=f32, alpha=inv,
+                                                           out=gout(f"{a}/ff_output{sid}/kernel")))
         dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
         put(f"{a}/filter_output{sid}/bias", ops.colsum(dpre1, alpha=inv))
-        put(f"{a}/filter_output{sid}/kernel", ops.gemm(h1, dpre1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                                       out=gout(f"{a}/filter_output{sid}/kernel")))
+        put(f"{a}/filter_output{sid}/kernel", self._wgrad_gemm(ctx, name, h1, dpre1, out_dtype=f32, alpha=inv,
+                                                               out=gout(f"{a}/filter_output{sid}/kernel")))
         dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
         # ---- LN1: h1 = LN(u1), u1 = att + vlad --------------------------------------------------
         du1, dg, db, dbo = ops.layernorm_joint_bwd(m["u1"], dh1, K * D, B, K, D, m["st1"], v[a + "/LayerNorm/gamma"],
@@ -760,14 +794,14 @@ class NetVladEngine:
         put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
         put(a + "/output_transform/bias", dbo)
         du1 = du1.view(rows, D)
-        put(a + "/output_transform/kernel", ops.gemm(m["o"], du1, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                                     out=gout(a + "/output_transform/kernel")))
+        put(a + "/output_transform/kernel", self._wgrad_gemm(ctx, name, m["o"], du1, out_dtype=f32, alpha=inv,
+                                                             out=gout(a + "/output_transform/kernel")))
         do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
         dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
         zn = m["zn"]
         for i, n in enumerate(("q", "k", "v")):
-            put(f"{a}/{n}/kernel", ops.gemm(zn, dqkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
-                                            out=gout(f"{a}/{n}/kernel")))
+            put(f"{a}/{n}/kernel", self._wgrad_gemm(ctx, name, zn, dqkv[:, i * D:(i + 1) * D], out_dtype=f32, alpha=inv,
+                                                    out=gout(f"{a}/{n}/kernel")))
         dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
         # ---- NetVLAD normalisation + aggregation + soft-assignment ------------------------------
         ct = sh[vs + "/centers_t"]
