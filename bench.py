@@ -229,6 +229,7 @@ def main():
     e1.record()
     barrier()
     train_ms = reduce_max(e0.elapsed_time(e1)) / args.steps
+    loss = loss.clone()          # the graph-replayed step returns a static tensor that later steps overwrite
     launches = (_lib.launch_count - l0) // args.steps
     overflow = tr.overflowed()
 
