@@ -744,20 +744,23 @@ class NetVladEngine:
             put("hidden1_weights", ctx["hidden_dw"](deferred_hidden[0], deferred_hidden[1], gout("hidden1_weights")))
         return grads
 
-    def _wgrad_gemm(self, ctx, name, a, b, **kw):
-        """Weight-gradient product dW = a^T b.  For the rgb modality it runs on the wgrad stream as a parallel branch (forked
-        after its operands exist on the main stream, joined at the end of the backward); operands stay referenced until
-        the join so that their memory cannot be recycled underneath the product."""
+    def _wgrad_run(self, ctx, name, operands, fn):
+        """Parameter-gradient work without a consumer before the optimiser.  For the rgb modality it runs on the wgrad
+        stream as a parallel branch (forked after its operands exist on the main stream, joined at the end of the
+        backward); the operands stay referenced until the join so that their memory cannot be recycled underneath it."""
         w = ctx.get("_wgrad")
         if w is None or name != "video":
-            return ops.gemm(a, b, a_mn=True, b_mn=True, **kw)
+            return fn()
         wstream, wfork, _, keep = w
-        main = torch.cuda.current_stream()
-        wfork.record(main)
+        wfork.record(torch.cuda.current_stream())
         wstream.wait_event(wfork)
-        keep.extend((a, b))
+        keep.extend(operands)
         with torch.cuda.stream(wstream):
-            return ops.gemm(a, b, a_mn=True, b_mn=True, **kw)
+            return fn()
+
+    def _wgrad_gemm(self, ctx, name, a, b, **kw):
+        """Weight-gradient product dW = a^T b (see _wgrad_run)."""
+        return self._wgrad_run(ctx, name, (a, b), lambda: ops.gemm(a, b, a_mn=True, b_mn=True, **kw))
 
     def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
@@ -784,7 +787,9 @@ class NetVladEngine:
         put(f"{a}/ff_output{sid}/kernel", self._wgrad_gemm(ctx, name, f1, dpre2, out_dtype=f32, alpha=inv,
                                                            out=gout(f"{a}/ff_output{sid}/kernel")))
         dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
-        put(f"{a}/filter_output{sid}/bias", ops.colsum(dpre1, alpha=inv))
+        # (written straight into the gradient view: `put` would otherwise copy on the main stream, racing the side stream)
+        bname = f"{a}/filter_output{sid}/bias"
+        put(bname, self._wgrad_run(ctx, name, (dpre1,), lambda: ops.colsum(dpre1, alpha=inv, out=gout(bname))))
         put(f"{a}/filter_output{sid}/kernel", self._wgrad_gemm(ctx, name, h1, dpre1, out_dtype=f32, alpha=inv,
                                                                out=gout(f"{a}/filter_output{sid}/kernel")))
         dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
