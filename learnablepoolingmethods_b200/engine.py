@@ -955,7 +955,8 @@ class InferenceGraph:
         eng = self.engine
         if tuple(model_input.shape) != tuple(self.x.shape) or model_input.dtype != self.x.dtype:
             raise ValueError(f"graph captured for {tuple(self.x.shape)} {self.x.dtype}, got {tuple(model_input.shape)} {model_input.dtype}")
-        self.x.copy_(model_input, non_blocking=True)
+        if model_input.data_ptr() != self.x.data_ptr():     # callers may fill `self.x` directly and skip this copy
+            self.x.copy_(model_input, non_blocking=True)
         self.nf.copy_(num_frames.to(torch.int32), non_blocking=True)
         if self.idx is not None:
             if frame_index is None:
