@@ -90,6 +90,18 @@ class FlatState:
         return self.offsets[name] + self.store.vars[name].numel()
 
 
+def head_gradient_span(flat: "FlatState"):
+    """(end offset, ok): the flat-gradient prefix [0, end) that holds every gradient produced by the head of the backward
+    (MoE, gating, hidden bias / batch norm) -- they are final before the modalities' backward starts, so their all-reduce
+    can travel underneath it.  ok is False when the layout does not have them in front (then one all-reduce at the end)."""
+    body = [n for n in flat.order if n not in flat.factored and n.startswith(("video_", "audio_", "input_bn"))]
+    head = [n for n in flat.order if n not in flat.factored and n not in body]
+    if not head or not body:
+        return 0, False
+    end = max(flat.end_offset(n) for n in head)
+    return end, all(flat.offsets[n] >= end for n in body)
+
+
 class ShardedHiddenUpdate:
     """Data-parallel update of hidden1_weights (85 % of the parameters) without moving its gradient or repeating its
     optimiser step on every rank.  Rank r owns rows [r*Kd/W, (r+1)*Kd/W) of W_h [Kd, H]:
@@ -314,10 +326,8 @@ class Trainer:
 
             # data parallel: the head's gradients (MoE, gating: the first ~40 % of the flat buffer) are all-reduced while
             # the modalities' backward runs; valid when the flat layout really has them in front
-            body = [n for n in f.order if n not in f.factored and n.startswith(("video_", "audio_", "input_bn"))]
-            head = [n for n in f.order if n not in f.factored and n not in body]
-            g["head_end"] = max(f.end_offset(n) for n in head)
-            g["split"] = dp and all(f.offsets[n] >= g["head_end"] for n in body)
+            g["head_end"], ok = head_gradient_span(f)
+            g["split"] = dp and ok
 
             eng.pre_head_hook = None                                 # the wait for the weight shards happens between graphs
             if self.shard is not None:

@@ -150,3 +150,66 @@ def test_bucketed_allreduce_sum_world2_gloo():
         assert ok, rank
         assert launched_at == [0, 1, 2, 3, 4]      # buckets complete at 256, 512, 768 and the 232-element tail at 1000
         assert launched == [(0, 256), (256, 512), (512, 768), (768, 1000)]
+
+
+def _cpu_store(model="NetVladV1"):
+    from learnablepoolingmethods_b200 import variables
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    cfg = NetVladConfig(model=model, iterations=16, cluster_size=32, hidden_size=32, vocab_size=50, rgb_dim=64, audio_dim=16,
+                        rgb_heads=4, audio_heads=2)
+    store = variables.VariableStore("cpu", seed=1)
+    NetVladEngine.build_variables(type("E", (), {"cfg": cfg, "store": store, "_dense_vars": NetVladEngine._dense_vars,
+                                                  "_ln_vars": NetVladEngine._ln_vars, "wc_suffix": NetVladEngine.wc_suffix})())
+    return store
+
+
+def _worker_split_allreduce(rank, world, port, q):
+    """The data-parallel graph step's exchange on gloo: the head span of the flat gradient is reduced first (it travels
+    under the modalities' backward on the GPU), the rest afterwards; together they are the plain SUM all-reduce."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from learnablepoolingmethods_b200.trainer import FlatState, head_gradient_span
+    store = _cpu_store()
+    tr = store.trainable()
+    head = [n for n in tr if not n.startswith(("video_", "audio_", "input_bn"))]
+    body = [n for n in tr if n not in head]
+    flat = FlatState(store, [n for n in head if n != "hidden1_weights"] + body, {}, factored=("hidden1_weights",))
+    end, ok = head_gradient_span(flat)
+    flat.g.copy_(torch.arange(flat.g.numel(), dtype=torch.float32) * (rank + 1))
+    h0 = dist.all_reduce(flat.g[:end], op=dist.ReduceOp.SUM, async_op=True)
+    h1 = dist.all_reduce(flat.g[end:], op=dist.ReduceOp.SUM, async_op=True)
+    h0.wait(); h1.wait()
+    want = torch.arange(flat.g.numel(), dtype=torch.float32) * sum(r + 1 for r in range(world))
+    q.put((rank, ok, end, bool(torch.equal(flat.g, want))))
+    dist.destroy_process_group()
+
+
+def test_head_gradient_span_and_split_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+    from learnablepoolingmethods_b200.trainer import FlatState, head_gradient_span
+    # layout rules on one process: the backward's order (head first) is splittable, hidden1_weights (factored) has no
+    # gradient storage, and an interleaved order is rejected (one all-reduce at the end instead)
+    store = _cpu_store("WillowModelReg")
+    tr = store.trainable()
+    head = [n for n in tr if not n.startswith(("video_", "audio_", "input_bn")) and n != "hidden1_weights"]
+    body = [n for n in tr if n.startswith(("video_", "audio_", "input_bn"))]
+    flat = FlatState(store, head + body, {}, factored=("hidden1_weights",))
+    end, ok = head_gradient_span(flat)
+    assert ok and end == flat.end_offset(head[-1]) and 0 < end < flat.g_total
+    assert "hidden1_weights" not in flat.grad_views and flat.g.numel() == flat.g_total
+    store2 = _cpu_store("WillowModelReg")
+    flat2 = FlatState(store2, body[:2] + head + body[2:], {}, factored=("hidden1_weights",))
+    assert head_gradient_span(flat2)[1] is False
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_split_allreduce, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert len({r[2] for r in res}) == 1                     # every rank splits at the same offset
+    for rank, ok, end, equal in res:
+        assert ok and equal, rank
