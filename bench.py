@@ -322,6 +322,7 @@ def main():
                              "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)"},
                    roofline_pool={"kernel": "netvlad_pool_fwd_kernel<256> (rgb, fused)", "bound": "tensor",
                                   "achieved": p_tf, "peak": burst, "unit": "TFLOP/s", "frac": p_tf / burst,
+                                  "frac_of_occupied_sms": p_tf / burst * 148.0 / min(148, B),
                                   "achieved_full_waves": pl_tf, "frac_full_waves": pl_tf / burst,
                                   "note": "B=80 fills 80 of 148 SMs (one CTA per video); full-wave figure at B=1184",
                                   "peak_source": f"{src} bf16 burst (kernel timed alone)"})
