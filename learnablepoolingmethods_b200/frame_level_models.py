@@ -55,8 +55,18 @@ class _NetVladBase(models.BaseModel):
                        sample_random_frames)
         engine = get_engine(cfg, unused_params.get("store"))
         from .autograd import netvlad_apply
-        pred = netvlad_apply(engine, model_input, num_frames, is_training,
-                             dropout_masks=unused_params.get("dropout_masks"), frame_index=unused_params.get("frame_index"))
+        if unused_params.get("cuda_graph") and not is_training:
+            # serving loops (eval.py / inference.py call the same graph once per batch): replay the captured forward;
+            # one engine.InferenceGraph per input shape, cached on the engine.  The returned tensor is static.
+            from .engine import InferenceGraph
+            graphs = engine.__dict__.setdefault("_inference_graphs", {})
+            key = (tuple(model_input.shape), model_input.dtype)
+            if key not in graphs:
+                graphs[key] = InferenceGraph(engine, model_input.shape[0], model_input.shape[1], model_input.dtype)
+            pred = graphs[key](model_input, num_frames, frame_index=unused_params.get("frame_index"))
+        else:
+            pred = netvlad_apply(engine, model_input, num_frames, is_training,
+                                 dropout_masks=unused_params.get("dropout_masks"), frame_index=unused_params.get("frame_index"))
         result = {"predictions": pred}
         if self._NAME == "WillowModelReg":
             # TF collects the orthogonal regulariser through REGULARIZATION_LOSSES (train.py:301-303); the eager

@@ -131,3 +131,22 @@ def test_graph_replayed_steps_equal_eager_steps(cuda, model):
     assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
     for k in runs[0][1]:
         assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+
+
+def test_create_model_with_cuda_graph(cuda):
+    """`create_model(..., is_training=False, cuda_graph=True)`: the registry entry point replays a captured forward (one
+    graph per input shape) and returns what the eager call returns."""
+    from learnablepoolingmethods_b200 import frame_level_models, variables
+    from oracle import netvlad_oracle as O
+    store = variables.reset_default_store(cuda, seed=5)
+    model = frame_level_models.NetVladV1()
+    kw = dict(vocab_size=60, iterations=64, cluster_size=64, hidden_size=64, is_training=False)
+    outs = []
+    for seed, B in ((1, 3), (2, 3), (3, 5)):
+        x, nf, _ = O.synthetic_batch(B, seed=seed, vocab=60)
+        want = model.create_model(x.to(cuda), num_frames=nf.to(cuda), **kw)["predictions"].clone()
+        got = model.create_model(x.to(cuda), num_frames=nf.to(cuda), cuda_graph=True, **kw)["predictions"]
+        assert torch.equal(got, want), (seed, B)
+        outs.append(got)
+    eng = next(iter(store._engines.values()))
+    assert len(eng._inference_graphs) == 2 and outs[0].data_ptr() == outs[1].data_ptr()      # one static output per shape
