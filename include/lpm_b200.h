@@ -369,9 +369,9 @@ int lpm_mha_core_bwd_bn(int mode, const void* qkv, long long ld, const void* o, 
                         float* stat_partial, void* dqkv, long long ldd, lpm_stream_t stream);
 /* tf.layers.dropout (transformer_utils.py:450): x *= keep/(1-rate); keep from mask_in (fp16 0/1) or a hash of
  * (seed + *seed_dev, index) -- seed_dev (device scalar, may be NULL) lets a captured CUDA graph draw a fresh mask on every
- * replay; the mask used is written to mask_out when given. */
+ * replay; the mask used is written to mask_out when given; out_f16 (may be NULL = in place) receives the result. */
 int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed,
-                    const unsigned long long* seed_dev, float rate, lpm_stream_t stream);
+                    const unsigned long long* seed_dev, float rate, void* out_f16, lpm_stream_t stream);
 /* out[b][d*K + k] = fp16(z[b][k][d]*rscale[b][k]): the reference's d-major flatten as an fp16 GEMM operand. */
 int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, int D, void* out, long long out_stride,
                              lpm_stream_t stream);

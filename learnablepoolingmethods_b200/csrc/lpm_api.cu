@@ -472,10 +472,10 @@ int lpm_mha_core_bwd_bn(int mode, const void* qkv, long long ld, const void* o, 
                     key_rstd, m1, m2, stat_partial, H16(dqkv), ldd, ST(stream));
 }
 int lpm_dropout_f16(void* x, long long n, const void* mask_in, void* mask_out, unsigned long long seed,
-                    const unsigned long long* seed_dev, float rate, lpm_stream_t stream) {
+                    const unsigned long long* seed_dev, float rate, void* out_f16, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && n > 0, "lpm_dropout_f16: bad arguments");
-  return dropout_f16(H16(x), n, CH16(mask_in), H16(mask_out), seed, seed_dev, rate, ST(stream));
+  return dropout_f16(H16(x), H16(out_f16), n, CH16(mask_in), H16(mask_out), seed, seed_dev, rate, ST(stream));
 }
 int lpm_netvlad_finalize_f16(const void* z, const float* rscale, int B, int K, int D, void* out, long long out_stride,
                              lpm_stream_t stream) {

@@ -134,7 +134,7 @@ int bn_bwd_apply(const void* dy, int dy_f32, const float* q, int T, __half* dx, 
                  const float* mean, const float* rstd, const float* gamma, const float* csum, int relu, cudaStream_t st);
 int sub_q_cast(const float* G, const float* q, long long rows, int T, int K, __half* out, cudaStream_t st);
 int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, int D, __half* out, cudaStream_t st);
-int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed,
+int dropout_f16(__half* x, __half* out, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed,
                 const unsigned long long* seed_dev, float rate, cudaStream_t st);
 int vlad_dmajor_f16(const __half* z, const float* rscale, int B, int K, int D, __half* out, long long out_stride,
                     cudaStream_t st);

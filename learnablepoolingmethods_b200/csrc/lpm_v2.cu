@@ -231,7 +231,7 @@ __device__ __forceinline__ uint32_t hash32(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
-__global__ void __launch_bounds__(256) dropout_kernel(__half* __restrict__ x, long long n, const __half* __restrict__ mask_in,
+__global__ void __launch_bounds__(256) dropout_kernel(const __half* x, __half* y, long long n, const __half* __restrict__ mask_in,
                                                       __half* __restrict__ mask_out, unsigned long long seed,
                                                       const unsigned long long* __restrict__ seed_dev, float rate) {
   // effective seed = seed + *seed_dev: the device part lets a captured CUDA graph draw a fresh mask on every replay
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(__half* __restrict__ x, lo
     if (mask_in) keep = __half2float(mask_in[i]);
     else keep = ((hash32(seed * 0x100000001B3ull + (uint64_t)i) >> 8) * (1.f / 16777216.f)) >= rate ? 1.f : 0.f;
     if (mask_out) mask_out[i] = __float2half_rn(keep);
-    x[i] = __float2half_rn(__half2float(x[i]) * keep * inv_keep);
+    y[i] = __float2half_rn(__half2float(x[i]) * keep * inv_keep);      // y may be x (in place)
   }
 }
 
@@ -385,10 +385,10 @@ int dmajor_to_kmajor_f16(const __half* in, long long in_stride, int B, int K, in
   return LPM_OK;
 }
 
-int dropout_f16(__half* x, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed,
+int dropout_f16(__half* x, __half* out, long long n, const __half* mask_in, __half* mask_out, unsigned long long seed,
                 const unsigned long long* seed_dev, float rate, cudaStream_t st) {
   LPM_REQUIRE(rate >= 0.f && rate < 1.f, "dropout: rate must be in [0,1)");
-  dropout_kernel<<<grid_for_v2(n, 256), 256, 0, st>>>(x, n, mask_in, mask_out, seed, seed_dev, rate);
+  dropout_kernel<<<grid_for_v2(n, 256), 256, 0, st>>>(x, out ? out : x, n, mask_in, mask_out, seed, seed_dev, rate);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -881,8 +881,8 @@ class NetVladEngine:
         du1 = du1.view(rows, D)
         datt = du1
         if m["mask"] is not None:
-            datt = du1.clone()
-            ops.dropout_f16(datt, c.dropout_rate, mask_in=m["mask"])
+            datt = torch.empty_like(du1)
+            ops.dropout_f16(du1, c.dropout_rate, mask_in=m["mask"], out=datt)
         # ---- MultiHeadAttentionBN ------------------------------------------------------------------
         put(a + "/output_transform/bias", ops.colsum(datt, alpha=inv))
         put(a + "/output_transform/kernel", ops.gemm(m["o_bn"], datt, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,

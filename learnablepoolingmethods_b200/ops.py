@@ -721,10 +721,10 @@ def affine_cols_f16(x, scale, shift, out=None):
     return out
 
 
-def dropout_f16(x, rate, *, mask_in=None, mask_out=None, seed=0, seed_dev=None):
+def dropout_f16(x, rate, *, mask_in=None, mask_out=None, seed=0, seed_dev=None, out=None):
     lib = _lib.load()
     check(lib.lpm_dropout_f16(ptr(x), _ll(x.numel()), ptr(mask_in), ptr(mask_out), C.c_ulonglong(seed), ptr(seed_dev),
-                              C.c_float(rate), stream_ptr()), "lpm_dropout_f16")
+                              C.c_float(rate), ptr(out), stream_ptr()), "lpm_dropout_f16")
     return x
 
 
