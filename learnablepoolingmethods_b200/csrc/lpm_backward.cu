@@ -192,6 +192,11 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
 }
+__device__ __forceinline__ void load8_regs(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
 __device__ __forceinline__ void store8(__half* p, const float* f) {
   uint4 v;
   v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]); v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
@@ -409,6 +414,56 @@ __global__ void __launch_bounds__(256) assign_bwd1_kernel(const float* __restric
   }
 }
 
+// K == 256 (the rgb pool of config 1): a lane owns 8 CONSECUTIVE clusters, so A / S / dShat move as 16-byte and G as two
+// 16-byte accesses per lane (the strided version above issues 2-byte loads: 64 bytes per warp request).  Same arithmetic,
+// same partial layout.
+__global__ void __launch_bounds__(256) assign_bwd1_k256_kernel(const float* __restrict__ G, const __half* __restrict__ A,
+                                                               const float* __restrict__ q, const __half* __restrict__ S,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               long long rows, int T, __half* __restrict__ dsh,
+                                                               float* __restrict__ partial) {
+  constexpr int K = 256;
+  extern __shared__ float sh[];  // [8 warps][2][K]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp = (long long)blockIdx.x * 8 + w, nwarps = (long long)gridDim.x * 8;
+  const int k0 = lane * 8;
+  float mu[8], rs[8], c1[8], c2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mu[j] = mean[k0 + j]; rs[j] = rstd[k0 + j]; c1[j] = c2[j] = 0.f; }
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long b = r / T;
+    const uint4 va = __ldg(reinterpret_cast<const uint4*>(A + r * K + k0));
+    const uint4 vs = __ldg(reinterpret_cast<const uint4*>(S + r * K + k0));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(G + r * K + k0)), g1 = __ldg(reinterpret_cast<const float4*>(G + r * K + k0 + 4));
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(q + b * K + k0)), q1 = __ldg(reinterpret_cast<const float4*>(q + b * K + k0 + 4));
+    float a[8], sv[8], da[8];
+    load8_regs(va, a); load8_regs(vs, sv);
+    da[0] = g0.x - q0.x; da[1] = g0.y - q0.y; da[2] = g0.z - q0.z; da[3] = g0.w - q0.w;
+    da[4] = g1.x - q1.x; da[5] = g1.y - q1.y; da[6] = g1.z - q1.z; da[7] = g1.w - q1.w;
+    float inner = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) inner += a[j] * da[j];
+    inner = warp_sum(inner);
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] = a[j] * (da[j] - inner);
+      const float shat = (sv[j] - mu[j]) * rs[j];
+      c1[j] += d[j];
+      c2[j] += d[j] * shat;
+    }
+    store8(dsh + r * K + k0, d);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh[(w * 2 + 0) * K + k0 + j] = c1[j]; sh[(w * 2 + 1) * K + k0 + j] = c2[j]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * K; i += 256) {
+    float s = 0.f;
+    for (int ww = 0; ww < 8; ++ww) s += sh[ww * 2 * K + i];
+    partial[(size_t)blockIdx.x * 2 * K + i] = s;
+  }
+}
+
 __global__ void __launch_bounds__(256) assign_bwd2_kernel(__half* __restrict__ dsh, const __half* __restrict__ S,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ csum,
@@ -568,7 +623,12 @@ int assign_bwd_blocks() { return num_sms() * 2; }
 int assign_bwd1(const float* G, const __half* A, const float* q, const __half* S, const float* mean,
                 const float* rstd, long long rows, int T, int K, __half* dsh, float* partial, cudaStream_t st) {
   LPM_REQUIRE(K <= 512, "assign_bwd1: K must be <= 512");
-  if (K > 256)
+  const bool al16 = ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(S) |
+                      reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(dsh)) & 15) == 0;
+  if (K == 256 && al16)
+    assign_bwd1_k256_kernel<<<assign_bwd_blocks(), 256, (size_t)16 * K * sizeof(float), st>>>(G, A, q, S, mean, rstd, rows, T, dsh,
+                                                                                             partial);
+  else if (K > 256)
     assign_bwd1_kernel<16><<<assign_bwd_blocks(), 256, (size_t)16 * K * sizeof(float), st>>>(G, A, q, S, mean, rstd, rows, T, K,
                                                                                              dsh, partial);
   else
