@@ -392,8 +392,21 @@ class Trainer:
         frame_index: optional int32 [B, iterations] (WillowModelReg: replaces the random frame draw)."""
         eng = self.engine
         if self._graph_ok(model_input):
-            loss, ctx = self._graph_step(model_input, num_frames, labels_u8, frame_index)
-            return self._optimizer_step(ctx, bool(self.flat.factored), loss)
+            captured = self.graph is not None and "graphs" in self.graph
+            try:
+                loss, ctx = self._graph_step(model_input, num_frames, labels_u8, frame_index)
+                return self._optimizer_step(ctx, bool(self.flat.factored), loss)
+            except Exception as e:                         # noqa: BLE001
+                if captured or self.world > 1:
+                    raise                                  # a failing replay is a real error; under data parallelism the
+                                                           # ranks must issue the same collectives, so no silent switch
+                # the CAPTURE failed (driver / allocator state): keep training with the same kernels issued eagerly
+                import sys
+                print(f"lpm-b200: CUDA-graph capture of the training step failed ({e!r}); continuing eagerly", file=sys.stderr)
+                self.use_graph, self.graph = False, None
+                torch.cuda.synchronize()
+                if self.shard is not None:
+                    eng.pre_head_hook = self.shard.wait_weights
         pred, ctx = eng.forward(model_input, num_frames, True, save_for_backward=True, frame_index=frame_index)
         ctx["reg_penalty"] = self.reg_penalty
         B = pred.shape[0]
