@@ -470,18 +470,36 @@ __global__ void __launch_bounds__(256) assign_bwd2_kernel(__half* __restrict__ d
                                                           long long rows, int K, float inv_n) {
   // csum: [2][K] totals of dShat and dShat*shat (still loss-scaled)
   const long long n = rows * K;
-  if (K % 8 == 0 && ((reinterpret_cast<uintptr_t>(dsh) | reinterpret_cast<uintptr_t>(S)) & 15) == 0) {
-    // eight clusters per thread, 16-byte accesses (same arithmetic per element as the scalar loop below)
+  if (K % 8 == 0 && K <= 512 && ((reinterpret_cast<uintptr_t>(dsh) | reinterpret_cast<uintptr_t>(S)) & 15) == 0) {
+    // eight clusters per thread, 16-byte accesses; the five per-cluster coefficients are folded into three and kept in
+    // shared memory (the scalar loop below re-reads five global arrays per element, which saturates L1):
+    //   dS = a_k * (d - b_k) - c_k * (s - mean_k)   with a = gamma*rstd, b = c1/N, c = a*rstd*c2/N
+    __shared__ __align__(16) float co[4][512];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float a = gamma[k] * rstd[k];
+      co[0][k] = a;
+      co[1][k] = csum[k] * inv_n;
+      co[2][k] = rstd[k] * csum[K + k] * inv_n;
+      co[3][k] = mean[k];
+    }
+    __syncthreads();
     for (long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i8 < n / 8; i8 += (long long)gridDim.x * blockDim.x) {
       const int k0 = (int)((i8 * 8) % K);
       float sv[8], dv[8], o[8];
       load8(S + i8 * 8, sv);
       load8_regs(*reinterpret_cast<const uint4*>(dsh + i8 * 8), dv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k0 + j;
-        const float shat = (sv[j] - mean[k]) * rstd[k];
-        o[j] = gamma[k] * rstd[k] * (dv[j] - csum[k] * inv_n - shat * csum[K + k] * inv_n);
+      for (int h = 0; h < 2; ++h) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&co[0][k0 + 4 * h]), b4 = *reinterpret_cast<const float4*>(&co[1][k0 + 4 * h]);
+        const float4 c4 = *reinterpret_cast<const float4*>(&co[2][k0 + 4 * h]), m4 = *reinterpret_cast<const float4*>(&co[3][k0 + 4 * h]);
+        const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // same value as gamma*rstd*(d - c1/N - shat*c2/N), shat = (s - mean)*rstd, regrouped
+          const float shat_c = (sv[4 * h + j] - mm[j]) * cc[j];
+          o[4 * h + j] = aa[j] * (dv[4 * h + j] - bb[j] - shat_c);
+        }
       }
       store8(dsh + i8 * 8, o);
     }
