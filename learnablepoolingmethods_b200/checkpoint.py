@@ -466,3 +466,64 @@ def save_from_store(store, prefix: str, trainer=None, tower_scope: bool = True):
                 out[f"{pre}{name}/Adam_1"] = flat.v[o:o + n].view(tr[name].shape).cpu().numpy()
     write_tf_checkpoint(prefix, out)
     update_checkpoint_state(os.path.dirname(os.path.abspath(prefix)), prefix)
+
+
+# ------------------------------------------------------------------------------------------------
+# command line: python -m learnablepoolingmethods_b200.checkpoint {list|to-torch|from-torch} ...
+# ------------------------------------------------------------------------------------------------
+def _main(argv=None) -> int:
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m learnablepoolingmethods_b200.checkpoint",
+                                 description="Inspect / convert TF-1.x V2 checkpoints of the reference trainer (no TensorFlow).")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    a = sub.add_parser("list", help="variables of a checkpoint (prefix, or a train_dir with a `checkpoint` state file)")
+    a.add_argument("path")
+    b = sub.add_parser("to-torch", help="checkpoint -> torch state dict (.pt) keyed by the VariableStore names")
+    b.add_argument("path"); b.add_argument("out")
+    b.add_argument("--keep-slots", action="store_true", help="also keep the Adam slots and global_step")
+    c = sub.add_parser("from-torch", help="torch state dict (.pt) -> checkpoint the reference's eval.py / inference.py restore")
+    c.add_argument("state"); c.add_argument("prefix")
+    c.add_argument("--no-tower-scope", action="store_true", help="write bare names instead of tower/<name>")
+    args = ap.parse_args(argv)
+
+    def resolve(p):
+        if os.path.isdir(p):
+            q = latest_checkpoint(p)
+            if q is None:
+                raise SystemExit(f"{p}: no `checkpoint` state file")
+            return q
+        return p
+
+    if args.cmd == "list":
+        prefix = resolve(args.path)
+        info = list_tf_checkpoint(prefix)
+        total = 0
+        for name, e in info.items():
+            n = int(np.prod(e["shape"])) if e["shape"] else 1
+            total += n
+            print(f"{name:72s} {str(_DT.get(e['dtype'], e['dtype']).__name__ if e['dtype'] in _DT else e['dtype']):8s} {e['shape']}")
+        print(f"{len(info)} tensors, {total} elements, {prefix}")
+        return 0
+    import torch
+    if args.cmd == "to-torch":
+        ck = read_tf_checkpoint(resolve(args.path))
+        out = {}
+        for k, v in ck.items():
+            slot = k.endswith(("/Adam", "/Adam_1")) or k in ("global_step", "beta1_power", "beta2_power")
+            if slot and not args.keep_slots:
+                continue
+            out[k[len(TOWER):] if k.startswith(TOWER) else k] = torch.from_numpy(np.array(v))
+        torch.save(out, args.out)
+        print(f"{len(out)} tensors -> {args.out}")
+        return 0
+    sd = torch.load(args.state, map_location="cpu")
+    pre = "" if args.no_tower_scope else TOWER
+    glob = ("global_step", "beta1_power", "beta2_power")
+    write_tf_checkpoint(args.prefix, {(k if k in glob else pre + k): v.detach().cpu().numpy() for k, v in sd.items()})
+    update_checkpoint_state(os.path.dirname(os.path.abspath(args.prefix)), args.prefix)
+    print(f"{len(sd)} tensors -> {args.prefix}.index / .data-00000-of-00001")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())

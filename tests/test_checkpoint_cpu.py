@@ -162,3 +162,23 @@ def test_store_round_trip_with_tower_scope(tmp_path):
     b.vars["hidden1_biases"] = torch.zeros(5)
     with pytest.raises(ValueError, match="shape"):
         ck.load_into_store(b, prefix, strict=False)
+
+
+def test_command_line_round_trip(tmp_path, capsys):
+    """python -m learnablepoolingmethods_b200.checkpoint from-torch / list / to-torch."""
+    import torch
+    sd = {"input_bn/gamma": torch.rand(8), "video_VLAD/cluster_weights": torch.randn(8, 4), "global_step": torch.tensor(12)}
+    pt = str(tmp_path / "state.pt")
+    torch.save(sd, pt)
+    prefix = str(tmp_path / "train_dir" / "model.ckpt-12")
+    assert ck._main(["from-torch", pt, prefix]) == 0
+    names = ck.list_tf_checkpoint(prefix)
+    assert set(names) == {"tower/input_bn/gamma", "tower/video_VLAD/cluster_weights", "global_step"}
+    assert ck._main(["list", str(tmp_path / "train_dir")]) == 0          # a train_dir resolves through its `checkpoint` file
+    assert "tower/video_VLAD/cluster_weights" in capsys.readouterr().out
+    back = str(tmp_path / "back.pt")
+    assert ck._main(["to-torch", prefix, back]) == 0
+    got = torch.load(back)
+    assert set(got) == {"input_bn/gamma", "video_VLAD/cluster_weights"}  # slots / global_step dropped by default
+    assert torch.equal(got["video_VLAD/cluster_weights"], sd["video_VLAD/cluster_weights"])
+    assert ck._main(["to-torch", prefix, back, "--keep-slots"]) == 0 and int(torch.load(back)["global_step"]) == 12
