@@ -24,3 +24,28 @@ def l2_normalize_frames(model_input):
     if not model_input.is_cuda:
         raise RuntimeError("model_input must live on the GPU (there is no CPU path)")
     return ops.l2_normalize_frames(model_input.contiguous().float())
+
+
+def _gather(model_input, frame_index):
+    B, _, F = model_input.shape
+    S = frame_index.shape[1]
+    x = model_input.contiguous() if model_input.dtype == torch.uint8 else model_input.contiguous().float()
+    one = torch.ones(F, dtype=torch.float32, device=x.device)
+    zero = torch.zeros(F, dtype=torch.float32, device=x.device)
+    return ops.gather_bn_apply(x, frame_index, S, one, zero).view(B, S, F)
+
+
+def SampleRandomFrames(model_input, num_frames, num_samples, uniform=None, seed=0):
+    """model_utils.py:54-73: `num_samples` frames drawn independently and uniformly from the first num_frames[b] frames.
+    Returns fp16 [B, num_samples, F] (uint8 codes are dequantised + L2-normalised on the way).  `uniform` (fp32
+    [B, num_samples] in [0,1)) replaces the generator (tf.random_uniform's values in a parity test)."""
+    nf = num_frames.reshape(-1).to(device=model_input.device, dtype=torch.int32).contiguous()
+    idx = ops.random_frame_index(nf, int(num_samples), model_input.shape[1], mode=0, uniform=uniform, seed=seed)
+    return _gather(model_input, idx)
+
+
+def SampleRandomSequence(model_input, num_frames, num_samples, uniform=None, seed=0):
+    """model_utils.py:26-51: a random window of `num_samples` consecutive frames (clipped to the last frame)."""
+    nf = num_frames.reshape(-1).to(device=model_input.device, dtype=torch.int32).contiguous()
+    idx = ops.random_frame_index(nf, int(num_samples), model_input.shape[1], mode=1, uniform=uniform, seed=seed)
+    return _gather(model_input, idx)

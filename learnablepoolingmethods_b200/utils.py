@@ -4,6 +4,17 @@ from __future__ import annotations
 import torch
 
 
+def Dequantize(feat_vector, max_quantized_value=2, min_quantized_value=-2):
+    """utils.py:28-43: byte codes -> floats, `q * range/255 + range/512 + min` (readers.py:185-193 calls it per feature).
+    Host-side helper for callers that want fp32 frames; the model entry points take the uint8 codes directly and
+    dequantise inside the gather kernels."""
+    assert max_quantized_value > min_quantized_value
+    quantized_range = max_quantized_value - min_quantized_value
+    scalar = quantized_range / 255.0
+    bias = (quantized_range / 512.0) + min_quantized_value
+    return feat_vector * scalar + bias
+
+
 def find_class_by_name(name, modules):
     """Searches the provided modules for the named class and returns it (train.py:187-190)."""
     modules = [getattr(module, name, None) for module in modules]

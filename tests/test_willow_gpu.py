@@ -294,3 +294,23 @@ def test_l2_normalize_prelude(cuda):
     xi = x.to(cuda).clone()
     ops.l2_normalize_frames(xi, out=xi)
     assert torch.equal(xi, got)
+
+
+def test_sample_random_mirrors(cuda):
+    """model_utils.SampleRandomFrames / SampleRandomSequence with injected draws vs the oracle's index rules; utils.Dequantize."""
+    from learnablepoolingmethods_b200 import model_utils, utils
+    from oracle import netvlad_oracle as O
+    B, S = 6, 40
+    x, nf, _, q = O.synthetic_batch(B, seed=3, vocab=20, return_codes=True)
+    u = _draws(B, S, 4)
+    want = O.gather_frames(x, O.sample_random_frame_indices(nf.numpy(), u))
+    got = model_utils.SampleRandomFrames(x.to(cuda), nf.to(cuda), S, uniform=torch.from_numpy(u))
+    assert tuple(got.shape) == (B, S, 1152) and float((got.float().cpu() - want).abs().max()) < 1e-3
+    want = O.gather_frames(x, O.sample_random_sequence_indices(nf.numpy(), S, u[:, 0]))
+    got = model_utils.SampleRandomSequence(x.to(cuda), nf.to(cuda), S, uniform=torch.from_numpy(u[:, 0].copy()))
+    assert float((got.float().cpu() - want).abs().max()) < 1e-3
+    got = model_utils.SampleRandomFrames(q.to(cuda), nf.to(cuda), S, uniform=torch.from_numpy(u))       # uint8 codes
+    full = O.l2_normalize(O.dequantize(q.float()), 2)
+    want = O.gather_frames(full, O.sample_random_frame_indices(nf.numpy(), u))
+    assert float((got.float().cpu() - want).abs().max()) < 1e-3
+    assert torch.equal(utils.Dequantize(q.float()), O.dequantize(q.float()))
