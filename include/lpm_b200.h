@@ -283,6 +283,16 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
                        const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                        const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2,
                        float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
+/* Same step with the bias-corrected step size read from device memory (lr_t_dev[0]) at execution time: the launch can
+ * then be captured in a CUDA graph and replayed while the learning-rate schedule (train.py:244-249) advances. */
+int lpm_adam_clip_step_dev(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
+                           const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
+                           const int* sh_cols, const long long* sh_ld, float clip, const float* lr_t_dev, float b1, float b2,
+                           float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
+/* Start-of-step latch of the overflow flag shared by the optimiser entry points: if *flag is set, *skipped += 1 and
+ * *flag = 0, so that one non-finite gradient norm skips exactly one update (the reference has no skip: TF would
+ * write NaNs into the variables, utils.py:181-188). */
+int lpm_step_begin(int* flag, int* skipped, lpm_stream_t stream);
 
 /* Split-phase variant for ONE tensor whose rows are sharded over data-parallel ranks (hidden1_weights under DP:
  * every rank owns rows [r*Kd/W, (r+1)*Kd/W), updates them, and the fp16 operand shards are all-gathered).
@@ -329,6 +339,14 @@ int lpm_rank_adam_step(const void* a16, long long lda, const void* g16, long lon
                        float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
                        long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace,
                        unsigned long long workspace_bytes, lpm_stream_t stream);
+/* lpm_rank_adam_step with two options: lr_t_dev (non-null: the step size is read from device memory, see
+ * lpm_adam_clip_step_dev) and tiled (non-zero: the same arithmetic, bit-identical, as 16-row CTAs of 128 threads and
+ * 4 KB of shared memory instead of persistent 512-thread CTAs -- meant for a low-priority stream underneath the
+ * backward, where the small CTAs co-reside with the GEMM CTAs and fill idle SMs). */
+int lpm_rank_adam_step_ex(const void* a16, long long lda, const void* g16, long long ldg, int R, long long Kd, int N,
+                          float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
+                          long long ldw16, float lr_t, const float* lr_t_dev, int tiled, float b1, float b2, float eps,
+                          void* workspace, unsigned long long workspace_bytes, lpm_stream_t stream);
 /* bytes of caller-owned device workspace lpm_rank_adam_step needs (the column-permuted copy of G); 0 when the
  * (R, N) pair is not supported (G must fit in shared memory): callers then keep the dense-gradient path */
 unsigned long long lpm_rank_adam_workspace_bytes(int R, int N);

@@ -446,14 +446,18 @@ def load_into_store(store, prefix: str, trainer=None, strict: bool = True, verif
 
 
 def save_from_store(store, prefix: str, trainer=None, tower_scope: bool = True):
-    """Write the variables (plus Adam slots / global_step / beta powers when a Trainer is given) under the names the
-    reference's Saver uses, so that the reference's eval.py / inference.py restore them unchanged."""
+    """Write the variables (plus Adam slots / beta powers when a Trainer is given) under the names the reference's
+    Saver uses.  `global_step` is ALWAYS written, as int32: the reference creates it with
+    `tf.Variable(0, trainable=False, name="global_step")` (train.py:228, eval.py:131), eval.py restores
+    `tf.train.Saver(tf.global_variables())` and train.py resumes through the Supervisor -- both need the key and the
+    dtype to match.  inference.py restores through `import_meta_graph` and additionally needs a `.meta` graph file,
+    which only TensorFlow can write."""
     pre = TOWER if tower_scope else ""
     if trainer is not None:
         trainer.sync_parameters()
     out = {pre + k: v.detach().cpu().numpy() for k, v in store.vars.items()}
+    out["global_step"] = np.array(trainer.global_step if trainer is not None else 0, dtype=np.int32)
     if trainer is not None:
-        out["global_step"] = np.array(trainer.global_step, dtype=np.int64)
         t = max(trainer.global_step, 0)
         out["beta1_power"] = np.array(0.9 ** (t + 1), dtype=np.float32)     # AdamOptimizer's non-slot variables
         out["beta2_power"] = np.array(0.999 ** (t + 1), dtype=np.float32)
@@ -519,7 +523,10 @@ def _main(argv=None) -> int:
     sd = torch.load(args.state, map_location="cpu")
     pre = "" if args.no_tower_scope else TOWER
     glob = ("global_step", "beta1_power", "beta2_power")
-    write_tf_checkpoint(args.prefix, {(k if k in glob else pre + k): v.detach().cpu().numpy() for k, v in sd.items()})
+    tensors = {(k if k in glob else pre + k): v.detach().cpu().numpy() for k, v in sd.items()}
+    # the reference's global_step variable is int32 (train.py:228); written even when the state dict has none
+    tensors["global_step"] = np.array(int(tensors.get("global_step", 0)), dtype=np.int32)
+    write_tf_checkpoint(args.prefix, tensors)
     update_checkpoint_state(os.path.dirname(os.path.abspath(args.prefix)), args.prefix)
     print(f"{len(sd)} tensors -> {args.prefix}.index / .data-00000-of-00001")
     return 0

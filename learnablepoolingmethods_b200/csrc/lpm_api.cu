@@ -354,8 +354,25 @@ int lpm_adam_clip_step(float* p, const float* g, float* m, float* v, const int* 
   DEVCHK();
   LPM_REQUIRE(p && g && m && v && table && chunk_begin && wd && partial && factor && norms && flag && n_chunks > 0 && n_tensors > 0,
               "lpm_adam_clip_step: bad arguments");
-  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, lr_t, b1, b2, eps, partial,
-                        factor, norms, flag, ST(stream));
+  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, lr_t, nullptr, b1, b2, eps,
+                        partial, factor, norms, flag, ST(stream));
+}
+
+int lpm_adam_clip_step_dev(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
+                           const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
+                           const int* sh_cols, const long long* sh_ld, float clip, const float* lr_t_dev, float b1, float b2,
+                           float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(p && g && m && v && table && chunk_begin && wd && partial && factor && norms && flag && lr_t_dev && n_chunks > 0 &&
+              n_tensors > 0, "lpm_adam_clip_step_dev: bad arguments");
+  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, 0.f, lr_t_dev, b1, b2, eps,
+                        partial, factor, norms, flag, ST(stream));
+}
+
+int lpm_step_begin(int* flag, int* skipped, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(flag && skipped, "lpm_step_begin: null pointer");
+  return step_begin(flag, skipped, ST(stream));
 }
 
 int lpm_shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
@@ -414,8 +431,18 @@ int lpm_rank_adam_step(const void* a16, long long lda, const void* g16, long lon
                        unsigned long long workspace_bytes, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(a16 && g16 && factor && flag && w && m && v && Kd > 0, "lpm_rank_adam_step: bad arguments");
-  return rank_adam_step(CH16(a16), lda, CH16(g16), ldg, R, Kd, N, alpha, factor, flag, w, m, v, H16(w16), ldw16, lr_t, b1, b2,
-                        eps, workspace, (size_t)workspace_bytes, ST(stream));
+  return rank_adam_step(CH16(a16), lda, CH16(g16), ldg, R, Kd, N, alpha, factor, flag, w, m, v, H16(w16), ldw16, lr_t, nullptr, 0,
+                        b1, b2, eps, workspace, (size_t)workspace_bytes, ST(stream));
+}
+
+int lpm_rank_adam_step_ex(const void* a16, long long lda, const void* g16, long long ldg, int R, long long Kd, int N,
+                          float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
+                          long long ldw16, float lr_t, const float* lr_t_dev, int tiled, float b1, float b2, float eps,
+                          void* workspace, unsigned long long workspace_bytes, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(a16 && g16 && factor && flag && w && m && v && Kd > 0, "lpm_rank_adam_step_ex: bad arguments");
+  return rank_adam_step(CH16(a16), lda, CH16(g16), ldg, R, Kd, N, alpha, factor, flag, w, m, v, H16(w16), ldw16, lr_t, lr_t_dev,
+                        tiled, b1, b2, eps, workspace, (size_t)workspace_bytes, ST(stream));
 }
 
 unsigned long long lpm_rank_adam_workspace_bytes(int R, int N) { return rank_adam_workspace_bytes(R, N); }

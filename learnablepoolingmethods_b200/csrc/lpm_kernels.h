@@ -87,15 +87,16 @@ int cast_scaled(const float* x, long long n, float alpha, __half* y, cudaStream_
 // lpm_optim.cu
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
                    const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
-                   const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2, float eps,
-                   float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
+                   const int* sh_cols, const long long* sh_ld, float clip, float lr_t, const float* lr_dev, float b1, float b2,
+                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
+int step_begin(int* flag, int* skipped, cudaStream_t st);
 
 int rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor, float* norm,
                    int* flag, cudaStream_t st);
 int rank_adam_step(const __half* a16, long long lda, const __half* g16, long long ldg, int R, long long Kd, int N,
                    float alpha, const float* factor, const int* flag, float* w, float* m, float* v, __half* w16,
-                   long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace, size_t workspace_bytes,
-                   cudaStream_t st);
+                   long long ldw16, float lr_t, const float* lr_dev, int tiled, float b1, float b2, float eps, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
 size_t rank_adam_workspace_bytes(int R, int N);
 int shard_sqnorm(const float* g, const float* p, const int* table, int n_chunks, const float* wd1, float* partial,
                  float* sumsq, cudaStream_t st);

@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(float* __restrict__ p, con
                                                       const float* __restrict__ factor, const int* __restrict__ flag,
                                                       const unsigned long long* __restrict__ sh_ptr,
                                                       const int* __restrict__ sh_cols, const long long* __restrict__ sh_ld,
-                                                      float lr_t, float b1, float b2, float eps) {
+                                                      float lr_t, const float* __restrict__ lr_dev, float b1, float b2, float eps) {
   if (*flag) return;  // overflow: skip the step
+  if (lr_dev != nullptr) lr_t = *lr_dev;   // step size kept in device memory (CUDA-graph replays)
   const int t = table[blockIdx.x * 4], len = table[blockIdx.x * 4 + 2];
   const long long start = (long long)(unsigned)table[blockIdx.x * 4 + 1] * 32;
   const long long eoff = (long long)(unsigned)table[blockIdx.x * 4 + 3] * 32;
@@ -191,8 +192,9 @@ __global__ void __launch_bounds__(512, 1) rank_adam_kernel(const __half* __restr
                                                            const float* __restrict__ factor, const int* __restrict__ flag,
                                                            float* __restrict__ w, float* __restrict__ m,
                                                            float* __restrict__ v, __half* __restrict__ w16, long long ldw16,
-                                                           float lr_t, float b1, float b2, float eps) {
+                                                           float lr_t, const float* __restrict__ lr_dev, float b1, float b2, float eps) {
   if (*flag) return;   // non-finite gradient norm somewhere: the whole step is skipped
+  if (lr_dev != nullptr) lr_t = *lr_dev;
   extern __shared__ __align__(16) uint8_t ra_sm[];
   const int Rp = (R + 15) & ~15;
   const int gs = N + 8, as = RA_ROWS + 8;                 // padded row strides (halves): conflict-free ldmatrix
@@ -321,6 +323,144 @@ __global__ void __launch_bounds__(512, 1) rank_adam_kernel(const __half* __restr
   ra_cp_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled variant of the factored Adam: the same arithmetic as rank_adam_kernel (bit-identical results) in many small,
+// short-lived CTAs -- 16 rows of W each, 128 threads, 4 KB of shared memory, no persistent loop.  It is meant to run
+// on a LOW-PRIORITY stream underneath the tensor-bound backward of the same step: its CTAs fit next to a resident
+// GEMM CTA (which owns ~200 KB of shared memory but only half of the register file) and fill the SMs that small
+// grids and kernel tails leave idle, so the 3.6 GB optimiser stream of hidden1_weights leaves the critical path.
+// The B fragments (G^T) come pre-arranged in fragment order from global memory (80 KB, L2-resident) instead of a
+// shared-memory copy per CTA; the w / m / v pieces are plain 16-byte loads issued before the tensor work.
+//   Gf layout: [q = N/32][ks = Rp/16][hf = 2][lane = 32] uint4; hf selects accumulator tiles {2hf, 2hf+1}:
+//   {b0(s), b1(s), b0(s+1), b1(s+1)} with b0 = {G[16ks+2t][c], G[16ks+2t+1][c]}, b1 = rows +8,
+//   c = 32q + 16(s/2) + 4(g/2) + 2(s%2) + g%2  (g = lane/4, t = lane%4: the column order of rank_permute_kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rank_gfrag_kernel(const __half* __restrict__ G, long long ldg, int R, int nks, int N,
+                                                         uint4* __restrict__ Gf) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = (N / 32) * nks * 64;
+  if (idx >= total) return;
+  const int lane = idx & 31, hf = (idx >> 5) & 1, rest = idx >> 6;
+  const int ks = rest % nks, q = rest / nks;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t out[4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int s = 2 * hf + u;
+    const int col = q * 32 + 16 * (s >> 1) + 4 * (g >> 1) + 2 * (s & 1) + (g & 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k0 = ks * 16 + 2 * t + 8 * h;
+      const __half lo = k0 < R ? G[(long long)k0 * ldg + col] : __float2half_rn(0.f);
+      const __half hi = k0 + 1 < R ? G[(long long)(k0 + 1) * ldg + col] : __float2half_rn(0.f);
+      out[2 * u + h] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+    }
+  }
+  Gf[idx] = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+constexpr int RT_AS = 24;   // padded row stride (halves) of the staged A tile [Rp][16]
+
+template <int NKS>
+__global__ void __launch_bounds__(128, 4) rank_adam_tile_kernel(const __half* __restrict__ A, long long lda,
+                                                             const uint4* __restrict__ Gf, int R, long long Kd, int N,
+                                                             float alpha, const float* __restrict__ factor,
+                                                             const int* __restrict__ flag, float* __restrict__ w,
+                                                             float* __restrict__ m, float* __restrict__ v,
+                                                             __half* __restrict__ w16, long long ldw16, float lr_t,
+                                                             const float* __restrict__ lr_dev, float b1, float b2, float eps) {
+  if (*flag) return;
+  if (lr_dev != nullptr) lr_t = *lr_dev;
+  __shared__ __align__(16) __half sA[16 * NKS * RT_AS];
+  constexpr int nks = NKS, Rp = 16 * NKS;
+  const int nq = N / 32;
+  const long long row0 = (long long)blockIdx.x * 16;
+  for (int c = threadIdx.x; c < Rp * 2; c += 128) {
+    const int r = c >> 1, ch = c & 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < R && row0 + ch * 8 < Kd) val = __ldg(reinterpret_cast<const uint4*>(A + (long long)r * lda + row0 + ch * 8));
+    *reinterpret_cast<uint4*>(sA + r * RT_AS + ch * 8) = val;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane >> 3, i = lane & 7, g = lane >> 2, t = lane & 3;
+  uint32_t af[NKS][4];
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks) {
+    const __half* asrc = sA + (ks * 16 + (j >> 1) * 8 + i) * RT_AS + (j & 1) * 8;
+    ra_ldsm_x4_t(smem_u32(asrc), af[ks][0], af[ks][1], af[ks][2], af[ks][3]);
+  }
+  const float f = alpha * factor[0];
+  const long long r_lo = row0 + g;
+  for (int q = warp; q < nq; q += 4) {
+    uint4 pc[12];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long r = r_lo + 8 * h;
+      const long long off = (r < Kd ? r : r_lo) * N + q * 32 + t * 4;
+      pc[h * 6 + 0] = *reinterpret_cast<const uint4*>(w + off);
+      pc[h * 6 + 1] = *reinterpret_cast<const uint4*>(w + off + 16);
+      pc[h * 6 + 2] = *reinterpret_cast<const uint4*>(m + off);
+      pc[h * 6 + 3] = *reinterpret_cast<const uint4*>(m + off + 16);
+      pc[h * 6 + 4] = *reinterpret_cast<const uint4*>(v + off);
+      pc[h * 6 + 5] = *reinterpret_cast<const uint4*>(v + off + 16);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+    const uint4* gq = Gf + (size_t)q * nks * 64 + lane;
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const uint4 b01 = __ldg(gq + ks * 64), b23 = __ldg(gq + ks * 64 + 32);
+      ra_mma16816(acc[0], af[ks], b01.x, b01.y);
+      ra_mma16816(acc[1], af[ks], b01.z, b01.w);
+      ra_mma16816(acc[2], af[ks], b23.x, b23.y);
+      ra_mma16816(acc[3], af[ks], b23.z, b23.w);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long r = r_lo + 8 * h;
+      if (r >= Kd) continue;
+      const long long off = r * N + q * 32 + t * 4;
+      float gr[8];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) { gr[2 * s] = acc[s][2 * h] * f; gr[2 * s + 1] = acc[s][2 * h + 1] * f; }
+      float* wv = reinterpret_cast<float*>(&pc[h * 6 + 0]);
+      float* mv = reinterpret_cast<float*>(&pc[h * 6 + 2]);
+      float* vv = reinterpret_cast<float*>(&pc[h * 6 + 4]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        mv[e] = b1 * mv[e] + (1.f - b1) * gr[e];
+        vv[e] = b2 * vv[e] + (1.f - b2) * gr[e] * gr[e];
+        wv[e] -= adam_update(mv[e], vv[e], lr_t, eps);
+      }
+      *reinterpret_cast<uint4*>(m + off) = pc[h * 6 + 2];
+      *reinterpret_cast<uint4*>(m + off + 16) = pc[h * 6 + 3];
+      *reinterpret_cast<uint4*>(v + off) = pc[h * 6 + 4];
+      *reinterpret_cast<uint4*>(v + off + 16) = pc[h * 6 + 5];
+      *reinterpret_cast<uint4*>(w + off) = pc[h * 6 + 0];
+      *reinterpret_cast<uint4*>(w + off + 16) = pc[h * 6 + 1];
+      if (w16 != nullptr) {
+        __half* dst = w16 + r * ldw16 + q * 32 + t * 4;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_half2(wv[0], wv[1]), pack_half2(wv[2], wv[3]));
+        *reinterpret_cast<uint2*>(dst + 16) = make_uint2(pack_half2(wv[4], wv[5]), pack_half2(wv[6], wv[7]));
+      }
+    }
+  }
+}
+
+// Start-of-step latch of the overflow flag: `skipped` counts the steps whose update was dropped (sticky, for
+// reporting), `flag` is cleared so that one non-finite gradient norm skips exactly one optimiser step.
+__global__ void step_begin_kernel(int* __restrict__ flag, int* __restrict__ skipped) {
+  if (*flag) { *skipped += 1; *flag = 0; }
+}
+
+int step_begin(int* flag, int* skipped, cudaStream_t st) {
+  step_begin_kernel<<<1, 1, 0, st>>>(flag, skipped);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
 // norm = alpha * sqrt(sum_ij GA_ij * GG_ij);  factor = clip / max(norm, clip)  (tf.clip_by_norm, utils.py:181-188)
 __global__ void __launch_bounds__(256) rank_grad_clip_kernel(const float* __restrict__ ga, const float* __restrict__ gg, int n,
                                                              float alpha, float clip, float* __restrict__ factor,
@@ -356,13 +496,13 @@ static size_t rank_adam_smem(int R, int N) {
 // 0 = this (rank, width) is not supported (the caller keeps the dense gradient path)
 size_t rank_adam_workspace_bytes(int R, int N) {
   if (R < 1 || R > 16 * RA_MAX_KS || N < 32 || N % 32 != 0 || rank_adam_smem(R, N) > 226 * 1024) return 0;
-  return (size_t)((R + 15) & ~15) * N * 2;
+  return (size_t)((R + 15) & ~15) * N * 2;     // either layout of G^T (permuted rows / fragment order): Rp x N halves
 }
 
 int rank_adam_step(const __half* a16, long long lda, const __half* g16, long long ldg, int R, long long Kd, int N,
                    float alpha, const float* factor, const int* flag, float* w, float* m, float* v, __half* w16,
-                   long long ldw16, float lr_t, float b1, float b2, float eps, void* workspace, size_t workspace_bytes,
-                   cudaStream_t st) {
+                   long long ldw16, float lr_t, const float* lr_dev, int tiled, float b1, float b2, float eps, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
   LPM_REQUIRE(R >= 1 && R <= 16 * RA_MAX_KS, "rank_adam_step: rank (tower batch) must be in [1,%d] (got %d)", 16 * RA_MAX_KS, R);
   LPM_REQUIRE(N % 32 == 0 && N >= 32, "rank_adam_step: output width must be a multiple of 32 (got %d)", N);
   LPM_REQUIRE(lda % 8 == 0 && ldg % 8 == 0 && ldw16 % 8 == 0 && Kd % 8 == 0, "rank_adam_step: strides must be multiples of 8");
@@ -370,6 +510,19 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
   if (workspace == nullptr || workspace_bytes < rank_adam_workspace_bytes(R, N))
     return fail(LPM_ERR_WORKSPACE, "rank_adam_step: workspace of %zu bytes required", rank_adam_workspace_bytes(R, N));
   const int Rp = (R + 15) & ~15;
+  if (tiled) {
+    const int nks = Rp / 16;
+    uint4* gf = reinterpret_cast<uint4*>(workspace);
+    rank_gfrag_kernel<<<((N / 32) * nks * 64 + 255) / 256, 256, 0, st>>>(g16, ldg, R, nks, N, gf);
+    const long long nblk = (Kd + 15) / 16;
+    LPM_REQUIRE(nblk <= 0x7fffffffLL, "rank_adam_step: too many row blocks");
+#define LPM_RT(NK) case NK: rank_adam_tile_kernel<NK><<<(unsigned)nblk, 128, 0, st>>>(a16, lda, gf, R, Kd, N, alpha, factor, flag, w, m, \
+                                                                                    v, w16, ldw16, lr_t, lr_dev, b1, b2, eps); break;
+    switch (nks) { LPM_RT(1) LPM_RT(2) LPM_RT(3) LPM_RT(4) LPM_RT(5) LPM_RT(6) LPM_RT(7) LPM_RT(8) default: break; }
+#undef LPM_RT
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
   const int nthr = N >= 512 ? 512 : 256;
   const size_t smem = rank_adam_smem(R, N);
   static size_t attr = 0;
@@ -381,7 +534,7 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
   rank_permute_kernel<<<(Rp * (N / 8) + 255) / 256, 256, 0, st>>>(g16, ldg, R, Rp, N, gp);
   const int npanels = (int)((Kd + RA_ROWS - 1) / RA_ROWS);
   const int grid = npanels < num_sms() ? npanels : num_sms();
-  rank_adam_kernel<<<grid, nthr, smem, st>>>(a16, lda, gp, R, Kd, N, alpha, factor, flag, w, m, v, w16, ldw16, lr_t, b1, b2, eps);
+  rank_adam_kernel<<<grid, nthr, smem, st>>>(a16, lda, gp, R, Kd, N, alpha, factor, flag, w, m, v, w16, ldw16, lr_t, lr_dev, b1, b2, eps);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -427,18 +580,18 @@ int shard_adam(float* p, const float* g, float* m, float* v, const int* table, i
                const float* sumsq, float clip, float* factor, float* norm, int* flag, const unsigned long long* sh_ptr,
                const int* sh_cols, const long long* sh_ld, float lr_t, float b1, float b2, float eps, cudaStream_t st) {
   shard_clip_kernel<<<1, 1, 0, st>>>(sumsq, clip, factor, norm, flag);
-  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd1, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, b1, b2, eps);
+  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd1, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, nullptr, b1, b2, eps);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
                    const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
-                   const int* sh_cols, const long long* sh_ld, float clip, float lr_t, float b1, float b2, float eps,
-                   float* partial, float* factor, float* norms, int* flag, cudaStream_t st) {
+                   const int* sh_cols, const long long* sh_ld, float clip, float lr_t, const float* lr_dev, float b1, float b2,
+                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st) {
   mt_sqnorm_kernel<<<n_chunks, 256, 0, st>>>(g, p, table, wd, partial);
   mt_clip_kernel<<<(n_tensors + 7) / 8, 256, 0, st>>>(partial, chunk_begin, n_tensors, clip, factor, norms, flag);
-  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, b1, b2, eps);
+  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, lr_dev, b1, b2, eps);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -87,12 +87,13 @@ class NetVladEngine:
 
     def _wgrad_stream(self):
         if self._wside is None:
-            self._wside = (torch.cuda.Stream(device=self.store.device), torch.cuda.Event(), torch.cuda.Event())
+            self._wside = (torch.cuda.Stream(device=self.store.device, priority=-1), torch.cuda.Event(), torch.cuda.Event())
         return self._wside
 
     def _side_stream(self):
         if self._side is None:
-            self._side = (torch.cuda.Stream(device=self.store.device), torch.cuda.Event(), torch.cuda.Event())
+            # priority -1 (high) like the trainer's capture stream: only the optimiser branch runs at the low priority 0
+            self._side = (torch.cuda.Stream(device=self.store.device, priority=-1), torch.cuda.Event(), torch.cuda.Event())
         return self._side
 
     # ------------------------------------------------------------------------------------------
@@ -687,6 +688,11 @@ class NetVladEngine:
             put("hidden1_weights", ops.gemm(hd["vlad"], dact16, a_mn=True, b_mn=True, out_dtype=f32, alpha=inv,
                                             out=gout("hidden1_weights")))
         dvlad = ops.gemm(dact16, sh["wh16"], b_mn=False)                      # [B, vlad_dim] fp16
+        after_head = ctx.get("after_head_hook")
+        if after_head is not None:
+            # single tower: that product was the last reader of the fp16 hidden1 operand in this step, so the trainer forks
+            # the factored update of hidden1_weights from here onto its low-priority stream (trainer._fork_hidden_update)
+            after_head(ctx)
         if stage == "head":
             ctx["_bwd_state"] = (dvlad, grads, put, deferred_hidden)
             return grads

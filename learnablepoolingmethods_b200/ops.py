@@ -600,13 +600,25 @@ def mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, *, scale):
     return dqkv
 
 
+def step_begin(flag, skipped):
+    """Start-of-step latch of the optimiser's overflow flag (skipped += flag; flag = 0)."""
+    check(_lib.load().lpm_step_begin(ptr(flag), ptr(skipped), stream_ptr()), "lpm_step_begin")
+
+
 def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, clip, lr_t, scratch,
-                   shadow=None, b1=0.9, b2=0.999, eps=1e-8):
-    """Per-tensor (grad + wd*p) -> clip_by_norm -> Adam over the flat buffers (three launches)."""
+                   shadow=None, b1=0.9, b2=0.999, eps=1e-8, lr_dev=None):
+    """Per-tensor (grad + wd*p) -> clip_by_norm -> Adam over the flat buffers (three launches).
+    lr_dev: fp32 [1] device tensor holding the bias-corrected step size (read at execution time: graph replays)."""
     lib = _lib.load()
     n_chunks, n_tensors = table.shape[0], wd.numel()
-    partial, factor, norms, flag = scratch
+    partial, factor, norms, flag = scratch[:4]
     sp, sc, sl = shadow if shadow is not None else (None, None, None)
+    if lr_dev is not None:
+        check(lib.lpm_adam_clip_step_dev(ptr(flat_p), ptr(flat_g), ptr(flat_m), ptr(flat_v), ptr(table), n_chunks,
+                                         ptr(chunk_begin), n_tensors, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), ptr(lr_dev),
+                                         C.c_float(b1), C.c_float(b2), C.c_float(eps), ptr(partial), ptr(factor), ptr(norms),
+                                         ptr(flag), stream_ptr()), "lpm_adam_clip_step")
+        return
     check(lib.lpm_adam_clip_step(ptr(flat_p), ptr(flat_g), ptr(flat_m), ptr(flat_v), ptr(table), n_chunks,
                                  ptr(chunk_begin), n_tensors, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), C.c_float(lr_t), C.c_float(b1),
                                  C.c_float(b2), C.c_float(eps), ptr(partial), ptr(factor), ptr(norms), ptr(flag),
@@ -676,19 +688,30 @@ def rank_grad_clip(gram_a, gram_g, alpha, clip, factor, norm, flag):
                                  ptr(flag), stream_ptr()), "lpm_rank_grad_clip")
 
 
-def rank_adam_step(a16, g16, alpha, factor, flag, w, m, v, w16, *, lr_t, b1=0.9, b2=0.999, eps=1e-8):
-    """Adam on w [Kd, N] (fp32, with moments m, v) for the never-materialised gradient alpha * a16^T g16."""
+def rank_adam_workspace_bytes(R, N) -> int:
+    lib = _lib.load()
+    lib.lpm_rank_adam_workspace_bytes.restype = C.c_ulonglong
+    return int(lib.lpm_rank_adam_workspace_bytes(int(R), int(N)))
+
+
+def rank_adam_step(a16, g16, alpha, factor, flag, w, m, v, w16, *, lr_t=0.0, b1=0.9, b2=0.999, eps=1e-8, lr_dev=None,
+                   tiled=False, workspace=None):
+    """Adam on w [Kd, N] (fp32, with moments m, v) for the never-materialised gradient alpha * a16^T g16.
+    lr_dev: fp32 [1] device tensor with the step size (instead of lr_t); tiled: the small-CTA kernel meant for a
+    low-priority stream underneath the backward (same results); workspace: caller-owned scratch (uint8, at least
+    rank_adam_workspace_bytes) -- required when the call runs concurrently with other users of the shared one."""
     lib = _lib.load()
     R, Kd = a16.shape
     N = g16.shape[1]
     assert g16.shape[0] == R and tuple(w.shape) == (Kd, N) and w.is_contiguous() and m.is_contiguous() and v.is_contiguous()
-    lib.lpm_rank_adam_workspace_bytes.restype = C.c_ulonglong
-    ws_bytes = int(lib.lpm_rank_adam_workspace_bytes(R, N))
-    ws = _workspace(ws_bytes, a16.device)
-    check(lib.lpm_rank_adam_step(ptr(a16), _ll(a16.stride(0)), ptr(g16), _ll(g16.stride(0)), R, _ll(Kd), N, C.c_float(alpha),
-                                 ptr(factor), ptr(flag), ptr(w), ptr(m), ptr(v), ptr(w16),
-                                 _ll(w16.stride(0) if w16 is not None else 0), C.c_float(lr_t), C.c_float(b1), C.c_float(b2),
-                                 C.c_float(eps), ptr(ws), C.c_ulonglong(ws_bytes), stream_ptr()), "lpm_rank_adam_step")
+    ws_bytes = rank_adam_workspace_bytes(R, N)
+    ws = workspace if workspace is not None else _workspace(ws_bytes, a16.device)
+    assert ws.numel() * ws.element_size() >= ws_bytes
+    check(lib.lpm_rank_adam_step_ex(ptr(a16), _ll(a16.stride(0)), ptr(g16), _ll(g16.stride(0)), R, _ll(Kd), N, C.c_float(alpha),
+                                    ptr(factor), ptr(flag), ptr(w), ptr(m), ptr(v), ptr(w16),
+                                    _ll(w16.stride(0) if w16 is not None else 0), C.c_float(lr_t), ptr(lr_dev),
+                                    1 if tiled else 0, C.c_float(b1), C.c_float(b2), C.c_float(eps), ptr(ws),
+                                    C.c_ulonglong(ws_bytes), stream_ptr()), "lpm_rank_adam_step")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -64,8 +64,10 @@ class FlatState:
         self.chunk_begin = torch.tensor(chunk_begin, dtype=torch.int32, device=dev)
         self.wd = torch.tensor([wd.get(n, 0.0) for n in self.order], dtype=torch.float32, device=dev)
         nt = len(self.order)
+        # partial sums | clip factors | norms | overflow flag (cleared at the start of every step) | skipped-step counter
         self.scratch = (torch.zeros(len(table), dtype=torch.float32, device=dev), torch.zeros(nt, dtype=torch.float32, device=dev),
-                        torch.zeros(nt, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+                        torch.zeros(nt, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                        torch.zeros(1, dtype=torch.int32, device=dev))
         self.shadow = None
         store.mark_dirty()
         store.layout_version += 1                      # every trainable variable now lives at a new address
@@ -190,9 +192,12 @@ class ShardedHiddenUpdate:
 
 
 class Trainer:
-    def __init__(self, engine: NetVladEngine, *, base_learning_rate=0.0002, learning_rate_decay=0.85,
+    def __init__(self, engine: NetVladEngine, *, base_learning_rate=0.01, learning_rate_decay=0.95,
                  learning_rate_decay_examples=4000000, clip_gradient_norm=1.0, regularization_penalty=1.0,
                  batch_size: int = 80, process_group=None, bucket_elems: int = 48 * 1024 * 1024):
+        """Keyword defaults are the reference's flag defaults (train.py:74-86: base_learning_rate 0.01,
+        learning_rate_decay 0.95, learning_rate_decay_examples 4000000, clip_gradient_norm 1.0,
+        regularization_penalty 1.0); the YT8M NetVLAD runs pass --base_learning_rate=0.0002 --learning_rate_decay=0.8."""
         self.engine, self.store, self.cfg = engine, engine.store, engine.cfg
         self.base_lr, self.decay, self.decay_examples = base_learning_rate, learning_rate_decay, learning_rate_decay_examples
         self.clip, self.reg_penalty, self.batch_size = clip_gradient_norm, regularization_penalty, batch_size
@@ -215,6 +220,13 @@ class Trainer:
         # (WillowModelReg frame indices: a static buffer filled before the replay; NetVladV2 dropout: a device-side seed)
         self.graph = None
         self.graph_after = 2           # eager steps before the capture (flat optimiser state, workspaces, attributes)
+        # single tower: the optimiser is captured too.  The step size lives in device memory (`lr_dev`, written before each
+        # replay); the hidden1_weights update (85 % of the parameters, HBM-bound) forks onto a LOW-PRIORITY stream right
+        # after the head of the backward -- the last reader of its fp16 operand -- and runs underneath the tensor-bound
+        # backward of the modalities as small CTAs that fill idle SMs (ops.rank_adam_step(tiled=True)).
+        self.lr_dev = None
+        self._prio = None              # (capture stream, optimiser stream, fork event, join event)
+        self.rank_ws = None
 
     def _factored_hidden(self, batch: int) -> bool:
         """hidden1_weights (85 % of the parameters) is updated from its gradient factors on a single tower: with
@@ -225,6 +237,7 @@ class Trainer:
                 and ops.rank_adam_supported(batch, c.hidden_size))
 
     on_flat_created = None
+    fuse_optimizer = True          # capture the optimiser inside the single-tower step graph (see __init__)
     disable_factored_hidden = False
     gather_hidden_factors = True
     shard_hidden_update = True
@@ -236,7 +249,25 @@ class Trainer:
         g_all = self.gather.wait("dact")
         return ops.gemm(a_all, g_all, a_mn=True, b_mn=True, out_dtype=torch.float32, alpha=inv, out=out)
 
-    def _factored_hidden_step(self, ctx, lr_t):
+    def _priority_streams(self):
+        if self._prio is None:
+            dev = self.store.device
+            # torch: lower number = higher priority; 0 is the lowest the device offers
+            self._prio = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=0),
+                          torch.cuda.Event(), torch.cuda.Event())
+        return self._prio
+
+    def _fork_hidden_update(self, ctx):
+        """engine.backward's after-head hook (captured): clip norm + Adam of hidden1_weights on the low-priority stream."""
+        _, opt, fork, join = self._priority_streams()
+        fork.record(torch.cuda.current_stream())
+        opt.wait_event(fork)
+        with torch.cuda.stream(opt):
+            self._factored_hidden_step(ctx, 0.0, lr_dev=self.lr_dev, tiled=True)()
+            join.record(opt)
+        ctx["_opt_join"] = join
+
+    def _factored_hidden_step(self, ctx, lr_t, lr_dev=None, tiled=False):
         f = self.flat
         vlad, dact16, inv = ctx["hidden_factors"]
         R = vlad.shape[0]
@@ -250,9 +281,13 @@ class Trainer:
         if self.rank_scratch is None:
             self.rank_scratch = torch.zeros(2, dtype=torch.float32, device=vlad.device)
         ops.rank_grad_clip(gram_a, gram_g, inv, self.clip, self.rank_scratch[0:1], self.rank_scratch[1:2], f.scratch[3])
+        if self.rank_ws is None:      # private scratch: the tiled update runs concurrently with users of the shared one
+            self.rank_ws = torch.empty(max(16, ops.rank_adam_workspace_bytes(R, dact16.shape[1])), dtype=torch.uint8,
+                                       device=vlad.device)
         return lambda: ops.rank_adam_step(vlad, dact16, inv, self.rank_scratch[0:1], f.scratch[3],
                                           self.store.vars["hidden1_weights"], *f.moment_views["hidden1_weights"],
-                                          self.store.shadows["wh16"], lr_t=lr_t)
+                                          self.store.shadows["wh16"], lr_t=lr_t, lr_dev=lr_dev, tiled=tiled,
+                                          workspace=self.rank_ws)
 
     # -- learning rate (train.py:244-249, tf.train.exponential_decay staircase) -------------------
     def learning_rate(self) -> float:
@@ -260,7 +295,9 @@ class Trainer:
         return self.base_lr * self.decay ** math.floor(ex / self.decay_examples)
 
     def _wd(self) -> Dict[str, float]:
-        l2 = self.cfg.moe_l2 * self.reg_penalty     # slim.l2_regularizer(moe_l2) * regularization_penalty
+        # slim.l2_regularizer(moe_l2) * regularization_penalty is part of EVERY tower's final_loss (train.py:299-311) and
+        # combine_gradients sums the towers (utils.py:205-211): the regulariser's gradient is num_towers * l2 * w
+        l2 = self.cfg.moe_l2 * self.reg_penalty * self.world
         return {"gates/weights": l2, "experts/weights": l2}
 
     # -- gradient all-reduce (SUM), bucketed over the flat buffer, overlapped with the backward -----
@@ -318,10 +355,12 @@ class Trainer:
                 loss, _ = ops.xent_fwd(pred, g["lab"])
                 return loss, ops.xent_bwd(pred, g["lab"], 1.0 / pred.shape[0])
 
-            def seg_c(ctx, dpred, stage=None):
+            def seg_c(ctx, dpred, stage=None, fused=False):
                 if stage != "body":
                     ctx["factored_hidden"] = bool(f.factored)
                     ctx["grad_views"] = f.grad_views
+                    if fused and f.factored:
+                        ctx["after_head_hook"] = self._fork_hidden_update
                 eng.backward(ctx, dpred, stage=stage)
 
             # data parallel: the head's gradients (MoE, gating: the first ~40 % of the flat buffer) are all-reduced while
@@ -345,11 +384,21 @@ class Trainer:
                 self.store.vars[k].copy_(v)
             n0 = _lib.launch_count
             graphs = [torch.cuda.CUDAGraph()]
+            g["fused"] = fuse = (not dp) and self.fuse_optimizer
             if not dp:
-                with torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
+                if fuse and self.lr_dev is None:
+                    self.lr_dev = torch.zeros(1, dtype=torch.float32, device=model_input.device)
+                # fused: captured on a high-priority stream so that the optimiser branch (priority 0) only takes what
+                # the forward / backward kernels leave free
+                cap = self._priority_streams()[0] if fuse else None
+                with torch.cuda.graph(graphs[0], stream=cap, capture_error_mode="thread_local"):
+                    if fuse:
+                        ops.step_begin(f.scratch[3], f.scratch[4])
                     g["ctx"] = seg_a()
                     g["loss"], dpred = seg_b(g["ctx"])
-                    seg_c(g["ctx"], dpred)
+                    seg_c(g["ctx"], dpred, fused=fuse)
+                    if fuse:
+                        self._captured_optimizer(g["ctx"])
             else:
                 with torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
                     g["ctx"] = seg_a()
@@ -369,6 +418,8 @@ class Trainer:
             eng.seed_dev.fill_(2 * eng.draws)        # NetVladV2's dropout: a fresh mask per replay (engine.forward, device_seed)
             eng.draws += 1
         graphs = g["graphs"]
+        if g["fused"]:
+            self.lr_dev.fill_(self._lr_t())          # read by the captured Adam kernels
         graphs[0].replay()
         if dp:
             self.shard.wait_weights()                # the fp16 weight shards gathered under the forward
@@ -395,6 +446,11 @@ class Trainer:
             captured = self.graph is not None and "graphs" in self.graph
             try:
                 loss, ctx = self._graph_step(model_input, num_frames, labels_u8, frame_index)
+                if self.graph["fused"]:                    # the optimiser ran inside the graph
+                    self.store.version += 1
+                    self.store.shadow_version = self.store.version
+                    self.global_step += 1
+                    return loss
                 return self._optimizer_step(ctx, bool(self.flat.factored), loss)
             except Exception as e:                         # noqa: BLE001
                 if captured or self.world > 1:
@@ -453,13 +509,29 @@ class Trainer:
             self.reducer.wait()
         return self._optimizer_step(ctx, factored, loss)
 
+    def _lr_t(self) -> float:
+        """TF Adam's bias-corrected step size for the step about to be applied (train.py:321-336)."""
+        t = self.global_step + 1
+        return self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+
+    def _captured_optimizer(self, ctx):
+        """Optimiser tail of the fused single-tower graph: clip + Adam of everything except hidden1_weights (whose update
+        forked after the head of the backward), then the join with that branch and the two odd operand layouts."""
+        f = self.flat
+        ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=0.0, scratch=f.scratch,
+                           shadow=f.shadow, lr_dev=self.lr_dev)
+        join = ctx.pop("_opt_join", None)
+        if join is not None:
+            torch.cuda.current_stream().wait_event(join)
+        self.engine.refresh_small_shadows()
+
     def _optimizer_step(self, ctx, factored, loss):
         eng = self.engine
         f = self.flat
-        t = self.global_step + 1
-        lr_t = self.learning_rate() * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        lr_t = self._lr_t()
         if factored != bool(f.factored):
             raise RuntimeError("the tower batch size changed across the factored-update limit after the first step")
+        ops.step_begin(f.scratch[3], f.scratch[4])       # a skip flag raised by the previous step is counted and cleared
         # norm first: it may raise the skip flag
         if self.use_shard:
             _, dact16, inv = ctx["hidden_factors"]
@@ -477,14 +549,22 @@ class Trainer:
         self.global_step += 1
         return loss
 
+    def skipped_steps(self) -> int:
+        """Optimiser steps dropped so far because a gradient norm was not finite (fp16 activation-gradient overflow).
+        The flag is cleared on the device at the start of every step, so one overflow skips exactly one update of the
+        tensors that follow it; hidden1_weights (its own clip norm, its own stream) and the rest skip independently.
+        global_step counts attempted steps, as a TF run would (the reference has no skip logic).  Host sync."""
+        if self.flat is None:
+            return 0
+        return int(self.flat.scratch[4].item()) + int(self.flat.scratch[3].item())
+
+    _seen_skips = 0
+
     def overflowed(self) -> bool:
         """True if any step since the last call saw a non-finite gradient norm (host sync)."""
-        if self.flat is None:
-            return False
-        flag = self.flat.scratch[3]
-        r = bool(int(flag.item()))
-        if r:
-            flag.zero_()
+        n = self.skipped_steps()
+        r = n > self._seen_skips
+        self._seen_skips = n
         return r
 
     def sync_parameters(self):

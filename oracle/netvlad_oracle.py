@@ -48,6 +48,32 @@ LN_EPS = 1e-12       # tf.contrib.layers.layer_norm variance_epsilon
 L2N_EPS = 1e-12      # tf.nn.l2_normalize epsilon
 XENT_EPS = 10e-6     # losses.py:46
 
+# Precision study only (tests/test_trained_parity_gpu.py, DESIGN.md "Numerics"): when set to "tf32" / "fp16" / "bf16"
+# every matrix product of the NetVladV1 path rounds its two operands to that format first (fp32 accumulation), which
+# is what a tensor-core run of the reference does (TF32 is TensorFlow's default matmul mode on Ampere and later).
+# None (the default, and the only mode parity is asserted against) = plain fp32 / fp64 products.
+OPERAND_ROUND = None
+
+
+def _round_operand(x: torch.Tensor) -> torch.Tensor:
+    if OPERAND_ROUND is None:
+        return x
+    if OPERAND_ROUND == "fp16":
+        return x.half().to(x.dtype)
+    if OPERAND_ROUND == "bf16":
+        return x.bfloat16().to(x.dtype)
+    if OPERAND_ROUND == "tf32":      # 10 explicit mantissa bits, round to nearest (ties away: cvt.rna.tf32.f32)
+        bits = x.detach().float().contiguous().view(torch.int32)
+        return ((bits + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
+    raise ValueError(OPERAND_ROUND)
+
+
+def mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tf.matmul (fp32 on the reference's CPU path); see OPERAND_ROUND."""
+    if OPERAND_ROUND is None:
+        return a @ b
+    return _round_operand(a) @ _round_operand(b)
+
 
 # --------------------------------------------------------------------------- #
 # TF library semantics
@@ -95,7 +121,7 @@ def layer_norm_joint(x, P, scope):
 
 def dense(x, P, scope, bias=True, relu=False):
     """tf.layers.dense: kernel [in, out] applied to the last axis."""
-    y = x @ P[scope + "/kernel"]
+    y = mm(x, P[scope + "/kernel"])
     if bias:
         y = y + P[scope + "/bias"]
     return torch.relu(y) if relu else y
@@ -153,7 +179,7 @@ def netvlad_forward(x, P, S, scope, max_frames, add_batch_norm, is_training, ret
     """x: [(B*T), D] -> [B, D*K] (d-major flatten)."""
     Wc = P[scope + "/cluster_weights"]                              # [D, K]
     D, K = Wc.shape
-    act = x @ Wc                                                    # :2781
+    act = mm(x, Wc)                                                 # :2781
     if add_batch_norm:
         act = batch_norm(act, P, S, scope + "/cluster_bn", is_training)   # :2783-2789
     else:
@@ -163,7 +189,7 @@ def netvlad_forward(x, P, S, scope, max_frames, add_batch_norm, is_training, ret
     a_sum = act.sum(dim=-2, keepdim=True)                           # :2803  [B,1,K]
     a = a_sum * P[scope + "/cluster_weights2"]                      # :2805-2810  [B,D,K]
     xr = x.reshape(-1, max_frames, D)
-    vlad = torch.matmul(act.transpose(1, 2), xr)                    # :2812-2815  [B,K,D]
+    vlad = mm(act.transpose(1, 2), xr)                              # :2812-2815  [B,K,D]
     vlad = vlad.transpose(1, 2) - a                                 # :2816-2817  [B,D,K]
     vlad = l2_normalize(vlad, 1)                                    # :2819 intra-norm over D
     vlad = vlad.reshape(-1, K * D)                                  # :2821 d-major flatten
@@ -246,8 +272,8 @@ def multi_head_attention(x, P, scope, num_heads):
     v = dense(x, P, scope + "/v", bias=False)
     q, k, v = _split_heads(q, num_heads), _split_heads(k, num_heads), _split_heads(v, num_heads)
     q = q * (hidden // num_heads) ** -0.5
-    w = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
-    out = _combine_heads(w @ v)
+    w = torch.softmax(mm(q, k.transpose(-1, -2)), dim=-1)
+    out = _combine_heads(mm(w, v))
     return dense(out, P, scope + "/output_transform", bias=True)
 
 
@@ -320,8 +346,8 @@ def netvlad_atten_cluster_forward(x, P, S, scope, max_frames, is_training, dropo
 # video_level_models.py:48-159  MoeModel (low_rank_gating=-1, prob gating off)
 # --------------------------------------------------------------------------- #
 def moe_forward(act, P, vocab_size, num_mixtures):
-    gate = act @ P["gates/weights"]                                 # no bias (:86-92)
-    expert = act @ P["experts/weights"] + P["experts/biases"]       # :109-114
+    gate = mm(act, P["gates/weights"])                              # no bias (:86-92)
+    expert = mm(act, P["experts/weights"]) + P["experts/biases"]     # :109-114
     gating = torch.softmax(gate.reshape(-1, num_mixtures + 1), dim=-1)
     experts = torch.sigmoid(expert.reshape(-1, num_mixtures))
     prob = (gating[:, :num_mixtures] * experts).sum(dim=1)
@@ -333,7 +359,7 @@ def moe_forward(act, P, vocab_size, num_mixtures):
 # --------------------------------------------------------------------------- #
 def head_forward(vlad, P, S, vocab_size, is_training, num_mixtures=2, gating=True,
                  remove_diag=False, return_intermediates=False, relu=False):
-    act = vlad @ P["hidden1_weights"]                               # :2319
+    act = mm(vlad, P["hidden1_weights"])                            # :2319
     if relu:                                                        # `add_batch_norm and relu` (:2321-2327)
         act = batch_norm(act, P, S, "hidden1_bn", is_training)
         act = torch.clamp(act, 0.0, 6.0)                            # tf.nn.relu6 (:2339-2340)
@@ -342,7 +368,7 @@ def head_forward(vlad, P, S, vocab_size, is_training, num_mixtures=2, gating=Tru
     hidden = act
     if gating:
         Wg = P["gating_weights_2"]
-        gates = act @ Wg                                            # :2347
+        gates = mm(act, Wg)                                         # :2347
         if remove_diag:
             gates = gates - torch.diagonal(Wg) * act                # :2349-2352
         gates = batch_norm(gates, P, S, "gating_bn", is_training)   # :2354-2360

@@ -148,6 +148,8 @@ def test_store_round_trip_with_tower_scope(tmp_path):
     names = ck.list_tf_checkpoint(prefix)
     assert "tower/video_VLAD/cluster_weights2" in names and names["tower/video_VLAD/cluster_weights2"]["shape"] == [1, 64, 8]
     assert "tower/audio_attention/filter_outputencode2/kernel" in names and "tower/gates/weights" in names
+    # the reference's Saver(tf.global_variables()) needs global_step: always present, int32 (train.py:228, eval.py:131)
+    assert names["global_step"]["shape"] == [] and ck.read_tf_checkpoint(prefix)["global_step"].dtype == np.int32
     b = variables.VariableStore("cpu", seed=2)
     for k, v in a.vars.items():
         b.vars[k] = torch.zeros_like(v)
@@ -182,3 +184,4 @@ def test_command_line_round_trip(tmp_path, capsys):
     assert set(got) == {"input_bn/gamma", "video_VLAD/cluster_weights"}  # slots / global_step dropped by default
     assert torch.equal(got["video_VLAD/cluster_weights"], sd["video_VLAD/cluster_weights"])
     assert ck._main(["to-torch", prefix, back, "--keep-slots"]) == 0 and int(torch.load(back)["global_step"]) == 12
+    assert ck.read_tf_checkpoint(prefix)["global_step"].dtype == np.int32

@@ -390,6 +390,44 @@ def test_rank_adam_step(cuda, R, Kd, N):
     assert torch.equal(before, wd)
 
 
+@pytest.mark.parametrize("R,Kd,N", [(80, 4096 + 128, 512), (4, 384, 64), (20, 136, 96), (96, 256, 512)])
+def test_rank_adam_tiled_equals_persistent(cuda, R, Kd, N):
+    """The small-CTA kernel that runs under the backward (lpm_rank_adam_step_ex, tiled=1, step size from device memory)
+    must produce bit-identical w / m / v / fp16 shadow to the persistent kernel."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(R * 7 + Kd + N)
+    A = torch.randn(R, Kd, generator=g).half().to(cuda)
+    G = (torch.randn(R, N, generator=g) * 3).half().to(cuda)
+    w0 = (torch.randn(Kd, N, generator=g) * 0.05).to(cuda)
+    m0, v0 = (torch.randn(Kd, N, generator=g) * 1e-3).to(cuda), (torch.rand(Kd, N, generator=g) * 1e-5).to(cuda)
+    factor = torch.full((1,), 0.37, device=cuda)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda)
+    lr = 3e-4
+    outs = []
+    for tiled in (False, True):
+        w, m, v = w0.clone(), m0.clone(), v0.clone()
+        w16 = torch.zeros(Kd, N, dtype=torch.float16, device=cuda)
+        kw = dict(lr_dev=torch.full((1,), lr, device=cuda), tiled=True,
+                  workspace=torch.empty(ops.rank_adam_workspace_bytes(R, N), dtype=torch.uint8, device=cuda)) if tiled else dict(lr_t=lr)
+        for _ in range(2):
+            ops.rank_adam_step(A, G, 1.0 / 64, factor, flag, w, m, v, w16, **kw)
+        outs.append((w, m, v, w16))
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[0][0], w0)
+
+
+def test_step_begin_latches_overflow_flag(cuda):
+    """lpm_step_begin: a raised skip flag is counted once and cleared, so one overflow skips exactly one update."""
+    from learnablepoolingmethods_b200 import ops
+    flag = torch.ones(1, dtype=torch.int32, device=cuda)
+    skipped = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.step_begin(flag, skipped)
+    ops.step_begin(flag, skipped)
+    assert int(flag) == 0 and int(skipped) == 1
+
+
 def test_eval_metrics_against_reference_golden(cuda):
     """lpm_eval_topk / lpm_eval_metrics against the frozen outputs of the reference's own
     eval_util.py (tests/golden/eval_golden.npz) and the numpy oracle: top-20 class sets identical, hit@1 / PERR exact to
