@@ -98,6 +98,19 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture of the same call (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when
+    no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel_key)
+    if not d:
+        return None, None
+    return float(d["dram_bytes_per_launch"]), d.get("source")
+
+
 def time_cuda(fn, iters, warmup=3):
     for _ in range(warmup):
         fn()
@@ -111,9 +124,11 @@ def time_cuda(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
-def cpu_reference(steps, warmup, sample_batch=8, train=True, model="NetVladV1"):
+def cpu_reference(steps, warmup, sample_batch=None, train=True, model="NetVladV1", budget_s=240.0):
     """The CPU oracle (torch-CPU port of the TF reference) on all host cores; one step = a train step on
-    `sample_batch` videos of the config-1 shape (a bounded sample of the 80-video tower batch)."""
+    `sample_batch` videos of the config-1 shape (default: the whole tower batch).  The first warm-up step is timed and
+    the number of timed steps is cut (never below 3) so that the whole leg stays inside `budget_s` seconds."""
+    sample_batch = sample_batch or CFG["batch"]
     from oracle import netvlad_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     sp = O.param_specs(model, iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
@@ -132,13 +147,23 @@ def cpu_reference(steps, warmup, sample_batch=8, train=True, model="NetVladV1"):
     else:
         fn = lambda xx, Pp, Ss: getattr(O, {"NetVladV1": "netvlad_v1", "NetVladV2": "netvlad_v2"}[model])(xx[0], xx[1], Pp, Ss, **kw)
     times = []
-    for i in range(warmup + steps):
+    warmup = max(1, warmup)
+    i = 0
+    while i < warmup + steps:
         t0 = time.perf_counter()
         O.train_step(fn, P, S, opt, [(x, nf)], [labels.bool()], step=i + 1, lr=2e-4, extra_reg=extra)
+        dt = time.perf_counter() - t0
+        if i == 0:
+            fit = int(budget_s / max(dt, 1e-3))
+            if warmup + steps > fit:                              # bounded: drop warm-up first, then timed steps
+                warmup = 1
+                steps = max(3, min(steps, fit - 1))
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        i += 1
     sec = sorted(times)[len(times) // 2]                       # median step
-    return sample_batch / sec, sec, torch.get_num_threads(), f"train step on {sample_batch} of 80 videos, {steps} timed steps (median)"
+    return (sample_batch / sec, sec, torch.get_num_threads(),
+            f"train step on {sample_batch} of {CFG['batch']} videos, {len(times)} timed steps (median), {warmup} warm-up", len(times), warmup)
 
 
 def main():
@@ -151,6 +176,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-registry-e2e", action="store_true", help="skip the create_model + CrossEntropyLoss + backward() timing")
+    ap.add_argument("--cpu-sample-batch", type=int, default=0, help="videos per CPU-oracle step (0 = the whole tower batch)")
     ap.add_argument("--model", default="NetVladV1", choices=["NetVladV1", "NetVladV2", "WillowModelReg"])
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: model_input = the reader's uint8 codes (dequantise + L2-normalise fused into the gather kernels); "
@@ -174,9 +201,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        v, sec, cores, sample = cpu_reference(steps, min(args.warmup, 1), model=args.model)
-        out = dict(base, impl="reference", value=v, ms_per_step=sec * 1e3, steps=steps, warmup=min(args.warmup, 1),
+        CFG["batch"] = args.batch
+        v, sec, cores, sample, steps, wu = cpu_reference(args.steps, args.warmup, sample_batch=args.cpu_sample_batch or None,
+                                                        model=args.model)
+        base["config"]["cpu_sample_batch"] = args.cpu_sample_batch or args.batch
+        base["config"]["parallelism"] = f"host cores x{cores} (rank 0 only)"
+        out = dict(base, impl="reference", value=v, ms_per_step=sec * 1e3, steps=steps, warmup=wu,
                    dtype="f32", n_gpus=args.gpus,
                    cpu_baseline={"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample},
                    e2e={"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,7 +277,8 @@ def main():
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_loop(n):
+    def e2e_loop(n, step_fn=None):
+        step_fn = step_fn or tr.train_step
         stage(0)
         for i in range(n):
             torch.cuda.current_stream().wait_event(ready[i % 2])
@@ -256,7 +287,7 @@ def main():
                     copy_stream.wait_event(consumed[(i + 1) % 2])
                 stage(i + 1)
             bx, bn, bl = bufs[i % 2]
-            ls = tr.train_step(bx, bn, bl)
+            ls = step_fn(bx, bn, bl)
             consumed[i % 2].record()
             loss_host.copy_(ls, non_blocking=True)
         torch.cuda.synchronize()
@@ -271,6 +302,47 @@ def main():
     e2e_ms = reduce_max(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident and end-to-end)
     h2d = xh.numel() * xh.element_size() + nfh.numel() * 4 + lh.numel()
+
+    # ---------------- the same, through the reference-facing registry entry (the drop-in boundary) ----------------
+    # find_class_by_name -> create_model(model_input, vocab_size, num_frames, ..., is_training=True)["predictions"]
+    # -> CrossEntropyLoss().calculate_loss -> loss.backward() (autograd.NetVladFunction: the hand-written CUDA backward)
+    # -> Trainer.apply_gradients (clip_gradient_norms + Adam, train.py:321-336).  Dense path: the 554 MB gradient of
+    # hidden1_weights is materialised, so this is slower than Trainer.train_step; it is what a caller of the reference's
+    # own loop structure gets.
+    reg_ms, reg_err = None, None
+    if world == 1 and not args.no_registry_e2e:
+        try:
+            from learnablepoolingmethods_b200 import frame_level_models, losses
+            from learnablepoolingmethods_b200.utils import find_class_by_name
+            store2 = variables.VariableStore(dev, seed=1810)
+            model = find_class_by_name(args.model, [frame_level_models])()
+            loss_fn = losses.CrossEntropyLoss()
+            kw = dict(vocab_size=CFG["vocab"], iterations=CFG["iterations"], cluster_size=CFG["cluster_size"],
+                      hidden_size=CFG["hidden_size"], is_training=True, store=store2)
+            reg = {"tr": None}
+
+            def registry_step(bx, bn, bl):
+                res = model.create_model(bx, num_frames=bn, **kw)
+                ls = loss_fn.calculate_loss(res["predictions"], bl)
+                ls.backward()
+                if reg["tr"] is None:
+                    reg["tr"] = Trainer(next(iter(store2._engines.values())), base_learning_rate=2e-4, learning_rate_decay=0.85,
+                                        batch_size=B)
+                reg["tr"].apply_gradients()
+                return ls.detach()
+
+            e2e_loop(3, registry_step)
+            barrier()
+            e0.record()
+            e2e_loop(args.steps, registry_step)
+            e1.record()
+            barrier()
+            reg_ms = e0.elapsed_time(e1) / args.steps
+            del store2, reg
+            torch.cuda.empty_cache()
+        except Exception as e:                                     # reported, never fatal for the headline numbers
+            reg_err = repr(e)
+            print(f"registry end-to-end path failed: {e!r}", file=sys.stderr)
 
     # ---------------- inference: forward only (is_training=False) ----------------
     with torch.no_grad():
@@ -296,6 +368,7 @@ def main():
         o = torch.empty(M, N, dtype=torch.float16, device=dev)
         g_ms = time_cuda(lambda: ops.gemm(a, w, out=o), 20)
         g_tf = 2.0 * M * N * K / g_ms / 1e9
+        g_traffic, g_traffic_src = ncu_traffic("gemm_f16_ffn_20480x4096x1024")
         # north-star kernel: fused NetVLAD pooling (rgb), 4*T*D*K FLOPs per video
         T, D, Kc = CFG["iterations"], 1024, 256
         xb = torch.randn(B * T, D, device=dev).half()
@@ -314,12 +387,17 @@ def main():
                    infer_graph_ms_per_step=graph_ms,
                    e2e={"value": B * world / (e2e_ms / 1e3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+                   e2e_registry=({"value": B / (reg_ms / 1e3), "unit": "videos/s", "ms_per_step": reg_ms,
+                                  "path": "create_model + CrossEntropyLoss + loss.backward() + Trainer.apply_gradients (dense gradients)",
+                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4} if reg_ms else {"unavailable": reg_err}),
                    gpu_launches=int(launches), clocks=clocks, loss=float(loss), loss_scale_overflow=bool(overflow),
+                   skipped_steps=int(tr.skipped_steps()),
                    roofline={"kernel": "gemm_f16_kernel<256,6,0,1,TWO=1> (tcgen05.mma.cta_group::2, FFN 20480x4096x1024 call)", "bound": "tensor",
-                             "achieved": g_tf, "peak": sustained, "unit": "TFLOP/s", "frac": g_tf / sustained,
-                             "traffic": 225.4e6, "traffic_unit": "bytes per launch (dram read 88.3 MB + write 137.1 MB, ncu --set full, "
-                             "profiles/r1j_ncu_summary.md; algorithmic 218 MB)",
-                             "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)"},
+                             "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst,
+                             "frac_of_sustained_peak": g_tf / sustained,
+                             "traffic": g_traffic, "traffic_source": g_traffic_src,
+                             "algorithmic_bytes": 2.0 * (M * K + K * N + M * N),
+                             "peak_source": f"{src} bf16 burst (the kernel is timed alone: 20 back-to-back launches, ~3 ms)"},
                    roofline_pool={"kernel": "netvlad_pool_fwd_kernel<256> (rgb, fused)", "bound": "tensor",
                                   "achieved": p_tf, "peak": burst, "unit": "TFLOP/s", "frac": p_tf / burst,
                                   "frac_of_occupied_sms": p_tf / burst * 148.0 / min(148, B),
@@ -327,7 +405,7 @@ def main():
                                   "note": "B=80 fills 80 of 148 SMs (one CTA per video); full-wave figure at B=1184",
                                   "peak_source": f"{src} bf16 burst (kernel timed alone)"})
         if args.gpus == 1 and not args.no_cpu_baseline:
-            v, sec, cores, sample = cpu_reference(3, 1, model=args.model)
+            v, sec, cores, sample, _, _ = cpu_reference(3, 1, sample_batch=args.cpu_sample_batch or None, model=args.model, budget_s=40.0)
             out["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:

@@ -215,6 +215,10 @@ int lpm_transpose_f32_dual(const float* src, int rows, int cols, float* dst32, v
 /* losses.py:44-51: dpred = -(y/(p+1e-5) - (1-y)/(1-p+1e-5)) * gscale  (gscale = upstream/B). */
 int lpm_xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred,
                  lpm_stream_t stream);
+/* Same with the upstream gradient of the loss read from device memory: gscale_effective = gscale * upstream_dev[0]
+ * (the autograd edge `loss.backward()` hands dLoss over as a device scalar; no host round trip). */
+int lpm_xent_bwd_dev(const float* pred, const uint8_t* labels, long long n, float gscale, const float* upstream_dev,
+                     float* dpred, lpm_stream_t stream);
 /* video_level_models.py:116-126: dlogits fp16 [B][ldo] (x loss_scale), padding columns zeroed. */
 int lpm_moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
                     float loss_scale, void* dlogits_f16, long long ldo, int ncols, lpm_stream_t stream);

@@ -264,7 +264,13 @@ int lpm_xent_bwd(const float* pred, const uint8_t* labels, long long n, float gs
                  lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(pred && labels && dpred && n > 0, "lpm_xent_bwd: bad arguments");
-  return xent_bwd(pred, labels, n, gscale, dpred, ST(stream));
+  return xent_bwd(pred, labels, n, gscale, nullptr, dpred, ST(stream));
+}
+int lpm_xent_bwd_dev(const float* pred, const uint8_t* labels, long long n, float gscale, const float* upstream_dev,
+                     float* dpred, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(pred && labels && dpred && upstream_dev && n > 0, "lpm_xent_bwd_dev: bad arguments");
+  return xent_bwd(pred, labels, n, gscale, upstream_dev, dpred, ST(stream));
 }
 int lpm_moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
                     float loss_scale, void* dlogits_f16, long long ldo, int ncols, lpm_stream_t stream) {

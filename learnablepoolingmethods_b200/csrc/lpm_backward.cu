@@ -19,7 +19,8 @@ static inline int grid_for_b(long long n, int threads, int per_sm = 8) {
 // losses.py:44-51 backward: dL/dpred = -(y/(p+eps) - (1-y)/(1-p+eps)) * gscale   (gscale = dL/B)
 // ------------------------------------------------------------------------------------------------
 __global__ void xent_bwd_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ labels, long long n,
-                                float gscale, float* __restrict__ dpred) {
+                                float gscale, const float* __restrict__ upstream, float* __restrict__ dpred) {
+  if (upstream != nullptr) gscale *= *upstream;     // dLoss of the autograd edge, left on the device (no host sync)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float p = pred[i];
     dpred[i] = labels[i] ? -gscale / (p + 1e-5f) : gscale / (1.f - p + 1e-5f);
@@ -569,8 +570,9 @@ __global__ void cast_scaled_kernel(const float* __restrict__ x, long long n, flo
 // ----------------------------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------------------------
-int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred, cudaStream_t st) {
-  xent_bwd_kernel<<<grid_for_b(n, 256), 256, 0, st>>>(pred, labels, n, gscale, dpred);
+int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, const float* upstream, float* dpred,
+             cudaStream_t st) {
+  xent_bwd_kernel<<<grid_for_b(n, 256), 256, 0, st>>>(pred, labels, n, gscale, upstream, dpred);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -55,7 +55,8 @@ int mha_bwd_bn(int mode, const __half* qkv, long long ld, const __half* o, const
                __half* dqkv, long long ldd, cudaStream_t st);
 
 // lpm_backward.cu
-int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, float* dpred, cudaStream_t st);
+int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, const float* upstream, float* dpred,
+             cudaStream_t st);
 int moe_mix_bwd(const float* logits, long long ld, int B, int V, int M, int expert_off, const float* dpred,
                 float loss_scale, __half* dl, long long ldo, int ncols, cudaStream_t st);
 int colsum_chunks(long long rows);

@@ -361,12 +361,17 @@ class NetVladEngine:
                                                         save_assign=save)
         if want_inter:
             ctx["inter"]["vlad_" + name] = ops.netvlad_finalize(z, rscale, d_major=True)
-        if c.d5_raw_reshape:
-            raise NotImplementedError("d5_raw_reshape: the raw-reshape alternative of SURVEY D5 is not wired yet")
         # ---- a9: attention block over the K cluster descriptors (rows = (b,k), cols = d) -------
         Z2 = z.view(B * K, D)
         rs = rscale.view(B * K)
-        if save:
+        if c.d5_raw_reshape:
+            # literal reading of frame_level_models.py:2290-2292 (SURVEY defect D5): the normalised, d-major flattened
+            # descriptor [B, D*K] is re-interpreted as [B, K, D] without a transpose
+            zn = torch.empty((B * K, D), dtype=torch.float16, device=z.device)
+            ops.netvlad_finalize_f16(z, rscale, zn.view(B, K * D), K * D)
+            qkv = ops.gemm(zn, sh[a + "/wqkv16"])
+            resid, resid_rs = zn, None
+        elif save:
             # training keeps the normalised descriptor as a GEMM operand for the weight gradients
             zn = ops.scale_rows_f16(Z2, rs)
             qkv = ops.gemm(zn, sh[a + "/wqkv16"])
@@ -816,6 +821,8 @@ class NetVladEngine:
         dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
         # ---- NetVLAD normalisation + aggregation + soft-assignment ------------------------------
         ct = sh[vs + "/centers_t"]
+        if c.d5_raw_reshape:     # the block's input was the d-major flattened descriptor: its gradient is d-major too
+            dzn = ops.dmajor_to_kmajor_f16(dzn.view(B, K * D), B, K, D)
         dz, q = ops.netvlad_norm_bwd(m["z"], m["rscale"], dzn.view(B, K, D), ct)
         X = m["X"]                                                            # [B*T, D] view, row stride = feature size
         wc16 = sh[vs + "/wc16"]

@@ -23,8 +23,8 @@ class _XentFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         pred, labels = ctx.saved_tensors
-        # dloss is a device scalar; the kernel takes the scale as a host float (one tiny sync, training API only)
-        return ops.xent_bwd(pred, labels, float(dloss) / pred.shape[0]), None
+        # dloss stays on the device: the kernel multiplies it into the 1/B scale itself (no host sync)
+        return ops.xent_bwd(pred, labels, 1.0 / pred.shape[0], upstream=dloss.detach().float().reshape(1)), None
 
 
 class CrossEntropyLoss(BaseLoss):

@@ -419,9 +419,15 @@ def _ll(v):
     return C.c_longlong(int(v))
 
 
-def xent_bwd(pred, labels_u8, gscale):
+def xent_bwd(pred, labels_u8, gscale, upstream=None):
+    """dLoss/dpred; `upstream` (optional fp32 device scalar) multiplies gscale on the device."""
     lib = _lib.load()
     dpred = torch.empty_like(pred)
+    if upstream is not None:
+        assert upstream.dtype == torch.float32 and upstream.numel() == 1 and upstream.is_cuda
+        check(lib.lpm_xent_bwd_dev(ptr(pred), ptr(labels_u8), _ll(pred.numel()), C.c_float(gscale), ptr(upstream), ptr(dpred),
+                                   stream_ptr()), "lpm_xent_bwd")
+        return dpred
     check(lib.lpm_xent_bwd(ptr(pred), ptr(labels_u8), _ll(pred.numel()), C.c_float(gscale), ptr(dpred), stream_ptr()),
           "lpm_xent_bwd")
     return dpred

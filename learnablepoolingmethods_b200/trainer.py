@@ -549,6 +549,38 @@ class Trainer:
         self.global_step += 1
         return loss
 
+    def apply_gradients(self, grads: Optional[Dict[str, torch.Tensor]] = None):
+        """Optimiser half of the reference loop (train.py:321-336: clip_gradient_norms + apply_gradients) for callers that
+        own the autograd edge themselves -- `create_model(..., is_training=True)` + `CrossEntropyLoss` + `loss.backward()`
+        (autograd.NetVladFunction).  grads: {variable name: fp32 gradient}; default: the variables' `.grad` (consumed and
+        reset).  Dense path: every gradient, hidden1_weights included, goes through the flat multi-tensor clip + Adam."""
+        if self.world > 1:
+            raise NotImplementedError("apply_gradients is the single-tower registry path; data parallel runs use train_step")
+        tr = self.store.trainable()
+        if self.flat is None:
+            if grads is None:
+                grads = {n: tr[n].grad for n in tr if tr[n].grad is not None}
+            with torch.no_grad():     # the variables may carry requires_grad from the autograd edge
+                self.flat = FlatState(self.store, list(tr.keys()), self._wd(), factored=())
+                self.flat.bind_shadows(self.engine)
+        elif self.flat.factored:
+            raise RuntimeError("this Trainer already runs the factored train_step path; use a separate Trainer")
+        f = self.flat
+        for n, view in f.grad_views.items():
+            g = grads[n] if grads is not None else tr[n].grad
+            if g is None:
+                raise KeyError(f"no gradient for {n}")
+            view.copy_(g.reshape(view.shape))
+            if grads is None:
+                tr[n].grad = None
+        ops.step_begin(f.scratch[3], f.scratch[4])
+        ops.adam_clip_step(f.p, f.g, f.m, f.v, f.table, f.chunk_begin, f.wd, clip=self.clip, lr_t=self._lr_t(), scratch=f.scratch,
+                           shadow=f.shadow)
+        self.store.version += 1
+        self.engine.refresh_small_shadows()
+        self.store.shadow_version = self.store.version
+        self.global_step += 1
+
     def skipped_steps(self) -> int:
         """Optimiser steps dropped so far because a gradient norm was not finite (fp16 activation-gradient overflow).
         The flag is cleared on the device at the start of every step, so one overflow skips exactly one update of the

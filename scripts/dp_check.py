@@ -19,7 +19,7 @@ res = {}
 for mode in (True, "gather", False):
     store = variables.VariableStore(dev, seed=11)
     eng = NetVladEngine(NetVladConfig(iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V), store)
-    tr = Trainer(eng, batch_size=B)
+    tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, batch_size=B)
     if mode is not True:
         tr.use_shard = False
     if mode is False:

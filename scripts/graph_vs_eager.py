@@ -17,7 +17,7 @@ for mode in sys.argv[2:] or ["eager", "graph"]:
     if "noaudio" in mode:
         cfg.overlap_audio = False
     eng = NetVladEngine(cfg, store)
-    tr = Trainer(eng, batch_size=C["batch"])
+    tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, batch_size=C["batch"])
     tr.use_graph = mode.startswith("graph")
     losses, grads = [], None
     for i in range(steps):

@@ -11,7 +11,7 @@ for line in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')):
     rows.append((name, line[8], float(line[-1]) / 1000.0))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 starts = [i for i, r in enumerate(rows) if r[0].startswith("sample_stats_kernel")]
-opt = [i for i, r in enumerate(rows) if r[0].startswith(("rank_adam_kernel", "mt_adam_kernel"))]
+opt = [i for i, r in enumerate(rows) if r[0].startswith(("rank_adam_kernel", "rank_adam_tile_kernel", "mt_adam_kernel"))]
 a, b = starts[-1], opt[-1] + 1
 while b < len(rows) and rows[b][0].startswith("transpose_2d_kernel"):      # refresh of the transposed centre shadows
     b += 1

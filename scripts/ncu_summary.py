@@ -1,4 +1,6 @@
-"""Summarise an .ncu-rep (ncu --set full) as a markdown table: one row per captured launch."""
+"""Summarise an .ncu-rep (ncu --set full) as a markdown table: one row per captured launch.
+usage: ncu_summary.py report.ncu-rep [traffic.json key regex]  -- the optional arguments record the mean DRAM bytes per
+launch of the kernels matching `regex` under `key` in the JSON file bench.py reads (profiles/ncu_traffic.json)."""
 import csv, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -28,3 +30,15 @@ for r in rows[2:]:
                 pass
         cells.append(v)
     print("| " + " | ".join(cells) + " |")
+
+if len(sys.argv) > 4:
+    import json, os, re
+    path, key, rx = sys.argv[2], sys.argv[3], re.compile(sys.argv[4])
+    ir, iw, ik, ig = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name"), hdr.index("Grid Size")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+            for r in rows[2:] if rx.search(r[ik] + " " + r[ig])]
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+              "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum, mean over {len(vals)} launches"}
+    json.dump(d, open(path, "w"), indent=1)

@@ -10,7 +10,7 @@ C = bench.CFG
 store = variables.VariableStore(dev, seed=1810)
 model = sys.argv[2] if len(sys.argv) > 2 else "NetVladV1"
 eng = NetVladEngine(NetVladConfig(model=model, iterations=C["iterations"], cluster_size=C["cluster_size"], hidden_size=C["hidden_size"], vocab_size=C["vocab"]), store)
-tr = Trainer(eng, batch_size=C["batch"])
+tr = Trainer(eng, base_learning_rate=2e-4, learning_rate_decay=0.85, batch_size=C["batch"])
 x, nf, lab = bench.synthetic(C["batch"], 20181000, device=dev, codes=True)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 for _ in range(n):

@@ -103,3 +103,51 @@ def test_netvlad_v2_gradients(cuda, B, K, Hd, V, T):
     # gradient, which amplifies the ~1e-3 upstream fp16 error to 2-5 % on the encoder parameters of this random-init
     # configuration (head / cluster_centers stay at 1e-3).
     assert not bad, bad
+
+
+def test_netvlad_v1_d5_raw_reshape(cuda):
+    """SURVEY defect D5 switch: the literal reading of frame_level_models.py:2290-2292 feeds the d-major flattened
+    descriptor [B, D*K], re-interpreted as [B, K, D], to the attention block.  Forward and gradients vs the oracle's
+    `d5_raw_reshape=True`."""
+    from learnablepoolingmethods_b200 import ops, variables
+    from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
+    from oracle import netvlad_oracle as O
+    from tests.helpers import oracle_params as _oracle_params, perturb as _perturb
+    B, K, Hd, V, T = 3, 64, 64, 100, 128
+    store = variables.VariableStore(cuda, seed=11)
+    cfg = NetVladConfig(model="NetVladV1", iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V, gating=False,
+                        d5_raw_reshape=True)
+    eng = NetVladEngine(cfg, store)
+    _perturb(store, seed=5)
+    x, nf, labels = O.synthetic_batch(B, seed=20181002, vocab=V)
+    P, S = _oracle_params(store)
+    with torch.no_grad():
+        ref_inf, inter = O.netvlad_v1(x, nf, P, {k: v.clone() for k, v in S.items()}, vocab_size=V, iterations=T, cluster_size=K,
+                                      is_training=False, gating=False, d5_raw_reshape=True, return_intermediates=True)
+        other = O.netvlad_v1(x, nf, P, {k: v.clone() for k, v in S.items()}, vocab_size=V, iterations=T, cluster_size=K,
+                             is_training=False, gating=False)
+    pred, ctx = eng.forward(x.to(cuda), nf.to(cuda), False, return_intermediates=True)
+    e_att = rel(ctx["inter"]["att_video"], inter["att_video"])
+    e_p = float((pred.cpu() - ref_inf).abs().max())
+    print(f"\n[d5 raw reshape] att rel-L2 {e_att:.2e}, pred max-abs {e_p:.2e} (transpose reading differs by {float((other - ref_inf).abs().max()):.2e})")
+    assert e_att < 3e-3 and e_p < 5e-3
+    assert float((other - ref_inf).abs().max()) > 10 * e_p        # the switch really selects a different computation
+    for p in P.values():
+        p.requires_grad_(True)
+    pred_ref = O.netvlad_v1(x, nf, P, S, vocab_size=V, iterations=T, cluster_size=K, is_training=True, gating=False,
+                            d5_raw_reshape=True)
+    O.cross_entropy_loss(pred_ref, labels).backward()
+    pred, ctx = eng.forward(x.to(cuda), nf.to(cuda), True, save_for_backward=True)
+    lab = labels.to(torch.uint8).to(cuda)
+    grads = eng.backward(ctx, ops.xent_bwd(pred, lab, 1.0 / B))
+    torch.cuda.synchronize()
+    gmax = max(float(p.grad.norm()) for p in P.values() if p.grad is not None)
+    bad = []
+    for name in sorted(P):
+        if name.startswith("gating"):
+            continue
+        e = rel(grads[name].reshape(P[name].shape), P[name].grad)
+        gn = float(P[name].grad.norm())
+        if not (e < (2e-2 if gn > 1e-7 * gmax else 2e-1)):
+            bad.append((name, e, gn))
+    assert not bad, bad

@@ -45,7 +45,7 @@ def test_checkpoint_round_trip_continues_training(cuda, tmp_path):
     ck.write_model_flags(str(tmp_path), ck.model_flags("NetVladV1"))
     ck.save_from_store(a, prefix, trainer=tra)
     names = ck.list_tf_checkpoint(prefix)
-    assert names["global_step"]["dtype"] == 9 and "tower/hidden1_weights/Adam_1" in names and "beta2_power" in names
+    assert names["global_step"]["dtype"] == 3 and "tower/hidden1_weights/Adam_1" in names and "beta2_power" in names
     assert ck.latest_checkpoint(str(tmp_path)) == prefix
     la = step(tra, 2)
 
