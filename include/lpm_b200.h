@@ -270,6 +270,13 @@ int lpm_center_bwd(const void* dV, const void* Z, const float* a_sum, int B, int
 int lpm_input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const float* E, int D, int K,
                       const float* gamma_in, float* dgamma_in, float* dbeta_in, lpm_stream_t stream);
 int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_stream_t stream);
+/* Split-precision operands for the head's products (context gating frame_level_models.py:2347, MoE
+ * video_level_models.py:86-114): x = hi + lo, hi = fp16(x), lo = fp16(x - hi).  A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo is
+ * then one lpm_gemm_f16 over a reduction of 3K:
+ *   along_rows = 0 (activations): src fp32 [rows][cols] -> dst fp16 [rows][3*cols] = [ hi | lo | hi ]
+ *   along_rows = 1 (weights [K][N]): dst rows [0,K) = hi, [K,2K) = hi, [2K,3K) = lo  (dst holds 3*rows rows) */
+int lpm_split_hi_lo_f16(const float* src, long long ld_src, int rows, int cols, void* dst_f16, long long ld_dst,
+                        int along_rows, lpm_stream_t stream);
 /* transformer_utils.py:563-581 backward: dqkv fp16 [B*L][ldd] in the qkv layout; L <= 256. */
 int lpm_mha_core_bwd(const void* qkv, long long ld, const void* o, const void* dout, long long ldo, const float* lse,
                      int B, int L, int Dm, int H, float scale, void* dqkv, long long ldd, lpm_stream_t stream);
@@ -345,8 +352,9 @@ int lpm_rank_adam_step(const void* a16, long long lda, const void* g16, long lon
                        unsigned long long workspace_bytes, lpm_stream_t stream);
 /* lpm_rank_adam_step with two options: lr_t_dev (non-null: the step size is read from device memory, see
  * lpm_adam_clip_step_dev) and tiled (non-zero: the same arithmetic, bit-identical, as 16-row CTAs of 128 threads and
- * 4 KB of shared memory instead of persistent 512-thread CTAs -- meant for a low-priority stream underneath the
- * backward, where the small CTAs co-reside with the GEMM CTAs and fill idle SMs). */
+ * 4 KB of shared memory instead of persistent 512-thread CTAs -- meant for a side stream underneath the
+ * backward, where the small CTAs co-reside with the GEMM CTAs and fill idle SMs; tiled > 1 additionally splits the
+ * N columns over that many CTAs per row block, i.e. shorter-lived CTAs). */
 int lpm_rank_adam_step_ex(const void* a16, long long lda, const void* g16, long long ldg, int R, long long Kd, int N,
                           float alpha, const float* factor, const int* flag, float* w, float* m, float* v, void* w16,
                           long long ldw16, float lr_t, const float* lr_t_dev, int tiled, float b1, float b2, float eps,

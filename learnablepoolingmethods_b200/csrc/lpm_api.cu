@@ -341,6 +341,14 @@ int lpm_input_bn_grad(const float* Wc, const float* dWc, const float* dCt, const
   LPM_REQUIRE(Wc && dWc && dCt && E && gamma_in && dgamma_in && dbeta_in, "lpm_input_bn_grad: null pointer");
   return input_bn_grad(Wc, dWc, dCt, E, D, K, gamma_in, dgamma_in, dbeta_in, ST(stream));
 }
+int lpm_split_hi_lo_f16(const float* src, long long ld_src, int rows, int cols, void* dst, long long ld_dst, int along_rows,
+                        lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_src >= cols, "lpm_split_hi_lo_f16: bad arguments");
+  LPM_REQUIRE(along_rows ? ld_dst >= cols : ld_dst >= 3ll * cols, "lpm_split_hi_lo_f16: destination row stride too small");
+  return split_hi_lo(src, ld_src, rows, cols, H16(dst), ld_dst, along_rows ? 1 : 0, ST(stream));
+}
+
 int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(x && y && n > 0, "lpm_cast_scaled_f16: bad arguments");

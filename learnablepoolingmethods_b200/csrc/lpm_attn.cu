@@ -5,6 +5,8 @@
 // each warp owns 16-query blocks, FA2-style online softmax in registers, mma.sync m16n8k16 fp16
 // with fp32 accumulation (depth-16 heads make one k-step per score tile: the op is exp/LSU bound,
 // not tensor bound, so the legacy warp-level MMA is the right-sized tool here).
+#include <cstdlib>
+
 #include "lpm_common.cuh"
 #include "lpm_kernels.h"
 
@@ -41,7 +43,26 @@ __device__ __forceinline__ void load_head_tile(uint8_t* dst, const __half* src, 
   }
 }
 
-template <int DH>
+// mma with a zero C operand (no accumulator initialisation instructions)
+__device__ __forceinline__ void mma16816_z(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // FMNMX3 (sm_100)
+  return d;
+}
+
+// Forward.  The kernel is bound by the MUFU (one ex2 per score: 335 M at config 1 = 74 us of XU time on 148 SMs), so
+// everything else is kept off the issue slots: logits come out of the MMA with a zero C operand, the softmax scale is
+// folded into the exponent FMA, the row maximum uses 3-input FMNMX, the running maximum is only moved (and O / l
+// rescaled) when it grows by more than 2^8 (fp16 probabilities hold values up to 256 without loss), and the row
+// sums l come from the tensor core -- an extra n-tile of P V against a column of ones -- instead of 32 FADDs.
+// FULL: L is a multiple of 64 (every 64-key step is complete: no tail predicates in the loop).
+template <int DH, bool AFFINE, bool FULL>
 __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__ qkv, long long ld, int L, int Dm,
                                                       int H, float scale_log2, const float* __restrict__ key_scale,
                                                       const float* __restrict__ key_shift, __half* __restrict__ out,
@@ -57,8 +78,7 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
   load_head_tile<DH>(sQ, base, ld, L);
   load_head_tile<DH>(sK, base + Dm, ld, L);
   load_head_tile<DH>(sV, base + 2 * Dm, ld, L);
-  const bool affine = key_scale != nullptr;
-  if (affine)
+  if (AFFINE)
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
       sKs[i] = key_scale[i] * 1.4426950408889634f;
       sKb[i] = key_shift[i] * 1.4426950408889634f;
@@ -68,6 +88,8 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV);
   const int nkb = L / 16;  // 16-key blocks
+  constexpr uint32_t ONES = 0x3C003C00u;   // half2(1, 1): B fragment of the row-sum tile
+  constexpr float LAZY = 8.f;              // log2 of the growth of the maximum that forces a rescale
 
   for (int qb = warp; qb < L / 16; qb += 4) {
     uint32_t qa0, qa1, qa2, qa3;
@@ -75,76 +97,81 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
       const int row = qb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
       ldsm_x4(q_s + tile_off(row, lane >> 4), qa0, qa1, qa2, qa3);
     }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    float o[DH / 8][4];
+    // m0 / m1: reference maxima of rows g and g+8, in the log2 domain for AFFINE, raw logits otherwise
+    float m0 = -INFINITY, m1 = -INFINITY;
+    float o[DH / 8][4], lacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < DH / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
 
     for (int kb0 = 0; kb0 < nkb; kb0 += 4) {  // up to 64 keys per step
-      const int nb = min(4, nkb - kb0);
+      const int nb = FULL ? 4 : min(4, nkb - kb0);
       float s[8][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < nb) {
+        if (FULL || j < nb) {
           uint32_t b0, b1, b2, b3;
           const int key = (kb0 + j) * 16 + (lane & 7) + (lane >> 4) * 8;
           ldsm_x4(k_s + tile_off(key, (lane >> 3) & 1), b0, b1, b2, b3);
-          s[2 * j][0] = s[2 * j][1] = s[2 * j][2] = s[2 * j][3] = 0.f;
-          s[2 * j + 1][0] = s[2 * j + 1][1] = s[2 * j + 1][2] = s[2 * j + 1][3] = 0.f;
-          mma16816(s[2 * j], qa0, qa1, qa2, qa3, b0, b1);
-          mma16816(s[2 * j + 1], qa0, qa1, qa2, qa3, b2, b3);
+          mma16816_z(s[2 * j], qa0, qa1, qa2, qa3, b0, b1);
+          mma16816_z(s[2 * j + 1], qa0, qa1, qa2, qa3, b2, b3);
+        } else {
+          s[2 * j][0] = s[2 * j][1] = s[2 * j][2] = s[2 * j][3] = -INFINITY;
+          s[2 * j + 1][0] = s[2 * j + 1][1] = s[2 * j + 1][2] = s[2 * j + 1][3] = -INFINITY;
         }
       }
-      // scale to log2 domain (+ optional per-key affine), block row max
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (AFFINE) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < 2 * nb) {
-          const int key = kb0 * 16 + j * 8 + (lane & 3) * 2;
-          if (affine) {
-            const float ks0 = sKs[key], ks1 = sKs[key + 1], kb_0 = sKb[key], kb_1 = sKb[key + 1];
-            s[j][0] = s[j][0] * ks0 + kb_0; s[j][1] = s[j][1] * ks1 + kb_1;
-            s[j][2] = s[j][2] * ks0 + kb_0; s[j][3] = s[j][3] * ks1 + kb_1;
-          } else {
-            s[j][0] *= scale_log2; s[j][1] *= scale_log2; s[j][2] *= scale_log2; s[j][3] *= scale_log2;
+        for (int j = 0; j < 8; ++j) {
+          if (FULL || j < 2 * nb) {
+            const int key = kb0 * 16 + j * 8 + (lane & 3) * 2;
+            const float2 ks = *reinterpret_cast<const float2*>(&sKs[key]);
+            const float2 kb = *reinterpret_cast<const float2*>(&sKb[key]);
+            s[j][0] = fmaf(s[j][0], ks.x, kb.x); s[j][1] = fmaf(s[j][1], ks.y, kb.y);
+            s[j][2] = fmaf(s[j][2], ks.x, kb.x); s[j][3] = fmaf(s[j][3], ks.y, kb.y);
           }
-          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
         }
       }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-      const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
-      m0 = mn0; m1 = mn1;
-      l0 *= c0; l1 *= c1;
+      // row maxima of this step (3-input max), then across the quad
+      float mx0 = fmax3(s[0][0], s[0][1], s[1][0]), mx1 = fmax3(s[0][2], s[0][3], s[1][2]);
+      mx0 = fmax3(mx0, s[1][1], s[2][0]); mx1 = fmax3(mx1, s[1][3], s[2][2]);
+      mx0 = fmax3(mx0, s[2][1], s[3][0]); mx1 = fmax3(mx1, s[2][3], s[3][2]);
+      mx0 = fmax3(mx0, s[3][1], s[4][0]); mx1 = fmax3(mx1, s[3][3], s[4][2]);
+      mx0 = fmax3(mx0, s[4][1], s[5][0]); mx1 = fmax3(mx1, s[4][3], s[5][2]);
+      mx0 = fmax3(mx0, s[5][1], s[6][0]); mx1 = fmax3(mx1, s[5][3], s[6][2]);
+      mx0 = fmax3(mx0, s[6][1], s[7][0]); mx1 = fmax3(mx1, s[6][3], s[7][2]);
+      mx0 = fmaxf(mx0, s[7][1]); mx1 = fmaxf(mx1, s[7][3]);
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      // lazy running maximum: move the reference only when it is exceeded by more than 2^LAZY (warp-uniform branch)
+      const float sc = AFFINE ? 1.f : scale_log2;     // raw logits are compared in units of 1/sc
+      const bool grow = (mx0 - m0) * sc > LAZY || (mx1 - m1) * sc > LAZY || m0 == -INFINITY;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = fast_exp2((m0 - mn0) * sc), c1 = fast_exp2((m1 - mn1) * sc);    // first step: 2^-inf = 0 on zeros
+        m0 = mn0; m1 = mn1;
+        lacc[0] *= c0; lacc[1] *= c0; lacc[2] *= c1; lacc[3] *= c1;
 #pragma unroll
-      for (int j = 0; j < DH / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < 2 * nb) {
-          s[j][0] = fast_exp2(s[j][0] - m0); s[j][1] = fast_exp2(s[j][1] - m0);
-          s[j][2] = fast_exp2(s[j][2] - m1); s[j][3] = fast_exp2(s[j][3] - m1);
-          l0 += s[j][0] + s[j][1];
-          l1 += s[j][2] + s[j][3];
-        }
+        for (int j = 0; j < DH / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
       }
-      // O += P V
+      const float nm0 = -m0 * sc, nm1 = -m1 * sc;
+      // P = 2^(s*sc - m*sc) straight into fp16 A fragments; O += P V; l += P 1
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < nb) {
-          const uint32_t a0 = pack_half2(s[2 * j][0], s[2 * j][1]), a1 = pack_half2(s[2 * j][2], s[2 * j][3]);
-          const uint32_t a2 = pack_half2(s[2 * j + 1][0], s[2 * j + 1][1]), a3 = pack_half2(s[2 * j + 1][2], s[2 * j + 1][3]);
+        if (FULL || j < nb) {
+          const uint32_t a0 = pack_half2(fast_exp2(fmaf(s[2 * j][0], sc, nm0)), fast_exp2(fmaf(s[2 * j][1], sc, nm0)));
+          const uint32_t a1 = pack_half2(fast_exp2(fmaf(s[2 * j][2], sc, nm1)), fast_exp2(fmaf(s[2 * j][3], sc, nm1)));
+          const uint32_t a2 = pack_half2(fast_exp2(fmaf(s[2 * j + 1][0], sc, nm0)), fast_exp2(fmaf(s[2 * j + 1][1], sc, nm0)));
+          const uint32_t a3 = pack_half2(fast_exp2(fmaf(s[2 * j + 1][2], sc, nm1)), fast_exp2(fmaf(s[2 * j + 1][3], sc, nm1)));
           uint32_t b0, b1, b2, b3;
           const int key = (kb0 + j) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           ldsm_x4_t(v_s + tile_off(key, lane >> 4), b0, b1, b2, b3);
           mma16816(o[0], a0, a1, a2, a3, b0, b1);
           if (DH == 16) mma16816(o[DH / 8 - 1], a0, a1, a2, a3, b2, b3);
+          mma16816(lacc, a0, a1, a2, a3, ONES, ONES);
         }
       }
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float l0 = lacc[0], l1 = lacc[2];       // every column of the ones tile holds the row sum
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     const int r0 = qb * 16 + (lane >> 2), r1 = r0 + 8;
     __half* o0 = out + ((long long)b * L + r0) * ldo + h * DH + (lane & 3) * 2;
@@ -156,8 +183,9 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
     }
     if (lse != nullptr && (lane & 3) == 0) {
       // natural-log log-sum-exp of the (scaled / affine) logits
-      lse[((long long)b * H + h) * L + r0] = (m0 + log2f(l0)) * 0.6931471805599453f;
-      lse[((long long)b * H + h) * L + r1] = (m1 + log2f(l1)) * 0.6931471805599453f;
+      const float sc = AFFINE ? 1.f : scale_log2;
+      lse[((long long)b * H + h) * L + r0] = (m0 * sc + log2f(l0)) * 0.6931471805599453f;
+      lse[((long long)b * H + h) * L + r1] = (m1 * sc + log2f(l1)) * 0.6931471805599453f;
     }
   }
 }
@@ -168,17 +196,21 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
   LPM_REQUIRE(DH * H == Dm && (DH == 8 || DH == 16), "mha_fwd: head depth must be 8 or 16 (Dm=%d H=%d)", Dm, H);
   LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 1024, "mha_fwd: length must be a multiple of 16 in [16,1024] (got %d)", L);
   LPM_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, "mha_fwd: leading dimensions must be multiples of 8");
+  LPM_REQUIRE(key_scale != nullptr || scale > 0.f, "mha_fwd: the softmax scale must be positive");
+  LPM_REQUIRE((key_scale == nullptr) == (key_shift == nullptr), "mha_fwd: key_scale and key_shift come together");
   const size_t smem = (size_t)L * 96 + (size_t)L * 8;
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (DH == 16) {
-    static bool set16 = false;
-    if (!set16) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); set16 = true; }
-    mha_fwd_kernel<16><<<B * H, 128, smem, st>>>(qkv, ld, L, Dm, H, scale_log2, key_scale, key_shift, out, ldo, lse);
-  } else {
-    static bool set8 = false;
-    if (!set8) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); set8 = true; }
-    mha_fwd_kernel<8><<<B * H, 128, smem, st>>>(qkv, ld, L, Dm, H, scale_log2, key_scale, key_shift, out, ldo, lse);
+#define LPM_MHA_FWD2(DHV, AFF, FUL)                                                                                      \
+  {                                                                                                                      \
+    static bool set = false;                                                                                             \
+    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_kernel<DHV, AFF, FUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); set = true; } \
+    mha_fwd_kernel<DHV, AFF, FUL><<<B * H, 128, smem, st>>>(qkv, ld, L, Dm, H, scale_log2, key_scale, key_shift, out, ldo, lse); \
   }
+#define LPM_MHA_FWD(DHV, AFF) { if (L % 64 == 0) LPM_MHA_FWD2(DHV, AFF, true) else LPM_MHA_FWD2(DHV, AFF, false) }
+  if (DH == 16) { if (key_scale) LPM_MHA_FWD(16, true) else LPM_MHA_FWD(16, false) }
+  else { if (key_scale) LPM_MHA_FWD(8, true) else LPM_MHA_FWD(8, false) }
+#undef LPM_MHA_FWD2
+#undef LPM_MHA_FWD
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
@@ -205,8 +237,10 @@ struct MhaBnArgs {
   float* stat_partial;                              // [B*H][2][L] (MODE 1)
 };
 
-template <int DH, int MODE>
-__global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
+// NT = threads per CTA: 512 (one CTA per SM, the whole dS^T of a 256-query chunk parked) or 256 with query chunks of 128:
+// two CTAs per SM, so that the load prologue and the pass barriers of one head hide under the other head's math.
+template <int DH, int MODE, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
                                                          const __half* __restrict__ o, const __half* __restrict__ dout,
                                                          long long ldo, const float* __restrict__ lse, int L, int Dm,
                                                          int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn,
@@ -297,18 +331,16 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-#pragma unroll
-        for (int n = 0; n < 2; ++n)
-          st[u][n][0] = st[u][n][1] = st[u][n][2] = st[u][n][3] = dp[u][n][0] = dp[u][n][1] = dp[u][n][2] = dp[u][n][3] = 0.f;
-        mma16816(st[u][0], ka0, ka1, ka2, ka3, qf[u][0], qf[u][1]);
-        mma16816(st[u][1], ka0, ka1, ka2, ka3, qf[u][2], qf[u][3]);
-        mma16816(dp[u][0], va0, va1, va2, va3, of[u][0], of[u][1]);
-        mma16816(dp[u][1], va0, va1, va2, va3, of[u][2], of[u][3]);
+        mma16816_z(st[u][0], ka0, ka1, ka2, ka3, qf[u][0], qf[u][1]);
+        mma16816_z(st[u][1], ka0, ka1, ka2, ka3, qf[u][2], qf[u][3]);
+        mma16816_z(dp[u][0], va0, va1, va2, va3, of[u][0], of[u][1]);
+        mma16816_z(dp[u][1], va0, va1, va2, va3, of[u][2], of[u][3]);
       }
       // columns of the transposed tiles are queries: n-tile n -> queries i*16 + n*8 + (lane&3)*2 + {0,1}
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const float live = (u == 0 || two) ? 1.f : 0.f;
+        const bool dead = !(u == 0 || two);     // masked repeat on an odd tail (never taken when the chunk is a multiple of 32)
+        const float live = dead ? 0.f : 1.f;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           const int qc = ib[u] * 16 + n * 8 + (lane & 3) * 2;
@@ -323,7 +355,7 @@ __global__ void __launch_bounds__(512, 1) mha_bwd_kernel(const __half* __restric
             p0 = fast_exp2(st[u][n][0] * ks0 + kb0 - l0); p1 = fast_exp2(st[u][n][1] * ks0 + kb0 - l1);
             p2 = fast_exp2(st[u][n][2] * ks1 + kb1 - l0); p3 = fast_exp2(st[u][n][3] * ks1 + kb1 - l1);
           }
-          p0 *= live; p1 *= live; p2 *= live; p3 *= live;
+          if (dead) { p0 = p1 = p2 = p3 = 0.f; }
           float g0 = p0 * (dp[u][n][0] - d0), g1 = p1 * (dp[u][n][1] - d1), g2 = p2 * (dp[u][n][2] - d0), g3 = p3 * (dp[u][n][3] - d1);
           if (MODE > 0) {
             const float h0 = (st[u][n][0] - mu0) * rs0, h1 = (st[u][n][1] - mu0) * rs0;
@@ -446,19 +478,25 @@ static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __hal
   LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 512, "mha_bwd: length must be a multiple of 16 in [16,512] (got %d)", L);
   LPM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0, "mha_bwd: leading dimensions must be multiples of 8");
   LPM_REQUIRE(mode == 0 || DH == 16, "mha_bwd: batch-normed logits need head depth 16");
-  const int QC = L <= 256 ? L : 128;     // query chunk whose dS^T is parked at a time
+  // query chunk whose dS^T is parked at a time.  L = 256 (the V1 cluster attention at config 1): chunks of 128 and
+  // 256-thread CTAs -> 104 KB of shared memory, two CTAs per SM.  LPM_MHA_BWD_WIDE=1 restores the one-CTA layout.
+  static const bool wide = getenv("LPM_MHA_BWD_WIDE") != nullptr && getenv("LPM_MHA_BWD_WIDE")[0] == '1';
+  const int QC = L < 256 ? L : (L == 256 && wide ? 256 : 128);
+  const int nt = (L > 256 || (L == 256 && wide)) ? 512 : 256;
   const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (mode ? (size_t)L * 24 : 0) + (size_t)L * (QC + 8) * 2;
   LPM_REQUIRE(smem <= 227 * 1024, "mha_bwd: shared memory budget exceeded (L=%d)", L);
-#define LPM_MHA_BWD(DHV, MODEV)                                                                                          \
+#define LPM_MHA_BWD2(DHV, MODEV, NTV)                                                                                    \
   {                                                                                                                      \
     static bool set = false;                                                                                             \
-    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; } \
-    mha_bwd_kernel<DHV, MODEV><<<B * H, (L >= 256 ? 512 : 256), smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn, QC);    \
+    if (!set) { LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_kernel<DHV, MODEV, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; } \
+    mha_bwd_kernel<DHV, MODEV, NTV><<<B * H, NTV, smem, st>>>(qkv, ld, o, dout, ldo, lse, L, Dm, H, scale, dqkv, ldd, bn, QC);    \
   }
+#define LPM_MHA_BWD(DHV, MODEV) { if (nt == 512) LPM_MHA_BWD2(DHV, MODEV, 512) else LPM_MHA_BWD2(DHV, MODEV, 256) }
   if (mode == 0) { if (DH == 16) LPM_MHA_BWD(16, 0) else LPM_MHA_BWD(8, 0) }
   else if (mode == 1) LPM_MHA_BWD(16, 1)
   else LPM_MHA_BWD(16, 2)
 #undef LPM_MHA_BWD
+#undef LPM_MHA_BWD2
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -760,6 +760,42 @@ int scale_rows(const __half* x, const float* rs, long long rows, int D, __half* 
   return LPM_OK;
 }
 
+// Split-precision operands for the head (context gating + MoE; frame_level_models.py:2342-2368, video_level_models.py:86-126):
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi), i.e. ~22 significant bits in two fp16 terms.  The product of two such
+// operands, A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo, is ONE tcgen05 GEMM over a 3x longer reduction:
+//   activations  [rows, cols] fp32 -> [rows, 3*cols] fp16 = [ hi | lo | hi ]             (mode 0: along the columns)
+//   weights      [rows, cols] fp32 -> rows [rows, 2*rows) = hi, [2*rows, 3*rows) = lo     (mode 1: along the rows; rows
+//                [0, rows) of the destination, the plain fp16 copy, are maintained by the optimiser's shadow refresh and
+//                are rewritten here too so that the three blocks are always consistent)
+// These few small products decide the predictions: with fp16 operands their error dominates the sigmoid outputs of a
+// trained model (numerics), with split operands the head is accurate to fp32 level at ~10 us per forward.
+__global__ void __launch_bounds__(256) split_hi_lo_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols,
+                                                          __half* __restrict__ dst, long long ld_dst, int mode) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const float x = src[(long long)r * ld_src + c];
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    if (mode == 0) {
+      __half* d = dst + (long long)r * ld_dst + c;
+      d[0] = hi; d[cols] = lo; d[2 * cols] = hi;
+    } else {
+      __half* d = dst + (long long)r * ld_dst + c;
+      d[0] = hi; d[(long long)rows * ld_dst] = hi; d[2ll * rows * ld_dst] = lo;
+    }
+  }
+}
+
+int split_hi_lo(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int mode, cudaStream_t st) {
+  const long long n = (long long)rows * cols;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_hi_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, mode);
+  LPM_CUDA_CHECK(cudaGetLastError());
+  return LPM_OK;
+}
+
 int transpose_2d(const float* src, int rows, int cols, float* dst, __half* dst16, cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_2d_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst, dst16);

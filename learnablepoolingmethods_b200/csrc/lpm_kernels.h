@@ -40,6 +40,7 @@ int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,
             cudaStream_t st);
 int transpose_2d(const float* src, int rows, int cols, float* dst, __half* dst16, cudaStream_t st);
+int split_hi_lo(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int mode, cudaStream_t st);
 int vlad_finalize(const __half* z, const float* rscale, int B, int K, int D, int d_major, float* out, cudaStream_t st);
 
 // lpm_attn.cu

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(128, 4) rank_adam_tile_kernel(const __half* __
   }
   const float f = alpha * factor[0];
   const long long r_lo = row0 + g;
-  for (int q = warp; q < nq; q += 4) {
+  for (int q = blockIdx.y * 4 + warp; q < nq; q += 4 * gridDim.y) {   // gridDim.y column splits: shorter-lived CTAs
     uint4 pc[12];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -516,8 +516,11 @@ int rank_adam_step(const __half* a16, long long lda, const __half* g16, long lon
     rank_gfrag_kernel<<<((N / 32) * nks * 64 + 255) / 256, 256, 0, st>>>(g16, ldg, R, nks, N, gf);
     const long long nblk = (Kd + 15) / 16;
     LPM_REQUIRE(nblk <= 0x7fffffffLL, "rank_adam_step: too many row blocks");
-#define LPM_RT(NK) case NK: rank_adam_tile_kernel<NK><<<(unsigned)nblk, 128, 0, st>>>(a16, lda, gf, R, Kd, N, alpha, factor, flag, w, m, \
-                                                                                    v, w16, ldw16, lr_t, lr_dev, b1, b2, eps); break;
+    int ysplit = tiled < 1 ? 1 : tiled;
+    if (ysplit > (N / 32 + 3) / 4) ysplit = (N / 32 + 3) / 4;
+    const dim3 tgrid((unsigned)nblk, (unsigned)ysplit);
+#define LPM_RT(NK) case NK: rank_adam_tile_kernel<NK><<<tgrid, 128, 0, st>>>(a16, lda, gf, R, Kd, N, alpha, factor, flag, w, m, \
+                                                                           v, w16, ldw16, lr_t, lr_dev, b1, b2, eps); break;
     switch (nks) { LPM_RT(1) LPM_RT(2) LPM_RT(3) LPM_RT(4) LPM_RT(5) LPM_RT(6) LPM_RT(7) LPM_RT(8) default: break; }
 #undef LPM_RT
     LPM_CUDA_CHECK(cudaGetLastError());

@@ -199,8 +199,18 @@ class NetVladEngine:
         specs.append(("experts/weights", "wmoe16", (c.hidden_size, g8 + e8), g8))
         return specs
 
+    # split-precision operands of the head (gate + MoE products): key -> [3*rows, cols] = [hi ; hi ; lo]; the plain fp16
+    # shadow (used by the backward, refreshed by the optimiser) is the view of the first `rows` rows
+    _SPLIT_SHADOWS = ("wg16", "wmoe16")
+
     def _shadow_buf(self, key, shape, dtype=torch.float16):
         sh = self.store.shadows
+        if key in self._SPLIT_SHADOWS:
+            big = self._shadow_buf(key + "x3", (3 * shape[0], shape[1]), dtype)
+            t = sh.get(key)
+            if t is None or t.data_ptr() != big.data_ptr() or tuple(t.shape) != tuple(shape):
+                sh[key] = big[:shape[0]]
+            return sh[key]
         t = sh.get(key)
         if t is None or tuple(t.shape) != tuple(shape):
             t = torch.zeros(shape, dtype=dtype, device=self.store.device)
@@ -227,6 +237,11 @@ class NetVladEngine:
         bm = self._shadow_buf("bmoe", (g8 + e8,), torch.float32)
         bm[g8:g8 + V * M].copy_(v["experts/biases"])
         sh["moe_g8"] = g8
+        # split-precision weight operands of the gate and MoE products: [hi ; hi ; lo] along the reduction
+        if "wg16x3" in sh and "wmoe16x3" in sh:
+            ops.split_hi_lo(v["gating_weights_2"], sh["wg16x3"], along_rows=True)
+            ops.split_hi_lo(v["gates/weights"], sh["wmoe16x3"], along_rows=True)
+            ops.split_hi_lo(v["experts/weights"], sh["wmoe16x3"][:, g8:], along_rows=True)
 
     def refresh_shadows(self, force=False):
         s = self.store
@@ -582,26 +597,32 @@ class NetVladEngine:
             self.pre_head_hook()    # data parallel: the all-gather of the updated fp16 weight shards lands here
         parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
         act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
-        act16 = torch.empty((B, Hn), dtype=torch.float16, device=vlad.device)
         hpre, hstats = None, None
         if c.netvlad_relu:
             hpre = act32
             ops.splitk_reduce(parts, out32=hpre)
             r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
                                         v["hidden1_bn/moving_variance"], training=training, save=save)
-            act32, act16 = r[0], r[1]
+            act32 = r[0]
             hstats = r[2] if save else None
         else:
-            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=act16)
+            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32)
+        # The gate and MoE products run with split-precision operands (x = hi + lo in two fp16 terms, one GEMM over a 3x
+        # longer reduction, ops.split_hi_lo): `hidden` is O(30) at this model's initialisation scale and feeds sigmoids, so
+        # 10-bit-mantissa operands in these two small products are what limits the predictions (numerics).
+        a3 = ops.split_hi_lo(act32)                                   # [B, 3H] = [hi | lo | hi]
+        act16 = a3[:, :Hn]                                            # plain fp16 view for the backward
         if c.gating:
-            gates = ops.gemm(act16, sh["wg16"], out_dtype=torch.float32)
+            gates = ops.gemm(a3, sh["wg16x3"], out_dtype=torch.float32)
             diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
             r = ops.gating_fwd(act32, gates, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
                                v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save)
-            gated32, gated16 = r[0], r[1]
+            gated32 = r[0]
+            g3 = ops.split_hi_lo(gated32)
         else:
-            gates, gated32, gated16, r = None, act32, act16, (None, None, None)
-        logits = ops.gemm(gated16, sh["wmoe16"], bias=sh["bmoe"], out_dtype=torch.float32)
+            gates, gated32, g3, r = None, act32, a3, (None, None, None)
+        gated16 = g3[:, :Hn]
+        logits = ops.gemm(g3, sh["wmoe16x3"], bias=sh["bmoe"], out_dtype=torch.float32)
         pred = ops.moe_mix_fwd(logits, c.vocab_size, c.num_mixtures, expert_off=sh["moe_g8"])
         if want_inter:
             ctx["inter"].update(hidden=act32, gated=gated32)

@@ -152,6 +152,20 @@ def cast_f16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, cols_dst: Op
     return dst
 
 
+def split_hi_lo(src: torch.Tensor, dst: Optional[torch.Tensor] = None, along_rows: bool = False):
+    """fp32 [rows, cols] -> split-precision fp16 operand: [rows, 3*cols] = [hi | lo | hi] (activations) or, along_rows,
+    the column block `dst` of a [3*rows, .] weight operand = [hi ; hi ; lo]."""
+    lib = _lib.load()
+    rows, cols = src.shape
+    assert src.dtype == torch.float32 and src.stride(1) == 1
+    if dst is None:
+        assert not along_rows
+        dst = torch.empty((rows, 3 * cols), dtype=torch.float16, device=src.device)
+    check(lib.lpm_split_hi_lo_f16(ptr(src), _ll(src.stride(0)), rows, cols, ptr(dst), _ll(dst.stride(0)), int(along_rows),
+                                  stream_ptr()), "lpm_split_hi_lo_f16")
+    return dst
+
+
 def transpose_f32(src: torch.Tensor):
     lib = _lib.load()
     rows, cols = src.shape
@@ -704,7 +718,7 @@ def rank_adam_step(a16, g16, alpha, factor, flag, w, m, v, w16, *, lr_t=0.0, b1=
                    tiled=False, workspace=None):
     """Adam on w [Kd, N] (fp32, with moments m, v) for the never-materialised gradient alpha * a16^T g16.
     lr_dev: fp32 [1] device tensor with the step size (instead of lr_t); tiled: the small-CTA kernel meant for a
-    low-priority stream underneath the backward (same results); workspace: caller-owned scratch (uint8, at least
+    side stream underneath the backward (same results; an int > 1 also splits the columns over that many CTAs); workspace: caller-owned scratch (uint8, at least
     rank_adam_workspace_bytes) -- required when the call runs concurrently with other users of the shared one."""
     lib = _lib.load()
     R, Kd = a16.shape
@@ -716,7 +730,7 @@ def rank_adam_step(a16, g16, alpha, factor, flag, w, m, v, w16, *, lr_t=0.0, b1=
     check(lib.lpm_rank_adam_step_ex(ptr(a16), _ll(a16.stride(0)), ptr(g16), _ll(g16.stride(0)), R, _ll(Kd), N, C.c_float(alpha),
                                     ptr(factor), ptr(flag), ptr(w), ptr(m), ptr(v), ptr(w16),
                                     _ll(w16.stride(0) if w16 is not None else 0), C.c_float(lr_t), ptr(lr_dev),
-                                    1 if tiled else 0, C.c_float(b1), C.c_float(b2), C.c_float(eps), ptr(ws),
+                                    int(tiled), C.c_float(b1), C.c_float(b2), C.c_float(eps), ptr(ws),
                                     C.c_ulonglong(ws_bytes), stream_ptr()), "lpm_rank_adam_step")
 
 

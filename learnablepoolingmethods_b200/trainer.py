@@ -8,6 +8,7 @@ Adam, learning rate decayed on global examples (train.py:244-249).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -104,6 +105,25 @@ def head_gradient_span(flat: "FlatState"):
     return end, all(flat.offsets[n] >= end for n in body)
 
 
+def shard_row_range(n_rows: int, world: int, rank: int):
+    """Rows [r0, r1) of hidden1_weights [n_rows, H] owned by `rank` (equal contiguous shards)."""
+    rows = n_rows // world
+    return rank * rows, (rank + 1) * rows
+
+
+def pack_descriptor_slices(vlad: torch.Tensor, world: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vlad [B, Kd] of this tower -> send buffer [world, B, Kd/world]: slice w holds the descriptor COLUMNS that are the
+    ROWS of hidden1_weights owned by rank w.  After all_to_all_single, recv.view(world*B, Kd/world) on rank r is
+    A_all[:, rows_r] for the towers in rank order -- the left factor of dW[rows_r] = A_all[:, rows_r]^T G_all."""
+    B, Kd = vlad.shape
+    rows = Kd // world
+    src = vlad.view(B, world, rows).transpose(0, 1)
+    if out is None:
+        return src.contiguous()
+    out.copy_(src)
+    return out
+
+
 class ShardedHiddenUpdate:
     """Data-parallel update of hidden1_weights (85 % of the parameters) without moving its gradient or repeating its
     optimiser step on every rank.  Rank r owns rows [r*Kd/W, (r+1)*Kd/W) of W_h [Kd, H]:
@@ -125,7 +145,7 @@ class ShardedHiddenUpdate:
         store, c = trainer.store, trainer.cfg
         Kd, H = c.vlad_dim, c.hidden_size
         self.rows, self.H = Kd // self.world, H
-        r0 = self.rank * self.rows
+        r0, _ = shard_row_range(Kd, self.world, self.rank)
         dev = store.device
         w = store.vars["hidden1_weights"]
         m, v = flat.moment_views["hidden1_weights"]
@@ -160,7 +180,7 @@ class ShardedHiddenUpdate:
             self.send = torch.empty((self.world, B, self.rows), dtype=vlad.dtype, device=vlad.device)
             self.recv = torch.empty_like(self.send)
             self.g_all = torch.empty((self.world * B, self.H), dtype=torch.float16, device=vlad.device)
-        self.send.copy_(vlad.view(B, self.world, self.rows).transpose(0, 1))      # pack (plumbing for the collective)
+        pack_descriptor_slices(vlad, self.world, out=self.send)                    # pack (plumbing for the collective)
         self.h_a2a = self.dist.all_to_all_single(self.recv, self.send, group=self.pg, async_op=True)
 
     def wait_weights(self):
@@ -186,7 +206,7 @@ class ShardedHiddenUpdate:
     def sync_master(self):
         """All-gather the fp32 master rows (and Adam moments) so that every rank holds the full tensors again."""
         self.wait_weights()
-        r0 = self.rank * self.rows
+        r0, _ = shard_row_range(self.rows * self.world, self.world, self.rank)
         for full in (self.w, self.m_full, self.v_full):
             self.dist.all_gather_into_tensor(full, full[r0:r0 + self.rows], group=self.pg)
 
@@ -221,9 +241,9 @@ class Trainer:
         self.graph = None
         self.graph_after = 2           # eager steps before the capture (flat optimiser state, workspaces, attributes)
         # single tower: the optimiser is captured too.  The step size lives in device memory (`lr_dev`, written before each
-        # replay); the hidden1_weights update (85 % of the parameters, HBM-bound) forks onto a LOW-PRIORITY stream right
+        # replay); the hidden1_weights update (85 % of the parameters, HBM-bound) forks onto a second stream right
         # after the head of the backward -- the last reader of its fp16 operand -- and runs underneath the tensor-bound
-        # backward of the modalities as small CTAs that fill idle SMs (ops.rank_adam_step(tiled=True)).
+        # backward of the modalities as small CTAs that share the SMs with it (ops.rank_adam_step(tiled=True)).
         self.lr_dev = None
         self._prio = None              # (capture stream, optimiser stream, fork event, join event)
         self.rank_ws = None
@@ -237,7 +257,13 @@ class Trainer:
                 and ops.rank_adam_supported(batch, c.hidden_size))
 
     on_flat_created = None
-    fuse_optimizer = True          # capture the optimiser inside the single-tower step graph (see __init__)
+    # capture the optimiser inside the single-tower step graph (see __init__).  Measured on B200 at config 1
+    # (profiles/r2_adam_overlap.md): eager optimiser after the graph 3.86 ms; forked at the SAME priority as the backward
+    # 3.76 ms; forked at a lower priority 4.07 ms (its CTAs are starved while multi-wave kernels have blocks pending and
+    # the update ends up exposed at the join); shorter-lived CTAs (LPM_ADAM_SPLIT=2/4) 3.86 / 3.95 ms.  Hence -1 / 1.
+    fuse_optimizer = os.environ.get("LPM_FUSE_OPT", "1") != "0"
+    opt_priority = int(os.environ.get("LPM_OPT_PRIORITY", "-1"))
+    adam_col_splits = int(os.environ.get("LPM_ADAM_SPLIT", "1"))   # column splits of the tiled hidden1 update (CTA lifetime)
     disable_factored_hidden = False
     gather_hidden_factors = True
     shard_hidden_update = True
@@ -253,7 +279,7 @@ class Trainer:
         if self._prio is None:
             dev = self.store.device
             # torch: lower number = higher priority; 0 is the lowest the device offers
-            self._prio = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=0),
+            self._prio = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=self.opt_priority),
                           torch.cuda.Event(), torch.cuda.Event())
         return self._prio
 
@@ -263,7 +289,7 @@ class Trainer:
         fork.record(torch.cuda.current_stream())
         opt.wait_event(fork)
         with torch.cuda.stream(opt):
-            self._factored_hidden_step(ctx, 0.0, lr_dev=self.lr_dev, tiled=True)()
+            self._factored_hidden_step(ctx, 0.0, lr_dev=self.lr_dev, tiled=self.adam_col_splits)()
             join.record(opt)
         ctx["_opt_join"] = join
 

@@ -53,6 +53,7 @@ XENT_EPS = 10e-6     # losses.py:46
 # is what a tensor-core run of the reference does (TF32 is TensorFlow's default matmul mode on Ampere and later).
 # None (the default, and the only mode parity is asserted against) = plain fp32 / fp64 products.
 OPERAND_ROUND = None
+OPERAND_ROUND_HEAD = True     # False: the head's products (hidden projection, gate, MoE) stay exact while the body rounds
 
 
 def _round_operand(x: torch.Tensor) -> torch.Tensor:
@@ -68,9 +69,9 @@ def _round_operand(x: torch.Tensor) -> torch.Tensor:
     raise ValueError(OPERAND_ROUND)
 
 
-def mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def mm(a: torch.Tensor, b: torch.Tensor, head: bool = False) -> torch.Tensor:
     """tf.matmul (fp32 on the reference's CPU path); see OPERAND_ROUND."""
-    if OPERAND_ROUND is None:
+    if OPERAND_ROUND is None or (head and not OPERAND_ROUND_HEAD):
         return a @ b
     return _round_operand(a) @ _round_operand(b)
 
@@ -346,8 +347,8 @@ def netvlad_atten_cluster_forward(x, P, S, scope, max_frames, is_training, dropo
 # video_level_models.py:48-159  MoeModel (low_rank_gating=-1, prob gating off)
 # --------------------------------------------------------------------------- #
 def moe_forward(act, P, vocab_size, num_mixtures):
-    gate = mm(act, P["gates/weights"])                              # no bias (:86-92)
-    expert = mm(act, P["experts/weights"]) + P["experts/biases"]     # :109-114
+    gate = mm(act, P["gates/weights"], head=True)                              # no bias (:86-92)
+    expert = mm(act, P["experts/weights"], head=True) + P["experts/biases"]     # :109-114
     gating = torch.softmax(gate.reshape(-1, num_mixtures + 1), dim=-1)
     experts = torch.sigmoid(expert.reshape(-1, num_mixtures))
     prob = (gating[:, :num_mixtures] * experts).sum(dim=1)
@@ -359,7 +360,7 @@ def moe_forward(act, P, vocab_size, num_mixtures):
 # --------------------------------------------------------------------------- #
 def head_forward(vlad, P, S, vocab_size, is_training, num_mixtures=2, gating=True,
                  remove_diag=False, return_intermediates=False, relu=False):
-    act = mm(vlad, P["hidden1_weights"])                            # :2319
+    act = mm(vlad, P["hidden1_weights"], head=True)                            # :2319
     if relu:                                                        # `add_batch_norm and relu` (:2321-2327)
         act = batch_norm(act, P, S, "hidden1_bn", is_training)
         act = torch.clamp(act, 0.0, 6.0)                            # tf.nn.relu6 (:2339-2340)
@@ -368,7 +369,7 @@ def head_forward(vlad, P, S, vocab_size, is_training, num_mixtures=2, gating=Tru
     hidden = act
     if gating:
         Wg = P["gating_weights_2"]
-        gates = mm(act, Wg)                                         # :2347
+        gates = mm(act, Wg, head=True)                                         # :2347
         if remove_diag:
             gates = gates - torch.diagonal(Wg) * act                # :2349-2352
         gates = batch_norm(gates, P, S, "gating_bn", is_training)   # :2354-2360

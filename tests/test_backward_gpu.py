@@ -121,12 +121,15 @@ def test_netvlad_v1_d5_raw_reshape(cuda):
     _perturb(store, seed=5)
     x, nf, labels = O.synthetic_batch(B, seed=20181002, vocab=V)
     P, S = _oracle_params(store)
+    # inference with context gating on (the conditioning of the other parity configurations); same variables
+    eng_g = NetVladEngine(NetVladConfig(model="NetVladV1", iterations=T, cluster_size=K, hidden_size=Hd, vocab_size=V,
+                                        d5_raw_reshape=True), store)
     with torch.no_grad():
         ref_inf, inter = O.netvlad_v1(x, nf, P, {k: v.clone() for k, v in S.items()}, vocab_size=V, iterations=T, cluster_size=K,
-                                      is_training=False, gating=False, d5_raw_reshape=True, return_intermediates=True)
+                                      is_training=False, d5_raw_reshape=True, return_intermediates=True)
         other = O.netvlad_v1(x, nf, P, {k: v.clone() for k, v in S.items()}, vocab_size=V, iterations=T, cluster_size=K,
-                             is_training=False, gating=False)
-    pred, ctx = eng.forward(x.to(cuda), nf.to(cuda), False, return_intermediates=True)
+                             is_training=False)
+    pred, ctx = eng_g.forward(x.to(cuda), nf.to(cuda), False, return_intermediates=True)
     e_att = rel(ctx["inter"]["att_video"], inter["att_video"])
     e_p = float((pred.cpu() - ref_inf).abs().max())
     print(f"\n[d5 raw reshape] att rel-L2 {e_att:.2e}, pred max-abs {e_p:.2e} (transpose reading differs by {float((other - ref_inf).abs().max()):.2e})")

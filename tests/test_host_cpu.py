@@ -213,3 +213,59 @@ def test_head_gradient_span_and_split_allreduce_world2_gloo():
     assert len({r[2] for r in res}) == 1                     # every rank splits at the same offset
     for rank, ok, end, equal in res:
         assert ok and equal, rank
+
+
+def _worker_sharded_exchange(rank, world, port, q):
+    """ShardedHiddenUpdate's exchange on gloo with CPU tensors: descriptor column slices by all-to-all, dLoss/dhidden by
+    all-gather, the shard's tower-summed gradient as ONE product over world*B rows, the clip norm of the whole tensor by
+    a scalar all-reduce, and the all-gather that makes every rank's copy of the updated rows complete again."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from learnablepoolingmethods_b200.trainer import pack_descriptor_slices, shard_row_range
+    B, Kd, H = 3, 16 * world, 5
+    towers = []
+    for r in range(world):                                  # every rank can rebuild every tower's factors (the reference sum)
+        g = torch.Generator().manual_seed(77 + r)
+        towers.append((torch.randn(B, Kd, generator=g), torch.randn(B, H, generator=g)))
+    vlad, dact = towers[rank]
+    r0, r1 = shard_row_range(Kd, world, rank)
+    send = pack_descriptor_slices(vlad, world)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    g_all = torch.empty(world * B, H)
+    dist.all_gather_into_tensor(g_all, dact.contiguous())
+    dw_shard = recv.view(world * B, r1 - r0).t() @ g_all                     # [rows_r, H]
+    dense = sum(a.t() @ g for a, g in towers)                                # utils.py:205-211: SUM over towers
+    ok = torch.allclose(dw_shard, dense[r0:r1], rtol=1e-5, atol=1e-5)
+    sumsq = (dw_shard * dw_shard).sum().reshape(1)
+    dist.all_reduce(sumsq, op=dist.ReduceOp.SUM)
+    ok = ok and abs(float(sumsq.sqrt()) - float(dense.norm())) < 1e-4 * float(dense.norm())
+    # shard-local update, then the gather of the updated rows (sync_master / the fp16 operand gather)
+    w = torch.zeros(Kd, H)
+    w[r0:r1] = dense[r0:r1] * 0.5
+    dist.all_gather_into_tensor(w, w[r0:r1].clone())
+    ok = ok and torch.allclose(w, dense * 0.5, rtol=1e-6, atol=1e-6)
+    q.put((rank, bool(ok), (r0, r1)))
+    dist.destroy_process_group()
+
+
+def test_sharded_hidden_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    from learnablepoolingmethods_b200.trainer import pack_descriptor_slices, shard_row_range
+    assert [shard_row_range(64, 4, r) for r in range(4)] == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    v = torch.arange(2 * 8, dtype=torch.float32).view(2, 8)
+    s = pack_descriptor_slices(v, 2)
+    assert s.shape == (2, 2, 4) and torch.equal(s[1], v[:, 4:])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_sharded_exchange, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[2] for r in res) == [(0, 16), (16, 32)]
+    for rank, ok, _ in res:
+        assert ok, rank

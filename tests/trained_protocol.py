@@ -51,6 +51,7 @@ def structured_batch(B, seed, protos, device, *, V=SHAPE["V"], max_frames=SHAPE[
 
 
 def train_model(device, *, steps, model="NetVladV1", lr=2e-4, seed=1810, log_every=100, strength=1.0, shape=SHAPE):
+    """Returns (engine, trainer, class directions, [(step, loss)])."""
     from learnablepoolingmethods_b200 import variables
     from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
     from learnablepoolingmethods_b200.trainer import Trainer
@@ -119,11 +120,13 @@ def evaluate(eng, protos, device, *, n_videos=1024, chunk=128, emulate=(), stren
         with torch.no_grad():
             ref, inter = O.netvlad_v1(xc, nfc, P, S, return_intermediates=True, **kw)
             for m in emulate:
-                O.OPERAND_ROUND = m
+                # "fp16-body": operands rounded everywhere except the head's three products (what a split-precision head
+                # on top of the fp16 body could reach at best)
+                O.OPERAND_ROUND, O.OPERAND_ROUND_HEAD = m.split("-")[0], not m.endswith("-body")
                 try:
                     emu_pred[m].append(O.netvlad_v1(xc, nfc, P, S, **kw).numpy())
                 finally:
-                    O.OPERAND_ROUND = None
+                    O.OPERAND_ROUND, O.OPERAND_ROUND_HEAD = None, True
         ref_pred.append(ref.numpy())
         labels.append(lab.cpu().numpy())
         # product side: batches of B (the benchmarked tower batch; the tail batch is smaller)
