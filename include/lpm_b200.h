@@ -181,6 +181,13 @@ int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, lo
                             int B, int rows, int D, float eps, const float* gamma1, const float* beta1, void* u1_out,
                             long long u1_stride, float* stats1, const float* gamma2, const float* beta2, void* u2_out,
                             long long u2_stride, float* stats2, void* y, long long y_stride, lpm_stream_t stream);
+/* Same, additionally writing y_lo = fp16(y - fp16(y)) with y's layout: (y, y_lo) is the split-precision left operand of
+ * the hidden projection (frame_level_models.py:2319), see lpm_split_hi_lo_f16. */
+int lpm_layernorm_chain_fwd_split(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,
+                                  int B, int rows, int D, float eps, const float* gamma1, const float* beta1, void* u1_out,
+                                  long long u1_stride, float* stats1, const float* gamma2, const float* beta2, void* u2_out,
+                                  long long u2_stride, float* stats2, void* y, long long y_stride, void* y_lo,
+                                  lpm_stream_t stream);
 
 /* Context gating (frame_level_models.py:2342-2368): act * sigmoid(BN_batch(g - diag*act)). */
 int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
@@ -274,7 +281,8 @@ int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_s
  * video_level_models.py:86-114): x = hi + lo, hi = fp16(x), lo = fp16(x - hi).  A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo is
  * then one lpm_gemm_f16 over a reduction of 3K:
  *   along_rows = 0 (activations): src fp32 [rows][cols] -> dst fp16 [rows][3*cols] = [ hi | lo | hi ]
- *   along_rows = 1 (weights [K][N]): dst rows [0,K) = hi, [K,2K) = hi, [2K,3K) = lo  (dst holds 3*rows rows) */
+ *   along_rows = 1 (weights [K][N]): dst rows [0,K) = hi, [K,2K) = hi, [2K,3K) = lo  (dst holds 3*rows rows)
+ *   along_rows = 2: dst fp16 [rows][cols] = lo only (hidden1_weights: the hi part is the ordinary fp16 operand) */
 int lpm_split_hi_lo_f16(const float* src, long long ld_src, int rows, int cols, void* dst_f16, long long ld_dst,
                         int along_rows, lpm_stream_t stream);
 /* transformer_utils.py:563-581 backward: dqkv fp16 [B*L][ldd] in the qkv layout; L <= 256. */

@@ -345,8 +345,9 @@ int lpm_split_hi_lo_f16(const float* src, long long ld_src, int rows, int cols, 
                         lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_src >= cols, "lpm_split_hi_lo_f16: bad arguments");
+  LPM_REQUIRE(along_rows >= 0 && along_rows <= 2, "lpm_split_hi_lo_f16: along_rows must be 0, 1 or 2");
   LPM_REQUIRE(along_rows ? ld_dst >= cols : ld_dst >= 3ll * cols, "lpm_split_hi_lo_f16: destination row stride too small");
-  return split_hi_lo(src, ld_src, rows, cols, H16(dst), ld_dst, along_rows ? 1 : 0, ST(stream));
+  return split_hi_lo(src, ld_src, rows, cols, H16(dst), ld_dst, along_rows, ST(stream));
 }
 
 int lpm_cast_scaled_f16(const float* x, long long n, float alpha, void* y, lpm_stream_t stream) {
@@ -429,7 +430,18 @@ int lpm_layernorm_chain_fwd(const void* a, long long a_stride, const void* b, lo
   DEVCHK();
   LPM_REQUIRE(a && b && y && gamma1 && beta1 && B > 0, "lpm_layernorm_chain_fwd: bad arguments");
   return layernorm_chain_fwd(CH16(a), a_stride, CH16(b), b_stride, b_row_scale, B, rows, D, eps, gamma1, beta1, H16(u1_out),
-                             u1_stride, stats1, gamma2, beta2, H16(u2_out), u2_stride, stats2, H16(y), y_stride, ST(stream));
+                             u1_stride, stats1, gamma2, beta2, H16(u2_out), u2_stride, stats2, H16(y), y_stride, nullptr, ST(stream));
+}
+
+int lpm_layernorm_chain_fwd_split(const void* a, long long a_stride, const void* b, long long b_stride, const float* b_row_scale,
+                                  int B, int rows, int D, float eps, const float* gamma1, const float* beta1, void* u1_out,
+                                  long long u1_stride, float* stats1, const float* gamma2, const float* beta2, void* u2_out,
+                                  long long u2_stride, float* stats2, void* y, long long y_stride, void* y_lo,
+                                  lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(a && b && y && y_lo && gamma1 && beta1 && B > 0, "lpm_layernorm_chain_fwd_split: bad arguments");
+  return layernorm_chain_fwd(CH16(a), a_stride, CH16(b), b_stride, b_row_scale, B, rows, D, eps, gamma1, beta1, H16(u1_out),
+                             u1_stride, stats1, gamma2, beta2, H16(u2_out), u2_stride, stats2, H16(y), y_stride, H16(y_lo), ST(stream));
 }
 
 int lpm_rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor,

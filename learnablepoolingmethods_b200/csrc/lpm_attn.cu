@@ -478,9 +478,11 @@ static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __hal
   LPM_REQUIRE(L % 16 == 0 && L >= 16 && L <= 512, "mha_bwd: length must be a multiple of 16 in [16,512] (got %d)", L);
   LPM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0, "mha_bwd: leading dimensions must be multiples of 8");
   LPM_REQUIRE(mode == 0 || DH == 16, "mha_bwd: batch-normed logits need head depth 16");
-  // query chunk whose dS^T is parked at a time.  L = 256 (the V1 cluster attention at config 1): chunks of 128 and
-  // 256-thread CTAs -> 104 KB of shared memory, two CTAs per SM.  LPM_MHA_BWD_WIDE=1 restores the one-CTA layout.
-  static const bool wide = getenv("LPM_MHA_BWD_WIDE") != nullptr && getenv("LPM_MHA_BWD_WIDE")[0] == '1';
+  // query chunk whose dS^T is parked at a time.  L = 256 (the V1 cluster attention at config 1): the whole dS^T (135 KB,
+  // one 512-thread CTA per SM).  Measured alternative (LPM_MHA_BWD_WIDE=0): chunks of 128 in 256-thread CTAs, two CTAs
+  // per SM -- 576 us instead of 403 us at [80, 64, 256, 16]: the second pass over the keys and the fp16 read-modify-write
+  // of dK / dV cost more than the overlapped prologue saves.
+  static const bool wide = !(getenv("LPM_MHA_BWD_WIDE") != nullptr && getenv("LPM_MHA_BWD_WIDE")[0] == '0');
   const int QC = L < 256 ? L : (L == 256 && wide ? 256 : 128);
   const int nt = (L > 256 || (L == 256 && wide)) ? 512 : 256;
   const size_t smem = (size_t)L * 128 + (size_t)L * 8 + (mode ? (size_t)L * 24 : 0) + (size_t)L * (QC + 8) * 2;

@@ -780,9 +780,11 @@ __global__ void __launch_bounds__(256) split_hi_lo_kernel(const float* __restric
     if (mode == 0) {
       __half* d = dst + (long long)r * ld_dst + c;
       d[0] = hi; d[cols] = lo; d[2 * cols] = hi;
-    } else {
+    } else if (mode == 1) {
       __half* d = dst + (long long)r * ld_dst + c;
       d[0] = hi; d[(long long)rows * ld_dst] = hi; d[2ll * rows * ld_dst] = lo;
+    } else {
+      dst[(long long)r * ld_dst + c] = lo;
     }
   }
 }

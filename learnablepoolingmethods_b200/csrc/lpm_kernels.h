@@ -111,7 +111,7 @@ int layernorm_chain_supported(int rows, int D);
 int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, long long b_stride, const float* b_row_scale,
                         int B, int rows, int D, float eps, const float* gamma1, const float* beta1, __half* u1_out,
                         long long u1_stride, float* stats1, const float* gamma2, const float* beta2, __half* u2_out,
-                        long long u2_stride, float* stats2, __half* y, long long y_stride, cudaStream_t st);
+                        long long u2_stride, float* stats2, __half* y, long long y_stride, __half* y_lo, cudaStream_t st);
 
 // lpm_eval.cu
 int eval_topk(const float* pred, long long ld, const unsigned char* labels, long long ldl, int B, int V, int k,

@@ -35,7 +35,10 @@ struct LnChainParams {
   const float* gamma2; const float* beta2;      // null -> single norm
   __half* u2_out; long long u2_stride; float* stats2;
   __half* y; long long y_stride;
+  __half* y_lo;                    // optional: fp16(y - fp16(y)) with the same layout (split-precision operand of the
+                                   // hidden projection, frame_level_models.py:2319), or null
 };
+
 
 __device__ __forceinline__ void ln_unpack(const uint4& v, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -46,6 +49,15 @@ __device__ __forceinline__ uint4 ln_pack(const float* f) {
   uint4 v;
   v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]); v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
   return v;
+}
+
+// low-order halves of 8 fp32 values whose high-order fp16 halves are `hi`
+__device__ __forceinline__ uint4 ln_pack_lo(const float* f, const uint4& hi) {
+  float h[8];
+  ln_unpack(hi, h);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = f[j] - h[j];
+  return ln_pack(h);
 }
 
 // (sum, sumsq) of this CTA -> cluster-wide (mean, rstd), reduced in rank order (deterministic)
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
 
   const bool two = p.gamma2 != nullptr;
   uint4* py = reinterpret_cast<uint4*>(p.y + sample * p.y_stride) + i0;
+  uint4* pyl = p.y_lo ? reinterpret_cast<uint4*>(p.y_lo + sample * p.y_stride) + i0 : nullptr;
   if (!two) {
     // ---- pass B (single norm): y = LN(u1) ----------------------------------------------------------------------
     for (int i = threadIdx.x; i < cnt; i += 256) {
@@ -139,7 +152,9 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (f[j] - mr1.x) * mr1.y * gg[j] + bb[j];
-      py[i] = ln_pack(f);
+      const uint4 hi = ln_pack(f);
+      py[i] = hi;
+      if (pyl) pyl[i] = ln_pack_lo(f, hi);
     }
     cluster.sync();                                // no CTA may exit while a peer can still read its slot
     return;
@@ -192,7 +207,9 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = (f[j] - mr2.x) * mr2.y * gg[j] + bb[j];
-    py[i] = ln_pack(f);
+    const uint4 hi = ln_pack(f);
+    py[i] = hi;
+    if (pyl) pyl[i] = ln_pack_lo(f, hi);
   }
   cluster.sync();
 }
@@ -215,7 +232,7 @@ int layernorm_chain_supported(int rows, int D) {
 int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, long long b_stride, const float* b_row_scale,
                         int B, int rows, int D, float eps, const float* gamma1, const float* beta1, __half* u1_out,
                         long long u1_stride, float* stats1, const float* gamma2, const float* beta2, __half* u2_out,
-                        long long u2_stride, float* stats2, __half* y, long long y_stride, cudaStream_t st) {
+                        long long u2_stride, float* stats2, __half* y, long long y_stride, __half* y_lo, cudaStream_t st) {
   LPM_REQUIRE(D % 8 == 0 && a_stride % 8 == 0 && b_stride % 8 == 0 && y_stride % 8 == 0 && u1_stride % 8 == 0 && u2_stride % 8 == 0,
               "layernorm_chain: D and sample strides must be multiples of 8");
   LPM_REQUIRE(a && b && gamma1 && beta1 && y && (gamma2 == nullptr) == (beta2 == nullptr), "layernorm_chain: bad arguments");
@@ -224,7 +241,7 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
   p.rows = rows; p.D = D; p.n8 = (long long)rows * D / 8; p.eps = eps;
   p.gamma1 = gamma1; p.beta1 = beta1; p.u1_out = u1_out; p.u1_stride = u1_stride; p.stats1 = stats1;
   p.gamma2 = gamma2; p.beta2 = beta2; p.u2_out = u2_out; p.u2_stride = u2_stride; p.stats2 = stats2;
-  p.y = y; p.y_stride = y_stride;
+  p.y = y; p.y_stride = y_stride; p.y_lo = y_lo;
   int cs = 1;
   if (!ln_chain_plan(p.n8, &cs, &p.per)) return fail(LPM_ERR_ARG, "layernorm_chain: sample of %d x %d does not fit", rows, D);
   const size_t smem = (size_t)p.per * 16;

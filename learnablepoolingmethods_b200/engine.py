@@ -46,6 +46,7 @@ class NetVladConfig:
     dropout_rate: float = 0.9      # D7: tf.layers.dropout(rate=1-0.1) in TransformerEncoderMod
     loss_scale: float = 0.0        # fp16 activation-gradient scale inside the backward; 0 = auto (8 x batch)
     hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
+    split_hidden_infer: bool = True  # NetVladV1 inference: hidden projection with split-precision operands (see _head)
     overlap_audio: bool = True     # run the audio modality (0.4 % of the FLOPs, ~1/3 of the launches) on a second stream
     overlap_wgrad: bool = True     # rgb weight-gradient GEMMs on a third stream: they have no consumer before the optimiser
                                    # and fill the SMs the data-gradient GEMMs leave idle (partial last waves, 128-tile grids)
@@ -243,6 +244,17 @@ class NetVladEngine:
             ops.split_hi_lo(v["gates/weights"], sh["wmoe16x3"], along_rows=True)
             ops.split_hi_lo(v["experts/weights"], sh["wmoe16x3"][:, g8:], along_rows=True)
 
+    def refresh_hidden_lo(self):
+        """Low-order fp16 half of hidden1_weights (W = fp16(W) + wh16lo) for the split-precision inference projection;
+        recomputed lazily when the variables changed since the last inference call (one 0.8 GB pass)."""
+        s = self.store
+        if s.__dict__.get("_hidden_lo_version") == s.version and "wh16lo" in s.shadows:
+            return
+        w = s.vars["hidden1_weights"]
+        lo = self._shadow_buf("wh16lo", tuple(w.shape))
+        ops.split_hi_lo(w, lo, along_rows=2)
+        s._hidden_lo_version = s.version
+
     def refresh_shadows(self, force=False):
         s = self.store
         if not force and s.shadow_version == s.version:
@@ -315,7 +327,11 @@ class NetVladEngine:
             ctx["xb"] = xb
             ctx["input_bn_stats"] = r[2]
 
-        vlad = torch.empty((B, c.vlad_dim), dtype=torch.float16, device=x.device)
+        # inference (NetVladV1): rows [B, 2B) hold the low-order halves of the descriptor, vlad = hi + lo (see _head)
+        split = c.model == "NetVladV1" and c.split_hidden_infer and not is_training and not save
+        vlad2 = torch.empty(((2 if split else 1) * B, c.vlad_dim), dtype=torch.float16, device=x.device)
+        vlad, vlad_lo = vlad2[:B], (vlad2[B:] if split else None)
+        ctx["_vlad2"] = vlad2 if split else None
         off = 0
         main = torch.cuda.current_stream()
         side, ev_fork, ev_join = self._side_stream() if c.overlap_audio else (None, None, None)
@@ -331,7 +347,7 @@ class NetVladEngine:
             with torch.cuda.stream(side if on_side else main):
                 if c.model == "NetVladV1":
                     m = self._v1_modality(name, X, B, T, D, K, H, sid, is_training, save, vlad[:, off:off + K * D], ctx,
-                                          return_intermediates)
+                                          return_intermediates, out_lo=None if vlad_lo is None else vlad_lo[:, off:off + K * D])
                 else:
                     mask = None if dropout_masks is None else dropout_masks.get(name)
                     m = self._v2_modality(name, X, B, T, D, K, is_training, save, vlad[:, off:off + K * D], ctx,
@@ -356,7 +372,7 @@ class NetVladEngine:
         """Second half of a forward started with head=False: hidden projection, gating, MoE -> predictions."""
         return self._head(ctx.pop("_vlad"), ctx["B"], ctx["training"], ctx["_save"], ctx, ctx["_want_inter"])
 
-    def _v1_modality(self, name, X, B, T, D, K, H, sid, training, save, out_view, ctx, want_inter):
+    def _v1_modality(self, name, X, B, T, D, K, H, sid, training, save, out_view, ctx, want_inter, out_lo=None):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         vs, a = name + "_VLAD", name + "_attention"
         m: Dict[str, object] = {}
@@ -410,7 +426,7 @@ class NetVladEngine:
         if ops.layernorm_chain_supported(K, D):
             # LN(f2 + h1) (FeedForwardNetwork, :712-713) and LN(. + h1) (TransformerEncoder, :410-411) in one pass
             rc = ops.layernorm_chain_fwd(f2, h1, B, K, D, v[la + "/gamma"], v[la + "/beta"], v[lb + "/gamma"], v[lb + "/beta"],
-                                         out=out_view, out_stride=out_view.stride(0), save=save)
+                                         out=out_view, out_stride=out_view.stride(0), save=save, out_lo=out_lo)
             u2, st2, h2, st3 = (rc[1], rc[2], rc[3], rc[4]) if save else (None, None, None, None)
         else:
             u2 = torch.empty_like(f2) if save else f2
@@ -421,6 +437,8 @@ class NetVladEngine:
             r3 = ops.layernorm_joint_fwd(h2, h1, None, B, K, D, v[lb + "/gamma"], v[lb + "/beta"],
                                          out=out_view, out_stride=out_view.stride(0), save=save)
             st3 = r3[1] if save else None
+            if out_lo is not None:
+                out_lo.zero_()          # the two-kernel fallback emits no low-order half
         if want_inter:
             ctx["inter"]["att_" + name] = out_view.float().reshape(B, K, D)
         if save:
@@ -595,18 +613,34 @@ class NetVladEngine:
         Hn = c.hidden_size
         if self.pre_head_hook is not None:
             self.pre_head_hook()    # data parallel: the all-gather of the updated fp16 weight shards lands here
-        parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
+        vlad2 = ctx.get("_vlad2")
         act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
         hpre, hstats = None, None
+        parts_lo = None
+        if vlad2 is not None:
+            # Inference: hidden = (v_hi + v_lo)(W_hi + W_lo) ~= [v_hi ; v_lo] W_hi + v_hi W_lo.  The 270 336-term products with
+            # 11-bit operands are what is left of the prediction error once the gate / MoE products are split (trained-weights
+            # protocol, DESIGN.md numerics); two passes over the fp16 weight bytes instead of one (+277 MB of HBM reads).
+            # M = 2B rows run as one 2-CTA (cta_group::2) tile per split, so W_hi is still streamed once.
+            self.refresh_hidden_lo()
+            parts = ops.gemm(vlad2, sh["wh16"], splits=max(2, c.hidden_splits))        # [S, 2B, H]
+            parts = parts.view(parts.shape[0] * 2, B, Hn)                              # hi and lo rows summed by the reduce
+            parts_lo = ops.gemm(vlad, sh["wh16lo"], splits=max(2, c.hidden_splits))    # [S, B, H]
+        else:
+            parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
         if c.netvlad_relu:
             hpre = act32
             ops.splitk_reduce(parts, out32=hpre)
+            if parts_lo is not None:
+                ops.splitk_reduce(parts_lo, out32=hpre, accumulate=True)
             r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
                                         v["hidden1_bn/moving_variance"], training=training, save=save)
             act32 = r[0]
             hstats = r[2] if save else None
         else:
             ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32)
+            if parts_lo is not None:
+                ops.splitk_reduce(parts_lo, out32=act32, accumulate=True)
         # The gate and MoE products run with split-precision operands (x = hi + lo in two fp16 terms, one GEMM over a 3x
         # longer reduction, ops.split_hi_lo): `hidden` is O(30) at this model's initialisation scale and feeds sigmoids, so
         # 10-bit-mantissa operands in these two small products are what limits the predictions (numerics).
@@ -999,6 +1033,8 @@ class InferenceGraph:
                 eng.draws += 1
             self.idx.copy_(frame_index.to(torch.int32), non_blocking=True)
         eng.refresh_shadows()                          # in place; a no-op unless values changed outside the trainer
+        if eng.cfg.model == "NetVladV1" and eng.cfg.split_hidden_infer:
+            eng.refresh_hidden_lo()                    # low-order half of hidden1_weights follows the variables (outside the graph)
         if self.graph is None or self.version != eng.store.layout_version:
             self._capture()
         self.graph.replay()

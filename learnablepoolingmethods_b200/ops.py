@@ -152,9 +152,9 @@ def cast_f16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, cols_dst: Op
     return dst
 
 
-def split_hi_lo(src: torch.Tensor, dst: Optional[torch.Tensor] = None, along_rows: bool = False):
-    """fp32 [rows, cols] -> split-precision fp16 operand: [rows, 3*cols] = [hi | lo | hi] (activations) or, along_rows,
-    the column block `dst` of a [3*rows, .] weight operand = [hi ; hi ; lo]."""
+def split_hi_lo(src: torch.Tensor, dst: Optional[torch.Tensor] = None, along_rows=False):
+    """fp32 [rows, cols] -> split-precision fp16 operand: [rows, 3*cols] = [hi | lo | hi] (activations); along_rows=True:
+    the column block `dst` of a [3*rows, .] weight operand = [hi ; hi ; lo]; along_rows=2: dst [rows, cols] = lo only."""
     lib = _lib.load()
     rows, cols = src.shape
     assert src.dtype == torch.float32 and src.stride(1) == 1
@@ -377,15 +377,24 @@ def layernorm_chain_supported(rows, D) -> bool:
     return bool(_lib.load().lpm_layernorm_chain_supported(int(rows), int(D)))
 
 
-def layernorm_chain_fwd(a, b, B, rows, D, gamma1, beta1, gamma2, beta2, *, out, out_stride, save=False, eps=LN_EPS):
+def layernorm_chain_fwd(a, b, B, rows, D, gamma1, beta1, gamma2, beta2, *, out, out_stride, save=False, eps=LN_EPS,
+                        out_lo=None):
     """y = LN(LN(a + b; gamma1, beta1) + b; gamma2, beta2) in one pass (transformer_utils.py:712-713 + :410-411).
-    save=True also returns (u1, stats1, u2, stats2) for the backward; a is left untouched."""
+    save=True also returns (u1, stats1, u2, stats2) for the backward; a is left untouched.
+    out_lo: optional fp16 tensor with out's layout that receives fp16(y - fp16(y)) (split-precision operand)."""
     lib = _lib.load()
     dev = a.device
     u1 = _f16((B, rows, D), dev) if save else None
     u2 = _f16((B, rows, D), dev) if save else None
     s1 = _f32((B, 2), dev) if save else None
     s2 = _f32((B, 2), dev) if save else None
+    if out_lo is not None:
+        assert out_lo.stride(0) == out_stride
+        check(lib.lpm_layernorm_chain_fwd_split(ptr(a), _ll(rows * D), ptr(b), _ll(rows * D), None, B, rows, D, C.c_float(eps),
+                                                ptr(gamma1), ptr(beta1), ptr(u1), _ll(rows * D), ptr(s1), ptr(gamma2),
+                                                ptr(beta2), ptr(u2), _ll(rows * D), ptr(s2), ptr(out), _ll(out_stride),
+                                                ptr(out_lo), stream_ptr()), "lpm_layernorm_chain_fwd")
+        return (out, u1, s1, u2, s2) if save else out
     check(lib.lpm_layernorm_chain_fwd(ptr(a), _ll(rows * D), ptr(b), _ll(rows * D), None, B, rows, D, C.c_float(eps),
                                       ptr(gamma1), ptr(beta1), ptr(u1), _ll(rows * D), ptr(s1), ptr(gamma2), ptr(beta2),
                                       ptr(u2), _ll(rows * D), ptr(s2), ptr(out), _ll(out_stride), stream_ptr()),

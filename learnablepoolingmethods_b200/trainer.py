@@ -275,6 +275,13 @@ class Trainer:
         g_all = self.gather.wait("dact")
         return ops.gemm(a_all, g_all, a_mn=True, b_mn=True, out_dtype=torch.float32, alpha=inv, out=out)
 
+    def _dp_side_stream(self):
+        if self._dp_side is None:
+            self._dp_side = torch.cuda.Stream(device=self.store.device)
+        return self._dp_side
+
+    _dp_side = None
+
     def _priority_streams(self):
         if self._prio is None:
             dev = self.store.device
@@ -446,6 +453,9 @@ class Trainer:
         graphs = g["graphs"]
         if g["fused"]:
             self.lr_dev.fill_(self._lr_t())          # read by the captured Adam kernels
+        elif dp:
+            ops.step_begin(f.scratch[3], f.scratch[4])    # before anything of this step can raise the skip flag
+            g["ctx"]["_latched"] = True
         graphs[0].replay()
         if dp:
             self.shard.wait_weights()                # the fp16 weight shards gathered under the forward
@@ -454,11 +464,23 @@ class Trainer:
             graphs[2].replay()
             d = torch.distributed
             if g["split"]:
+                # the head of the backward is done: dLoss/dhidden exists and hidden1's fp16 operand has had its last reader.
+                # The whole sharded update of hidden1_weights (all-gather of dLoss/dhidden, the shard's gradient GEMM, norm
+                # all-reduce, clip + Adam on the shard, start of the fp16 all-gather) runs on a second stream underneath the
+                # modalities' backward, like the single-tower step's forked update.
+                cur = torch.cuda.current_stream()
+                side = self._dp_side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _, dact16, inv = g["ctx"]["hidden_factors"]
+                    self.shard.step(dact16, inv, self.clip, self._lr_t())()
+                g["ctx"]["_hidden_done"] = True
                 h0 = d.all_reduce(f.g[:g["head_end"]], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
                 graphs[3].replay()
                 h1 = d.all_reduce(f.g[g["head_end"]:], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
                 h0.wait()
                 h1.wait()
+                cur.wait_stream(side)
             else:
                 d.all_reduce(f.g, op=d.ReduceOp.SUM, group=self.pg)
         _lib.launch_count += g["launches"]
@@ -557,9 +579,12 @@ class Trainer:
         lr_t = self._lr_t()
         if factored != bool(f.factored):
             raise RuntimeError("the tower batch size changed across the factored-update limit after the first step")
-        ops.step_begin(f.scratch[3], f.scratch[4])       # a skip flag raised by the previous step is counted and cleared
+        if not ctx.pop("_latched", False):
+            ops.step_begin(f.scratch[3], f.scratch[4])   # a skip flag raised by the previous step is counted and cleared
         # norm first: it may raise the skip flag
-        if self.use_shard:
+        if ctx.pop("_hidden_done", False):
+            hidden_update = None                         # already applied underneath the backward (_graph_step)
+        elif self.use_shard:
             _, dact16, inv = ctx["hidden_factors"]
             hidden_update = self.shard.step(dact16, inv, self.clip, lr_t)
         else:
