@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(1024) gating_bwd_kernel(const float* __restric
 //   pass 2: du = rstd*(dy*gamma - c1/N - xhat*c2/N) ; optional du_masked = du o (mask>0) (ReLU backward of the
 //           pre-residual branch) ; optional column sums of du_masked (or du when there is no mask)
 // ------------------------------------------------------------------------------------------------
-constexpr int LNB_CHUNKS = 4;
+// 7 row chunks per sample: 560 CTAs at batch 80 = one resident wave of 4 CTAs per SM on 148 SMs (4 chunks = 320 CTAs
+// ran as 2.2 waves with a 16 %-full tail)
+constexpr int LNB_CHUNKS = 7;
 
 __device__ __forceinline__ void load8(const __half* p, float* f) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(256) ln_bwd1_kernel(const __half* __restrict__
   for (int j = 0; j < 8; ++j) gacc[j] = bacc[j] = 0.f;
   const __half* us = u + (size_t)sample * rows * D;
   const __half* ds = dy + (size_t)sample * dy_stride;
+#pragma unroll 2
   for (int r = r0 + tr; r < r1; r += rpi) {
     float uu[8], dd[8];
     load8(us + (size_t)r * D + tc * 8, uu);
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(256) ln_bwd2_kernel(const __half* __restrict__
   for (int j = 0; j < 8; ++j) { ga[j] = gamma[tc * 8 + j]; acc[j] = 0.f; }
   const size_t sbase = (size_t)sample * rows * D;
   const __half* ds = dy + (size_t)sample * dy_stride;
+#pragma unroll 2
   for (int r = r0 + tr; r < r1; r += rpi) {
     float uu[8], dd[8], mm[8], o[8];
     const size_t off = (size_t)r * D + tc * 8;
@@ -431,6 +435,7 @@ __global__ void __launch_bounds__(256) assign_bwd1_k256_kernel(const float* __re
   float mu[8], rs[8], c1[8], c2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mu[j] = mean[k0 + j]; rs[j] = rstd[k0 + j]; c1[j] = c2[j] = 0.f; }
+#pragma unroll 2
   for (long long r = warp; r < rows; r += nwarps) {
     const long long b = r / T;
     const uint4 va = __ldg(reinterpret_cast<const uint4*>(A + r * K + k0));

@@ -21,6 +21,27 @@ from . import ops
 from .variables import VariableStore
 
 
+class no_gc_during_capture:
+    """Cyclic garbage collection stays off while a CUDA graph is being captured.  A collection that happens to run in the
+    middle of a capture can destroy an OLD torch.cuda.CUDAGraph (e.g. a previous Trainer caught in a reference cycle);
+    its destructor resets the graph -- an operation that is not permitted while a stream is capturing and that
+    invalidates the capture in progress.  Collect first, then capture with the collector disabled."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.collect()
+        gc.collect()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+        return False
+
+
 def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -1013,7 +1034,7 @@ class InferenceGraph:
         self.graph = torch.cuda.CUDAGraph()
         from . import _lib
         n0 = _lib.launch_count
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        with no_gc_during_capture(), torch.cuda.graph(self.graph), torch.no_grad():
             self.pred, _ = eng.forward(self.x, self.nf, False, frame_index=self.idx)
         self.launches = _lib.launch_count - n0       # kernels one replay launches (bench.py's gpu_launches)
         _lib.launch_count = n0

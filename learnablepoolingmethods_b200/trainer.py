@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from .dp import BucketedAllReduce, FactorGather
-from .engine import NetVladConfig, NetVladEngine
+from .engine import NetVladConfig, NetVladEngine, no_gc_during_capture
 from .variables import VariableStore
 
 CHUNK = 32768           # elements per optimiser chunk
@@ -424,7 +424,7 @@ class Trainer:
                 # fused: captured on a high-priority stream so that the optimiser branch (priority 0) only takes what
                 # the forward / backward kernels leave free
                 cap = self._priority_streams()[0] if fuse else None
-                with torch.cuda.graph(graphs[0], stream=cap, capture_error_mode="thread_local"):
+                with no_gc_during_capture(), torch.cuda.graph(graphs[0], stream=cap, capture_error_mode="thread_local"):
                     if fuse:
                         ops.step_begin(f.scratch[3], f.scratch[4])
                     g["ctx"] = seg_a()
@@ -433,14 +433,15 @@ class Trainer:
                     if fuse:
                         self._captured_optimizer(g["ctx"])
             else:
-                with torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
+                with no_gc_during_capture(), torch.cuda.graph(graphs[0], capture_error_mode="thread_local"):
                     g["ctx"] = seg_a()
                 graphs.append(torch.cuda.CUDAGraph())
-                with torch.cuda.graph(graphs[1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
+                with no_gc_during_capture(), torch.cuda.graph(graphs[1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
                     g["loss"], g["dpred"] = seg_b(g["ctx"])
                 for stage in (("head", "body") if g["split"] else (None,)):
                     graphs.append(torch.cuda.CUDAGraph())
-                    with torch.cuda.graph(graphs[-1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
+                    with no_gc_during_capture(), torch.cuda.graph(graphs[-1], pool=graphs[0].pool(),
+                                                                  capture_error_mode="thread_local"):
                         seg_c(g["ctx"], g["dpred"], stage)
             g["graphs"], g["launches"] = graphs, _lib.launch_count - n0     # kernels one replay launches
             g["layout"] = self.store.layout_version
@@ -506,7 +507,10 @@ class Trainer:
                                                            # ranks must issue the same collectives, so no silent switch
                 # the CAPTURE failed (driver / allocator state): keep training with the same kernels issued eagerly
                 import sys
+                import traceback
                 print(f"lpm-b200: CUDA-graph capture of the training step failed ({e!r}); continuing eagerly", file=sys.stderr)
+                if os.environ.get("LPM_DEBUG"):
+                    traceback.print_exc()
                 self.use_graph, self.graph = False, None
                 torch.cuda.synchronize()
                 if self.shard is not None:

@@ -1,0 +1,32 @@
+"""BASELINE.json north-star acceptance at the config-1 shape (B=80, 256 of 300 frames, K=256/64, hidden 512, vocab 3862)
+with TRAINED weights: tests/trained_protocol.py trains the CUDA path on structured synthetic videos, copies the trained
+variables into the CPU oracle and compares inference on 1024 held-out videos.
+
+  relative L2 error <= 1e-3 on the VLAD descriptor, max-abs error <= 5e-3 on the sigmoid predictions, identical top-20
+  label sets on >= 99.9 % of the videos (top-k as in eval_util.top_k_triplets, eval_util.py:128-135).
+
+The model is run exactly as benchmarked (fp16 operands / fp32 accumulation in the body; split-precision operands in the
+head, engine._head).  scripts/trained_parity.py runs the same protocol with the precision study (the oracle with TF32 /
+fp16-rounded operands) and writes profiles/r2_trained_parity.json."""
+import json
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trained_weights_acceptance_config1(cuda):
+    from tests import trained_protocol as TP
+    eng, tr, protos, losses = TP.train_model(cuda, steps=2000)
+    assert tr.skipped_steps() == 0 and tr.graph is not None          # the captured, fused step is what trained the model
+    assert losses[-1][1] < 0.02 * losses[0][1], losses                # the loss fell from ~4000 to the label-prior level
+    rep = TP.evaluate(eng, protos, cuda, n_videos=1024)
+    print("\n[trained-weights acceptance, config 1] " + json.dumps({k: rep[k] for k in (
+        "vlad_video_rel_l2", "vlad_audio_rel_l2", "vlad_video_rel_l2_worst_video", "att_video_rel_l2", "hidden_rel_l2",
+        "gated_rel_l2", "pred_max_abs", "pred_median_abs", "top20_identical", "top20_identical_up_to_ties",
+        "top20_mean_overlap", "gap_oracle", "gap_gpu", "hit1_oracle", "n_videos", "top20_differences")}))
+    assert rep["vlad_video_rel_l2"] <= 1e-3 and rep["vlad_audio_rel_l2"] <= 1e-3 and rep["vlad_video_rel_l2_worst_video"] <= 1e-3
+    assert rep["pred_max_abs"] <= 5e-3
+    assert rep["top20_identical"] >= 0.999
+    assert rep["gpu_topk_kernel_consistent"] == 1.0                  # lpm_eval_topk picks what numpy picks from the same scores
+    assert abs(rep["gap_gpu"] - rep["gap_oracle"]) < 1e-4

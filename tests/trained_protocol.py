@@ -84,6 +84,7 @@ def top20_compare(ref, other, err_bound):
     a_sets, g_sets = E.top_k_sets(ref, 20), E.top_k_sets(other, 20)
     ident = tie = 0
     overlap = 0
+    diffs = []
     for r, (a, g) in enumerate(zip(a_sets, g_sets)):
         a, g = set(a), set(g)
         overlap += len(a & g)
@@ -92,9 +93,12 @@ def top20_compare(ref, other, err_bound):
             tie += 1
             continue
         kth = np.sort(ref[r])[-20]
+        diffs.append({"video": r, "kth_ref_score": float(kth),
+                      "labels": [(int(lab), float(ref[r, lab]), float(other[r, lab])) for lab in sorted(a ^ g)]})
         if all(abs(float(ref[r, lab]) - kth) <= err_bound for lab in (a ^ g)):
             tie += 1
     n = ref.shape[0]
+    top20_compare.last_diffs = diffs
     return ident / n, tie / n, overlap / n
 
 
@@ -113,6 +117,10 @@ def evaluate(eng, protos, device, *, n_videos=1024, chunk=128, emulate=(), stren
     emu_pred = {m: [] for m in emulate}
     vl = {"vlad_video": [0.0, 0.0], "vlad_audio": [0.0, 0.0], "att_video": [0.0, 0.0], "hidden": [0.0, 0.0], "gated": [0.0, 0.0]}
     worst_vlad = 0.0
+    # TensorFlow's CPU kernels run with flush-to-zero / denormals-are-zero (tensorflow/core/platform/denormal.h,
+    # ScopedFlushDenormal in its executor threads); the saturated predictions of this model (most sigmoids < 1e-38)
+    # make that visible in the tail of the ranking, so the checker computes the same way
+    ftz_was = torch.set_flush_denormal(True)
     for c0 in range(0, n_videos, chunk):
         n = min(chunk, n_videos - c0)
         x, nf, lab = structured_batch(n, 900000 + c0, protos, device, V=s["V"], max_frames=s["max_frames"], strength=strength)
@@ -143,6 +151,7 @@ def evaluate(eng, protos, device, *, n_videos=1024, chunk=128, emulate=(), stren
                 vl[k][1] += float((r ** 2).sum())
                 if k == "vlad_video":
                     worst_vlad = max(worst_vlad, float(((a - r).norm(dim=1) / r.norm(dim=1)).max()))
+    torch.set_flush_denormal(False)
     ref_pred, gpu_pred = np.concatenate(ref_pred), np.concatenate(gpu_pred)
     gpu_top, labels = np.concatenate(gpu_top), np.concatenate(labels)
     err = np.abs(gpu_pred - ref_pred)
@@ -152,7 +161,8 @@ def evaluate(eng, protos, device, *, n_videos=1024, chunk=128, emulate=(), stren
     out["pred_median_abs"] = float(np.median(err))
     out["pred_p999_abs"] = float(np.quantile(err, 0.999))
     ident, tie, ov = top20_compare(ref_pred, gpu_pred, 2 * float(err.max()))
-    out.update(top20_identical=ident, top20_identical_up_to_ties=tie, top20_mean_overlap=ov)
+    out.update(top20_identical=ident, top20_identical_up_to_ties=tie, top20_mean_overlap=ov,
+               top20_differences=top20_compare.last_diffs[:8])
     # the product's own on-GPU top-k (lpm_eval_topk) must select exactly the labels numpy selects from its predictions
     own = sum(sorted(gpu_top[r].tolist()) == sorted(np.argsort(-gpu_pred[r], kind="stable")[:20].tolist())
               for r in range(gpu_pred.shape[0]))
