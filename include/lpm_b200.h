@@ -79,6 +79,12 @@ int lpm_gemm_splits(int K, int requested_splits);
 int lpm_splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols,
                       const float* bias, int relu, float alpha, int accumulate, float* out_f32,
                       void* out_f16, lpm_stream_t stream);
+/* Same with two options used by the hidden projection (frame_level_models.py:2319-2334): part2 (may be NULL) is a second
+ * set of partials summed in -- the low-order pass of the split-precision product -- and split3 != 0 makes out_f16 the
+ * split-precision operand [n / cols][3 * cols] = [ hi | lo | hi ] of the result (see lpm_split_hi_lo_f16). */
+int lpm_splitk_reduce_ex(const float* part, int splits, long long split_stride, const float* part2, int splits2,
+                         long long split_stride2, long long n, int cols, const float* bias, int relu, float alpha,
+                         int accumulate, float* out_f32, void* out_f16, int split3, lpm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Frame sampling + input batch norm.
@@ -194,6 +200,13 @@ int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* 
                    const float* beta, float* moving_mean, float* moving_var, float decay, float eps,
                    int training, float* out_f32, void* out_f16, float* save_mean, float* save_rstd,
                    lpm_stream_t stream);
+/* Same, fed straight from the gate product's split-K partials: g = [g_splits][B][H] (g_split_stride elements apart) is
+ * summed in a fixed order into g_sum [B][H] (kept for the backward) before the batch norm; split3 != 0 makes out_f16
+ * the split-precision operand [B][3H] = [ hi | lo | hi ] of the gated activation for the MoE product. */
+int lpm_gating_fwd_ex(const float* act, const float* g, int g_splits, long long g_split_stride, float* g_sum, int B, int H,
+                      const float* wg_diag, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                      float decay, float eps, int training, float* out_f32, void* out_f16, int split3, float* save_mean,
+                      float* save_rstd, lpm_stream_t stream);
 
 /* MoE mixing (video_level_models.py:116-126): logits fp32 [B][ld]; gates V*(M+1) at column 0, experts V*M at
  * column expert_off (lets the caller pad the gate block to a 16-byte boundary). */

@@ -123,7 +123,17 @@ int lpm_splitk_reduce(const float* part, int splits, long long split_stride, lon
                       void* out_f16, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(part && splits > 0 && n > 0 && cols > 0, "lpm_splitk_reduce: bad arguments");
-  return splitk_reduce(part, splits, split_stride, n, cols, bias, relu, alpha, accumulate, out_f32, H16(out_f16), ST(stream));
+  return splitk_reduce(part, splits, split_stride, nullptr, 0, 0, n, cols, bias, relu, alpha, accumulate, out_f32, H16(out_f16), 0,
+                       ST(stream));
+}
+
+int lpm_splitk_reduce_ex(const float* part, int splits, long long split_stride, const float* part2, int splits2,
+                         long long split_stride2, long long n, int cols, const float* bias, int relu, float alpha,
+                         int accumulate, float* out_f32, void* out_f16, int split3, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(part && splits > 0 && n > 0 && cols > 0 && (part2 == nullptr || splits2 > 0), "lpm_splitk_reduce_ex: bad arguments");
+  return splitk_reduce(part, splits, split_stride, part2, splits2, split_stride2, n, cols, bias, relu, alpha, accumulate, out_f32,
+                       H16(out_f16), split3, ST(stream));
 }
 
 int lpm_sample_stats_blocks(void) { return sample_stats_blocks(); }
@@ -223,8 +233,19 @@ int lpm_gating_fwd(const float* act, const float* g, int B, int H, const float* 
                    lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(act && g && gamma && beta && moving_mean && moving_var && out_f32, "lpm_gating_fwd: null pointer");
-  return gating_fwd(act, g, B, H, wg_diag, gamma, beta, moving_mean, moving_var, decay, eps, training, out_f32,
+  return gating_fwd(act, g, 1, 0, nullptr, 0, B, H, wg_diag, gamma, beta, moving_mean, moving_var, decay, eps, training, out_f32,
                     H16(out_f16), save_mean, save_rstd, ST(stream));
+}
+
+int lpm_gating_fwd_ex(const float* act, const float* g, int g_splits, long long g_split_stride, float* g_sum, int B, int H,
+                      const float* wg_diag, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                      float decay, float eps, int training, float* out_f32, void* out_f16, int split3, float* save_mean,
+                      float* save_rstd, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(act && g && gamma && beta && moving_mean && moving_var && out_f32, "lpm_gating_fwd_ex: null pointer");
+  LPM_REQUIRE(g_splits >= 1 && (g_splits == 1 || g_sum != nullptr), "lpm_gating_fwd_ex: split-K partials need g_sum");
+  return gating_fwd(act, g, g_splits, g_split_stride, g_sum, split3, B, H, wg_diag, gamma, beta, moving_mean, moving_var, decay, eps,
+                    training, out_f32, H16(out_f16), save_mean, save_rstd, ST(stream));
 }
 
 int lpm_moe_mix_fwd(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred,

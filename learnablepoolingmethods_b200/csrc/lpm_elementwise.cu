@@ -419,11 +419,14 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const __half* __restrict_
 // split-K reduction + bias (+ReLU):  out[r][c] = act( sum_s part[s][r][c] + bias[c] )  -> fp32 and/or fp16
 // (hidden projection, frame_level_models.py:2319,2329-2334, and split-K weight gradients)
 // ------------------------------------------------------------------------------------------------
+// part2 (optional): a second set of partials summed in (the low-order pass of a split-precision product).  split3: out16
+// is [n / cols][3 * cols] = [hi | lo | hi] of the result (the split-precision operand of the next product).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits,
-                                                            long long split_stride, long long n, int cols,
+                                                            long long split_stride, const float* __restrict__ part2,
+                                                            int splits2, long long split_stride2, long long n, int cols,
                                                             const float* __restrict__ bias, int relu, float alpha,
                                                             int accumulate, float* __restrict__ out32,
-                                                            __half* __restrict__ out16) {
+                                                            __half* __restrict__ out16, int split3) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     // four independent partial sums: the loop is load-latency bound (up to 148 splits), order stays fixed
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -434,11 +437,26 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
     for (; k < splits; ++k) s0 += part[k * split_stride + i];
     float s = (s0 + s1) + (s2 + s3);
+    if (part2 != nullptr) {
+      float t0 = 0.f, t1 = 0.f;
+      for (k = 0; k + 1 < splits2; k += 2) { t0 += part2[k * split_stride2 + i]; t1 += part2[(k + 1) * split_stride2 + i]; }
+      for (; k < splits2; ++k) t0 += part2[k * split_stride2 + i];
+      s += t0 + t1;
+    }
     s *= alpha;
     if (bias) s += __ldg(bias + (i % cols));
     if (relu) s = fmaxf(s, 0.f);
-    if (out32) out32[i] = accumulate ? out32[i] + s : s;
-    if (out16) out16[i] = __float2half_rn(s);
+    if (out32) { if (accumulate) s += out32[i]; out32[i] = s; }
+    if (out16) {
+      const __half hi = __float2half_rn(s);
+      if (split3) {
+        const long long r = i / cols;
+        __half* d = out16 + r * 3 * cols + (i - r * cols);
+        d[0] = hi; d[cols] = __float2half_rn(s - __half2float(hi)); d[2 * cols] = hi;
+      } else {
+        out16[i] = hi;
+      }
+    }
   }
 }
 
@@ -446,7 +464,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // Context gating (frame_level_models.py:2342-2368): gates = BN_batch(g [- diag(Wg) * act]) ;
 // act *= sigmoid(gates).  One thread per hidden unit, loops over the (small) batch.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) gating_fwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int B, int H,
+// g_splits > 1: g holds split-K partials [g_splits][B][H] (g_split_stride apart) of the gate product; they are summed here
+// (fixed order) and the sum is stored to g_sum for the backward.  split3: out16 is [B][3H] = [hi | lo | hi].
+__global__ void __launch_bounds__(1024) gating_fwd_kernel(const float* __restrict__ act, const float* __restrict__ g, int g_splits,
+                                  long long g_split_stride, float* __restrict__ g_sum, int split3, int B, int H,
                                   const float* __restrict__ wg_diag, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
                                   float* __restrict__ moving_var, float decay, float eps, int training,
@@ -459,6 +480,15 @@ __global__ void __launch_bounds__(1024) gating_fwd_kernel(const float* __restric
   const int c = blockIdx.x * 32 + cx;
   const bool ok = c < H;
   const float dg = (wg_diag && ok) ? wg_diag[c] : 0.f;
+  if (g_splits > 1) {
+    if (ok)
+      for (int b = ky; b < B; b += 32) {
+        float t = 0.f;
+        for (int k = 0; k < g_splits; ++k) t += g[k * g_split_stride + (size_t)b * H + c];
+        g_sum[(size_t)b * H + c] = t;
+      }
+    g = g_sum;                 // a thread re-reads only the elements it wrote itself
+  }
   if (training) {
     double s = 0.0, q = 0.0;
     if (ok)
@@ -495,7 +525,15 @@ __global__ void __launch_bounds__(1024) gating_fwd_kernel(const float* __restric
     const float v = (g[(size_t)b * H + c] - dg * a) * sc + sh;
     const float o = a / (1.f + __expf(-v));
     out32[(size_t)b * H + c] = o;
-    if (out16) out16[(size_t)b * H + c] = __float2half_rn(o);
+    if (out16) {
+      const __half hi = __float2half_rn(o);
+      if (split3) {
+        __half* d = out16 + (size_t)b * 3 * H + c;
+        d[0] = hi; d[H] = __float2half_rn(o - __half2float(hi)); d[2 * H] = hi;
+      } else {
+        out16[(size_t)b * H + c] = hi;
+      }
+    }
   }
 }
 
@@ -715,19 +753,20 @@ int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, __half
   return LPM_OK;
 }
 
-int splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols, const float* bias,
-                  int relu, float alpha, int accumulate, float* out32, __half* out16, cudaStream_t st) {
-  splitk_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(part, splits, split_stride, n, cols, bias, relu, alpha,
-                                                         accumulate, out32, out16);
+int splitk_reduce(const float* part, int splits, long long split_stride, const float* part2, int splits2, long long split_stride2,
+                  long long n, int cols, const float* bias, int relu, float alpha, int accumulate, float* out32, __half* out16,
+                  int split3, cudaStream_t st) {
+  splitk_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(part, splits, split_stride, part2, splits2, split_stride2, n, cols, bias,
+                                                         relu, alpha, accumulate, out32, out16, split3);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }
 
-int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
-               const float* beta, float* mm, float* mv, float decay, float eps, int training, float* out32,
-               __half* out16, float* save_mean, float* save_rstd, cudaStream_t st) {
-  gating_fwd_kernel<<<(H + 31) / 32, 1024, 0, st>>>(act, g, B, H, wg_diag, gamma, beta, mm, mv, decay, eps, training,
-                                                  out32, out16, save_mean, save_rstd);
+int gating_fwd(const float* act, const float* g, int g_splits, long long g_split_stride, float* g_sum, int split3, int B, int H,
+               const float* wg_diag, const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps,
+               int training, float* out32, __half* out16, float* save_mean, float* save_rstd, cudaStream_t st) {
+  gating_fwd_kernel<<<(H + 31) / 32, 1024, 0, st>>>(act, g, g_splits, g_split_stride, g_sum, split3, B, H, wg_diag, gamma, beta, mm,
+                                                  mv, decay, eps, training, out32, out16, save_mean, save_rstd);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

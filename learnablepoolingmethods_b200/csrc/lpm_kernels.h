@@ -30,11 +30,12 @@ int scale_rows(const __half* x, const float* rs, long long rows, int D, __half* 
 int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, __half* u_out, int B, int rows, int D,
                     long long a_stride, long long b_stride, const float* gamma, const float* beta, float eps,
                     __half* y, long long y_stride, float* partial, float* save_mean_rstd, cudaStream_t st);
-int splitk_reduce(const float* part, int splits, long long split_stride, long long n, int cols, const float* bias,
-                  int relu, float alpha, int accumulate, float* out32, __half* out16, cudaStream_t st);
-int gating_fwd(const float* act, const float* g, int B, int H, const float* wg_diag, const float* gamma,
-               const float* beta, float* mm, float* mv, float decay, float eps, int training, float* out32,
-               __half* out16, float* save_mean, float* save_rstd, cudaStream_t st);
+int splitk_reduce(const float* part, int splits, long long split_stride, const float* part2, int splits2, long long split_stride2,
+                  long long n, int cols, const float* bias, int relu, float alpha, int accumulate, float* out32, __half* out16,
+                  int split3, cudaStream_t st);
+int gating_fwd(const float* act, const float* g, int g_splits, long long g_split_stride, float* g_sum, int split3, int B, int H,
+               const float* wg_diag, const float* gamma, const float* beta, float* mm, float* mv, float decay, float eps,
+               int training, float* out32, __half* out16, float* save_mean, float* save_rstd, cudaStream_t st);
 int moe_mix(const float* logits, long long ld, int B, int V, int M, int expert_off, float* pred, cudaStream_t st);
 int xent_loss(const float* pred, const uint8_t* labels, int B, int V, float* row_loss, float* loss, cudaStream_t st);
 int cast_2d(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int cols_dst,

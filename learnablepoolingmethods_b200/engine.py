@@ -651,29 +651,27 @@ class NetVladEngine:
             parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
         if c.netvlad_relu:
             hpre = act32
-            ops.splitk_reduce(parts, out32=hpre)
-            if parts_lo is not None:
-                ops.splitk_reduce(parts_lo, out32=hpre, accumulate=True)
+            ops.splitk_reduce(parts, out32=hpre, parts2=parts_lo)
             r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
                                         v["hidden1_bn/moving_variance"], training=training, save=save)
             act32 = r[0]
             hstats = r[2] if save else None
+            a3 = ops.split_hi_lo(act32)                               # [B, 3H] = [hi | lo | hi]
         else:
-            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32)
-            if parts_lo is not None:
-                ops.splitk_reduce(parts_lo, out32=act32, accumulate=True)
+            # one kernel: sum of the partials (both passes), bias, fp32 activation and its split-precision operand
+            a3 = torch.empty((B, 3 * Hn), dtype=torch.float16, device=vlad.device)
+            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=a3, parts2=parts_lo, split3=True)
         # The gate and MoE products run with split-precision operands (x = hi + lo in two fp16 terms, one GEMM over a 3x
         # longer reduction, ops.split_hi_lo): `hidden` is O(30) at this model's initialisation scale and feeds sigmoids, so
         # 10-bit-mantissa operands in these two small products are what limits the predictions (numerics).
-        a3 = ops.split_hi_lo(act32)                                   # [B, 3H] = [hi | lo | hi]
         act16 = a3[:, :Hn]                                            # plain fp16 view for the backward
         if c.gating:
-            gates = ops.gemm(a3, sh["wg16x3"], out_dtype=torch.float32)
+            # split-K partials of the gate product go straight into the gating kernel (summed there in a fixed order)
+            gparts = ops.gemm(a3, sh["wg16x3"], splits=6)
             diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
-            r = ops.gating_fwd(act32, gates, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
-                               v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save)
-            gated32 = r[0]
-            g3 = ops.split_hi_lo(gated32)
+            r = ops.gating_fwd(act32, gparts, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
+                               v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save, split3=True)
+            gated32, g3, gates = r[0], r[1], r[3].view(B, Hn)
         else:
             gates, gated32, g3, r = None, act32, a3, (None, None, None)
         gated16 = g3[:, :Hn]

@@ -128,14 +128,25 @@ def _f16(shape, dev):
     return torch.empty(shape, dtype=torch.float16, device=dev)
 
 
-def splitk_reduce(parts, *, bias=None, relu=False, alpha=1.0, out32=None, out16=None, accumulate=False):
+def splitk_reduce(parts, *, bias=None, relu=False, alpha=1.0, out32=None, out16=None, accumulate=False, parts2=None,
+                  split3=False):
+    """Deterministic sum of split-K partials [splits, ...] (+ a second set `parts2`), bias / ReLU, fp32 and fp16 outputs;
+    split3: out16 is [rows, 3*cols] = [hi | lo | hi] (split-precision operand, see split_hi_lo)."""
     lib = _lib.load()
     splits = parts.shape[0]
     n = parts[0].numel()
     cols = parts.shape[-1]
-    check(lib.lpm_splitk_reduce(ptr(parts), splits, C.c_longlong(parts.stride(0)), C.c_longlong(n), cols, ptr(bias),
-                                int(relu), C.c_float(alpha), int(accumulate), ptr(out32), ptr(out16), stream_ptr()),
-          "lpm_splitk_reduce")
+    if parts2 is None and not split3:
+        check(lib.lpm_splitk_reduce(ptr(parts), splits, C.c_longlong(parts.stride(0)), C.c_longlong(n), cols, ptr(bias),
+                                    int(relu), C.c_float(alpha), int(accumulate), ptr(out32), ptr(out16), stream_ptr()),
+              "lpm_splitk_reduce")
+        return
+    assert parts2 is None or parts2[0].numel() == n
+    check(lib.lpm_splitk_reduce_ex(ptr(parts), splits, C.c_longlong(parts.stride(0)), ptr(parts2),
+                                   0 if parts2 is None else parts2.shape[0],
+                                   C.c_longlong(0 if parts2 is None else parts2.stride(0)), C.c_longlong(n), cols, ptr(bias),
+                                   int(relu), C.c_float(alpha), int(accumulate), ptr(out32), ptr(out16), int(split3),
+                                   stream_ptr()), "lpm_splitk_reduce")
 
 
 def cast_f16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, cols_dst: Optional[int] = None):
@@ -403,17 +414,28 @@ def layernorm_chain_fwd(a, b, B, rows, D, gamma1, beta1, gamma2, beta2, *, out, 
 
 
 def gating_fwd(act, g, gamma, beta, moving_mean, moving_var, *, training, wg_diag=None, save=False,
-               decay=BN_DECAY, eps=BN_EPS):
+               decay=BN_DECAY, eps=BN_EPS, split3=False):
+    """Context gating.  g: the gate pre-activations [B, H], or their split-K partials [S, B, H] (summed inside; the sum is
+    returned as 4th result).  split3: the fp16 output is the split-precision operand [B, 3H] = [hi | lo | hi]."""
     lib = _lib.load()
     B, H = act.shape
     dev = act.device
-    out32, out16 = _f32((B, H), dev), _f16((B, H), dev)
+    out32, out16 = _f32((B, H), dev), _f16((B, 3 * H if split3 else H), dev)
     sm = _f32((2, H), dev) if save else None
-    check(lib.lpm_gating_fwd(ptr(act), ptr(g), B, H, ptr(wg_diag), ptr(gamma), ptr(beta), ptr(moving_mean),
-                             ptr(moving_var), C.c_float(decay), C.c_float(eps), int(training), ptr(out32), ptr(out16),
-                             ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
+    if g.dim() == 2 and not split3:
+        check(lib.lpm_gating_fwd(ptr(act), ptr(g), B, H, ptr(wg_diag), ptr(gamma), ptr(beta), ptr(moving_mean),
+                                 ptr(moving_var), C.c_float(decay), C.c_float(eps), int(training), ptr(out32), ptr(out16),
+                                 ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
+              "lpm_gating_fwd")
+        return (out32, out16, sm) if save else (out32, out16)
+    splits = g.shape[0] if g.dim() == 3 else 1
+    g_sum = _f32((B, H), dev) if splits > 1 else g
+    check(lib.lpm_gating_fwd_ex(ptr(act), ptr(g), splits, _ll(g.stride(0) if splits > 1 else 0), ptr(g_sum) if splits > 1 else None,
+                                B, H, ptr(wg_diag), ptr(gamma), ptr(beta), ptr(moving_mean), ptr(moving_var), C.c_float(decay),
+                                C.c_float(eps), int(training), ptr(out32), ptr(out16), int(split3),
+                                ptr(sm[0]) if save else None, ptr(sm[1]) if save else None, stream_ptr()),
           "lpm_gating_fwd")
-    return (out32, out16, sm) if save else (out32, out16)
+    return (out32, out16, sm, g_sum) if save else (out32, out16, None, g_sum)
 
 
 def moe_mix_fwd(logits, V, M, expert_off=None):

@@ -48,7 +48,7 @@ for K in Ks:
         if rank == 0:
             print(json.dumps({"config": "infer sweep", "n_gpus": world, "K": K, "batch_per_gpu": B, "num_frames": "U{1..300}",
                               "ms": round(ms, 3), "videos_per_s": round(B * world / ms * 1e3, 1), "ms_graph": round(ms_g, 3),
-                              "videos_per_s_graph": round(B * world / ms_g * 1e3, 1)}), flush=True)
+                              "videos_per_s_graph": round(B * world / ms_g * 1e3, 1)}), file=bench._JSON_OUT, flush=True)
         del ig, x
     del eng, store
     torch.cuda.empty_cache()
