@@ -31,17 +31,22 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 // (conflict-free ldmatrix).
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
 
+// Asynchronous (cp.async, 16 bytes per request) so that every chunk of every tile of a head is in flight at once: the
+// register-staged version (LDG -> STS per chunk in a run-time loop) serialised the round trips and the prologue was 40 %
+// of the forward kernel's warp time (ncu: long-scoreboard stalls).  Callers finish with head_tiles_wait() + barrier.
 template <int DH>
 __device__ __forceinline__ void load_head_tile(uint8_t* dst, const __half* src, long long ld, int L) {
   // src: first element of this head's columns in row 0; DH halves per row
   constexpr int CH = DH / 8;
   for (int i = threadIdx.x; i < L * 2; i += blockDim.x) {
     const int r = i >> 1, c = i & 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (c < CH) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
-    *reinterpret_cast<uint4*>(dst + tile_off(r, c)) = v;
+    const bool real = c < CH;                       // depth-8 heads: the second 16-byte chunk of a row is zero padding
+    const __half* g = src + (long long)r * ld + (real ? c * 8 : 0);
+    const int bytes = real ? 16 : 0;                // src-size 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + tile_off(r, c))), "l"(g), "r"(bytes) : "memory");
   }
 }
+__device__ __forceinline__ void head_tiles_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // mma with a zero C operand (no accumulator initialisation instructions)
 __device__ __forceinline__ void mma16816_z(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -83,6 +88,7 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const __half* __restrict__
       sKs[i] = key_scale[i] * 1.4426950408889634f;
       sKb[i] = key_shift[i] * 1.4426950408889634f;
     }
+  head_tiles_wait();
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mha_bwd_kernel(const __
       sBn[5 * L + r] = MODE == 2 ? bn.m2[r] : 0.f;
     }
   }
+  head_tiles_wait();
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

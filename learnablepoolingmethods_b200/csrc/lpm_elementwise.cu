@@ -556,11 +556,7 @@ __global__ void moe_mix_kernel(const float* __restrict__ logits, long long ld, i
       den += e;
       if (m < M) num += e / (1.f + __expf(-el[m]));
     }
-    // flush-to-zero like the reference's runtime (TensorFlow executes its CPU kernels with FTZ/DAZ set, and its GPU
-    // kernels are built with -ftz): a saturated model emits most of its sigmoids below FLT_MIN, and leaving denormals in
-    // would order the zero tail of every top-k ranking by rounding noise
-    const float pv = num / den;
-    pred[i] = pv < 1.17549435e-38f ? 0.f : pv;
+    pred[i] = num / den;
   }
 }
 
