@@ -245,8 +245,12 @@ struct MhaBnArgs {
 
 // NT = threads per CTA: 512 (one CTA per SM, the whole dS^T of a 256-query chunk parked) or 256 with query chunks of 128:
 // two CTAs per SM, so that the load prologue and the pass barriers of one head hide under the other head's math.
+// Registers: 96 per thread for the 512-thread layout (92 used, no spills) = 48 K of the SM's 64 K registers, which leaves
+// room for one 128-thread CTA of the tiled factored Adam (rank_adam_tile_kernel, 16 K registers, 5 KB of shared memory)
+// next to it: this kernel is issue-bound and moves < 1 TB/s, so the HBM-bound hidden1_weights update hides under it
+// (trainer._fork_hidden_update).  __maxnreg__ and __launch_bounds__ are mutually exclusive.
 template <int DH, int MODE, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
+__global__ void __maxnreg__(NT == 512 ? 96 : 128) mha_bwd_kernel(const __half* __restrict__ qkv, long long ld,
                                                          const __half* __restrict__ o, const __half* __restrict__ dout,
                                                          long long ldo, const float* __restrict__ lse, int L, int Dm,
                                                          int H, float scale, __half* __restrict__ dqkv, long long ldd, const MhaBnArgs bn,

@@ -546,32 +546,47 @@ __global__ void __launch_bounds__(256) center_bwd_kernel(const __half* __restric
   E[(size_t)k * D + d] = s2 + s1 * (centers_t[(size_t)k * D + d] - beta_in[d]);
 }
 
-// D % 8 == 0: a thread owns 8 consecutive features of one cluster (16-byte loads of dV / Z, four videos in flight)
-__global__ void __launch_bounds__(128) center_bwd_vec_kernel(const __half* __restrict__ dV, const __half* __restrict__ Z,
-                                                             const float* __restrict__ a_sum, int B, int K, int D,
+// D % 8 == 0: a thread owns 8 consecutive features of one cluster (16-byte loads of dV / Z); the 256 threads of a block
+// are `cgs` column groups x 256 / cgs video lanes (a lane walks every (256 / cgs)-th video), the lanes' partial sums are
+// combined through shared memory in lane order (deterministic).  grid = (ceil(D / 8 / cgs), K).
+__global__ void __launch_bounds__(256) center_bwd_vec_kernel(const __half* __restrict__ dV, const __half* __restrict__ Z,
+                                                             const float* __restrict__ a_sum, int B, int K, int D, int cgs,
                                                              const float* __restrict__ centers_t,
                                                              const float* __restrict__ beta_in, float inv_scale,
                                                              float* __restrict__ dCt, float* __restrict__ E) {
+  __shared__ float sh[2][256 * 8];
+  const int lanes = 256 / cgs;
+  const int cg = threadIdx.x % cgs, vl = threadIdx.x / cgs;
   const int k = blockIdx.y;
-  const int d0 = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (d0 >= D) return;
+  const int d0 = (blockIdx.x * cgs + cg) * 8;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (d0 < D) {
 #pragma unroll 4
-  for (int b = 0; b < B; ++b) {
-    const size_t i = ((size_t)b * K + k) * D + d0;
-    float dv[8], zz[8];
-    load8(dV + i, dv); load8(Z + i, zz);
-    const float as = __ldg(a_sum + b * K + k);
+    for (int b = vl; b < B; b += lanes) {
+      const size_t i = ((size_t)b * K + k) * D + d0;
+      float dv[8], zz[8];
+      load8(dV + i, dv); load8(Z + i, zz);
+      const float as = __ldg(a_sum + b * K + k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] = fmaf(as, dv[j], s1[j]); s2[j] = fmaf(dv[j], zz[j], s2[j]); }
+      for (int j = 0; j < 8; ++j) { s1[j] = fmaf(as, dv[j], s1[j]); s2[j] = fmaf(dv[j], zz[j], s2[j]); }
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float a = s1[j] * inv_scale, b2 = s2[j] * inv_scale;
-    dCt[(size_t)k * D + d0 + j] = -a;
-    E[(size_t)k * D + d0 + j] = b2 + a * (centers_t[(size_t)k * D + d0 + j] - beta_in[d0 + j]);
+  for (int j = 0; j < 8; ++j) { sh[0][(vl * cgs + cg) * 8 + j] = s1[j]; sh[1][(vl * cgs + cg) * 8 + j] = s2[j]; }
+  __syncthreads();
+  // cgs * 8 output columns per block, one thread each (cgs * 8 <= 256)
+  const int c = threadIdx.x;
+  if (c < cgs * 8) {
+    const int d = blockIdx.x * cgs * 8 + c;
+    if (d < D) {
+      float a = 0.f, b2 = 0.f;
+      for (int l = 0; l < lanes; ++l) { a += sh[0][l * cgs * 8 + c]; b2 += sh[1][l * cgs * 8 + c]; }
+      a *= inv_scale; b2 *= inv_scale;
+      dCt[(size_t)k * D + d] = -a;
+      E[(size_t)k * D + d] = b2 + a * (centers_t[(size_t)k * D + d] - beta_in[d]);
+    }
   }
 }
 
@@ -720,8 +735,10 @@ int assign_bwd2(__half* dsh, const __half* S, const float* mean, const float* rs
 int center_bwd(const __half* dV, const __half* Z, const float* a_sum, int B, int K, int D, const float* centers_t,
                const float* beta_in, float inv_scale, float* dCt, float* E, cudaStream_t st) {
   if (D % 8 == 0 && ((reinterpret_cast<uintptr_t>(dV) | reinterpret_cast<uintptr_t>(Z)) & 15) == 0) {
-    dim3 grid((D / 8 + 127) / 128, K);
-    center_bwd_vec_kernel<<<grid, 128, 0, st>>>(dV, Z, a_sum, B, K, D, centers_t, beta_in, inv_scale, dCt, E);
+    int cgs = 32;                                  // column groups per block (power of two <= 32 that covers D / 8)
+    while (cgs > 1 && cgs > D / 8) cgs >>= 1;
+    dim3 grid((D / 8 + cgs - 1) / cgs, K);
+    center_bwd_vec_kernel<<<grid, 256, 0, st>>>(dV, Z, a_sum, B, K, D, cgs, centers_t, beta_in, inv_scale, dCt, E);
     LPM_CUDA_CHECK(cudaGetLastError());
     return LPM_OK;
   }

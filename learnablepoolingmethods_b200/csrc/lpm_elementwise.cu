@@ -460,6 +460,52 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// Many partials, few outputs (the hidden projection: 74-222 partials of an [80, 512] result): a block owns 32 consecutive
+// outputs, its 8 warps each sum every 8th partial (coalesced 128-byte rows, four loads in flight), and warp 0 adds the
+// eight sums in warp order (deterministic).  The one-thread-per-output kernel above walks the partials serially.
+__global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float* __restrict__ part, int splits,
+                                                                 long long split_stride, const float* __restrict__ part2,
+                                                                 int splits2, long long split_stride2, long long n, int cols,
+                                                                 const float* __restrict__ bias, int relu, float alpha,
+                                                                 int accumulate, float* __restrict__ out32,
+                                                                 __half* __restrict__ out16, int split3) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n) {
+    int k = w;
+    for (; k + 24 < splits; k += 32) {
+      s0 += part[k * split_stride + i]; s1 += part[(k + 8) * split_stride + i];
+      s2 += part[(k + 16) * split_stride + i]; s3 += part[(k + 24) * split_stride + i];
+    }
+    for (; k < splits; k += 8) s0 += part[k * split_stride + i];
+    if (part2 != nullptr)
+      for (k = w; k < splits2; k += 8) s1 += part2[k * split_stride2 + i];
+  }
+  sh[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += sh[ww][lane];
+    s *= alpha;
+    if (bias) s += __ldg(bias + (i % cols));
+    if (relu) s = fmaxf(s, 0.f);
+    if (out32) { if (accumulate) s += out32[i]; out32[i] = s; }
+    if (out16) {
+      const __half hi = __float2half_rn(s);
+      if (split3) {
+        const long long r = i / cols;
+        __half* d = out16 + r * 3 * cols + (i - r * cols);
+        d[0] = hi; d[cols] = __float2half_rn(s - __half2float(hi)); d[2 * cols] = hi;
+      } else {
+        out16[i] = hi;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Context gating (frame_level_models.py:2342-2368): gates = BN_batch(g [- diag(Wg) * act]) ;
 // act *= sigmoid(gates).  One thread per hidden unit, loops over the (small) batch.
@@ -752,6 +798,12 @@ int layernorm_joint(__half* a, const __half* b, const float* b_row_scale, __half
 int splitk_reduce(const float* part, int splits, long long split_stride, const float* part2, int splits2, long long split_stride2,
                   long long n, int cols, const float* bias, int relu, float alpha, int accumulate, float* out32, __half* out16,
                   int split3, cudaStream_t st) {
+  if (splits + splits2 >= 32 && n <= (1 << 20)) {
+    splitk_reduce_wide_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(part, splits, split_stride, part2, splits2, split_stride2, n,
+                                                                        cols, bias, relu, alpha, accumulate, out32, out16, split3);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
   splitk_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(part, splits, split_stride, part2, splits2, split_stride2, n, cols, bias,
                                                          relu, alpha, accumulate, out32, out16, split3);
   LPM_CUDA_CHECK(cudaGetLastError());
@@ -828,8 +880,77 @@ __global__ void __launch_bounds__(256) split_hi_lo_kernel(const float* __restric
   }
 }
 
+// cols % 8 == 0, 16-byte aligned rows: 8 elements per thread, 32-byte loads and 16-byte stores
+__global__ void __launch_bounds__(256) split_hi_lo_vec_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols,
+                                                              __half* __restrict__ dst, long long ld_dst, int mode) {
+  const int c8 = cols / 8;
+  const long long n = (long long)rows * c8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / c8), c = (int)(i - (long long)r * c8) * 8;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld_src + c));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld_src + c + 4));
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half h0 = __float2half_rn(x[2 * j]), h1 = __float2half_rn(x[2 * j + 1]);
+      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[j] = pack_half2(x[2 * j] - __half2float(h0), x[2 * j + 1] - __half2float(h1));
+    }
+    const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    __half* d = dst + (long long)r * ld_dst + c;
+    if (mode == 0) {
+      *reinterpret_cast<uint4*>(d) = vh; *reinterpret_cast<uint4*>(d + cols) = vl; *reinterpret_cast<uint4*>(d + 2 * cols) = vh;
+    } else if (mode == 1) {
+      *reinterpret_cast<uint4*>(d) = vh; *reinterpret_cast<uint4*>(d + (long long)rows * ld_dst) = vh;
+      *reinterpret_cast<uint4*>(d + 2ll * rows * ld_dst) = vl;
+    } else {
+      *reinterpret_cast<uint4*>(d) = vl;
+    }
+  }
+}
+
+// cols % 2 == 0 (the MoE weights: 3 * 3862 and 2 * 3862 columns): two elements per thread, 8-byte loads, 4-byte stores
+__global__ void __launch_bounds__(256) split_hi_lo_pair_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols,
+                                                               __half* __restrict__ dst, long long ld_dst, int mode) {
+  const int c2 = cols / 2;
+  const long long n = (long long)rows * c2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / c2), c = (int)(i - (long long)r * c2) * 2;
+    const float2 x = __ldg(reinterpret_cast<const float2*>(src + (long long)r * ld_src + c));
+    const __half h0 = __float2half_rn(x.x), h1 = __float2half_rn(x.y);
+    const uint32_t vh = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    const uint32_t vl = pack_half2(x.x - __half2float(h0), x.y - __half2float(h1));
+    __half* d = dst + (long long)r * ld_dst + c;
+    if (mode == 0) {
+      *reinterpret_cast<uint32_t*>(d) = vh; *reinterpret_cast<uint32_t*>(d + cols) = vl; *reinterpret_cast<uint32_t*>(d + 2 * cols) = vh;
+    } else if (mode == 1) {
+      *reinterpret_cast<uint32_t*>(d) = vh; *reinterpret_cast<uint32_t*>(d + (long long)rows * ld_dst) = vh;
+      *reinterpret_cast<uint32_t*>(d + 2ll * rows * ld_dst) = vl;
+    } else {
+      *reinterpret_cast<uint32_t*>(d) = vl;
+    }
+  }
+}
+
 int split_hi_lo(const float* src, long long ld_src, int rows, int cols, __half* dst, long long ld_dst, int mode, cudaStream_t st) {
   const long long n = (long long)rows * cols;
+  if (cols % 8 != 0 && cols % 2 == 0 && ld_src % 2 == 0 && ld_dst % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    long long blocks = (n / 2 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_hi_lo_pair_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, mode);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
+  if (cols % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_hi_lo_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, mode);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
+  }
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   split_hi_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst, mode);

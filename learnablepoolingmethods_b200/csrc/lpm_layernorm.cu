@@ -15,6 +15,8 @@
 // two-kernel path it replaces read a, b, wrote u, re-read u and wrote y, per norm.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "lpm_common.cuh"
 #include "lpm_kernels.h"
 
@@ -61,6 +63,7 @@ __device__ __forceinline__ uint4 ln_pack_lo(const float* f, const uint4& hi) {
 }
 
 // (sum, sumsq) of this CTA -> cluster-wide (mean, rstd), reduced in rank order (deterministic)
+template <int NW>
 __device__ __forceinline__ float2 ln_cluster_moments(float s, float q, float* red, float2* slot, double n, float eps) {
   cg::cluster_group cluster = cg::this_cluster();
   s = warp_sum(s); q = warp_sum(q);
@@ -70,7 +73,7 @@ __device__ __forceinline__ float2 ln_cluster_moments(float s, float q, float* re
   if (threadIdx.x == 0) {
     float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+    for (int i = 0; i < NW; ++i) { ts += red[i]; tq += red[8 + i]; }
     *slot = make_float2(ts, tq);
   }
   cluster.sync();                                  // every CTA's slot is written and visible cluster-wide
@@ -91,9 +94,15 @@ __device__ __forceinline__ float2 ln_cluster_moments(float s, float q, float* re
   return make_float2(red[16], red[17]);
 }
 
-__global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
+// STAGE = true: this CTA's slice of u lives in shared memory between the passes (64 KB per CTA at config 1: three CTAs per
+// SM, 640 CTAs = 1.45 waves).  STAGE = false: no shared-memory slice -- the later passes re-read a and b, which are still in
+// the 126 MB L2 (a sample is 1 MB, a resident wave of samples < 100 MB), and recompute u: every CTA of the launch is
+// resident at once and HBM still sees one pass.  Same arithmetic, same rounding points (u and y1 are rounded to fp16
+// exactly where the staged version stores them).
+template <bool STAGE, int NT>
+__global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
   extern __shared__ __align__(16) uint8_t ln_sm[];
-  uint4* sU = reinterpret_cast<uint4*>(ln_sm);                 // this CTA's slice of u (fp16)
+  uint4* sU = reinterpret_cast<uint4*>(ln_sm);                 // this CTA's slice of u (fp16), STAGE only
   __shared__ float red[32];
   __shared__ float2 slots[2];
   cg::cluster_group cluster = cg::this_cluster();
@@ -109,16 +118,16 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
 
   // ---- pass A: u1 = a + b*rs -> shared memory (+ global when the backward wants it), moments ------------------
   float s = 0.f, q = 0.f;
-  for (int base = 0; base < cnt; base += 4 * 256) {
+  for (int base = 0; base < cnt; base += 4 * NT) {
     uint4 va[4], vb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = base + k * 256 + threadIdx.x;
+      const int i = base + k * NT + threadIdx.x;
       if (i < cnt) { va[k] = pa[i]; vb[k] = __ldg(pb + i); }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = base + k * 256 + threadIdx.x;
+      const int i = base + k * NT + threadIdx.x;
       if (i < cnt) {
         float fa[8], fb[8];
         ln_unpack(va[k], fa); ln_unpack(vb[k], fb);
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) fa[j] += fb[j] * rs;
         const uint4 vu = ln_pack(fa);
-        sU[i] = vu;
+        if (STAGE) sU[i] = vu;
         if (pu1) pu1[i] = vu;
         ln_unpack(vu, fa);                       // moments of the stored (fp16-rounded) values
 #pragma unroll
@@ -134,17 +143,28 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
       }
     }
   }
-  const float2 mr1 = ln_cluster_moments(s, q, red, &slots[0], n, p.eps);
+  const float2 mr1 = ln_cluster_moments<NT / 32>(s, q, red, &slots[0], n, p.eps);
   if (p.stats1 && rank == 0 && threadIdx.x == 0) { p.stats1[sample * 2] = mr1.x; p.stats1[sample * 2 + 1] = mr1.y; }
 
+  // u1 piece i of this CTA's slice: from shared memory, or recomputed from a and b (L2 hits) with the same rounding
+  auto load_u1 = [&](int i, float* f) {
+    if (STAGE) { ln_unpack(sU[i], f); return; }
+    float fb[8];
+    ln_unpack(__ldg(pa + i), f); ln_unpack(__ldg(pb + i), fb);
+    const float rs = rsc ? __ldg(rsc + ((i0 + i) * 8) / p.D) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += fb[j] * rs;
+    ln_unpack(ln_pack(f), f);
+  };
   const bool two = p.gamma2 != nullptr;
   uint4* py = reinterpret_cast<uint4*>(p.y + sample * p.y_stride) + i0;
   uint4* pyl = p.y_lo ? reinterpret_cast<uint4*>(p.y_lo + sample * p.y_stride) + i0 : nullptr;
   if (!two) {
     // ---- pass B (single norm): y = LN(u1) ----------------------------------------------------------------------
-    for (int i = threadIdx.x; i < cnt; i += 256) {
+#pragma unroll 2
+    for (int i = threadIdx.x; i < cnt; i += NT) {
       float f[8];
-      ln_unpack(sU[i], f);
+      load_u1(i, f);
       const int d = (int)(((i0 + i) * 8) % p.D);
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d + 4));
@@ -162,19 +182,19 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
   // ---- pass B (chained): y1 = LN(u1) (rounded to fp16 as the unfused path stores it); u2 = y1 + b -------------
   uint4* pu2 = p.u2_out ? reinterpret_cast<uint4*>(p.u2_out + sample * p.u2_stride) + i0 : nullptr;
   s = 0.f; q = 0.f;
-  for (int base = 0; base < cnt; base += 4 * 256) {
+  for (int base = 0; base < cnt; base += 4 * NT) {
     uint4 vb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = base + k * 256 + threadIdx.x;
+      const int i = base + k * NT + threadIdx.x;
       if (i < cnt) vb[k] = __ldg(pb + i);          // second use of the residual: an L2 hit
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = base + k * 256 + threadIdx.x;
+      const int i = base + k * NT + threadIdx.x;
       if (i < cnt) {
         float f[8], fb[8];
-        ln_unpack(sU[i], f); ln_unpack(vb[k], fb);
+        load_u1(i, f); ln_unpack(vb[k], fb);
         const int d = (int)(((i0 + i) * 8) % p.D);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d + 4));
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += fb[j];
         const uint4 vu = ln_pack(f);
-        sU[i] = vu;
+        if (STAGE) sU[i] = vu;
         if (pu2) pu2[i] = vu;
         ln_unpack(vu, f);
 #pragma unroll
@@ -194,12 +214,30 @@ __global__ void __launch_bounds__(256) ln_chain_kernel(const LnChainParams p) {
       }
     }
   }
-  const float2 mr2 = ln_cluster_moments(s, q, red, &slots[1], n, p.eps);
+  const float2 mr2 = ln_cluster_moments<NT / 32>(s, q, red, &slots[1], n, p.eps);
   if (p.stats2 && rank == 0 && threadIdx.x == 0) { p.stats2[sample * 2] = mr2.x; p.stats2[sample * 2 + 1] = mr2.y; }
   // ---- pass C: y2 = LN(u2) ---------------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < cnt; i += 256) {
+#pragma unroll 2
+  for (int i = threadIdx.x; i < cnt; i += NT) {
     float f[8];
-    ln_unpack(sU[i], f);
+    if (STAGE) {
+      ln_unpack(sU[i], f);
+    } else {
+      // u2 = fp16(fp16(LN1(u1)) + b), recomputed
+      float fb[8];
+      load_u1(i, f); ln_unpack(__ldg(pb + i), fb);
+      const int d1 = (int)(((i0 + i) * 8) % p.D);
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d1)), h1 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + d1 + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d1)), c1 = __ldg(reinterpret_cast<const float4*>(p.beta1 + d1 + 4));
+      const float hg[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      const float hb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mr1.x) * mr1.y * hg[j] + hb[j];
+      ln_unpack(ln_pack(f), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += fb[j];
+      ln_unpack(ln_pack(f), f);
+    }
     const int d = (int)(((i0 + i) * 8) % p.D);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma2 + d)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma2 + d + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta2 + d)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta2 + d + 4));
@@ -244,22 +282,27 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
   p.y = y; p.y_stride = y_stride; p.y_lo = y_lo;
   int cs = 1;
   if (!ln_chain_plan(p.n8, &cs, &p.per)) return fail(LPM_ERR_ARG, "layernorm_chain: sample of %d x %d does not fit", rows, D);
-  const size_t smem = (size_t)p.per * 16;
+  // the shared-memory slice pays only when the batch is small enough that a and b may have left the L2 by the time the
+  // later passes want them again (never at the shapes of this model); LPM_LN_STAGE=1 forces it (measurement switch)
+  static const bool force_stage = getenv("LPM_LN_STAGE") != nullptr && getenv("LPM_LN_STAGE")[0] == '1';
+  const bool stage = force_stage || a == u1_out;          // in-place u1 (a aliased): the re-read would see u1, not a
+  const size_t smem = stage ? (size_t)p.per * 16 : 0;
   static size_t attr = 0;
   if (smem > attr) {
-    LPM_CUDA_CHECK(cudaFuncSetAttribute(ln_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LPM_CUDA_CHECK(cudaFuncSetAttribute(ln_chain_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * cs));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(stage ? 256 : 128);     // unstaged: 128-thread CTAs, six per SM by registers -> the whole launch resident
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel, p));
+  if (stage) LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<true, 256>, p));
+  else LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<false, 128>, p));
   return LPM_OK;
 }
 

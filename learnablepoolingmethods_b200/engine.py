@@ -887,6 +887,12 @@ class NetVladEngine:
         put(a + "/output_transform/kernel", self._wgrad_gemm(ctx, name, m["o"], du1, out_dtype=f32, alpha=inv,
                                                              out=gout(a + "/output_transform/kernel")))
         do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
+        pre_attn = ctx.get("before_attention_bwd_hook") if name == "video" else None
+        if pre_attn is not None:
+            # single tower: the factored update of hidden1_weights forks HERE -- the attention-core backward that follows is
+            # issue-bound, moves < 1 TB/s and leaves a quarter of the register file free, so the HBM-bound update's small
+            # CTAs run next to it (trainer._fork_hidden_update)
+            pre_attn(ctx)
         dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
         zn = m["zn"]
         for i, n in enumerate(("q", "k", "v")):

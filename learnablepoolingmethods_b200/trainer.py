@@ -263,6 +263,10 @@ class Trainer:
     # the update ends up exposed at the join); shorter-lived CTAs (LPM_ADAM_SPLIT=2/4) 3.86 / 3.95 ms.  Hence -1 / 1.
     fuse_optimizer = os.environ.get("LPM_FUSE_OPT", "1") != "0"
     opt_priority = int(os.environ.get("LPM_OPT_PRIORITY", "-1"))
+    # where the hidden1 update forks: "head" (after the head of the backward) | "attn" (right before the rgb attention-core
+    # backward, which leaves a quarter of the register file free).  Measured: head 3.74 ms, attn 4.01 ms -- next to the
+    # update's CTAs the issue-bound attention kernel loses more than the update gains.
+    adam_fork = os.environ.get("LPM_ADAM_FORK", "head")
     adam_col_splits = int(os.environ.get("LPM_ADAM_SPLIT", "1"))   # column splits of the tiled hidden1 update (CTA lifetime)
     disable_factored_hidden = False
     gather_hidden_factors = True
@@ -393,7 +397,10 @@ class Trainer:
                     ctx["factored_hidden"] = bool(f.factored)
                     ctx["grad_views"] = f.grad_views
                     if fused and f.factored:
-                        ctx["after_head_hook"] = self._fork_hidden_update
+                        # NetVladV1: fork right before the rgb attention-core backward (see engine._v1_modality_bwd);
+                        # other models (or LPM_ADAM_FORK=head): right after the head of the backward
+                        at_attn = self.cfg.model == "NetVladV1" and self.adam_fork == "attn"
+                        ctx["before_attention_bwd_hook" if at_attn else "after_head_hook"] = self._fork_hidden_update
                 eng.backward(ctx, dpred, stage=stage)
 
             # data parallel: the head's gradients (MoE, gating: the first ~40 % of the flat buffer) are all-reduced while

@@ -10,11 +10,14 @@ for line in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')):
     name = re.sub(r"\(.*", "", name).replace("lpm::", "")
     rows.append((name, line[8], float(line[-1]) / 1000.0))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-starts = [i for i, r in enumerate(rows) if r[0].startswith("sample_stats_kernel")]
+starts = [i for i, r in enumerate(rows) if r[0].startswith(("sample_stats_kernel", "sample_stats_warp_kernel", "step_begin_kernel"))]
 opt = [i for i, r in enumerate(rows) if r[0].startswith(("rank_adam_kernel", "rank_adam_tile_kernel", "mt_adam_kernel"))]
-a, b = starts[-1], opt[-1] + 1
-while b < len(rows) and rows[b][0].startswith("transpose_2d_kernel"):      # refresh of the transposed centre shadows
-    b += 1
+b = opt[-1] + 1
+a = max(i for i in starts if i < opt[-1] and rows[i][0].startswith(("step_begin_kernel", "sample_stats")) and
+        (rows[i][0].startswith("step_begin_kernel") or not any(rows[j][0].startswith("step_begin_kernel") for j in range(max(0, i - 3), i))))
+while b < len(rows) and rows[b][0].startswith(("transpose_2d_kernel", "split_hi_lo_kernel", "rank_adam", "mt_")) or \
+        (b < len(rows) and "elementwise_kernel" in rows[b][0] and b + 1 < len(rows) and rows[b + 1][0].startswith("split_hi_lo_kernel")):
+    b += 1      # refresh of the transposed centre shadows and of the split-precision weight operands
 
 
 def table(title, seg):
@@ -35,4 +38,6 @@ def table(title, seg):
 
 
 table("train step", rows[a:b])
-table("inference forward", rows[b:])
+# the LAST inference forward (steady state): it starts with input_bn's finalize right before the last sample_apply
+last_apply = max(i for i, r in enumerate(rows) if r[0].startswith("sample_apply"))
+table("inference forward", rows[last_apply - 1:])

@@ -18,5 +18,7 @@ for _ in range(n):
 torch.cuda.synchronize()
 print("overflow", tr.overflowed())
 with torch.no_grad():
-    eng.forward(x, nf, False)
+    eng.forward(x, nf, False)      # first inference call after training: refreshes the low-order half of hidden1_weights
+    torch.cuda.synchronize()
+    eng.forward(x, nf, False)      # steady state (the one scripts/launch_summary.py reports)
 torch.cuda.synchronize()

@@ -20,7 +20,7 @@ dev = torch.device("cuda:0")
 t0 = time.time()
 eng, tr, protos, losses = TP.train_model(dev, steps=steps, lr=lr, strength=strength)
 t1 = time.time()
-rep = TP.evaluate(eng, protos, dev, n_videos=n_videos, emulate=emu, strength=strength)
+rep = TP.evaluate(eng, protos, dev, n_videos=n_videos, emulate=emu, strength=strength, fp64=True)
 rep.update(train_steps=steps, lr=lr, strength=strength, losses=losses, train_seconds=t1 - t0, eval_seconds=time.time() - t1,
            skipped_steps=int(tr.skipped_steps()) if hasattr(tr, "skipped_steps") else None,
            shape=TP.SHAPE, host_cores=os.cpu_count())

@@ -453,3 +453,41 @@ def test_eval_metrics_against_reference_golden(cuda):
         assert abs(m[2] - float(G[f"gap{seed}"])) < 1e-6
         assert abs(m[2] - E.gap(pred, labels)) < 1e-6
     assert abs(GE.calculate_gap(p, a) - float(G[f"gap{seed}"])) < 1e-6
+
+
+@pytest.mark.parametrize("splits,splits2", [(5, 0), (40, 0), (74, 37), (3, 2)])
+def test_splitk_reduce_variants_and_split_operands(cuda, splits, splits2):
+    """lpm_splitk_reduce_ex (narrow and wide kernels, second partial set, split-precision output) and
+    lpm_split_hi_lo_f16 (all three layouts; 8-wide, pair and scalar kernels): hi + lo reproduces fp32 to ~2^-22."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(splits * 100 + splits2)
+    B, H = 80, 512
+    parts = torch.randn(splits, B, H, generator=g).to(cuda)
+    parts2 = torch.randn(splits2, B, H, generator=g).to(cuda) if splits2 else None
+    bias = torch.randn(H, generator=g).to(cuda)
+    want = parts.double().sum(0) + (parts2.double().sum(0) if splits2 else 0) + bias.double()
+    out32 = torch.empty(B, H, device=cuda)
+    a3 = torch.empty(B, 3 * H, dtype=torch.float16, device=cuda)
+    ops.splitk_reduce(parts, bias=bias, out32=out32, out16=a3, parts2=parts2, split3=True)
+    assert float((out32.double() - want).abs().max()) < 1e-4
+    assert torch.equal(a3[:, :H], a3[:, 2 * H:]) and torch.equal(a3[:, :H], out32.half())
+    rec = a3[:, :H].double() + a3[:, H:2 * H].double()
+    # hi + lo carries ~22 bits; the low-order half bottoms out at fp16's subnormal spacing (6e-8 absolute)
+    assert bool(((rec - out32.double()).abs() <= 3e-7 * out32.double().abs() + 6.1e-8).all())
+    if not splits2:       # the plain entry point (no second set, plain fp16 output) agrees with the extended one
+        out16 = torch.empty(B, H, dtype=torch.float16, device=cuda)
+        ops.splitk_reduce(parts, bias=bias, out32=out32, out16=out16)
+        assert torch.equal(out16, a3[:, :H])
+    for cols in (64, 3 * 3862 % 1000 + 2, 37):              # 8-wide, pair and scalar kernels
+        w = (torch.randn(48, cols, generator=g) * 0.1).to(cuda)
+        act = ops.split_hi_lo(w)
+        assert torch.equal(act[:, :cols], w.half()) and torch.equal(act[:, :cols], act[:, 2 * cols:])
+        assert float((act[:, :cols].double() + act[:, cols:2 * cols].double() - w.double()).abs().max()) < 1e-7
+        pad = (cols + 7) // 8 * 8
+        dst = torch.zeros(3 * 48, pad, dtype=torch.float16, device=cuda)
+        ops.split_hi_lo(w, dst, along_rows=True)
+        assert torch.equal(dst[:48, :cols], w.half()) and torch.equal(dst[48:96, :cols], w.half())
+        assert torch.equal(dst[96:, :cols], act[:, cols:2 * cols])
+        lo = torch.zeros(48, pad, dtype=torch.float16, device=cuda)
+        ops.split_hi_lo(w, lo, along_rows=2)
+        assert torch.equal(lo[:, :cols], act[:, cols:2 * cols])
