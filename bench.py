@@ -205,6 +205,7 @@ def main():
         v, sec, cores, sample, steps, wu = cpu_reference(args.steps, args.warmup, sample_batch=args.cpu_sample_batch or None,
                                                         model=args.model)
         base["config"]["cpu_sample_batch"] = args.cpu_sample_batch or args.batch
+        base["config"]["model_input"] = "fp32 frames [B,300,1152], dequantised and L2-normalised (the same synthetic videos)"
         base["config"]["parallelism"] = f"host cores x{cores} (rank 0 only)"
         out = dict(base, impl="reference", value=v, ms_per_step=sec * 1e3, steps=steps, warmup=wu,
                    dtype="f32", n_gpus=args.gpus,

@@ -50,19 +50,24 @@ def structured_batch(B, seed, protos, device, *, V=SHAPE["V"], max_frames=SHAPE[
     return x, nf.to(device), labels.to(device)
 
 
-def train_model(device, *, steps, model="NetVladV1", lr=2e-4, seed=1810, log_every=100, strength=1.0, shape=SHAPE):
-    """Returns (engine, trainer, class directions, [(step, loss)])."""
+def train_model(device, *, steps, model="NetVladV1", lr=2e-4, seed=1810, log_every=100, strength=1.0, shape=SHAPE,
+                resume=None):
+    """Returns (engine, trainer, class directions, [(step, loss)]).  resume=(engine, trainer, directions): continue that
+    run up to `steps` total steps (batch i is always seeded 5000 + i)."""
     from learnablepoolingmethods_b200 import variables
     from learnablepoolingmethods_b200.engine import NetVladConfig, NetVladEngine
     from learnablepoolingmethods_b200.trainer import Trainer
     s = shape
-    store = variables.VariableStore(device, seed=seed)
-    cfg = NetVladConfig(model=model, iterations=s["T"], cluster_size=s["K"], hidden_size=s["Hd"], vocab_size=s["V"])
-    eng = NetVladEngine(cfg, store)
-    tr = Trainer(eng, base_learning_rate=lr, learning_rate_decay=0.85, batch_size=s["B"])
-    protos = class_directions(s["V"], s["F"])
+    if resume is None:
+        store = variables.VariableStore(device, seed=seed)
+        cfg = NetVladConfig(model=model, iterations=s["T"], cluster_size=s["K"], hidden_size=s["Hd"], vocab_size=s["V"])
+        eng = NetVladEngine(cfg, store)
+        tr = Trainer(eng, base_learning_rate=lr, learning_rate_decay=0.85, batch_size=s["B"])
+        protos = class_directions(s["V"], s["F"])
+    else:
+        eng, tr, protos = resume
     losses = []
-    for i in range(steps):
+    for i in range(tr.global_step, steps):
         x, nf, lab = structured_batch(s["B"], 5000 + i, protos, device, V=s["V"], max_frames=s["max_frames"], strength=strength)
         loss = tr.train_step(x, nf, lab)
         if i % log_every == 0 or i == steps - 1:
