@@ -42,6 +42,30 @@ class no_gc_during_capture:
         return False
 
 
+import functools
+import os
+
+_NVTX = os.environ.get("LPM_NVTX", "0") == "1"
+
+
+def nvtx_range(name):
+    """LPM_NVTX=1: wrap a stage of the engine in an NVTX range (nsys / ncu --nvtx timelines; SURVEY section 5 tracing).
+    Off by default: the decorator then returns the function unchanged (no per-call cost)."""
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        @functools.wraps(fn)
+        def wrapped(*a, **kw):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
+
+
 def _ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -292,6 +316,7 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
+    @nvtx_range("lpm.forward")
     def forward(self, model_input: torch.Tensor, num_frames: torch.Tensor, is_training: bool,
                 save_for_backward: bool = False, dropout_masks=None, return_intermediates: bool = False,
                 frame_index=None, device_seed: bool = False, head: bool = True):
@@ -393,6 +418,7 @@ class NetVladEngine:
         """Second half of a forward started with head=False: hidden projection, gating, MoE -> predictions."""
         return self._head(ctx.pop("_vlad"), ctx["B"], ctx["training"], ctx["_save"], ctx, ctx["_want_inter"])
 
+    @nvtx_range("lpm.v1_modality")
     def _v1_modality(self, name, X, B, T, D, K, H, sid, training, save, out_view, ctx, want_inter, out_lo=None):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         vs, a = name + "_VLAD", name + "_attention"
@@ -628,6 +654,7 @@ class NetVladEngine:
                           want_value=False)
         put(vs + "/cluster_weights2", dC)
 
+    @nvtx_range("lpm.head")
     def _head(self, vlad, B, training, save, ctx, want_inter):
         """frame_level_models.py:2309-2377 + video_level_models.py:48-159."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
@@ -687,6 +714,7 @@ class NetVladEngine:
     # ------------------------------------------------------------------------------------------
     # backward (NetVladV1): hand-written autodiff of the forward above
     # ------------------------------------------------------------------------------------------
+    @nvtx_range("lpm.backward")
     def backward(self, ctx, dpred: torch.Tensor, stage: Optional[str] = None) -> Dict[str, torch.Tensor]:
         """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
         Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled.
@@ -777,6 +805,7 @@ class NetVladEngine:
             return grads
         return self._backward_body(ctx, dvlad, grads, put, deferred_hidden)
 
+    @nvtx_range("lpm.backward_body")
     def _backward_body(self, ctx, dvlad, grads, put, deferred_hidden):
         c, v = self.cfg, self.store.vars
         f32 = torch.float32
@@ -847,6 +876,7 @@ class NetVladEngine:
         """Weight-gradient product dW = a^T b (see _wgrad_run)."""
         return self._wgrad_run(ctx, name, (a, b), lambda: ops.gemm(a, b, a_mn=True, b_mn=True, **kw))
 
+    @nvtx_range("lpm.v1_modality_bwd")
     def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         S = ctx["loss_scale"]

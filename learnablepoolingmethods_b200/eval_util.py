@@ -19,11 +19,25 @@ def _prep(predictions, actuals):
     return p, a
 
 
+GAP_KERNEL_LIMIT = 16384     # lpm_eval_metrics ranks the B*k triplets of a batch in one CTA's shared memory
+
+
 def batch_metrics(predictions, actuals, top_k=20):
-    """Device tensor [3] = (hit@1, PERR, GAP) of the batch: one fused evaluation, no host transfer."""
+    """Device tensor [3] = (hit@1, PERR, GAP) of the batch: one fused evaluation, no host transfer.
+    Batches with B*k > 16384 (the reference's default --batch_size 1024 at k = 20) exceed the single-CTA ranking of
+    `lpm_eval_metrics`: hit@1 / PERR are then the means of the per-video statistics `lpm_eval_topk` already produced, and
+    the global ranking behind GAP (average_precision_calculator.py:203-262) is one stable device sort of the B*k scores."""
     p, a = _prep(predictions, actuals)
     tv, _, tl, rs = ops.eval_topk(p, a, top_k)
-    return ops.eval_metrics(tv, tl, rs)
+    if tv.numel() <= GAP_KERNEL_LIMIT:
+        return ops.eval_metrics(tv, tl, rs)
+    hit, perr, numpos = rs[:, 0].mean(), rs[:, 1].mean(), rs[:, 2].sum()
+    order = torch.sort(tv.reshape(-1), descending=True, stable=True).indices        # ties keep (video, rank) order
+    lab = tl.reshape(-1)[order].to(torch.float64)
+    ranks = torch.arange(1, lab.numel() + 1, device=lab.device, dtype=torch.float64)
+    gap = (torch.cumsum(lab, 0) / ranks * lab).sum() / numpos.to(torch.float64).clamp_min(1.0)
+    gap = torch.where(numpos > 0, gap, torch.zeros_like(gap))
+    return torch.stack([hit, perr, gap.to(torch.float32)])
 
 
 def calculate_hit_at_one(predictions, actuals):

@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from .dp import BucketedAllReduce, FactorGather
-from .engine import NetVladConfig, NetVladEngine, no_gc_during_capture
+from .engine import NetVladConfig, NetVladEngine, no_gc_during_capture, nvtx_range
 from .variables import VariableStore
 
 CHUNK = 32768           # elements per optimiser chunk
@@ -494,6 +494,7 @@ class Trainer:
         _lib.launch_count += g["launches"]
         return g["loss"], g["ctx"]
 
+    @nvtx_range("lpm.train_step")
     def train_step(self, model_input, num_frames, labels_u8, frame_index=None):
         """One step on this rank's tower batch.  Returns the label loss (device scalar, fp32).
         frame_index: optional int32 [B, iterations] (WillowModelReg: replaces the random frame draw)."""
@@ -584,6 +585,7 @@ class Trainer:
             torch.cuda.current_stream().wait_event(join)
         self.engine.refresh_small_shadows()
 
+    @nvtx_range("lpm.optimizer_step")
     def _optimizer_step(self, ctx, factored, loss):
         eng = self.engine
         f = self.flat

@@ -453,6 +453,12 @@ def test_eval_metrics_against_reference_golden(cuda):
         assert abs(m[2] - float(G[f"gap{seed}"])) < 1e-6
         assert abs(m[2] - E.gap(pred, labels)) < 1e-6
     assert abs(GE.calculate_gap(p, a) - float(G[f"gap{seed}"])) < 1e-6
+    # the reference's default --batch_size (1024) at k = 20 exceeds the single-CTA ranking: large-batch path vs the oracle
+    pred, labels = E.synthetic_eval_batch(77, 1024, 500)
+    p, a = torch.from_numpy(pred).to(cuda), torch.from_numpy(labels).to(cuda)
+    m = GE.batch_metrics(p, a).cpu().double().numpy()
+    assert abs(m[0] - E.hit_at_one(pred, labels)) < 1e-6 and abs(m[1] - E.perr(pred, labels)) < 1e-6
+    assert abs(m[2] - E.gap(pred, labels)) < 1e-6
 
 
 @pytest.mark.parametrize("splits,splits2", [(5, 0), (40, 0), (74, 37), (3, 2)])
