@@ -65,12 +65,18 @@ class _NetVladBase(models.BaseModel):
                 graphs[key] = InferenceGraph(engine, model_input.shape[0], model_input.shape[1], model_input.dtype)
             pred = graphs[key](model_input, num_frames, frame_index=unused_params.get("frame_index"))
         else:
+            ensure_parsed()
+            penalty = unused_params.get("regularization_penalty")
             pred = netvlad_apply(engine, model_input, num_frames, is_training,
-                                 dropout_masks=unused_params.get("dropout_masks"), frame_index=unused_params.get("frame_index"))
+                                 dropout_masks=unused_params.get("dropout_masks"), frame_index=unused_params.get("frame_index"),
+                                 reg_penalty=FLAGS.regularization_penalty if penalty is None else penalty)
         result = {"predictions": pred}
         if self._NAME == "WillowModelReg":
             # TF collects the orthogonal regulariser through REGULARIZATION_LOSSES (train.py:301-303); the eager
-            # mirror hands it back under the key train.py:296-297 already honours
+            # mirror hands its VALUE back under the key train.py:296-297 already honours.  It is detached: its gradient is
+            # part of this model's hand-written backward, scaled by `regularization_penalty=` (default: the flag), so a
+            # caller must NOT add `penalty * regularization_loss` to the loss it differentiates.  The MoE weight decay
+            # (slim.l2_regularizer(moe_l2)) is applied by Trainer.apply_gradients / Trainer.train_step.
             result["regularization_loss"] = engine.regularization_loss()
         return result
 
