@@ -29,6 +29,8 @@
 // and epilogue (two groups of four warps: one per 128-row tile / TMEM lane quarter), warps 10-11 epilogue
 // TMA agents (one per group): each output slab is handled as two 32-column halves in two 64B-swizzled
 // buffers, so the centre load of the next half and the store of the previous one overlap the arithmetic.
+#include <cstdlib>
+
 #include "lpm_common.cuh"
 #include "lpm_kernels.h"
 
@@ -595,8 +597,16 @@ int netvlad_pool_fwd(const __half* x, long long ldx, long long x_batch_stride, c
   if (int rc = make_tmap_3d(&tc, centers_t16, 2, D, K, 1, D, 0, 32, 128, 64)) return rc;
   if (assign == nullptr) ta = tz;      // unused
   else if (int rc = make_tmap_3d(&ta, assign, 2, K, T, B, K, (uint64_t)T * K, 64, 256)) return rc;
+  // Experiment switch: LPM_POOL_SPLIT=1 runs 129..256 clusters as a 2-CTA cluster per video (128 clusters per CTA, half the
+  // assignment tile per CTA -> a 4-stage X ring in phase 2 instead of 2).  Measured at config 1 (gpurun r2t, cycles per CTA):
+  // logits 15.6 k | softmax 7.7 k | a_sum 3.6 k | aggregation 27.1 k = 54.0 k, i.e. 108 k SM-cycles per video against 70.7 k
+  // for one CTA per video (304 vs 419 TFLOP/s at B = 80, 516 vs 710 at full waves): half the clusters do not halve the
+  // logits phase (X is streamed by both CTAs) and the aggregation stays paced by the centre-load -> update -> store chain
+  // of its two staging half-buffers (3.4 k cycles per slab pair whatever the ring depth).  Off by default.
+  static const bool split256 = getenv("LPM_POOL_SPLIT") != nullptr && getenv("LPM_POOL_SPLIT")[0] == '1';
   if (K <= 64) return launch_pool<64, 1>(tx, tw, tz, tc, ta, p, st);
   if (K <= 128) return launch_pool<128, 1>(tx, tw, tz, tc, ta, p, st);
+  if (K <= 256 && split256 && assign_in == nullptr) return launch_pool<128, 2>(tx, tw, tz, tc, ta, p, st);
   if (K <= 256) return launch_pool<256, 1>(tx, tw, tz, tc, ta, p, st);
   return launch_pool<256, 2>(tx, tw, tz, tc, ta, p, st);
 }
