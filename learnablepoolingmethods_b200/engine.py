@@ -719,10 +719,16 @@ class NetVladEngine:
         """dpred: fp32 [B, vocab] = dLoss/dpredictions.  Returns {variable name: fp32 gradient}.
         Activation gradients travel as fp16 scaled by cfg.loss_scale; parameter gradients are unscaled.
         stage: None = the whole backward; "head" = MoE, gating and hidden projection only (stops once dLoss/dvlad exists);
-        "body" = the rest (after a "head" call on the same ctx).  The data-parallel trainer replays the two stages as
+        "body" = the rest (after a "head" call on the same ctx); NetVladV1 can split the rest once more: "body1" = the
+        attention blocks of both modalities and the audio pooling (every gradient except the rgb pooling's and input_bn's is
+        final afterwards), "body2" = the rgb pooling backward.  The data-parallel trainer replays the two stages as
         separate CUDA graphs and starts the all-reduce of the head's gradients in between."""
         if stage == "body":
             return self._backward_body(ctx, *ctx.pop("_bwd_state"))
+        if stage == "body1":      # NetVladV1: attention blocks of both modalities + the audio pooling (see _backward_body)
+            return self._backward_body(ctx, *ctx["_bwd_state"], part="body1")
+        if stage == "body2":      # the rgb pooling backward + input_bn
+            return self._backward_body(ctx, *ctx.pop("_bwd_state"), part="body2")
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         B, hd = ctx["B"], ctx["head"]
         # dLoss/dpred scales as 1/B; LayerNorm over the L2-normalised descriptor has rstd ~ 200, so the scale
@@ -806,10 +812,22 @@ class NetVladEngine:
         return self._backward_body(ctx, dvlad, grads, put, deferred_hidden)
 
     @nvtx_range("lpm.backward_body")
-    def _backward_body(self, ctx, dvlad, grads, put, deferred_hidden):
+    def _backward_body(self, ctx, dvlad, grads, put, deferred_hidden, part=None):
         c, v = self.cfg, self.store.vars
         f32 = torch.float32
         gout = ctx["_gout"]
+        if part == "body2":
+            # second half of the split NetVladV1 body: the rgb pooling backward (main stream only), then input_bn
+            dgamma_in, dbeta_in = ctx.pop("_dbn_in")
+            name, col0, D, K, H, sid = list(c.modalities())[0]
+            self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, 0:K * D], dgamma_in, dbeta_in, put, part="pool")
+            put("input_bn/gamma", dgamma_in)
+            put("input_bn/beta", dbeta_in)
+            if deferred_hidden is not None:
+                put("hidden1_weights", ctx["hidden_dw"](deferred_hidden[0], deferred_hidden[1], gout("hidden1_weights")))
+            return grads
+        if part == "body1" and c.model != "NetVladV1":
+            raise ValueError("the three-stage backward exists for NetVladV1 only")
         dgamma_in = torch.zeros(c.feature_size, dtype=f32, device=dvlad.device)
         dbeta_in = torch.zeros(c.feature_size, dtype=f32, device=dvlad.device)
         off = 0
@@ -835,7 +853,8 @@ class NetVladEngine:
                 side.wait_event(ev_fork)
             with torch.cuda.stream(side if on_side else main):
                 if c.model == "NetVladV1":
-                    self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m)
+                    self._v1_modality_bwd(ctx, name, col0, D, K, H, sid, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m,
+                                          part="attn" if (part == "body1" and name == "video") else None)
                 elif c.model == "WillowModelReg":
                     self._willow_modality_bwd(ctx, name, col0, D, K, dvlad[:, o0:o0 + K * D], dgamma_in, dbeta_in, put_m)
                 else:
@@ -852,6 +871,9 @@ class NetVladEngine:
             ctx["_wgrad"] = None
         for n, g in deferred:
             put(n, g)
+        if part == "body1":
+            ctx["_dbn_in"] = (dgamma_in, dbeta_in)      # the rgb pooling's share is still to come (body2)
+            return grads
         put("input_bn/gamma", dgamma_in)
         put("input_bn/beta", dbeta_in)
         if deferred_hidden is not None:
@@ -877,7 +899,9 @@ class NetVladEngine:
         return self._wgrad_run(ctx, name, (a, b), lambda: ops.gemm(a, b, a_mn=True, b_mn=True, **kw))
 
     @nvtx_range("lpm.v1_modality_bwd")
-    def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put):
+    def _v1_modality_bwd(self, ctx, name, col0, D, K, H, sid, dv, dgamma_in, dbeta_in, put, part=None):
+        """part: None = the whole modality; "attn" = the attention block only (stops once the gradient of the normalised
+        descriptor exists), "pool" = the NetVLAD normalisation / aggregation / soft-assignment backward after an "attn" call."""
         c, v, sh = self.cfg, self.store.vars, self.store.shadows
         S = ctx["loss_scale"]
         inv = 1.0 / S
@@ -885,50 +909,56 @@ class NetVladEngine:
         a, vs = name + "_attention", name + "_VLAD"
         f32 = torch.float32
         gout = ctx["_gout"]
-        rows = B * K
-        # ---- LN3: out = LN(u3), u3 = h2 + h1 ----------------------------------------------------
-        du3, dg, db = ops.layernorm_joint_bwd(m["u3"], dv, dv.stride(0), B, K, D, m["st3"], v[a + "/LayerNorm_2/gamma"],
-                                              inv_scale=inv)
-        put(a + "/LayerNorm_2/gamma", dg); put(a + "/LayerNorm_2/beta", db)
-        # ---- LN2: h2 = LN(u2), u2 = relu(f2pre) + h1 -------------------------------------------
-        (du2, dpre2), dg, db, db2 = ops.layernorm_joint_bwd(m["u2"], du3, K * D, B, K, D, m["st2"],
-                                                            v[a + "/LayerNorm_1/gamma"], inv_scale=inv, mask=m["f2"],
-                                                            want_du_colsum=True)
-        put(a + "/LayerNorm_1/gamma", dg); put(a + "/LayerNorm_1/beta", db)
-        put(f"{a}/ff_output{sid}/bias", db2)
-        h1 = m["h1"].view(rows, D)
-        f1 = m["f1"]
-        dpre2 = dpre2.view(rows, D)
-        put(f"{a}/ff_output{sid}/kernel", self._wgrad_gemm(ctx, name, f1, dpre2, out_dtype=f32, alpha=inv,
-                                                           out=gout(f"{a}/ff_output{sid}/kernel")))
-        dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
-        # (written straight into the gradient view: `put` would otherwise copy on the main stream, racing the side stream)
-        bname = f"{a}/filter_output{sid}/bias"
-        put(bname, self._wgrad_run(ctx, name, (dpre1,), lambda: ops.colsum(dpre1, alpha=inv, out=gout(bname))))
-        put(f"{a}/filter_output{sid}/kernel", self._wgrad_gemm(ctx, name, h1, dpre1, out_dtype=f32, alpha=inv,
-                                                               out=gout(f"{a}/filter_output{sid}/kernel")))
-        dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
-        # ---- LN1: h1 = LN(u1), u1 = att + vlad --------------------------------------------------
-        du1, dg, db, dbo = ops.layernorm_joint_bwd(m["u1"], dh1, K * D, B, K, D, m["st1"], v[a + "/LayerNorm/gamma"],
-                                                   inv_scale=inv, want_du_colsum=True)
-        put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
-        put(a + "/output_transform/bias", dbo)
-        du1 = du1.view(rows, D)
-        put(a + "/output_transform/kernel", self._wgrad_gemm(ctx, name, m["o"], du1, out_dtype=f32, alpha=inv,
-                                                             out=gout(a + "/output_transform/kernel")))
-        do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
-        pre_attn = ctx.get("before_attention_bwd_hook") if name == "video" else None
-        if pre_attn is not None:
-            # single tower: the factored update of hidden1_weights forks HERE -- the attention-core backward that follows is
-            # issue-bound, moves < 1 TB/s and leaves a quarter of the register file free, so the HBM-bound update's small
-            # CTAs run next to it (trainer._fork_hidden_update)
-            pre_attn(ctx)
-        dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
-        zn = m["zn"]
-        for i, n in enumerate(("q", "k", "v")):
-            put(f"{a}/{n}/kernel", self._wgrad_gemm(ctx, name, zn, dqkv[:, i * D:(i + 1) * D], out_dtype=f32, alpha=inv,
-                                                    out=gout(f"{a}/{n}/kernel")))
-        dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
+        if part != "pool":
+            rows = B * K
+            # ---- LN3: out = LN(u3), u3 = h2 + h1 ----------------------------------------------------
+            du3, dg, db = ops.layernorm_joint_bwd(m["u3"], dv, dv.stride(0), B, K, D, m["st3"], v[a + "/LayerNorm_2/gamma"],
+                                                  inv_scale=inv)
+            put(a + "/LayerNorm_2/gamma", dg); put(a + "/LayerNorm_2/beta", db)
+            # ---- LN2: h2 = LN(u2), u2 = relu(f2pre) + h1 -------------------------------------------
+            (du2, dpre2), dg, db, db2 = ops.layernorm_joint_bwd(m["u2"], du3, K * D, B, K, D, m["st2"],
+                                                                v[a + "/LayerNorm_1/gamma"], inv_scale=inv, mask=m["f2"],
+                                                                want_du_colsum=True)
+            put(a + "/LayerNorm_1/gamma", dg); put(a + "/LayerNorm_1/beta", db)
+            put(f"{a}/ff_output{sid}/bias", db2)
+            h1 = m["h1"].view(rows, D)
+            f1 = m["f1"]
+            dpre2 = dpre2.view(rows, D)
+            put(f"{a}/ff_output{sid}/kernel", self._wgrad_gemm(ctx, name, f1, dpre2, out_dtype=f32, alpha=inv,
+                                                               out=gout(f"{a}/ff_output{sid}/kernel")))
+            dpre1 = ops.gemm(dpre2, sh[a + "/w2_16"], b_mn=False, mask=f1, N=4 * D, K=D)      # [rows, 4D], ReLU mask fused
+            # (written straight into the gradient view: `put` would otherwise copy on the main stream, racing the side stream)
+            bname = f"{a}/filter_output{sid}/bias"
+            put(bname, self._wgrad_run(ctx, name, (dpre1,), lambda: ops.colsum(dpre1, alpha=inv, out=gout(bname))))
+            put(f"{a}/filter_output{sid}/kernel", self._wgrad_gemm(ctx, name, h1, dpre1, out_dtype=f32, alpha=inv,
+                                                                   out=gout(f"{a}/filter_output{sid}/kernel")))
+            dh1 = ops.gemm(dpre1, sh[a + "/w1_16"], b_mn=False, add1=du3.view(rows, D), add2=du2.view(rows, D))
+            # ---- LN1: h1 = LN(u1), u1 = att + vlad --------------------------------------------------
+            du1, dg, db, dbo = ops.layernorm_joint_bwd(m["u1"], dh1, K * D, B, K, D, m["st1"], v[a + "/LayerNorm/gamma"],
+                                                       inv_scale=inv, want_du_colsum=True)
+            put(a + "/LayerNorm/gamma", dg); put(a + "/LayerNorm/beta", db)
+            put(a + "/output_transform/bias", dbo)
+            du1 = du1.view(rows, D)
+            put(a + "/output_transform/kernel", self._wgrad_gemm(ctx, name, m["o"], du1, out_dtype=f32, alpha=inv,
+                                                                 out=gout(a + "/output_transform/kernel")))
+            do = ops.gemm(du1, sh[a + "/wo16"], b_mn=False)
+            pre_attn = ctx.get("before_attention_bwd_hook") if name == "video" else None
+            if pre_attn is not None:
+                # single tower: the factored update of hidden1_weights forks HERE -- the attention-core backward that follows is
+                # issue-bound, moves < 1 TB/s and leaves a quarter of the register file free, so the HBM-bound update's small
+                # CTAs run next to it (trainer._fork_hidden_update)
+                pre_attn(ctx)
+            dqkv = ops.mha_core_bwd(m["qkv"], m["o"], do, m["lse"], B, K, D, H, scale=(D // H) ** -0.5)
+            zn = m["zn"]
+            for i, n in enumerate(("q", "k", "v")):
+                put(f"{a}/{n}/kernel", self._wgrad_gemm(ctx, name, zn, dqkv[:, i * D:(i + 1) * D], out_dtype=f32, alpha=inv,
+                                                        out=gout(f"{a}/{n}/kernel")))
+            dzn = ops.gemm(dqkv, sh[a + "/wqkv16"], b_mn=False, add1=du1)        # + residual branch
+            if part == "attn":
+                ctx["_dzn_" + name] = dzn
+                return
+        else:
+            dzn = ctx.pop("_dzn_" + name)
         # ---- NetVLAD normalisation + aggregation + soft-assignment ------------------------------
         ct = sh[vs + "/centers_t"]
         if c.d5_raw_reshape:     # the block's input was the d-major flattened descriptor: its gradient is d-major too

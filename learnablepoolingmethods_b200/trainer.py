@@ -124,6 +124,28 @@ def pack_descriptor_slices(vlad: torch.Tensor, world: int, out: Optional[torch.T
     return out
 
 
+def three_stage_order(order: List[str]) -> List[str]:
+    """Flat-gradient order for the three-stage NetVladV1 backward: head | rgb attention block | audio (all) | rgb pooling |
+    input_bn -- the rgb pooling's gradients (video_VLAD/*) are the only ones still open after stage "body1"."""
+    pool = [n for n in order if n.startswith("video_VLAD/")]
+    inbn = [n for n in order if n.startswith("input_bn")]
+    rest = [n for n in order if n not in pool and n not in inbn]
+    return rest + pool + inbn
+
+
+def body_gradient_spans(flat: "FlatState"):
+    """(head_end, mid_end, ok) for the three-stage backward: [0, head_end) = head gradients, [head_end, mid_end) = final after
+    "body1" (rgb attention block, audio modality), [mid_end, g_total) = rgb pooling + input_bn (final after "body2")."""
+    head_end, ok = head_gradient_span(flat)
+    tail = [n for n in flat.order if n not in flat.factored and (n.startswith("video_VLAD/") or n.startswith("input_bn"))]
+    mid = [n for n in flat.order if n not in flat.factored and n.startswith(("video_attention", "audio_"))]
+    if not ok or not tail or not mid:
+        return head_end, flat.g_total, False
+    mid_end = min(flat.offsets[n] for n in tail)
+    good = all(flat.end_offset(n) <= mid_end for n in mid) and all(flat.offsets[n] >= head_end for n in mid)
+    return head_end, mid_end, good
+
+
 class ShardedHiddenUpdate:
     """Data-parallel update of hidden1_weights (85 % of the parameters) without moving its gradient or repeating its
     optimiser step on every rank.  Rank r owns rows [r*Kd/W, (r+1)*Kd/W) of W_h [Kd, H]:
@@ -267,6 +289,7 @@ class Trainer:
     # backward, which leaves a quarter of the register file free).  Measured: head 3.74 ms, attn 4.01 ms -- next to the
     # update's CTAs the issue-bound attention kernel loses more than the update gains.
     adam_fork = os.environ.get("LPM_ADAM_FORK", "head")
+    three_stage = os.environ.get("LPM_DP_THREE_STAGE", "1") != "0"  # data parallel NetVladV1: body split around the rgb pooling
     adam_col_splits = int(os.environ.get("LPM_ADAM_SPLIT", "1"))   # column splits of the tiled hidden1 update (CTA lifetime)
     disable_factored_hidden = False
     gather_hidden_factors = True
@@ -339,8 +362,21 @@ class Trainer:
 
     # -- gradient all-reduce (SUM), bucketed over the flat buffer, overlapped with the backward -----
     def _hook(self, name, g):
-        if self.reducer is not None:
-            self.reducer.mark_done(self.flat.end_offset(name))
+        """Eager data-parallel steps: a bucket may go out once every gradient in front of it in the flat LAYOUT is final.  The
+        layout need not be the production order (three_stage_order puts the rgb pooling's gradients behind the audio
+        modality's), so the final prefix is tracked by name."""
+        if self.reducer is None:
+            return
+        self._produced.add(name)
+        order = self._layout_names
+        while self._hook_pos < len(order) and order[self._hook_pos] in self._produced:
+            self._hook_pos += 1
+        if self._hook_pos > 0:
+            self.reducer.mark_done(self.flat.end_offset(order[self._hook_pos - 1]))
+
+    def _hook_reset(self):
+        self._produced, self._hook_pos = set(), 0
+        self._layout_names = [n for n in self.flat.order if n not in self.flat.factored]
 
     use_graph = True
 
@@ -407,6 +443,10 @@ class Trainer:
             # the modalities' backward runs; valid when the flat layout really has them in front
             g["head_end"], ok = head_gradient_span(f)
             g["split"] = dp and ok
+            # NetVladV1: split the body once more -- everything but the rgb pooling's gradients is final after "body1", so
+            # that all-reduce (13 M parameters) travels under the rgb pooling backward instead of after the step
+            _, g["mid_end"], ok3 = body_gradient_spans(f)
+            g["split3"] = g["split"] and ok3 and self.cfg.model == "NetVladV1" and self.three_stage
 
             eng.pre_head_hook = None                                 # the wait for the weight shards happens between graphs
             if self.shard is not None:
@@ -445,7 +485,7 @@ class Trainer:
                 graphs.append(torch.cuda.CUDAGraph())
                 with no_gc_during_capture(), torch.cuda.graph(graphs[1], pool=graphs[0].pool(), capture_error_mode="thread_local"):
                     g["loss"], g["dpred"] = seg_b(g["ctx"])
-                for stage in (("head", "body") if g["split"] else (None,)):
+                for stage in (("head", "body1", "body2") if g["split3"] else ("head", "body") if g["split"] else (None,)):
                     graphs.append(torch.cuda.CUDAGraph())
                     with no_gc_during_capture(), torch.cuda.graph(graphs[-1], pool=graphs[0].pool(),
                                                                   capture_error_mode="thread_local"):
@@ -485,9 +525,17 @@ class Trainer:
                 g["ctx"]["_hidden_done"] = True
                 h0 = d.all_reduce(f.g[:g["head_end"]], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
                 graphs[3].replay()
-                h1 = d.all_reduce(f.g[g["head_end"]:], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
-                h0.wait()
-                h1.wait()
+                if g["split3"]:
+                    h1 = d.all_reduce(f.g[g["head_end"]:g["mid_end"]], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
+                    graphs[4].replay()
+                    h2 = d.all_reduce(f.g[g["mid_end"]:], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
+                    h0.wait()
+                    h1.wait()
+                    h2.wait()
+                else:
+                    h1 = d.all_reduce(f.g[g["head_end"]:], op=d.ReduceOp.SUM, group=self.pg, async_op=True)
+                    h0.wait()
+                    h1.wait()
                 cur.wait_stream(side)
             else:
                 d.all_reduce(f.g, op=d.ReduceOp.SUM, group=self.pg)
@@ -539,6 +587,8 @@ class Trainer:
         if self.flat is None:
             ctx["grad_hook"] = lambda n, g: order.append(n)
             grads = eng.backward(ctx, dpred)
+            if self.world > 1 and self.cfg.model == "NetVladV1":
+                order = three_stage_order(order)        # lets the body's all-reduce start before the rgb pooling backward
             self.flat = FlatState(self.store, order, self._wd(), factored=("hidden1_weights",) if factored else ())
             self.flat.bind_shadows(eng)
             if self.on_flat_created is not None:        # checkpoint.load_into_store: restored Adam moments
@@ -562,6 +612,7 @@ class Trainer:
             ctx["grad_hook"] = self._hook
             if self.reducer is not None:
                 self.reducer.reset()
+                self._hook_reset()
             eng.backward(ctx, dpred)
             if self.reducer is not None:
                 self.reducer.flush()
