@@ -150,6 +150,13 @@ int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride,
 void lpm_debug_set_pool_clock(long long* buf);
 /* Measurement aid: 0 = lpm_gemm_f16 never uses 2-CTA (cta_group::2) tiles, 1 = automatic (default). */
 void lpm_debug_set_gemm_pair_mode(int mode);
+/* Measurement aid: 0 = lpm_mha_core_fwd / _bwd always use the warp-level (mma.sync) kernels, 1 = the tcgen05 / TMEM
+ * kernels whenever the shape is eligible (depth 16, length 256, heads a multiple of 4; default, or LPM_MHA_TC=0). */
+void lpm_debug_set_mha_tc_mode(int mode);
+/* Profiling aid: when non-NULL, CTA 0 of the tcgen05 attention backward writes clock64 stamps per unit:
+ * [4 warpgroups][16 units][4] (unit begins, S/dP available, math issued, operand slots free) then [16 units][4] of the
+ * MMA-issuing warp at offset 256 (next S/dP issued, P/dS visible, gradient MMAs issued). */
+void lpm_debug_set_mha_clock(long long* buf);
 /* vlad = z * rscale as fp32: d_major!=0 -> [B][D*K] (reference flatten, :2821), else [B][K][D]. */
 int lpm_netvlad_finalize(const void* z, const float* rscale, int B, int K, int D, int d_major, float* out,
                          lpm_stream_t stream);

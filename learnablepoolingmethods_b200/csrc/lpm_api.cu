@@ -112,6 +112,8 @@ int lpm_gemm_tile_n(int N) { return gemm_pick_bn(N); }
 
 int lpm_gemm_splits(int K, int requested_splits) { return gemm_effective_splits(K, requested_splits); }
 void lpm_debug_set_gemm_pair_mode(int mode) { gemm_set_pair_mode(mode); }
+void lpm_debug_set_mha_tc_mode(int mode) { mha_set_tc_mode(mode); }
+void lpm_debug_set_mha_clock(long long* buf) { mha_set_debug_clock(buf); }
 
 #define ST(s) static_cast<cudaStream_t>(s)
 #define H16(p) reinterpret_cast<__half*>(p)

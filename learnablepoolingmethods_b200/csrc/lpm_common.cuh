@@ -175,6 +175,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
           smem_u32(bar))
       : "memory");
 }
+// Warp-collective issue: the WHOLE warp runs the issuing loop on warp-uniform values and one elected lane executes
+// the instruction.  With the loop inside an `if (lane == 0)` region ptxas cannot keep the descriptors in uniform
+// registers and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~17 instructions, ~80 clk
+// per MMA on a single warp: measured on the N = 16 attention MMAs), which paces MMAs shorter than that.
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (elect_one()) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+}
+// warp index as a provably warp-uniform value (lets the compiler use uniform branches / registers in role code)
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(

@@ -263,7 +263,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_index_uniform();
   const int lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
@@ -357,12 +357,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0 && crank == 0) {
+    // The whole warp runs the loop on warp-uniform values and an elected lane issues each instruction (umma_f16_w,
+    // lpm_common.cuh): inside an `if (lane == 0)` region every tcgen05.mma was wrapped in a ~17-instruction uniform-
+    // register waterfall, ~80 clk of issue per MMA.
+    if (crank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM * MT, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int tile = work_id; tile < total_tiles; tile += work_stride) {
         const int sp = tile / (tiles_per_batch * p.batch);
         const int kb0 = sp * p.kb_per_split;
@@ -373,23 +377,27 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t a0 = A_MN ? umma_smem_desc(sa, 8192, 1024) : umma_smem_desc(sa, 16, 1024);
+          const uint64_t b0 = B_MN ? umma_smem_desc(sb, 8192, 1024) : umma_smem_desc(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t adesc = A_MN ? umma_smem_desc(sa + ks * 2048, 8192, 1024)
-                                        : umma_smem_desc(sa + ks * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + ks * 2048, 8192, 1024)
-                                        : umma_smem_desc(sb + ks * 32, 16, 1024);
-            if (TWO) g2_umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-            else umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t adesc = a0 + ((A_MN ? ks * 2048 : ks * 32) >> 4);
+              const uint64_t bdesc = b0 + ((B_MN ? ks * 2048 : ks * 32) >> 4);
+              if (TWO) g2_umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+              else umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if (TWO) g2_umma_commit(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (TWO) g2_umma_commit(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (TWO) g2_umma_commit(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+        if (elect_one()) { if (TWO) g2_umma_commit(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]); }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

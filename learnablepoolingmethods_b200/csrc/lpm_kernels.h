@@ -56,6 +56,15 @@ int mha_bwd_bn(int mode, const __half* qkv, long long ld, const __half* o, const
                const float* key_mean, const float* key_rstd, const float* m1, const float* m2, float* stat_partial,
                __half* dqkv, long long ldd, cudaStream_t st);
 
+// lpm_attn_tc.cu: tcgen05 / TMEM attention core for depth-16 heads at length 256 (four heads per CTA)
+void mha_set_tc_mode(int mode);
+void mha_set_debug_clock(long long* buf);
+bool mha_tc_eligible(int L, int Dm, int H, long long ld, long long ldo, const void* p0, const void* p1, const void* p2);
+int mha_fwd_tc(const __half* qkv, long long ld, int B, int Dm, int H, float scale, __half* out, long long ldo, float* lse,
+               cudaStream_t st);
+int mha_bwd_tc(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse, int B,
+               int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st);
+
 // lpm_backward.cu
 int xent_bwd(const float* pred, const uint8_t* labels, long long n, float gscale, const float* upstream, float* dpred,
              cudaStream_t st);

@@ -152,7 +152,7 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sRed + 12);
   float2* sStat = reinterpret_cast<float2*>(smem + Cfg::STG_OFF);   // mailbox for the peer's (max, sum); dead before the epilogue
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int crank = KSPLIT > 1 ? (int)(blockIdx.x % KSPLIT) : 0;    // == %cluster_ctarank for (KSPLIT,1,1) clusters
   const int b = blockIdx.x / KSPLIT;
   const int k0 = crank * KCT;                  // first cluster owned by this CTA
@@ -226,55 +226,61 @@ netvlad_pool_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    // The whole warp runs the loops on warp-uniform values; an elected lane issues the instructions of a stage
+    // back to back (see umma_f16_w in lpm_common.cuh: an `if (lane == 0)` region costs ~80 clk of issue per MMA,
+    // more than the 64 clk an N = 128 aggregation MMA runs).
+    {
       constexpr uint32_t idesc1 = umma_idesc_f16(128, KCT, 0, 1);   // A = X (K-major), B = Wc (MN-major)
       constexpr uint32_t idesc2 = umma_idesc_f16(128, 128, 1, 1);   // A = P^T (MN-major), B = X (MN-major), slab pair
       constexpr uint32_t idesc2t = umma_idesc_f16(128, 64, 1, 1);   // odd tail slab
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0; uint32_t phase = 0;
       for (int dc = 0; dc < n_dc1; ++dc) {
         mbar_wait(&full1[stage], phase);
         tc_fence_after();
-        const uint32_t sx = smem_u32(smem + stage * Cfg::ST1_BYTES);
-        const uint32_t sw = sx + Cfg::XS_BYTES;
-        for (int ft = 0; ft < n_ft; ++ft) {
+        const uint32_t sx = smem_base + stage * Cfg::ST1_BYTES;
+        const uint64_t xd = umma_smem_desc(sx, 16, 1024), wd = umma_smem_desc(sx + Cfg::XS_BYTES, 8192, 1024);
+        if (elect_one()) {
+          for (int ft = 0; ft < n_ft; ++ft) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma_smem_desc(sx + ft * 16384 + ks * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc(sw + ks * 2048, 8192, 1024);
-            umma_f16(tmem_base + ft * KCT, ad, bd, idesc1, (dc > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(tmem_base + ft * KCT, xd + ((ft * 16384 + ks * 32) >> 4), wd + ((ks * 2048) >> 4), idesc1,
+                       (dc > 0 || ks > 0) ? 1u : 0u);
           }
+          umma_commit(&empty1[stage]);
         }
-        umma_commit(&empty1[stage]);
+        __syncwarp();
         if (++stage == Cfg::NS1) { stage = 0; phase ^= 1; }
       }
-      if (!p.assign_in) umma_commit(s_full);
+      if (!p.assign_in) umma_commit_w(s_full);
 
       mbar_wait(p_ready, 0);
       tc_fence_after();
       stage = 0; phase = 0;
       int buf = 0; uint32_t bphase = 0;
-      const uint32_t sp = smem_u32(sP);
+      const uint64_t pd = umma_smem_desc(smem_u32(sP), TP * 128, 1024);
       for (int dp = 0; dp < (n_dc + 1) / 2; ++dp) {
         const uint32_t idesc = (n_dc - 2 * dp >= 2) ? idesc2 : idesc2t;
         mbar_wait(&acc_empty[buf], bphase ^ 1);
         for (int ft = 0; ft < n_ft; ++ft) {
           mbar_wait(&full2[stage], phase);
           tc_fence_after();
-          const uint32_t sx = smem_u32(sRing2 + stage * Cfg::XT_BYTES);
+          const uint64_t xd = umma_smem_desc(smem_u32(sRing2) + stage * Cfg::XT_BYTES, 16384, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int mt = 0; mt < Cfg::KCP / 128; ++mt) {
-            const uint32_t d_tmem = tmem_base + buf * (Cfg::KCP / 128) * 128 + mt * 128;
+            for (int mt = 0; mt < Cfg::KCP / 128; ++mt) {
+              const uint32_t d_tmem = tmem_base + buf * (Cfg::KCP / 128) * 128 + mt * 128;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ad = umma_smem_desc(sp + mt * 2 * (TP * 128) + (ft * 8 + ks) * 2048, TP * 128, 1024);
-              const uint64_t bd = umma_smem_desc(sx + ks * 2048, 16384, 1024);
-              umma_f16(d_tmem, ad, bd, idesc, (ft > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 8; ++ks)
+                umma_f16(d_tmem, pd + ((mt * 2 * (TP * 128) + (ft * 8 + ks) * 2048) >> 4), xd + ((ks * 2048) >> 4), idesc,
+                         (ft > 0 || ks > 0) ? 1u : 0u);
             }
+            umma_commit(&empty2[stage]);
           }
-          umma_commit(&empty2[stage]);
+          __syncwarp();
           if (++stage == Cfg::NS2) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit_w(&acc_full[buf]);
         if (++buf == 2) { buf = 0; bphase ^= 1; }
       }
     }
