@@ -150,8 +150,10 @@ int lpm_netvlad_pool_fwd(const void* x, long long ldx, long long x_batch_stride,
 void lpm_debug_set_pool_clock(long long* buf);
 /* Measurement aid: 0 = lpm_gemm_f16 never uses 2-CTA (cta_group::2) tiles, 1 = automatic (default). */
 void lpm_debug_set_gemm_pair_mode(int mode);
-/* Measurement aid: 0 = lpm_mha_core_fwd / _bwd always use the warp-level (mma.sync) kernels, 1 = the tcgen05 / TMEM
- * kernels whenever the shape is eligible (depth 16, length 256, heads a multiple of 4; default, or LPM_MHA_TC=0). */
+/* Measurement aid.  Low two bits select the backward of lpm_mha_core_bwd when the shape is eligible (depth 16, length 256,
+ * heads a multiple of 4): 0 = warp-level (mma.sync) kernel, 1 = tcgen05 kernel with the P / dS operands in shared memory,
+ * 2 = tcgen05 kernel with the dV / dK operands in TMEM (default; LPM_MHA_TC=0/1/2).  Bit 2 (value 4) routes the forward
+ * lpm_mha_core_fwd through the tcgen05 kernel as well (default off; LPM_MHA_TC_FWD=1). */
 void lpm_debug_set_mha_tc_mode(int mode);
 /* Profiling aid: when non-NULL, CTA 0 of the tcgen05 attention backward writes clock64 stamps per unit:
  * [4 warpgroups][16 units][4] (unit begins, S/dP available, math issued, operand slots free) then [16 units][4] of the

@@ -205,10 +205,9 @@ int mha_fwd(const __half* qkv, long long ld, int B, int L, int Dm, int H, float 
   LPM_REQUIRE(key_scale != nullptr || scale > 0.f, "mha_fwd: the softmax scale must be positive");
   LPM_REQUIRE((key_scale == nullptr) == (key_shift == nullptr), "mha_fwd: key_scale and key_shift come together");
   // depth-16 heads at 256 positions (the cluster attention of config 1): tcgen05 / TMEM kernel, four heads per CTA
-  // (forward: opt-in with LPM_MHA_TC_FWD=1 -- measured 170 us against 121 us for the warp-level kernel below, whose
+  // (forward: opt-in with LPM_MHA_TC_FWD=1 or lpm_debug_set_mha_tc_mode(4 | m) -- measured 170 us against 121 us for the warp-level kernel below, whose
   // running-maximum softmax needs one pass; the backward is the default: 285 us against 366 us)
-  static const bool tc_fwd = getenv("LPM_MHA_TC_FWD") != nullptr && getenv("LPM_MHA_TC_FWD")[0] == '1';
-  if (tc_fwd && key_scale == nullptr && mha_tc_eligible(L, Dm, H, ld, ldo, qkv, out, out))
+  if (mha_tc_forward_enabled() && key_scale == nullptr && mha_tc_eligible(L, Dm, H, ld, ldo, qkv, out, out))
     return mha_fwd_tc(qkv, ld, B, Dm, H, scale, out, ldo, lse, st);
   const size_t smem = (size_t)L * 96 + (size_t)L * 8;
   const float scale_log2 = scale * 1.4426950408889634f;
@@ -522,7 +521,7 @@ static int mha_bwd_launch(int mode, const __half* qkv, long long ld, const __hal
 
 int mha_bwd(const __half* qkv, long long ld, const __half* o, const __half* dout, long long ldo, const float* lse,
             int B, int L, int Dm, int H, float scale, __half* dqkv, long long ldd, cudaStream_t st) {
-  if (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && mha_tc_eligible(L, Dm, H, ld, ldo, qkv, dout, dqkv)) {
+  if (mha_tc_backward_mode() != 0 && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && mha_tc_eligible(L, Dm, H, ld, ldo, qkv, dout, dqkv)) {
     LPM_REQUIRE(scale > 0.f, "mha_bwd: the softmax scale must be positive");
     return mha_bwd_tc(qkv, ld, o, dout, ldo, lse, B, Dm, H, scale, dqkv, ldd, st);
   }

@@ -34,6 +34,13 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // byte offset of 16-byte chunk c (8 fp16 columns) of row r inside a 128B-swizzled [rows][64] tile
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 
+// L2 prefetch of one TMA box (no shared memory involved): the CTAs of a wave run in lock step -- all load, all compute,
+// all store -- so each CTA asks for the tiles of the CTA that will follow it on the machine while it computes.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // 16-byte store to a shared-memory address (explicit state space: a pointer selected at run time among several
 // buffers otherwise compiles to generic ST.E stores, which go through the local/global queue)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -256,12 +263,13 @@ struct BwdSmem {
   static constexpr int SLOT_OFF = 4 * TILE_BYTES;          // 3 operand slots x [2 key blocks][128 query rows][128 B]
   static constexpr int SLOT_BYTES = 2 * HALF_TILE;
   static constexpr int BAR_OFF = SLOT_OFF + 3 * SLOT_BYTES;   // 229376
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 192 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
 // TMEM columns: [0,256) two halves of (S 64 | dP 64) for the unit in flight; [256 + 96 a, +96) accumulators of head
 // parity a: dQ (2 query tiles x 16) | dK (2 key tiles x 16) | dV (2 key tiles x 16).
+constexpr int NEXT_WAVE = 148;   // one CTA per SM: CTA i + 148 follows CTA i (L2 prefetch distance)
 constexpr int ACC_COL = 256;
 constexpr int ACC_COLS = 96;
 
@@ -280,11 +288,13 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
   uint64_t* tile_full = bars;          // [1]
   uint64_t* sdp_full = bars + 1;       // [2] S | dP of one 64-key half of the unit are in TMEM
   uint64_t* sdp_empty = bars + 3;      // [2] ... and have been read (8 warps arrive)
-  uint64_t* pds_ready = bars + 5;      // [1] P and dS of the unit are in shared memory (16 warps arrive)
+  uint64_t* slot_full = bars + 13;     // [3] an operand slot has been written (16 warps arrive).  The issuing warps wait on
+                                       //     the SLOT barriers: a slot cannot be refilled before its readers' MMAs retired, so a
+                                       //     reader is never two phases behind (a per-unit barrier can lap a slow reader)
   uint64_t* slot_free = bars + 6;      // [3] the MMAs reading an operand slot retired
   uint64_t* acc_full = bars + 9;       // [2] gradients of a head complete in TMEM
   uint64_t* acc_empty = bars + 11;     // [2] ... and read (16 warps arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int groups = H >> 2;
@@ -301,7 +311,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
         mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
         mbar_init(&acc_full[i], 3); mbar_init(&acc_empty[i], 16);     // three issuing warps commit a head
       }
-      mbar_init(pds_ready, 16);
+      for (int i = 0; i < 3; ++i) mbar_init(&slot_full[i], 16);
       for (int i = 0; i < 3; ++i) mbar_init(&slot_free[i], 2);        // two of the issuing warps read every slot
       mbar_fence_init();
     }
@@ -325,6 +335,16 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
         tma_load_3d(sK + ft * HALF_TILE, &tmap_qkv, tile_full, Dm + h0 * 16, ft * 128, b);
         tma_load_3d(sV + ft * HALF_TILE, &tmap_qkv, tile_full, 2 * Dm + h0 * 16, ft * 128, b);
         tma_load_3d(sdO + ft * HALF_TILE, &tmap_do, tile_full, h0 * 16, ft * 128, b);
+      }
+      const int nxt = blockIdx.x + NEXT_WAVE;            // the group a later CTA of this SM count will load
+      if (nxt < (int)gridDim.x) {
+        const int nb = nxt / groups, nh = (nxt % groups) * 4;
+        for (int ft = 0; ft < 2; ++ft) {
+          tma_prefetch_l2_3d(&tmap_qkv, nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_qkv, Dm + nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_qkv, 2 * Dm + nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_do, nh * 16, ft * 128, nb);
+        }
       }
     }
     __syncwarp();
@@ -361,14 +381,15 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
       const int hp = u >> 2, ft = (u >> 1) & 1, kc = u & 1, a = hp & 1;
       if (role == 0 && u + 1 < 16) issue_1(u + 1);
       if (stamp) dbg[256 + role * 64 + u * 4 + 0] = clock64();   // (warp 16) S/dP of unit u + 1 issued
-      mbar_wait(pds_ready, u & 1);
+      const int kp = 2 * u, kd = 2 * u + 1;
+      if (role < 2) mbar_wait(&slot_full[kp % 3], (kp / 3) & 1);       // dV reads P; dK also arrives on the P slot
+      if (role > 0) mbar_wait(&slot_full[kd % 3], (kd / 3) & 1);       // dK, dQ read dS
       tc_fence_after();
       if (stamp) dbg[256 + role * 64 + u * 4 + 1] = clock64();   // P / dS of unit u visible
       if ((u & 3) == 0 && hp >= 2) {
         mbar_wait(&acc_empty[a], ((hp >> 1) & 1) ^ 1);
         tc_fence_after();
       }
-      const int kp = 2 * u, kd = 2 * u + 1;
       const uint32_t sp = (uint32_t)((kp % 3) * BwdSmem::SLOT_BYTES) >> 4, sd = (uint32_t)((kd % 3) * BwdSmem::SLOT_BYTES) >> 4;
       const uint32_t acc = tmem_base + ACC_COL + a * ACC_COLS;
       const uint32_t bq = (uint32_t)(ft * HALF_TILE + hp * 32) >> 4;     // rows of query tile ft, columns of head hp
@@ -505,7 +526,7 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_ready);
+      if (lane == 0) { mbar_arrive(&slot_full[kp % 3]); mbar_arrive(&slot_full[kd % 3]); }
       if ((u & 3) == 1 && hp >= 1) epilogue(hp - 1);    // one unit late: the head's last MMAs have retired by now
     }
     epilogue(3);
@@ -522,7 +543,329 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
         tma_store_3d(&tmap_dqkv, sV + ft * HALF_TILE, 2 * Dm + h0 * 16, ft * 128, b);
       }
       bulk_commit();
-      bulk_wait<0>();
+      bulk_wait_read<0>();     // the tiles have left shared memory; the global writes complete before the grid does
+    }
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward, version 2: keys on the TMEM lanes.  S^T = K Q^T and dP^T = V dO^T put a KEY on every lane, so P^T and
+// dS^T -- the A operands of dV += P^T dO and dK += dS^T Q -- are written back to TMEM (packed fp16, in place over
+// the consumed logits) and read by the tensor core from there: only dS^T for dQ += dS K still goes through shared
+// memory (32 KB per unit instead of 64 KB written + 96 KB re-read by the MMAs).  A unit is (128 keys x 128 queries);
+// its two 64-query halves belong to two warpgroup pairs that run out of phase (own barriers), so one pair's math
+// fills the MUFU while the other waits for its next logits.  lse / delta are per COLUMN here: each warpgroup keeps
+// the 32 values of its columns in a small shared-memory scratch (one warp computes them, broadcast LDS.128 reads).
+// ------------------------------------------------------------------------------------------------------------------
+struct Bwd2Smem {
+  static constexpr int Q_OFF = 0, K_OFF = TILE_BYTES, V_OFF = 2 * TILE_BYTES, DO_OFF = 3 * TILE_BYTES;
+  static constexpr int SLOT_OFF = 4 * TILE_BYTES;          // 3 dS^T slots x [2 query blocks][128 key rows][128 B]
+  static constexpr int SLOT_BYTES = 2 * HALF_TILE;
+  static constexpr int ROWC_OFF = SLOT_OFF + 3 * SLOT_BYTES;  // [4 warpgroups][2][32] float2 (-lse*log2e, delta)
+  static constexpr int BAR_OFF = ROWC_OFF + 4 * 2 * 32 * 8;
+  static constexpr int TOTAL = BAR_OFF + 192;
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(576, 1)
+mha_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                   const __grid_constant__ CUtensorMap tmap_dqkv, const __half* __restrict__ o, long long ldo,
+                   const float* __restrict__ lse, int H, int Dm, float scale, long long* dbg, int pair_delay) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem + Bwd2Smem::Q_OFF;
+  uint8_t* sK = smem + Bwd2Smem::K_OFF;
+  uint8_t* sV = smem + Bwd2Smem::V_OFF;
+  uint8_t* sdO = smem + Bwd2Smem::DO_OFF;
+  uint8_t* sSlot = smem + Bwd2Smem::SLOT_OFF;
+  float2* sRowc = reinterpret_cast<float2*>(smem + Bwd2Smem::ROWC_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Bwd2Smem::BAR_OFF);
+  uint64_t* tile_full = bars;          // [1]
+  uint64_t* sdp_full = bars + 1;       // [2] S^T | dP^T of one 64-query half are in TMEM
+  uint64_t* pds_ready = bars + 3;      // [2] P^T, dS^T of a half are in TMEM / shared memory (8 warps arrive)
+  uint64_t* slot_free = bars + 5;      // [3] the dQ MMAs reading a dS^T slot retired
+  uint64_t* acc_full = bars + 8;       // [2] gradients of a head complete in TMEM (both issuing warps commit)
+  uint64_t* acc_empty = bars + 10;     // [2] ... and read (16 warps arrive)
+  uint64_t* slot_full = bars + 16;     // [3] a dS^T slot has been written (16 warps arrive): what the dQ warp waits on -- it may
+                                       //     trail the pairs by up to three units, and a per-unit barrier would lap it
+  uint64_t* rowc_ready = bars + 12;    // [4] column constants of a warpgroup are in its scratch (its first warp arrives)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+  const int groups = H >> 2;
+  const int b = blockIdx.x / groups, h0 = (blockIdx.x % groups) * 4;
+  const float scale_log2 = scale * 1.4426950408889634f;
+
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_do);
+      tma_prefetch_desc(&tmap_dqkv);
+      mbar_init(tile_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sdp_full[i], 1); mbar_init(&pds_ready[i], 8);
+        mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 16);
+      }
+      for (int i = 0; i < 3; ++i) { mbar_init(&slot_free[i], 1); mbar_init(&slot_full[i], 16); }
+      for (int i = 0; i < 4; ++i) mbar_init(&rowc_ready[i], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 16) {
+    // warp 16: TMA loads, S^T / dP^T and the TMEM-operand chains dV, dK (in order on one thread: the next logits of a
+    // half overwrite its P^T / dS^T only after the MMAs reading them); warp 17: dQ from the shared-memory dS^T slots
+    const int role = warp - 16;
+    if (role == 0 && lane == 0) {
+      mbar_expect_tx(tile_full, 4 * TILE_BYTES);
+      for (int ft = 0; ft < 2; ++ft) {
+        tma_load_3d(sQ + ft * HALF_TILE, &tmap_qkv, tile_full, h0 * 16, ft * 128, b);
+        tma_load_3d(sK + ft * HALF_TILE, &tmap_qkv, tile_full, Dm + h0 * 16, ft * 128, b);
+        tma_load_3d(sV + ft * HALF_TILE, &tmap_qkv, tile_full, 2 * Dm + h0 * 16, ft * 128, b);
+        tma_load_3d(sdO + ft * HALF_TILE, &tmap_do, tile_full, h0 * 16, ft * 128, b);
+      }
+      const int nxt = blockIdx.x + NEXT_WAVE;            // the group a later CTA of this SM count will load
+      if (nxt < (int)gridDim.x) {
+        const int nb = nxt / groups, nh = (nxt % groups) * 4;
+        for (int ft = 0; ft < 2; ++ft) {
+          tma_prefetch_l2_3d(&tmap_qkv, nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_qkv, Dm + nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_qkv, 2 * Dm + nh * 16, ft * 128, nb);
+          tma_prefetch_l2_3d(&tmap_do, nh * 16, ft * 128, nb);
+        }
+      }
+    }
+    __syncwarp();
+    mbar_wait(tile_full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_1 = umma_idesc_f16(128, 64, 0, 0);    // S^T / dP^T half: both operands K-major
+    constexpr uint32_t idesc_ts = umma_idesc_f16(128, 16, 0, 1);   // dV, dK: A = P^T / dS^T in TMEM, B MN-major
+    constexpr uint32_t idesc_q = umma_idesc_f16(128, 16, 1, 1);    // dQ: A = dS (MN-major view of dS^T), B = K (MN-major)
+    const uint64_t q_k = umma_smem_desc(smem_u32(sQ), 16, 1024), k_k = umma_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t v_k = umma_smem_desc(smem_u32(sV), 16, 1024), do_k = umma_smem_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t q_m = umma_smem_desc(smem_u32(sQ), HALF_TILE, 1024), k_m = umma_smem_desc(smem_u32(sK), HALF_TILE, 1024);
+    const uint64_t do_m = umma_smem_desc(smem_u32(sdO), HALF_TILE, 1024);
+    const uint64_t slot_m = umma_smem_desc(smem_u32(sSlot), HALF_TILE, 1024);
+    // unit u = (head hp, query tile ft, key chunk kc) = (u >> 2, (u >> 1) & 1, u & 1); half = 64 queries of the tile
+    auto issue_1 = [&](int u, int half) {
+      const int hp = u >> 2, ft = (u >> 1) & 1, kc = u & 1;
+      const uint32_t ko = (uint32_t)(kc * HALF_TILE + hp * 32) >> 4;                     // 128 key rows of chunk kc
+      const uint32_t qo = (uint32_t)((ft * 128 + half * 64) * 128 + hp * 32) >> 4;       // 64 query rows
+      umma_f16_w(tmem_base + half * 128, k_k + ko, q_k + qo, idesc_1, 0u);
+      umma_f16_w(tmem_base + half * 128 + 64, v_k + ko, do_k + qo, idesc_1, 0u);
+      umma_commit_w(&sdp_full[half]);
+    };
+    if (role == 0) {
+      // The second pair starts half a period late: its math then runs while the first pair is storing / waiting for its
+      // next logits instead of competing with it for the MUFU (the pairs keep whatever phase they start with).
+      issue_1(0, 0);
+      const long long t_start = clock64();
+      while (clock64() - t_start < pair_delay) { }
+      issue_1(0, 1);
+    }
+#pragma unroll 1
+    for (int u = 0; u < 16; ++u) {
+      const int hp = u >> 2, ft = (u >> 1) & 1, kc = u & 1, a = hp & 1;
+      const uint32_t acc = tmem_base + ACC_COL + a * ACC_COLS;
+      if (role == 0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&pds_ready[half], u & 1);
+          tc_fence_after();
+          if ((u & 3) == 0 && hp >= 2 && half == 0) {
+            mbar_wait(&acc_empty[a], ((hp >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t bq = (uint32_t)((ft * 128 + half * 64) * 128 + hp * 32) >> 4;   // query rows of this half
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // queries 16 ks .. 16 ks + 15 of the half: packed fp16 pairs in 8 TMEM columns of warpgroup (ks >> 1)
+            const uint32_t acol = tmem_base + half * 128 + (ks >> 1) * 32 + (ks & 1) * 8;
+            const uint32_t first = (ft > 0 || half > 0 || ks > 0) ? 1u : 0u;
+            if (elect_one()) {
+              umma_f16_ts(acc + 64 + kc * 16, acol, do_m + bq + ((ks * 2048) >> 4), idesc_ts, first);       // dV
+              umma_f16_ts(acc + 32 + kc * 16, acol + 64, q_m + bq + ((ks * 2048) >> 4), idesc_ts, first);   // dK
+            }
+            __syncwarp();
+          }
+          if (u + 1 < 16) issue_1(u + 1, half);
+        }
+      } else {
+        mbar_wait(&slot_full[u % 3], (u / 3) & 1);
+        tc_fence_after();
+        if ((u & 3) == 0 && hp >= 2) {
+          mbar_wait(&acc_empty[a], ((hp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t sd = (uint32_t)((u % 3) * Bwd2Smem::SLOT_BYTES) >> 4;
+        const uint32_t bk = (uint32_t)(kc * HALF_TILE + hp * 32) >> 4;
+        // dQ[queries of tile ft] += dS K   (A = rows of dS^T: 16 keys per k-step, 128 queries = two 64-query blocks)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_f16_w(acc + ft * 16, slot_m + sd + ((ks * 2048) >> 4), k_m + bk + ((ks * 2048) >> 4), idesc_q,
+                     (kc > 0 || ks > 0) ? 1u : 0u);
+        umma_commit_w(&slot_free[u % 3]);
+      }
+      if ((u & 3) == 3) umma_commit_w(&acc_full[a]);
+    }
+  } else {
+    // ------------- gradient warps: warpgroup g owns queries [32 g, 32 g + 32) of every 128-query tile -------------
+    const int g = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;                 // key row inside the chunk = TMEM lane
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const int half = g >> 1, cofs = (g & 1) * 32;
+    const uint32_t slot_base = smem_u32(sSlot);
+    uint4 o_pref[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    float lse_pref = 0.f;
+    auto prefetch = [&](int combo) {      // combo = (hp, ft): O row and lse of query g * 32 + lane of that tile
+      const int hp = combo >> 1, q = (combo & 1) * 128 + g * 32 + lane;
+      const __half* orow = o + ((long long)b * AL + q) * ldo + (h0 + hp) * 16;
+      o_pref[0] = __ldg(reinterpret_cast<const uint4*>(orow));
+      o_pref[1] = __ldg(reinterpret_cast<const uint4*>(orow) + 1);
+      lse_pref = __ldg(lse + ((long long)b * H + h0 + hp) * AL + q);
+    };
+    if (quarter == 0) prefetch(0);
+    mbar_wait(tile_full, 0);
+
+    auto epilogue = [&](int hp) {
+      const int a = hp & 1;
+      mbar_wait(&acc_full[a], (hp >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int pc = g + 4 * t;           // piece: 0,1 = dQ tiles; 2,3 = dK tiles; 4,5 = dV tiles
+        if (pc < 6) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + lane_addr + ACC_COL + a * ACC_COLS + pc * 16, v);
+          tmem_ld_wait();
+          const float f = pc < 4 ? scale : 1.f;
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_half2(__uint_as_float(v[2 * i]) * f, __uint_as_float(v[2 * i + 1]) * f);
+          const uint32_t tile = smem_u32(pc < 2 ? sQ : (pc < 4 ? sK : sV));
+          const int r = (pc & 1) * 128 + row;
+          sts128(tile + sw128(r, 2 * hp), pk[0], pk[1], pk[2], pk[3]);
+          sts128(tile + sw128(r, 2 * hp + 1), pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+    };
+
+#pragma unroll 1
+    for (int u = 0; u < 16; ++u) {
+      const int hp = u >> 2, ft = (u >> 1) & 1;
+      float2* rowc = sRowc + (g * 2 + ((u >> 1) & 1)) * 32;
+      if ((u & 1) == 0) {
+        // column constants of this warpgroup's 32 queries for the two units of (hp, ft): one warp computes them from
+        // the O row / lse it fetched one unit earlier (no global-memory latency in front of the warpgroup barrier)
+        if (quarter == 0) {
+          const int q = ft * 128 + g * 32 + lane;
+          const uint4 d0 = *reinterpret_cast<const uint4*>(sdO + sw128(q, 2 * hp));
+          const uint4 d1 = *reinterpret_cast<const uint4*>(sdO + sw128(q, 2 * hp + 1));
+          const __half2* a0 = reinterpret_cast<const __half2*>(&o_pref[0]);
+          const __half2* a1 = reinterpret_cast<const __half2*>(&o_pref[1]);
+          const __half2* b0 = reinterpret_cast<const __half2*>(&d0);
+          const __half2* b1 = reinterpret_cast<const __half2*>(&d1);
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = __half22float2(a0[i]), y = __half22float2(b0[i]);
+            const float2 z = __half22float2(a1[i]), t = __half22float2(b1[i]);
+            d += x.x * y.x + x.y * y.y + z.x * t.x + z.y * t.y;
+          }
+          rowc[lane] = make_float2(-lse_pref * 1.4426950408889634f, d);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rowc_ready[g]);     // release: the other three warps only wait, nobody waits for them
+        }
+        mbar_wait(&rowc_ready[g], (u >> 1) & 1);
+      } else if (quarter == 0 && u + 1 < 16) {
+        prefetch((u + 1) >> 1);
+      }
+      long long* dg = (dbg != nullptr && blockIdx.x == 0 && quarter == 0 && lane == 0) ? dbg + g * 128 + u * 8 : nullptr;
+      if (dg) dg[0] = clock64();          // unit begins (column constants done)
+      mbar_wait(&sdp_full[half], u & 1);
+      tc_fence_after();
+      if (dg) dg[1] = clock64();          // S^T / dP^T available
+      uint32_t s[32], dp[32];
+      tmem_ld32(tmem_base + lane_addr + half * 128 + cofs, s);
+      tmem_ld32(tmem_base + lane_addr + half * 128 + 64 + cofs, dp);
+      tmem_ld_wait();
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 c = *reinterpret_cast<const float4*>(&rowc[2 * i]);     // (-lse2, delta) of queries 2i, 2i + 1
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * i]), scale_log2, c.x));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), scale_log2, c.z));
+        pk[i] = pack_half2(p0, p1);
+        dk[i] = pack_half2(p0 * (__uint_as_float(dp[2 * i]) - c.y), p1 * (__uint_as_float(dp[2 * i + 1]) - c.w));
+      }
+      if (dg) dg[2] = clock64();          // math issued
+      // A operands of dV / dK: back into TMEM, in place over this thread's consumed columns
+      tmem_st16(tmem_base + lane_addr + half * 128 + cofs, pk);
+      tmem_st16(tmem_base + lane_addr + half * 128 + 64 + cofs, dk);
+      // dS^T row of this key for dQ: [query block = half][key row][64 queries], 128B-swizzled
+      mbar_wait(&slot_free[u % 3], ((u / 3) & 1) ^ 1);
+      if (dg) dg[3] = clock64();          // dS^T slot free
+      const uint32_t bd = slot_base + (u % 3) * Bwd2Smem::SLOT_BYTES + half * HALF_TILE;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(bd + sw128(row, (g & 1) * 4 + j), dk[4 * j], dk[4 * j + 1], dk[4 * j + 2], dk[4 * j + 3]);
+      if (dg) dg[4] = clock64();          // stores issued
+      fence_proxy_async_smem();
+      if (dg) dg[5] = clock64();          // proxy fence done
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&slot_full[u % 3]); mbar_arrive(&pds_ready[half]); }
+      if (dg) dg[6] = clock64();          // arrived
+      if ((u & 3) == 1 && hp >= 1) epilogue(hp - 1);
+    }
+    epilogue(3);
+    fence_proxy_async_smem();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    if (lane == 0) {
+      for (int ft = 0; ft < 2; ++ft) {
+        tma_store_3d(&tmap_dqkv, sQ + ft * HALF_TILE, h0 * 16, ft * 128, b);
+        tma_store_3d(&tmap_dqkv, sK + ft * HALF_TILE, Dm + h0 * 16, ft * 128, b);
+        tma_store_3d(&tmap_dqkv, sV + ft * HALF_TILE, 2 * Dm + h0 * 16, ft * 128, b);
+      }
+      bulk_commit();
+      bulk_wait_read<0>();     // the tiles have left shared memory; the global writes complete before the grid does
     }
     __syncwarp();
     tc_fence_after();
@@ -531,12 +874,13 @@ mha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
 }
 
 long long* g_mha_dbg = nullptr;
-int g_mha_tc_mode = -1;   // -1: read LPM_MHA_TC once; 0: legacy mma.sync kernels only; 1: tensor-memory kernels when eligible
+int g_mha_tc_mode = -1;   // -1: read LPM_MHA_TC once; 0: warp-level mma.sync kernels only; 1: tcgen05 backward with operands in shared
+                          // memory; 2 (default): tcgen05 backward with the dV / dK operands in TMEM
 
 bool tc_enabled() {
   if (g_mha_tc_mode < 0) {
     const char* e = getenv("LPM_MHA_TC");
-    g_mha_tc_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_mha_tc_mode = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
   return g_mha_tc_mode != 0;
 }
@@ -545,11 +889,24 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
-void mha_set_tc_mode(int mode) { g_mha_tc_mode = mode ? 1 : 0; }
+int g_mha_tc_fwd = -1;    // forward on the tcgen05 kernel: -1 = read LPM_MHA_TC_FWD once (default off), 0 / 1
+void mha_set_tc_mode(int mode) {
+  g_mha_tc_fwd = (mode >> 2) & 1;
+  mode &= 3;
+  g_mha_tc_mode = mode > 2 ? 2 : mode;
+}
+int mha_tc_backward_mode() { tc_enabled(); return g_mha_tc_mode; }
+bool mha_tc_forward_enabled() {
+  if (g_mha_tc_fwd < 0) {
+    const char* e = getenv("LPM_MHA_TC_FWD");
+    g_mha_tc_fwd = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_mha_tc_fwd != 0;
+}
 void mha_set_debug_clock(long long* buf) { g_mha_dbg = buf; }
 
 bool mha_tc_eligible(int L, int Dm, int H, long long ld, long long ldo, const void* p0, const void* p1, const void* p2) {
-  return tc_enabled() && H > 0 && Dm == H * 16 && L == AL && (H & 3) == 0 && ld % 8 == 0 && ldo % 8 == 0 &&
+  return H > 0 && Dm == H * 16 && L == AL && (H & 3) == 0 && ld % 8 == 0 && ldo % 8 == 0 &&
          aligned16(p0) && aligned16(p1) && aligned16(p2);
 }
 
@@ -578,6 +935,17 @@ int mha_bwd_tc(const __half* qkv, long long ld, const __half* o, const __half* d
   if (!set) {
     LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
     set = true;
+  }
+  if (g_mha_tc_mode == 2) {
+    static const int pair_delay = getenv("LPM_MHA_PAIR_DELAY") ? atoi(getenv("LPM_MHA_PAIR_DELAY")) : 1400;
+    static bool set2 = false;
+    if (!set2) {
+      LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::TOTAL));
+      set2 = true;
+    }
+    mha_bwd_tc2_kernel<<<B * (H / 4), 576, Bwd2Smem::TOTAL, st>>>(tq, tdo, td, o, ldo, lse, H, Dm, scale, g_mha_dbg, pair_delay);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
   }
   mha_bwd_tc_kernel<<<B * (H / 4), 608, BwdSmem::TOTAL, st>>>(tq, tdo, td, o, ldo, lse, H, Dm, scale, g_mha_dbg);
   LPM_CUDA_CHECK(cudaGetLastError());

@@ -58,6 +58,8 @@ int mha_bwd_bn(int mode, const __half* qkv, long long ld, const __half* o, const
 
 // lpm_attn_tc.cu: tcgen05 / TMEM attention core for depth-16 heads at length 256 (four heads per CTA)
 void mha_set_tc_mode(int mode);
+bool mha_tc_forward_enabled();
+int mha_tc_backward_mode();
 void mha_set_debug_clock(long long* buf);
 bool mha_tc_eligible(int L, int Dm, int H, long long ld, long long ldo, const void* p0, const void* p1, const void* p2);
 int mha_fwd_tc(const __half* qkv, long long ld, int B, int Dm, int H, float scale, __half* out, long long ldo, float* lse,

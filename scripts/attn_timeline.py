@@ -16,9 +16,7 @@ torch.cuda.synchronize()
 lib.lpm_debug_set_mha_clock(None)
 d = dbg.cpu()
 t0 = int(d[0])
-wg = d[:256].reshape(4, 16, 4) - t0
-iss = d[256:448].reshape(3, 16, 4) - t0
-print("unit | wg0: begin sdp_ok math slots_ok | wg3: begin sdp_ok math slots_ok | warp16: next_sdp_issued pds_seen dV_issued | warp17 dK_issued | warp18 dQ_issued")
+wg = d[:512].reshape(4, 16, 8) - t0
+print("v2 unit | wg0 (pair 0): begin sdp_ok math slot_ok stored fenced arrived | wg3 (pair 1): same")
 for u in range(16):
-    print(u, "|", " ".join(f"{int(x):6d}" for x in wg[0, u]), "|", " ".join(f"{int(x):6d}" for x in wg[3, u]), "|",
-          " ".join(f"{int(x):6d}" for x in iss[0, u, :3]), "|", int(iss[1, u, 2]), "|", int(iss[2, u, 2]))
+    print(u, "|", " ".join(f"{int(x):6d}" for x in wg[0, u, :7]), "|", " ".join(f"{int(x):6d}" for x in wg[3, u, :7]))

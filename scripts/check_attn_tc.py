@@ -34,27 +34,27 @@ ref = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
 ref.backward(do.double())
 lse_ref = torch.logsumexp(logits, -1).reshape(-1)
 res = {}
-for mode in (0, 1):
+for mode in (0, 1, 2):
     lib.lpm_debug_set_mha_tc_mode(mode)
     o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=scale, want_lse=True)
     torch.cuda.synchronize()
     print(f"mode {mode} fwd: out rel {rel(o, ref):.2e}  lse rel {rel(lse.reshape(-1), lse_ref):.2e}")
-    if mode == 1:
+    if mode == 3:
         breakdown("out vs fp64", o, ref.detach(), B, L, Dm, H)
     dqkv = ops.mha_core_bwd(qkv, o, do, lse, B, L, Dm, H, scale=scale)
     torch.cuda.synchronize()
     for i, nm in enumerate("qkv"):
         e = rel(dqkv[:, i * Dm:(i + 1) * Dm], t.grad[:, i * Dm:(i + 1) * Dm])
         print(f"mode {mode} bwd d{nm} rel {e:.2e}")
-        if mode == 1:
+        if mode == 2 and e > 1e-3:
             breakdown(f"d{nm} vs fp64", dqkv[:, i * Dm:(i + 1) * Dm], t.grad[:, i * Dm:(i + 1) * Dm], B, L, Dm, H)
     res[mode] = (o, lse, dqkv)
-print("tc vs legacy: out", rel(res[1][0], res[0][0]), "lse", rel(res[1][1], res[0][1]), "dqkv", rel(res[1][2], res[0][2]))
+print("tc vs legacy: dqkv v1", rel(res[1][2], res[0][2]), "v2", rel(res[2][2], res[0][2]))
 
 B = 80
 qkv = (torch.randn(B * L, 3 * Dm, device=dev) * 0.5).half()
 do = (torch.randn(B * L, Dm, device=dev) * 0.1).half()
-for mode in (0, 1):
+for mode in (0, 1, 2):
     lib.lpm_debug_set_mha_tc_mode(mode)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for _ in range(3):
@@ -70,4 +70,4 @@ for mode in (0, 1):
     ev[2].record()
     torch.cuda.synchronize()
     print(f"mode {mode} [B=80 H=64 L=256 dh=16] fwd {ev[0].elapsed_time(ev[1]) / iters * 1e3:.1f} us  bwd {ev[1].elapsed_time(ev[2]) / iters * 1e3:.1f} us")
-lib.lpm_debug_set_mha_tc_mode(1)
+lib.lpm_debug_set_mha_tc_mode(2)

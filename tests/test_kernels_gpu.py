@@ -497,3 +497,40 @@ def test_splitk_reduce_variants_and_split_operands(cuda, splits, splits2):
         lo = torch.zeros(48, pad, dtype=torch.float16, device=cuda)
         ops.split_hi_lo(w, lo, along_rows=2)
         assert torch.equal(lo[:, :cols], act[:, cols:2 * cols])
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_mha_tcgen05_paths_agree(cuda, B):
+    """lpm_attn_tc.cu: the tcgen05 / TMEM attention kernels (four heads per CTA; backward with the operands in shared memory
+    or in TMEM; opt-in forward) against fp64 autograd of transformer_utils.py:563-581 and against the warp-level kernels."""
+    from learnablepoolingmethods_b200 import ops
+    from learnablepoolingmethods_b200._lib import load
+    lib = load()
+    L, Dm, H = 256, 1024, 64
+    g = torch.Generator().manual_seed(11 + B)
+    qkv = torch.randn(B * L, 3 * Dm, generator=g).half()
+    dout = (torch.randn(B * L, Dm, generator=g) * 0.5).half()
+    ref_in = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(B, L, H, 16).permute(0, 2, 1, 3) for t in ref_in.split(Dm, dim=1)]
+    logits = (q * 0.25) @ k.transpose(-1, -2)
+    out_ref = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, Dm)
+    out_ref.backward(dout.double())
+    qg, dg = qkv.to(cuda), dout.to(cuda)
+    res = {}
+    try:
+        for mode in (0, 1, 2, 4):
+            lib.lpm_debug_set_mha_tc_mode(mode)
+            o, lse = ops.mha_core_fwd(qg, B, L, Dm, H, scale=0.25, want_lse=True)
+            dqkv = ops.mha_core_bwd(qg, o, dg, lse, B, L, Dm, H, scale=0.25)
+            torch.cuda.synchronize()
+            assert rel(o.float(), out_ref.detach()) < 2e-3, mode
+            assert rel(lse.reshape(-1), torch.logsumexp(logits.detach(), -1).reshape(-1)) < 1e-4, mode
+            for i in range(3):
+                e = rel(dqkv[:, i * Dm:(i + 1) * Dm].float(), ref_in.grad[:, i * Dm:(i + 1) * Dm])
+                assert e < 4e-3, (mode, "qkv"[i], e)
+            res[mode] = (o, dqkv)
+    finally:
+        lib.lpm_debug_set_mha_tc_mode(2)
+    # same fp16 P / dS operands, fp32 accumulation in a different order
+    assert rel(res[1][1].float(), res[0][1].float()) < 1e-4 and rel(res[2][1].float(), res[0][1].float()) < 1e-4
+    assert rel(res[4][0].float(), res[0][0].float()) < 1e-3
