@@ -16,6 +16,7 @@
 // Replaces the tf.matmul / tf.layers.dense / slim.fully_connected call sites of the hot path:
 //   frame_level_models.py:2319,2347  transformer_utils.py:559-561,583-585,701-711
 //   video_level_models.py:86-114 and their autodiff transposes.
+#include <cstdlib>
 #include <cstring>
 
 #include "lpm_common.cuh"
@@ -50,6 +51,7 @@ struct GemmKernelParams {
   const __half* add2;
   long long ld_add;
   int tma_store;        // 1: epilogue stages 128-byte-row slabs in smem and writes them with TMA
+  int nt_fast;          // tile order: 0 = m-tiles fastest (concurrent tiles share the B tile), 1 = n-tiles fastest (they share A)
 };
 
 template <int BN, int STAGES>     // BN = B columns staged by ONE CTA per k-block
@@ -303,9 +305,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = work_id; tile < total_tiles; tile += work_stride) {
-        int t = tile;
-        const int mt = t % m_units;   t /= m_units;
-        const int nt = t % p.n_tiles; t /= p.n_tiles;
+        int t = tile, mt, nt;
+        if (p.nt_fast) { nt = t % p.n_tiles; t /= p.n_tiles; mt = t % m_units; t /= m_units; }
+        else           { mt = t % m_units;   t /= m_units;   nt = t % p.n_tiles; t /= p.n_tiles; }
         const int bz = t % p.batch;   t /= p.batch;
         const int sp = t;
         const int kb0 = sp * p.kb_per_split;
@@ -415,9 +417,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t tempty_leader[2] = {TWO ? g2_mapa(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        TWO ? g2_mapa(smem_u32(&tempty_bar[1]), 0) : 0u};
     for (int tile = work_id; tile < total_tiles; tile += work_stride) {
-      int t = tile;
-      const int mu = t % m_units;   t /= m_units;
-      const int nt = t % p.n_tiles; t /= p.n_tiles;
+      int t = tile, mu, nt;
+      if (p.nt_fast) { nt = t % p.n_tiles; t /= p.n_tiles; mu = t % m_units; t /= m_units; }
+      else           { mu = t % m_units;   t /= m_units;   nt = t % p.n_tiles; t /= p.n_tiles; }
       const int bz = t % p.batch;   t /= p.batch;
       const int sp = t;
       const int mt = mu * MT + crank;          // this CTA's 128-row tile
@@ -633,6 +635,15 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
   if (p.tma_store) {
     rc = make_tmap_3d(&tc, g.out, es, g.N, g.M, (uint64_t)p.splits * p.batch, g.ldc, zstride, g.out_f32 ? 32 : 64, BM);
     if (rc) return rc;
+  }
+  // Tile order.  With m-tiles fastest the tiles in flight share one B tile and stream distinct A rows, so A is read
+  // n_tiles times unless it stays in L2 (FFN2 / the dX of FFN1 at config 1: A = 168 MB against 126 MB of L2, four
+  // n-tiles -> 671 MB of DRAM reads, 105 us of a 120 us product); n-tiles fastest reads A once and re-reads the
+  // (L2-resident) B instead.
+  {
+    const double a_bytes = 2.0 * g.M * g.K * (p.a_batched ? 1 : 1), b_bytes = 2.0 * g.N * g.K;
+    static const int force = getenv("LPM_GEMM_NT_FAST") ? atoi(getenv("LPM_GEMM_NT_FAST")) : -1;
+    p.nt_fast = force >= 0 ? force : ((a_bytes > 64e6 && b_bytes <= 48e6 && p.n_tiles > 1) ? 1 : 0);
   }
   if (two) return dispatch_major<256, 6, 1>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
   if (BN == 256) return dispatch_major<256, 4, 0>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
