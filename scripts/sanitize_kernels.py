@@ -22,6 +22,21 @@ if which in ("all", "gemm"):
         o = ops.gemm(a, b, **kw)
         torch.cuda.synchronize()
         print("gemm", M, N, K, kw, float(o.float().abs().mean()))
+if which in ("all", "attn_tc"):
+    # tcgen05 / TMEM attention (lpm_attn_tc.cu): one sample, 8 heads of depth 16 at 256 positions = two CTAs per kernel;
+    # forward opt-in kernel, both backward kernels
+    from learnablepoolingmethods_b200._lib import load
+    lib = load()
+    B, L, Dm, H = 1, 256, 128, 8
+    qkv = (r(B * L, 3 * Dm) * 0.5).half()
+    do = (r(B * L, Dm) * 0.1).half()
+    for mode in (4 | 2, 1):
+        lib.lpm_debug_set_mha_tc_mode(mode)
+        o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=0.25, want_lse=True)
+        d = ops.mha_core_bwd(qkv, o, do, lse, B, L, Dm, H, scale=0.25)
+        torch.cuda.synchronize()
+        print("attn_tc mode", mode, float(o.float().abs().mean()), float(d.float().abs().mean()))
+    lib.lpm_debug_set_mha_tc_mode(2)
 if which in ("all", "misc"):
     B, R, D = 2, 64, 128
     a, b = r(B, R, D).half(), r(B, R, D).half()
