@@ -330,6 +330,15 @@ int lpm_adam_clip_step_dev(float* p, const float* g, float* m, float* v, const i
                            const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                            const int* sh_cols, const long long* sh_ld, float clip, const float* lr_t_dev, float b1, float b2,
                            float eps, float* partial, float* factor, float* norms, int* flag, lpm_stream_t stream);
+/* The same step restricted to tensors tensor0 .. tensor0 + n_tensors - 1, whose chunks are chunk0 .. chunk0 + n_chunks - 1 of
+ * `table` (all arrays stay indexed by absolute chunk / tensor ids).  Clipping is per tensor (utils.py:181-188), so a group of
+ * variables can be updated as soon as ITS gradients are final: the trainer updates the MoE / gating variables (43 % of the
+ * non-factored parameters) underneath the modalities' backward.  lr_t_dev non-NULL overrides lr_t. */
+int lpm_adam_clip_step_range(float* p, const float* g, float* m, float* v, const int* table, int chunk0, int n_chunks,
+                             const int* chunk_begin, int tensor0, int n_tensors, const float* wd,
+                             const unsigned long long* sh_ptr, const int* sh_cols, const long long* sh_ld, float clip, float lr_t,
+                             const float* lr_t_dev, float b1, float b2, float eps, float* partial, float* factor, float* norms,
+                             int* flag, lpm_stream_t stream);
 /* Start-of-step latch of the overflow flag shared by the optimiser entry points: if *flag is set, *skipped += 1 and
  * *flag = 0, so that one non-finite gradient norm skips exactly one update (the reference has no skip: TF would
  * write NaNs into the variables, utils.py:181-188). */

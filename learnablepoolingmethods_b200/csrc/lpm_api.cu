@@ -407,6 +407,18 @@ int lpm_adam_clip_step_dev(float* p, const float* g, float* m, float* v, const i
                         partial, factor, norms, flag, ST(stream));
 }
 
+int lpm_adam_clip_step_range(float* p, const float* g, float* m, float* v, const int* table, int chunk0, int n_chunks,
+                             const int* chunk_begin, int tensor0, int n_tensors, const float* wd,
+                             const unsigned long long* sh_ptr, const int* sh_cols, const long long* sh_ld, float clip, float lr_t,
+                             const float* lr_t_dev, float b1, float b2, float eps, float* partial, float* factor, float* norms,
+                             int* flag, lpm_stream_t stream) {
+  DEVCHK();
+  LPM_REQUIRE(p && g && m && v && table && chunk_begin && wd && partial && factor && norms && flag && n_chunks > 0 &&
+              n_tensors > 0 && chunk0 >= 0 && tensor0 >= 0, "lpm_adam_clip_step_range: bad arguments");
+  return adam_clip_step(p, g, m, v, table, n_chunks, chunk_begin, n_tensors, wd, sh_ptr, sh_cols, sh_ld, clip, lr_t, lr_t_dev, b1, b2,
+                        eps, partial, factor, norms, flag, ST(stream), chunk0, tensor0);
+}
+
 int lpm_step_begin(int* flag, int* skipped, lpm_stream_t stream) {
   DEVCHK();
   LPM_REQUIRE(flag && skipped, "lpm_step_begin: null pointer");

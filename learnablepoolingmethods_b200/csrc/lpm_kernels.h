@@ -102,7 +102,7 @@ int cast_scaled(const float* x, long long n, float alpha, __half* y, cudaStream_
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
                    const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                    const int* sh_cols, const long long* sh_ld, float clip, float lr_t, const float* lr_dev, float b1, float b2,
-                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st);
+                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st, int chunk0 = 0, int tensor0 = 0);
 int step_begin(int* flag, int* skipped, cudaStream_t st);
 
 int rank_grad_clip(const float* gram_a, const float* gram_g, int R, float alpha, float clip, float* factor, float* norm,

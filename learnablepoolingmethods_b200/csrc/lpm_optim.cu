@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const float* __restrict_
 
 // one warp per tensor
 __global__ void __launch_bounds__(256) mt_clip_kernel(const float* __restrict__ partial, const int* __restrict__ chunk_begin,
-                                                      int n_tensors, float clip, float* __restrict__ factor,
+                                                      int tensor0, int n_tensors, float clip, float* __restrict__ factor,
                                                       float* __restrict__ norms, int* __restrict__ flag) {
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (t >= n_tensors) return;
+  const int t = tensor0 + blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= tensor0 + n_tensors) return;
   double s = 0.0;
   for (int c = chunk_begin[t] + lane; c < chunk_begin[t + 1]; c += 32) s += partial[c];
 #pragma unroll
@@ -588,13 +588,16 @@ int shard_adam(float* p, const float* g, float* m, float* v, const int* table, i
   return LPM_OK;
 }
 
+// chunk0 / tensor0: first chunk / tensor of the range to update (chunks chunk0 .. chunk0 + n_chunks - 1 must be exactly the
+// chunks of tensors tensor0 .. tensor0 + n_tensors - 1); all arrays are indexed by ABSOLUTE chunk / tensor ids
 int adam_clip_step(float* p, const float* g, float* m, float* v, const int* table, int n_chunks,
                    const int* chunk_begin, int n_tensors, const float* wd, const unsigned long long* sh_ptr,
                    const int* sh_cols, const long long* sh_ld, float clip, float lr_t, const float* lr_dev, float b1, float b2,
-                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st) {
-  mt_sqnorm_kernel<<<n_chunks, 256, 0, st>>>(g, p, table, wd, partial);
-  mt_clip_kernel<<<(n_tensors + 7) / 8, 256, 0, st>>>(partial, chunk_begin, n_tensors, clip, factor, norms, flag);
-  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table, wd, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, lr_dev, b1, b2, eps);
+                   float eps, float* partial, float* factor, float* norms, int* flag, cudaStream_t st, int chunk0, int tensor0) {
+  mt_sqnorm_kernel<<<n_chunks, 256, 0, st>>>(g, p, table + 4 * (size_t)chunk0, wd, partial + chunk0);
+  mt_clip_kernel<<<(n_tensors + 7) / 8, 256, 0, st>>>(partial, chunk_begin, tensor0, n_tensors, clip, factor, norms, flag);
+  mt_adam_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, table + 4 * (size_t)chunk0, wd, factor, flag, sh_ptr, sh_cols, sh_ld, lr_t, lr_dev,
+                                           b1, b2, eps);
   LPM_CUDA_CHECK(cudaGetLastError());
   return LPM_OK;
 }

@@ -657,13 +657,23 @@ def step_begin(flag, skipped):
 
 
 def adam_clip_step(flat_p, flat_g, flat_m, flat_v, table, chunk_begin, wd, *, clip, lr_t, scratch,
-                   shadow=None, b1=0.9, b2=0.999, eps=1e-8, lr_dev=None):
+                   shadow=None, b1=0.9, b2=0.999, eps=1e-8, lr_dev=None, tensor_range=None, chunk_range=None):
     """Per-tensor (grad + wd*p) -> clip_by_norm -> Adam over the flat buffers (three launches).
-    lr_dev: fp32 [1] device tensor holding the bias-corrected step size (read at execution time: graph replays)."""
+    lr_dev: fp32 [1] device tensor holding the bias-corrected step size (read at execution time: graph replays).
+    tensor_range / chunk_range: (first, count) of the tensors to update and of their chunks in `table` (default: all)."""
     lib = _lib.load()
     n_chunks, n_tensors = table.shape[0], wd.numel()
     partial, factor, norms, flag = scratch[:4]
     sp, sc, sl = shadow if shadow is not None else (None, None, None)
+    if tensor_range is not None:
+        (t0, nt), (c0, nc) = tensor_range, chunk_range
+        if nt <= 0 or nc <= 0:
+            return
+        check(lib.lpm_adam_clip_step_range(ptr(flat_p), ptr(flat_g), ptr(flat_m), ptr(flat_v), ptr(table), c0, nc, ptr(chunk_begin),
+                                           t0, nt, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), C.c_float(lr_t), ptr(lr_dev),
+                                           C.c_float(b1), C.c_float(b2), C.c_float(eps), ptr(partial), ptr(factor), ptr(norms),
+                                           ptr(flag), stream_ptr()), "lpm_adam_clip_step")
+        return
     if lr_dev is not None:
         check(lib.lpm_adam_clip_step_dev(ptr(flat_p), ptr(flat_g), ptr(flat_m), ptr(flat_v), ptr(table), n_chunks,
                                          ptr(chunk_begin), n_tensors, ptr(wd), ptr(sp), ptr(sc), ptr(sl), C.c_float(clip), ptr(lr_dev),
