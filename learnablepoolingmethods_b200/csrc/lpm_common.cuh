@@ -240,6 +240,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, ui
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---- programmatic dependent launch ----
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start before the kernel in front of it
+// in the stream has completed; everything it reads or overwrites that the predecessor touches must come after this wait
+// (a no-op for a normally launched kernel).  Block-local set-up (mbarrier init, TMEM allocation, descriptor prefetch)
+// goes in front of it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- misc math ----
 // 2^x on the MUFU (ex2.approx.ftz, rel. error 2^-22, -inf -> 0): exp2f() without -use_fast_math wraps the same
 // instruction in a denormal-range rescale (4 extra instructions per call), which shows in the softmax-bound kernels

@@ -31,6 +31,7 @@ struct LnChainParams {
   int rows, D;
   long long n8;                    // rows * D / 8
   int per;                         // 16-byte pieces per CTA
+  int stage_cnt;                   // pieces [0, stage_cnt) of the slice live in shared memory, the rest are recomputed from a / b
   float eps;
   const float* gamma1; const float* beta1;
   __half* u1_out; long long u1_stride; float* stats1;
@@ -99,8 +100,8 @@ __device__ __forceinline__ float2 ln_cluster_moments(float s, float q, float* re
 // the 126 MB L2 (a sample is 1 MB, a resident wave of samples < 100 MB), and recompute u: every CTA of the launch is
 // resident at once and HBM still sees one pass.  Same arithmetic, same rounding points (u and y1 are rounded to fp16
 // exactly where the staged version stores them).
-template <bool STAGE, int NT>
-__global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
+template <bool STAGE, int NT, int DEPTH, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ln_chain_kernel(const LnChainParams p) {
   extern __shared__ __align__(16) uint8_t ln_sm[];
   uint4* sU = reinterpret_cast<uint4*>(ln_sm);                 // this CTA's slice of u (fp16), STAGE only
   __shared__ float red[32];
@@ -118,15 +119,16 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
 
   // ---- pass A: u1 = a + b*rs -> shared memory (+ global when the backward wants it), moments ------------------
   float s = 0.f, q = 0.f;
-  for (int base = 0; base < cnt; base += 4 * NT) {
-    uint4 va[4], vb[4];
+  const int stage_cnt = STAGE ? p.stage_cnt : 0;
+  for (int base = 0; base < cnt; base += DEPTH * NT) {
+    uint4 va[DEPTH], vb[DEPTH];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < DEPTH; ++k) {
       const int i = base + k * NT + threadIdx.x;
       if (i < cnt) { va[k] = pa[i]; vb[k] = __ldg(pb + i); }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < DEPTH; ++k) {
       const int i = base + k * NT + threadIdx.x;
       if (i < cnt) {
         float fa[8], fb[8];
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) fa[j] += fb[j] * rs;
         const uint4 vu = ln_pack(fa);
-        if (STAGE) sU[i] = vu;
+        if (i < stage_cnt) sU[i] = vu;
         if (pu1) pu1[i] = vu;
         ln_unpack(vu, fa);                       // moments of the stored (fp16-rounded) values
 #pragma unroll
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
 
   // u1 piece i of this CTA's slice: from shared memory, or recomputed from a and b (L2 hits) with the same rounding
   auto load_u1 = [&](int i, float* f) {
-    if (STAGE) { ln_unpack(sU[i], f); return; }
+    if (i < stage_cnt) { ln_unpack(sU[i], f); return; }
     float fb[8];
     ln_unpack(__ldg(pa + i), f); ln_unpack(__ldg(pb + i), fb);
     const float rs = rsc ? __ldg(rsc + ((i0 + i) * 8) / p.D) : 1.f;
@@ -182,15 +184,15 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
   // ---- pass B (chained): y1 = LN(u1) (rounded to fp16 as the unfused path stores it); u2 = y1 + b -------------
   uint4* pu2 = p.u2_out ? reinterpret_cast<uint4*>(p.u2_out + sample * p.u2_stride) + i0 : nullptr;
   s = 0.f; q = 0.f;
-  for (int base = 0; base < cnt; base += 4 * NT) {
-    uint4 vb[4];
+  for (int base = 0; base < cnt; base += DEPTH * NT) {
+    uint4 vb[DEPTH];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < DEPTH; ++k) {
       const int i = base + k * NT + threadIdx.x;
       if (i < cnt) vb[k] = __ldg(pb + i);          // second use of the residual: an L2 hit
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < DEPTH; ++k) {
       const int i = base + k * NT + threadIdx.x;
       if (i < cnt) {
         float f[8], fb[8];
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += fb[j];
         const uint4 vu = ln_pack(f);
-        if (STAGE) sU[i] = vu;
+        if (i < stage_cnt) sU[i] = vu;
         if (pu2) pu2[i] = vu;
         ln_unpack(vu, f);
 #pragma unroll
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(NT) ln_chain_kernel(const LnChainParams p) {
 #pragma unroll 2
   for (int i = threadIdx.x; i < cnt; i += NT) {
     float f[8];
-    if (STAGE) {
+    if (i < stage_cnt) {
       ln_unpack(sU[i], f);
     } else {
       // u2 = fp16(fp16(LN1(u1)) + b), recomputed
@@ -287,10 +289,18 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
   // default; LPM_LN_STAGE=0 selects the L2 re-read variant (measurement switch).
   static const bool unstaged = getenv("LPM_LN_STAGE") != nullptr && getenv("LPM_LN_STAGE")[0] == '0';
   const bool stage = !unstaged || a == u1_out;            // in-place u1 (a aliased): the re-read would see u1, not a
-  const size_t smem = stage ? (size_t)p.per * 16 : 0;
+  // Hybrid (LPM_LN_HYBRID=1, experiment): when the fully staged launch does not fit in one wave (three 64 KB CTAs per SM at
+  // 74 registers: 640 CTAs = 1.45 waves at config 1), stage only 40 KB of each slice, recompute the rest from L2, and cap the
+  // registers for five CTAs per SM so that every cluster of the launch is resident at once.
+  static const bool hybrid_on = getenv("LPM_LN_HYBRID") != nullptr && getenv("LPM_LN_HYBRID")[0] == '1';
+  const bool hybrid = hybrid_on && stage && a != u1_out && (long long)B * cs > 3ll * num_sms() && (long long)B * cs <= 5ll * num_sms() &&
+                      (size_t)p.per * 16 > 40 * 1024;
+  p.stage_cnt = hybrid ? 40 * 1024 / 16 : p.per;
+  const size_t smem = stage ? (size_t)p.stage_cnt * 16 : 0;
   static size_t attr = 0;
   if (smem > attr) {
-    LPM_CUDA_CHECK(cudaFuncSetAttribute(ln_chain_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LPM_CUDA_CHECK(cudaFuncSetAttribute(ln_chain_kernel<true, 256, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LPM_CUDA_CHECK(cudaFuncSetAttribute(ln_chain_kernel<true, 256, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 44 * 1024));
     attr = smem;
   }
   cudaLaunchConfig_t cfg{};
@@ -302,8 +312,9 @@ int layernorm_chain_fwd(const __half* a, long long a_stride, const __half* b, lo
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (stage) LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<true, 256>, p));
-  else LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<false, 128>, p));
+  if (hybrid) LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<true, 256, 2, 5>, p));
+  else if (stage) LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<true, 256, 4, 3>, p));
+  else LPM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ln_chain_kernel<false, 128, 4, 6>, p));
   return LPM_OK;
 }
 
