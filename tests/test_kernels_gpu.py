@@ -534,3 +534,63 @@ def test_mha_tcgen05_paths_agree(cuda, B):
     # same fp16 P / dS operands, fp32 accumulation in a different order
     assert rel(res[1][1].float(), res[0][1].float()) < 1e-4 and rel(res[2][1].float(), res[0][1].float()) < 1e-4
     assert rel(res[4][0].float(), res[0][0].float()) < 1e-3
+
+
+def test_mha_tcgen05_strided_views_and_fallbacks(cuda):
+    """The tcgen05 attention path takes q/k/v as a column view of a wider buffer (row stride > 3*Dm, as the engine's fused
+    projections produce) and writes dq/dk/dv likewise; shapes outside its envelope (length != 256, depth 8, heads not a
+    multiple of 4) must quietly take the warp-level kernels with the same results as lpm_debug_set_mha_tc_mode(0)."""
+    from learnablepoolingmethods_b200 import ops
+    from learnablepoolingmethods_b200._lib import load
+    lib = load()
+    g = torch.Generator().manual_seed(5)
+    B, L, Dm, H = 2, 256, 256, 16
+    wide = torch.randn(B * L, 3 * Dm + 64, generator=g).half().to(cuda)
+    qkv = wide[:, 32:32 + 3 * Dm]                       # 64-byte column offset, row stride 3*Dm + 64
+    dout = (torch.randn(B * L, Dm, generator=g) * 0.5).half().to(cuda)
+    res = {}
+    try:
+        for mode in (0, 2):
+            lib.lpm_debug_set_mha_tc_mode(mode)
+            o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=0.25, want_lse=True)
+            res[mode] = ops.mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, scale=0.25)
+        torch.cuda.synchronize()
+        assert rel(res[2].float(), res[0].float()) < 1e-4
+        # outside the envelope: identical bits with the switch on or off (same kernel runs)
+        for (L2, Dm2, H2) in ((128, 256, 16), (256, 128, 16), (256, 96, 6)):
+            q2 = torch.randn(B * L2, 3 * Dm2, generator=g).half().to(cuda)
+            d2 = torch.randn(B * L2, Dm2, generator=g).half().to(cuda)
+            outs = []
+            for mode in (0, 2):
+                lib.lpm_debug_set_mha_tc_mode(mode)
+                o, lse = ops.mha_core_fwd(q2, B, L2, Dm2, H2, scale=(Dm2 // H2) ** -0.5, want_lse=True)
+                outs.append(ops.mha_core_bwd(q2, o, d2, lse, B, L2, Dm2, H2, scale=(Dm2 // H2) ** -0.5))
+            torch.cuda.synchronize()
+            assert torch.equal(outs[0], outs[1]), (L2, Dm2, H2)
+    finally:
+        lib.lpm_debug_set_mha_tc_mode(2)
+
+
+def test_mha_tcgen05_benchmark_batch(cuda):
+    """Config-1 shape [80, 64 heads, 256, 16]: every CTA of the 1280-CTA launch against the warp-level kernel, twice (the
+    second launch exercises the L2-prefetched tiles of the first)."""
+    from learnablepoolingmethods_b200 import ops
+    from learnablepoolingmethods_b200._lib import load
+    lib = load()
+    B, L, Dm, H = 80, 256, 1024, 64
+    g = torch.Generator(device=cuda).manual_seed(3)
+    qkv = (torch.randn(B * L, 3 * Dm, device=cuda, generator=g) * 0.5).half()
+    dout = (torch.randn(B * L, Dm, device=cuda, generator=g) * 0.1).half()
+    try:
+        lib.lpm_debug_set_mha_tc_mode(0)
+        o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=0.25, want_lse=True)
+        ref = ops.mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, scale=0.25)
+        lib.lpm_debug_set_mha_tc_mode(2)
+        a = ops.mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, scale=0.25)
+        b = ops.mha_core_bwd(qkv, o, dout, lse, B, L, Dm, H, scale=0.25)
+        torch.cuda.synchronize()
+    finally:
+        lib.lpm_debug_set_mha_tc_mode(2)
+    assert torch.equal(a, b)                                   # deterministic
+    per_sample = (a.float() - ref.float()).reshape(B, -1).norm(dim=1) / ref.float().reshape(B, -1).norm(dim=1)
+    assert float(per_sample.max()) < 1e-4, per_sample.max()
