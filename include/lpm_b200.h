@@ -152,8 +152,9 @@ void lpm_debug_set_pool_clock(long long* buf);
 void lpm_debug_set_gemm_pair_mode(int mode);
 /* Measurement aid.  Low two bits select the backward of lpm_mha_core_bwd when the shape is eligible (depth 16, length 256,
  * heads a multiple of 4): 0 = warp-level (mma.sync) kernel, 1 = tcgen05 kernel with the P / dS operands in shared memory,
- * 2 = tcgen05 kernel with the dV / dK operands in TMEM (default; LPM_MHA_TC=0/1/2).  Bit 2 (value 4) routes the forward
- * lpm_mha_core_fwd through the tcgen05 kernel as well (default off; LPM_MHA_TC_FWD=1). */
+ * 2 = tcgen05 kernel with the dV / dK operands in TMEM (default; LPM_MHA_TC=0/1/2).  Bits 2-3 select the forward of
+ * lpm_mha_core_fwd: 0 = warp-level kernel (default), 4 = tcgen05 with P through shared memory, 8 = tcgen05 with P in TMEM and
+ * two CTAs per SM (LPM_MHA_TC_FWD=0/1/2). */
 void lpm_debug_set_mha_tc_mode(int mode);
 /* Profiling aid: when non-NULL, CTA 0 of the tcgen05 attention backward writes clock64 stamps per unit:
  * [4 warpgroups][16 units][4] (unit begins, S/dP available, math issued, operand slots free) then [16 units][4] of the

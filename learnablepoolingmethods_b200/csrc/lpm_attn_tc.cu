@@ -47,6 +47,25 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
@@ -252,6 +271,195 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_con
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward, version 2: P stays in TMEM.  One warpgroup + one issuing warp per CTA, 256 TMEM columns and 96 KB of shared
+// memory (the three staged tiles), so TWO CTAs share an SM: one CTA's exponentials run while the other waits for its
+// logits / P V, and the load / store phases of the CTAs no longer run in lock step.  Per unit (head, 128 queries):
+//   S [128 x 256] = Q K^T in columns 0..255; pass 1 row maximum; pass 2 p = 2^((s - m) c) packed as fp16 into columns
+//   0..127 IN PLACE (chunk c of 32 logits becomes 16 columns at 16 c: always behind the columns still to be read);
+//   O = P V with P as the TMEM A operand, four interleaved accumulation chains in columns 128..191.
+// ------------------------------------------------------------------------------------------------------------------
+struct Fwd2Smem {
+  static constexpr int Q_OFF = 0, K_OFF = TILE_BYTES, V_OFF = 2 * TILE_BYTES;
+  static constexpr int BAR_OFF = 3 * TILE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 64 + 1024;      // + alignment slack
+  static_assert(2 * (TOTAL + 1024) <= 233472, "two CTAs per SM must fit");
+};
+
+__global__ void __launch_bounds__(160, 2)
+mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+                   int H, int Dm, float scale_log2, float* __restrict__ lse, int nch) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sQ = smem + Fwd2Smem::Q_OFF;
+  uint8_t* sK = smem + Fwd2Smem::K_OFF;
+  uint8_t* sV = smem + Fwd2Smem::V_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Fwd2Smem::BAR_OFF);
+  uint64_t* tile_full = bars;          // the three tiles have landed
+  uint64_t* s_full = bars + 1;         // logits of the unit are in TMEM
+  uint64_t* p_ready = bars + 2;        // probabilities are in TMEM (4 warps arrive)
+  uint64_t* o_full = bars + 3;         // P V retired
+  uint64_t* o_empty = bars + 4;        // the accumulators have been read (4 warps arrive): the next logits may land
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  constexpr int OCOL = 128;            // P V partial accumulators (4 chains x 16 columns)
+
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+  const int groups = H >> 2;
+  const int b = blockIdx.x / groups, h0 = (blockIdx.x % groups) * 4;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_out);
+      mbar_init(tile_full, 1);
+      mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(o_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(tile_full, 3 * TILE_BYTES);
+      for (int ft = 0; ft < 2; ++ft) {
+        tma_load_3d(sQ + ft * HALF_TILE, &tmap_qkv, tile_full, h0 * 16, ft * 128, b);
+        tma_load_3d(sK + ft * HALF_TILE, &tmap_qkv, tile_full, Dm + h0 * 16, ft * 128, b);
+        tma_load_3d(sV + ft * HALF_TILE, &tmap_qkv, tile_full, 2 * Dm + h0 * 16, ft * 128, b);
+      }
+    }
+    __syncwarp();
+    mbar_wait(tile_full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, 256, 0, 0);   // A = Q (K-major), B = K (K-major), N = 256 keys
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 16, 0, 1);    // A = P (TMEM), B = V (MN-major), N = depth
+    const uint64_t q_d = umma_smem_desc(smem_u32(sQ), 16, 1024), k_d = umma_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t v_d = umma_smem_desc(smem_u32(sV), HALF_TILE, 1024);
+#pragma unroll 1
+    for (int u = 0; u < 8; ++u) {
+      const int hp = u >> 1, ft = u & 1;
+      mbar_wait(o_empty, (u & 1) ^ 1);         // unit u - 1 drained (passes immediately for u = 0)
+      tc_fence_after();
+      umma_f16_w(tmem_base, q_d + ((ft * HALF_TILE + hp * 32) >> 4), k_d + ((hp * 32) >> 4), idesc_s, 0u);
+      umma_commit_w(s_full);
+      mbar_wait(p_ready, u & 1);
+      tc_fence_after();
+      const uint64_t vb = v_d + ((hp * 32) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_f16_ts(tmem_base + OCOL + (ks & 3) * 16, tmem_base + ks * 8, vb + ((ks * 2048) >> 4), idesc_o, ks >= 4 ? 1u : 0u);
+        umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t s_addr = tmem_base + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+    for (int u = 0; u < 8; ++u) {
+      const int hp = u >> 1, ft = u & 1;
+      mbar_wait(s_full, u & 1);
+      tc_fence_after();
+      float m = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        auto rmax = [&](const uint32_t* v) {
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) { m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1])); }
+          m = fmaxf(m, fmaxf(m0, m1));
+        };
+        tmem_ld32(s_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32(s_addr + (c + 1) * 32, vb);
+          rmax(va);
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld32(s_addr + (c + 2) * 32, va);
+          rmax(vb);
+        }
+      }
+      const float nm = -m * scale_log2;
+      float sum0 = 0.f, sum1 = 0.f;
+      {
+        uint32_t va[32], vb[32];
+        auto emit = [&](const uint32_t* v, int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2, nm));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, nm));
+            sum0 += e0; sum1 += e1;
+            pk[i] = pack_half2(e0, e1);
+          }
+          tmem_st16(s_addr + c * 16, pk);      // in place: columns 16 c .. 16 c + 15 were read at least one chunk ago
+        };
+        tmem_ld32(s_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32(s_addr + (c + 1) * 32, vb);
+          emit(va, c);
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld32(s_addr + (c + 2) * 32, va);
+          emit(vb, c + 1);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      const float l = sum0 + sum1;
+      const float inv = 1.f / l;
+      const int q = ft * 128 + row;
+      if (lse != nullptr)
+        lse[((long long)b * H + h0 + hp) * AL + q] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
+      mbar_wait(o_full, u & 1);
+      tc_fence_after();
+      uint32_t ov[32], ow[32];
+      tmem_ld32(s_addr + OCOL, ov);
+      tmem_ld32(s_addr + OCOL + 32, ow);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = (__uint_as_float(ov[2 * i]) + __uint_as_float(ov[16 + 2 * i])) +
+                         (__uint_as_float(ow[2 * i]) + __uint_as_float(ow[16 + 2 * i]));
+        const float x1 = (__uint_as_float(ov[2 * i + 1]) + __uint_as_float(ov[16 + 2 * i + 1])) +
+                         (__uint_as_float(ow[2 * i + 1]) + __uint_as_float(ow[16 + 2 * i + 1]));
+        pk[i] = pack_half2(x0 * inv, x1 * inv);
+      }
+      const uint32_t qt = smem_u32(sQ);
+      sts128(qt + sw128(q, 2 * hp), pk[0], pk[1], pk[2], pk[3]);
+      sts128(qt + sw128(q, 2 * hp + 1), pk[4], pk[5], pk[6], pk[7]);
+    }
+    fence_proxy_async_smem();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int ft = 0; ft < 2; ++ft) tma_store_3d(&tmap_out, sQ + ft * HALF_TILE, h0 * 16, ft * 128, b);
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -571,25 +779,6 @@ struct Bwd2Smem {
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __global__ void __launch_bounds__(576, 1)
 mha_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_dqkv, const __half* __restrict__ o, long long ldo,
@@ -885,9 +1074,11 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
-int g_mha_tc_fwd = -1;    // forward on the tcgen05 kernel: -1 = read LPM_MHA_TC_FWD once (default off), 0 / 1
+constexpr int MHA_TC_FWD_DEFAULT = 0;
+int g_mha_tc_fwd = -1;    // forward on a tcgen05 kernel: -1 = read LPM_MHA_TC_FWD once; 0 = warp-level kernel, 1 = P through shared
+                          // memory, 2 = P in TMEM, two CTAs per SM
 void mha_set_tc_mode(int mode) {
-  g_mha_tc_fwd = (mode >> 2) & 1;
+  g_mha_tc_fwd = (mode >> 2) & 3;
   mode &= 3;
   g_mha_tc_mode = mode > 2 ? 2 : mode;
 }
@@ -895,7 +1086,7 @@ int mha_tc_backward_mode() { tc_enabled(); return g_mha_tc_mode; }
 bool mha_tc_forward_enabled() {
   if (g_mha_tc_fwd < 0) {
     const char* e = getenv("LPM_MHA_TC_FWD");
-    g_mha_tc_fwd = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_mha_tc_fwd = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : MHA_TC_FWD_DEFAULT;
   }
   return g_mha_tc_fwd != 0;
 }
@@ -915,6 +1106,16 @@ int mha_fwd_tc(const __half* qkv, long long ld, int B, int Dm, int H, float scal
   if (!set) {
     LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
     set = true;
+  }
+  if (g_mha_tc_fwd == 2) {
+    static bool set2 = false;
+    if (!set2) {
+      LPM_CUDA_CHECK(cudaFuncSetAttribute(mha_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
+      set2 = true;
+    }
+    mha_fwd_tc2_kernel<<<B * (H / 4), 160, Fwd2Smem::TOTAL, st>>>(tq, to, H, Dm, scale * 1.4426950408889634f, lse, AL / 32);
+    LPM_CUDA_CHECK(cudaGetLastError());
+    return LPM_OK;
   }
   mha_fwd_tc_kernel<<<B * (H / 4), 288, FwdSmem::TOTAL, st>>>(tq, to, H, Dm, scale * 1.4426950408889634f, lse, AL / 32);   // nch: run-time trip count (keeps ptxas from flattening the softmax loops)
   LPM_CUDA_CHECK(cudaGetLastError());

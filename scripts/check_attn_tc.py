@@ -49,12 +49,19 @@ for mode in (0, 1, 2):
         if mode == 2 and e > 1e-3:
             breakdown(f"d{nm} vs fp64", dqkv[:, i * Dm:(i + 1) * Dm], t.grad[:, i * Dm:(i + 1) * Dm], B, L, Dm, H)
     res[mode] = (o, lse, dqkv)
+for fm in (1, 2):
+    lib.lpm_debug_set_mha_tc_mode((fm << 2) | 2)
+    o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=scale, want_lse=True)
+    torch.cuda.synchronize()
+    print(f"forward tc v{fm}: out rel {rel(o, ref):.2e}  lse rel {rel(lse.reshape(-1), lse_ref):.2e}  vs warp-level {rel(o, res[0][0]):.2e}")
+    if rel(o, ref) > 1e-3:
+        breakdown("out vs fp64", o, ref.detach(), B, L, Dm, H)
 print("tc vs legacy: dqkv v1", rel(res[1][2], res[0][2]), "v2", rel(res[2][2], res[0][2]))
 
 B = 80
 qkv = (torch.randn(B * L, 3 * Dm, device=dev) * 0.5).half()
 do = (torch.randn(B * L, Dm, device=dev) * 0.1).half()
-for mode in (0, 1, 2):
+for mode in (0, 1, 2, 6, 10):
     lib.lpm_debug_set_mha_tc_mode(mode)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for _ in range(3):

@@ -30,7 +30,7 @@ if which in ("all", "attn_tc"):
     B, L, Dm, H = 1, 256, 128, 8
     qkv = (r(B * L, 3 * Dm) * 0.5).half()
     do = (r(B * L, Dm) * 0.1).half()
-    for mode in (4 | 2, 1):
+    for mode in (4 | 2, 8 | 1):
         lib.lpm_debug_set_mha_tc_mode(mode)
         o, lse = ops.mha_core_fwd(qkv, B, L, Dm, H, scale=0.25, want_lse=True)
         d = ops.mha_core_bwd(qkv, o, do, lse, B, L, Dm, H, scale=0.25)

@@ -518,7 +518,7 @@ def test_mha_tcgen05_paths_agree(cuda, B):
     qg, dg = qkv.to(cuda), dout.to(cuda)
     res = {}
     try:
-        for mode in (0, 1, 2, 4):
+        for mode in (0, 1, 2, 4, 8):
             lib.lpm_debug_set_mha_tc_mode(mode)
             o, lse = ops.mha_core_fwd(qg, B, L, Dm, H, scale=0.25, want_lse=True)
             dqkv = ops.mha_core_bwd(qg, o, dg, lse, B, L, Dm, H, scale=0.25)
@@ -533,7 +533,7 @@ def test_mha_tcgen05_paths_agree(cuda, B):
         lib.lpm_debug_set_mha_tc_mode(2)
     # same fp16 P / dS operands, fp32 accumulation in a different order
     assert rel(res[1][1].float(), res[0][1].float()) < 1e-4 and rel(res[2][1].float(), res[0][1].float()) < 1e-4
-    assert rel(res[4][0].float(), res[0][0].float()) < 1e-3
+    assert rel(res[4][0].float(), res[0][0].float()) < 1e-3 and rel(res[8][0].float(), res[0][0].float()) < 1e-3
 
 
 def test_mha_tcgen05_strided_views_and_fallbacks(cuda):
