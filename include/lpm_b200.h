@@ -66,6 +66,35 @@ typedef struct lpm_gemm_desc {
 } lpm_gemm_desc;
 
 int lpm_gemm_f16(const lpm_gemm_desc* desc, lpm_stream_t stream);
+/* ---------------------------------------------------------------------------------------------
+ * K3: the hidden projection with the context-gating epilogue fused INTO the split-K GEMM kernel
+ * (frame_level_models.py:2314-2368: hidden1_weights product + biases, gating_weights product, gating_bn,
+ * sigmoid, element-wise product).  `desc` must describe a split-K product with fp32 partial output
+ * [splits][B][H] (B <= 128 rows, N = H); all CTAs of the launch are resident (grid <= SM count), so after its last
+ * tile every CTA
+ *   1. waits on a grid-wide barrier (tail->counters, four ints, zero before the first call; the kernel leaves them zero),
+ *   2. sums a slice of H/grid-rounded-to-4 columns of all partials in a fixed order (plus the partials `part2` of an
+ *      earlier launch: the other pass of the split-precision product), adds the bias -> act32 / act16,
+ *   3. waits on a second barrier, forms the gate pre-activations of ITS columns in fp32 from act32 and the fp32 gating
+ *      weights (exact: no fp16 operands), batch-norms them over the B rows (training: batch statistics + moving-average
+ *      update; else moving statistics), and writes act * sigmoid(.) -> out32 / out16.
+ * act16 / out16: fp16 [B][H], or with *_split3 != 0 the split-precision operand [B][3H] = [hi | lo | hi].
+ * Replaces lpm_gemm_f16 + lpm_splitk_reduce_ex + lpm_gemm_f16 (gate) + lpm_gating_fwd_ex: one launch instead of four.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lpm_gating_tail {
+  int* counters;                                   /* [4] grid-barrier scratch */
+  const float* part2; int splits2; long long split_stride2;   /* optional second partial set [splits2][B][H] */
+  const float* bias;                               /* hidden1_biases [H] or NULL */
+  float* act32; void* act16; int act_split3;       /* hidden activation */
+  const float* wg; long long ldwg;                 /* gating_weights fp32 [H][ldwg] */
+  const float* wg_diag;                            /* diag(gating_weights) for --gating_remove_diag, or NULL */
+  const float* gamma; const float* beta; float* moving_mean; float* moving_var;
+  float decay, eps; int training;
+  float* g_sum;                                    /* [B][H] gate pre-activations (for the backward) */
+  float* out32; void* out16; int out_split3;       /* gated activation */
+  float* save_mean; float* save_rstd;              /* [H] or NULL */
+} lpm_gating_tail;
+int lpm_gemm_splitk_gated_fwd(const lpm_gemm_desc* desc, const lpm_gating_tail* tail, lpm_stream_t stream);
 /* N-tile width the kernel will use for a given N (for sizing stat partial buffers). */
 int lpm_gemm_tile_n(int N);
 /* Number of non-empty K splits the kernel will use. */

@@ -33,6 +33,23 @@ class GemmDesc(C.Structure):
     ]
 
 
+class GatingTail(C.Structure):
+    """lpm_gating_tail (include/lpm_b200.h): the context-gating tail of lpm_gemm_splitk_gated_fwd."""
+    _fields_ = [
+        ("counters", C.c_void_p),
+        ("part2", C.c_void_p), ("splits2", C.c_int), ("split_stride2", C.c_longlong),
+        ("bias", C.c_void_p),
+        ("act32", C.c_void_p), ("act16", C.c_void_p), ("act_split3", C.c_int),
+        ("wg", C.c_void_p), ("ldwg", C.c_longlong),
+        ("wg_diag", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("moving_mean", C.c_void_p), ("moving_var", C.c_void_p),
+        ("decay", C.c_float), ("eps", C.c_float), ("training", C.c_int),
+        ("g_sum", C.c_void_p),
+        ("out32", C.c_void_p), ("out16", C.c_void_p), ("out_split3", C.c_int),
+        ("save_mean", C.c_void_p), ("save_rstd", C.c_void_p),
+    ]
+
+
 _lib = None
 
 

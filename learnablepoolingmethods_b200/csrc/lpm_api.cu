@@ -108,6 +108,12 @@ int lpm_gemm_f16(const lpm_gemm_desc* desc, lpm_stream_t stream) {
   return gemm_f16(*desc, static_cast<cudaStream_t>(stream));
 }
 
+int lpm_gemm_splitk_gated_fwd(const lpm_gemm_desc* desc, const lpm_gating_tail* tail, lpm_stream_t stream) {
+  if (!desc || !tail) return fail(LPM_ERR_ARG, "lpm_gemm_splitk_gated_fwd: null argument");
+  if (int rc = check_device()) return rc;
+  return gemm_f16(*desc, static_cast<cudaStream_t>(stream), tail);
+}
+
 int lpm_gemm_tile_n(int N) { return gemm_pick_bn(N); }
 
 int lpm_gemm_splits(int K, int requested_splits) { return gemm_effective_splits(K, requested_splits); }

@@ -51,6 +51,8 @@ struct GemmKernelParams {
   const __half* add2;
   long long ld_add;
   int tma_store;        // 1: epilogue stages 128-byte-row slabs in smem and writes them with TMA
+  int gated;            // run the context-gating tail (GemmKernelParams::tail) after the last tile
+  lpm_gating_tail tail;
   int nt_fast;          // tile order: 0 = m-tiles fastest (concurrent tiles share the B tile), 1 = n-tiles fastest (they share A)
 };
 
@@ -176,6 +178,203 @@ __device__ __forceinline__ void epi_store_direct(const float* v, const GemmKerne
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < p.N) o[i] = __float2half_rn(v[i]);
+    }
+  }
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// K3 tail: split-K reduction + bias + context gating, run by the 256 epilogue threads of every CTA after its last
+// tile (lpm_gemm_splitk_gated_fwd, include/lpm_b200.h; frame_level_models.py:2319-2368).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier_one_thread(int* counter, int expected) {
+  __threadfence();
+  atomicAdd(counter, 1);
+  uint32_t spins = 0;
+  while (*reinterpret_cast<volatile int*>(counter) < expected) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) { printf("lpm: gated GEMM grid barrier timeout block=%d\n", (int)blockIdx.x); __trap(); }
+  }
+  __threadfence();
+}
+__device__ __forceinline__ void store_act16(__half* dst16, int split3, int B, int H, int r, int c, float v) {
+  const __half hi = __float2half_rn(v);
+  if (split3) {
+    __half* d = dst16 + (size_t)r * 3 * H + c;
+    d[0] = hi; d[H] = __float2half_rn(v - __half2float(hi)); d[2 * H] = hi;
+  } else {
+    dst16[(size_t)r * H + c] = hi;
+  }
+}
+
+// tid: 0..255 (epilogue threads); scratch: >= 16 KB of shared memory (the idle operand ring)
+__device__ void gating_tail(const GemmKernelParams& p, int tid, uint8_t* scratch) {
+  const lpm_gating_tail& t = p.tail;
+  const int B = p.M, H = p.N, G = (int)gridDim.x;
+  int cw = (H + G - 1) / G;
+  cw = (cw + 3) & ~3;                                   // columns per CTA, a multiple of 4
+  const int c0 = (int)blockIdx.x * cw;
+  const int nc = max(0, min(cw, H - c0));               // this CTA's columns (0 for the last CTAs)
+  const int lane = tid & 31, warp = tid >> 5;
+  float* sred = reinterpret_cast<float*>(scratch);      // [KG][256][4] partial sums of the k-groups
+  float* sg = sred + 8 * 256 * 4;                       // [B][cw] gate pre-activations, then statistics
+  float* sact = sg + (size_t)B * cw + 2 * cw + (size_t)H * 4;   // [B][cw] this CTA's slice of the hidden activation
+
+  // ---- barrier 1: every partial tile of this launch is in global memory ----
+  named_barrier(5, 256);
+  if (tid == 0) grid_barrier_one_thread(t.counters + 0, G);
+  named_barrier(5, 256);
+
+  // ---- phase A: this CTA's CONTIGUOUS chunk of the [B x H] activation = bias + sum of the partials.  Consecutive threads
+  //      read consecutive 16-byte pieces of a slab (full 128-byte lines; a column slice per CTA would touch a 32-byte
+  //      sector per 16 bytes); the slabs are split over k-groups of threads and added in a fixed order ----
+  const float* part = reinterpret_cast<const float*>(p.out);
+  {
+    const int n4 = B * H / 4;                            // float4 pieces of the activation (ldc == H: slabs are contiguous)
+    const int per = (n4 + G - 1) / G;
+    const int i0 = (int)blockIdx.x * per, npos = max(0, min(per, n4 - i0));
+    int KG = npos > 0 ? 256 / npos : 1; if (KG > 8) KG = 8; if (KG < 1) KG = 1;
+    for (int pbase = 0; pbase < npos; pbase += 256 / KG) {      // one pass unless the chunk exceeds 256 pieces
+      const int np = min(256 / KG, npos - pbase);
+      const int pos = tid % (256 / KG), kg = tid / (256 / KG);
+      if (pos < np && kg < KG) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        auto sum_set = [&](const float* base, int n_slabs, long long stride, float4& acc) {
+          const float4* src = reinterpret_cast<const float4*>(base) + i0 + pbase + pos;
+          for (int k = kg; k < n_slabs; k += 8 * KG) {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int kk = k + u * KG;
+              x[u] = kk < n_slabs ? __ldcg(src + (size_t)kk * (stride / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+          }
+        };
+        sum_set(part, p.splits, p.out_split_stride, a0);
+        if (t.part2 != nullptr) sum_set(t.part2, t.splits2, t.split_stride2, a1);
+        *reinterpret_cast<float4*>(sred + ((size_t)kg * 256 + pos) * 4) =
+            make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+      }
+      named_barrier(5, 256);
+      if (tid < np) {
+        float4 sum = *reinterpret_cast<const float4*>(sred + (size_t)tid * 4);
+        for (int g = 1; g < KG; ++g) {
+          const float4 x = *reinterpret_cast<const float4*>(sred + ((size_t)g * 256 + tid) * 4);
+          sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+        }
+        const int e = (i0 + pbase + tid) * 4;            // first element: row e / H, columns e % H .. +3 (H % 4 == 0)
+        const int r = e / H, c = e - r * H;
+        float v[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (t.bias) v[j] += __ldg(t.bias + c + j);
+          if (t.act16) store_act16(reinterpret_cast<__half*>(t.act16), t.act_split3, B, H, r, c + j, v[j]);
+        }
+        *reinterpret_cast<float4*>(t.act32 + e) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      named_barrier(5, 256);
+    }
+  }
+
+  // ---- barrier 2: the whole hidden activation is in global memory ----
+  if (tid == 0) grid_barrier_one_thread(t.counters + 1, G);
+  named_barrier(5, 256);
+
+  if (nc > 0) {
+    for (int i = tid; i < B * nc; i += 256) {           // this CTA's columns of the activation (for the statistics and the gate)
+      const int r = i / nc, j = i - r * nc;
+      sact[(size_t)r * cw + j] = __ldcg(t.act32 + (size_t)r * H + c0 + j);
+    }
+    // ---- phase B: g[r][j] = sum_k hidden[r][k] * Wg[k][c0 + j] in fp32: a warp per row, lanes over k.  The CTA's
+    //      column slice of Wg (H x 4 floats per pass) is staged in shared memory: with the operand ring taking the SM's
+    //      shared memory the L1 cannot hold its 512 lines, and every row would re-fetch them from L2 ----
+    float* swg = sg + (size_t)B * cw + 2 * cw;          // [H][4]
+    for (int cg = 0; cg < nc; cg += 4) {
+      named_barrier(5, 256);
+      for (int k = tid; k < H; k += 256)
+        *reinterpret_cast<float4*>(swg + (size_t)k * 4) = __ldg(reinterpret_cast<const float4*>(t.wg + (size_t)k * t.ldwg + c0 + cg));
+      named_barrier(5, 256);
+      for (int r = warp; r < B; r += 8) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int kb = 0; kb < H; kb += 512) {           // 16 loads of the row in flight per lane (L2 round trips, not FMAs, cost)
+          float h[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int k = kb + u * 32 + lane;
+            h[u] = k < H ? __ldcg(t.act32 + (size_t)r * H + k) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int k = kb + u * 32 + lane;
+            if (k < H) {
+              const float4 w = *reinterpret_cast<const float4*>(swg + (size_t)k * 4);
+              a0 = fmaf(h[u], w.x, a0); a1 = fmaf(h[u], w.y, a1); a2 = fmaf(h[u], w.z, a2); a3 = fmaf(h[u], w.w, a3);
+            }
+          }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        if (lane == 0) {
+          float* d = sg + (size_t)r * cw + cg;
+          d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+        }
+      }
+    }
+    named_barrier(5, 256);
+    // ---- batch norm over the rows of each owned column (frame_level_models.py:2354-2362), then the gate ----
+    float* sstat = sg + (size_t)B * cw;                 // [cw][2]: mean, var
+    for (int j = warp; j < nc; j += 8) {                 // a warp per column, lanes over the rows, fixed reduction order
+      const int c = c0 + j;
+      const float dg = t.wg_diag ? t.wg_diag[c] : 0.f;
+      float mean, var;
+      if (t.training) {
+        double s = 0.0, q = 0.0;
+        for (int r = lane; r < B; r += 32) {
+          const float v = sg[(size_t)r * cw + j] - dg * sact[(size_t)r * cw + j];
+          s += v; q += (double)v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        const double m = s / B;
+        double vv = q / B - m * m;
+        if (vv < 0.0) vv = 0.0;
+        mean = (float)m; var = (float)vv;
+        if (lane == 0) {
+          const double corr = B > 1 ? (double)B / (B - 1) : 1.0;
+          t.moving_mean[c] = t.moving_mean[c] * t.decay + (float)m * (1.f - t.decay);
+          t.moving_var[c] = t.moving_var[c] * t.decay + (float)(vv * corr) * (1.f - t.decay);
+        }
+      } else {
+        mean = t.moving_mean[c]; var = t.moving_var[c];
+      }
+      if (lane == 0) {
+        sstat[2 * j] = mean; sstat[2 * j + 1] = var;
+        if (t.save_mean) { t.save_mean[c] = mean; t.save_rstd[c] = rsqrtf(var + t.eps); }
+      }
+    }
+    named_barrier(5, 256);
+    for (int i = tid; i < B * nc; i += 256) {
+      const int r = i / nc, j = i - r * nc, c = c0 + j;
+      const float dg = t.wg_diag ? t.wg_diag[c] : 0.f;
+      const float rstd = rsqrtf(sstat[2 * j + 1] + t.eps);
+      const float sc = t.gamma[c] * rstd, sh = t.beta[c] - sstat[2 * j] * sc;
+      const float a = sact[(size_t)r * cw + j];
+      const float g = sg[(size_t)r * cw + j];
+      if (t.g_sum) t.g_sum[(size_t)r * H + c] = g;
+      const float v = (g - dg * a) * sc + sh;
+      const float o = a / (1.f + __expf(-v));
+      t.out32[(size_t)r * H + c] = o;
+      if (t.out16) store_act16(reinterpret_cast<__half*>(t.out16), t.out_split3, B, H, r, c, o);
+    }
+  }
+  // ---- leave the counters at zero for the next launch: the last CTA through resets them ----
+  named_barrier(5, 256);
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(t.counters + 2, 1) == G - 1) {
+      t.counters[0] = 0; t.counters[1] = 0; t.counters[2] = 0;
+      __threadfence();
     }
   }
 }
@@ -512,6 +711,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.tma_store && leader) bulk_wait<0>();   // all output slabs written before exit
+    if (p.gated) gating_tail(p, (int)threadIdx.x - 64, smem);   // K3: reduction + context gating, all CTAs of the launch
   }
 
   tc_fence_before();
@@ -587,7 +787,7 @@ int gemm_pick_bn(int N) {
   return 64;
 }
 
-int gemm_f16(const GemmArgs& g, cudaStream_t st) {
+int gemm_f16(const GemmArgs& g, cudaStream_t st, const lpm_gating_tail* tail) {
   LPM_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0, "gemm: bad dims M=%d N=%d K=%d batch=%d", g.M, g.N, g.K, g.batch);
   LPM_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (TMA 16B strides), got %lld %lld", g.lda, g.ldb);
   LPM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0, "gemm: A/B must be 16B aligned");
@@ -655,6 +855,19 @@ int gemm_f16(const GemmArgs& g, cudaStream_t st) {
     const double a_bytes = 2.0 * g.M * g.K * (p.a_batched ? 1 : 1), b_bytes = 2.0 * g.N * g.K;
     static const int force = getenv("LPM_GEMM_NT_FAST") ? atoi(getenv("LPM_GEMM_NT_FAST")) : -1;
     p.nt_fast = force >= 0 ? force : ((a_bytes > 64e6 && b_bytes <= 48e6 && p.n_tiles > 1) ? 1 : 0);
+  }
+  if (tail != nullptr) {
+    const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batch * p.splits;
+    LPM_REQUIRE(!two && p.m_tiles == 1 && p.batch == 1 && g.out_f32 && g.out_split_stride > 0 && g.ldc == g.N &&
+                g.N % 4 == 0 && tiles <= num_sms() && g.alpha == 1.f,
+                "gated GEMM: needs a split-K product of <= 128 rows with contiguous fp32 partials [splits][M][N] and at most "
+                "one tile per SM (M=%d N=%d tiles=%lld)", g.M, g.N, tiles);
+    LPM_REQUIRE(tail->counters && tail->act32 && tail->wg && tail->gamma && tail->beta && tail->moving_mean && tail->moving_var &&
+                tail->out32 && tail->ldwg % 4 == 0 && (reinterpret_cast<uintptr_t>(tail->wg) & 15) == 0 &&
+                (tail->part2 == nullptr || (reinterpret_cast<uintptr_t>(tail->part2) & 15) == 0),
+                "gated GEMM: bad tail arguments");
+    p.gated = 1;
+    p.tail = *tail;
   }
   if (two) return dispatch_major<256, 6, 1>(g.a_mn, g.b_mn, ta, tb, tc, p, st);
   if (BN == 256) return dispatch_major<256, 4, 0>(g.a_mn, g.b_mn, ta, tb, tc, p, st);

@@ -10,7 +10,7 @@ namespace lpm {
 
 using GemmArgs = lpm_gemm_desc;
 
-int gemm_f16(const GemmArgs& g, cudaStream_t st);
+int gemm_f16(const GemmArgs& g, cudaStream_t st, const lpm_gating_tail* tail = nullptr);
 int gemm_pick_bn(int N);
 int gemm_effective_splits(int K, int splits);
 void gemm_set_pair_mode(int mode);

@@ -11,6 +11,8 @@ transformer_utils.py:374-457,507-767, video_level_models.py:48-159, model_utils.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import dataclass, field
 from typing import Dict, Optional
@@ -91,6 +93,12 @@ class NetVladConfig:
     dropout_rate: float = 0.9      # D7: tf.layers.dropout(rate=1-0.1) in TransformerEncoderMod
     loss_scale: float = 0.0        # fp16 activation-gradient scale inside the backward; 0 = auto (8 x batch)
     hidden_splits: int = 74        # split-K factor of the hidden projection (2 N-tiles x 74 = 148 CTAs)
+    # K3: reduce the split-K partials and run the context gating in the tail of the hidden-projection GEMM kernel (one launch
+    # instead of GEMM + reduce + gate GEMM + gating; the gate product in exact fp32).  "infer" (default): inference / eval
+    # forward only; "all" (LPM_FUSED_GATING=1): training too; "off" (=0): the four-launch path.  Training keeps the
+    # four-launch head by default: the gain there is 10 us of 3.5 ms, and a different summation order moves the training
+    # trajectory (same accuracy per step, another trained state: DESIGN.md section 2 lists both).
+    fused_gating: str = {"1": "all", "0": "off"}.get(os.environ.get("LPM_FUSED_GATING", "infer"), "infer")
     split_hidden_infer: bool = True  # NetVladV1 inference: hidden projection with split-precision operands (see _head)
     overlap_audio: bool = True     # run the audio modality (0.4 % of the FLOPs, ~1/3 of the launches) on a second stream
     overlap_wgrad: bool = True     # rgb weight-gradient GEMMs on a third stream: they have no consumer before the optimiser
@@ -662,46 +670,71 @@ class NetVladEngine:
         if self.pre_head_hook is not None:
             self.pre_head_hook()    # data parallel: the all-gather of the updated fp16 weight shards lands here
         vlad2 = ctx.get("_vlad2")
-        act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
-        hpre, hstats = None, None
-        parts_lo = None
-        if vlad2 is not None:
-            # Inference: hidden = (v_hi + v_lo)(W_hi + W_lo) ~= [v_hi ; v_lo] W_hi + v_hi W_lo.  The 270 336-term products with
-            # 11-bit operands are what is left of the prediction error once the gate / MoE products are split (trained-weights
-            # protocol, DESIGN.md numerics); two passes over the fp16 weight bytes instead of one (+277 MB of HBM reads).
-            # M = 2B rows run as one 2-CTA (cta_group::2) tile per split, so W_hi is still streamed once.
-            self.refresh_hidden_lo()
-            parts = ops.gemm(vlad2, sh["wh16"], splits=max(2, c.hidden_splits))        # [S, 2B, H]
-            parts = parts.view(parts.shape[0] * 2, B, Hn)                              # hi and lo rows summed by the reduce
-            parts_lo = ops.gemm(vlad, sh["wh16lo"], splits=max(2, c.hidden_splits))    # [S, B, H]
-        else:
-            parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
-        if c.netvlad_relu:
-            hpre = act32
-            ops.splitk_reduce(parts, out32=hpre, parts2=parts_lo)
-            r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
-                                        v["hidden1_bn/moving_variance"], training=training, save=save)
-            act32 = r[0]
-            hstats = r[2] if save else None
-            a3 = ops.split_hi_lo(act32)                               # [B, 3H] = [hi | lo | hi]
-        else:
-            # one kernel: sum of the partials (both passes), bias, fp32 activation and its split-precision operand
-            a3 = torch.empty((B, 3 * Hn), dtype=torch.float16, device=vlad.device)
-            ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=a3, parts2=parts_lo, split3=True)
-        # The gate and MoE products run with split-precision operands (x = hi + lo in two fp16 terms, one GEMM over a 3x
-        # longer reduction, ops.split_hi_lo): `hidden` is O(30) at this model's initialisation scale and feeds sigmoids, so
-        # 10-bit-mantissa operands in these two small products are what limits the predictions (numerics).
-        act16 = a3[:, :Hn]                                            # plain fp16 view for the backward
-        if c.gating:
-            # split-K partials of the gate product go straight into the gating kernel (summed there in a fixed order)
-            gparts = ops.gemm(a3, sh["wg16x3"], splits=6)
+        fg = {True: "all", False: "off"}.get(c.fused_gating, c.fused_gating)      # booleans accepted too
+        fused = (fg == "all" or (fg == "infer" and not training)) and c.gating and not c.netvlad_relu and B <= 128 and Hn % 4 == 0
+        if fused:
+            # K3 as one launch (ops.gemm_splitk_gated): every CTA of the split-K product stays for the tail -- grid barrier,
+            # fixed-order sum of a column slice of all partials (+ bias), grid barrier, the gate product of its columns in fp32,
+            # gating_bn over the batch rows, sigmoid, product, split-precision operand of the MoE product.
+            sp = max(2, min(c.hidden_splits, 148 // -(-Hn // 256)))
+            p1 = None
+            a_in, w_in = vlad, sh["wh16"]
+            if vlad2 is not None:
+                # inference: hidden = [v_hi ; v_lo] W_hi + v_hi W_lo (see below); the first pass leaves its partials, the second
+                # pass carries the tail and sums both
+                self.refresh_hidden_lo()
+                p1 = ops.gemm(vlad2, sh["wh16"], splits=max(2, c.hidden_splits))
+                p1 = p1.view(p1.shape[0] * 2, B, Hn)
+                w_in = sh["wh16lo"]
             diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
-            r = ops.gating_fwd(act32, gparts, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
-                               v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save, split3=True)
-            gated32, g3, gates = r[0], r[1], r[3].view(B, Hn)
+            act32, a3, gated32, g3, gstats, gates, _ = ops.gemm_splitk_gated(
+                a_in, w_in, splits=sp, bias=v["hidden1_biases"], wg=v["gating_weights_2"], gamma=v["gating_bn/gamma"],
+                beta=v["gating_bn/beta"], moving_mean=v["gating_bn/moving_mean"], moving_var=v["gating_bn/moving_variance"],
+                training=training, wg_diag=diag, save=save, parts2=p1)
+            act16, gated16 = a3[:, :Hn], g3[:, :Hn]
+            hpre, hstats = None, None
+            r = (gated32, g3, gstats, gates)
         else:
-            gates, gated32, g3, r = None, act32, a3, (None, None, None)
-        gated16 = g3[:, :Hn]
+            act32 = torch.empty((B, Hn), dtype=torch.float32, device=vlad.device)
+            hpre, hstats = None, None
+            parts_lo = None
+            if vlad2 is not None:
+                # Inference: hidden = (v_hi + v_lo)(W_hi + W_lo) ~= [v_hi ; v_lo] W_hi + v_hi W_lo.  The 270 336-term products with
+                # 11-bit operands are what is left of the prediction error once the gate / MoE products are split (trained-weights
+                # protocol, DESIGN.md numerics); two passes over the fp16 weight bytes instead of one (+277 MB of HBM reads).
+                # M = 2B rows run as one 2-CTA (cta_group::2) tile per split, so W_hi is still streamed once.
+                self.refresh_hidden_lo()
+                parts = ops.gemm(vlad2, sh["wh16"], splits=max(2, c.hidden_splits))        # [S, 2B, H]
+                parts = parts.view(parts.shape[0] * 2, B, Hn)                              # hi and lo rows summed by the reduce
+                parts_lo = ops.gemm(vlad, sh["wh16lo"], splits=max(2, c.hidden_splits))    # [S, B, H]
+            else:
+                parts = ops.gemm(vlad, sh["wh16"], splits=max(2, c.hidden_splits))
+            if c.netvlad_relu:
+                hpre = act32
+                ops.splitk_reduce(parts, out32=hpre, parts2=parts_lo)
+                r = ops.hidden_bn_relu6_fwd(hpre, v["hidden1_bn/gamma"], v["hidden1_bn/beta"], v["hidden1_bn/moving_mean"],
+                                            v["hidden1_bn/moving_variance"], training=training, save=save)
+                act32 = r[0]
+                hstats = r[2] if save else None
+                a3 = ops.split_hi_lo(act32)                               # [B, 3H] = [hi | lo | hi]
+            else:
+                # one kernel: sum of the partials (both passes), bias, fp32 activation and its split-precision operand
+                a3 = torch.empty((B, 3 * Hn), dtype=torch.float16, device=vlad.device)
+                ops.splitk_reduce(parts, bias=v["hidden1_biases"], out32=act32, out16=a3, parts2=parts_lo, split3=True)
+            # The gate and MoE products run with split-precision operands (x = hi + lo in two fp16 terms, one GEMM over a 3x
+            # longer reduction, ops.split_hi_lo): `hidden` is O(30) at this model's initialisation scale and feeds sigmoids, so
+            # 10-bit-mantissa operands in these two small products are what limits the predictions (numerics).
+            act16 = a3[:, :Hn]                                            # plain fp16 view for the backward
+            if c.gating:
+                # split-K partials of the gate product go straight into the gating kernel (summed there in a fixed order)
+                gparts = ops.gemm(a3, sh["wg16x3"], splits=6)
+                diag = torch.diagonal(v["gating_weights_2"]).contiguous() if c.remove_diag else None
+                r = ops.gating_fwd(act32, gparts, v["gating_bn/gamma"], v["gating_bn/beta"], v["gating_bn/moving_mean"],
+                                   v["gating_bn/moving_variance"], training=training, wg_diag=diag, save=save, split3=True)
+                gated32, g3, gates = r[0], r[1], r[3].view(B, Hn)
+            else:
+                gates, gated32, g3, r = None, act32, a3, (None, None, None)
+            gated16 = g3[:, :Hn]
         logits = ops.gemm(g3, sh["wmoe16x3"], bias=sh["bmoe"], out_dtype=torch.float32)
         pred = ops.moe_mix_fwd(logits, c.vocab_size, c.num_mixtures, expert_off=sh["moe_g8"])
         if want_inter:

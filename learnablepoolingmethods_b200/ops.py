@@ -112,6 +112,55 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = T
     return out
 
 
+_gated_counters = {}
+
+
+def gemm_splitk_gated(a, w, *, splits, bias, wg, gamma, beta, moving_mean, moving_var, training, wg_diag=None, save=False,
+                      parts2=None, act_split3=True, out_split3=True, decay=0.999, eps=1e-3):
+    """K3 (frame_level_models.py:2314-2368) as ONE launch: hidden = a @ w (+ the partials `parts2` of an earlier split-K
+    launch) + bias; gates = BN(hidden @ wg [- diag(wg) * hidden]); out = hidden * sigmoid(gates).  a: fp16 [B <= 128, Kd];
+    w: fp16 [Kd, H] (row-major weight); wg: fp32 [H, H].  The reduction of the split-K partials and the whole gating run in
+    the tail of the GEMM kernel (lpm_gemm_splitk_gated_fwd), with the gate product in exact fp32.
+    Returns (act32, act16 or [hi|lo|hi], out32, out16 or [hi|lo|hi], (mean, rstd) or None, g_sum, partials)."""
+    lib = _lib.load()
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and wg.dtype == torch.float32
+    B, Kd = a.shape
+    H = w.shape[1]
+    dev = a.device
+    eff = lib.lpm_gemm_splits(Kd, splits)
+    parts = torch.empty((eff, B, H), dtype=torch.float32, device=dev)
+    d = GemmDesc()
+    d.A, d.a_mn, d.lda, d.a_batch_stride = ptr(a), 0, _lda(a), 0
+    d.B, d.b_mn, d.ldb, d.b_batch_stride = ptr(w), 1, _lda(w), 0
+    d.M, d.N, d.K, d.batch, d.splits, d.force_bn = B, H, Kd, 1, eff, 0
+    d.out, d.out_f32, d.ldc, d.out_batch_stride, d.out_split_stride = ptr(parts), 1, H, 0, parts.stride(0)
+    d.alpha = 1.0
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream if False else 0)
+    if key not in _gated_counters:
+        _gated_counters[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    act32, out32, g_sum = _f32((B, H), dev), _f32((B, H), dev), _f32((B, H), dev)
+    act16 = _f16((B, 3 * H if act_split3 else H), dev)
+    out16 = _f16((B, 3 * H if out_split3 else H), dev)
+    sm = _f32((2, H), dev) if save else None
+    t = _lib.GatingTail()
+    t.counters = ptr(_gated_counters[key])
+    if parts2 is not None:
+        assert parts2.dtype == torch.float32 and parts2.is_contiguous() and parts2.shape[-2:] == (B, H)
+        p2 = parts2.reshape(-1, B, H)
+        t.part2, t.splits2, t.split_stride2 = ptr(p2), p2.shape[0], p2.stride(0)
+    t.bias = ptr(bias)
+    t.act32, t.act16, t.act_split3 = ptr(act32), ptr(act16), int(act_split3)
+    t.wg, t.ldwg, t.wg_diag = ptr(wg), wg.stride(0), ptr(wg_diag)
+    t.gamma, t.beta, t.moving_mean, t.moving_var = ptr(gamma), ptr(beta), ptr(moving_mean), ptr(moving_var)
+    t.decay, t.eps, t.training = float(decay), float(eps), int(training)
+    t.g_sum = ptr(g_sum)
+    t.out32, t.out16, t.out_split3 = ptr(out32), ptr(out16), int(out_split3)
+    if save:
+        t.save_mean, t.save_rstd = ptr(sm[0]), ptr(sm[1])
+    check(lib.lpm_gemm_splitk_gated_fwd(C.byref(d), C.byref(t), stream_ptr()), "lpm_gemm_splitk_gated_fwd")
+    return act32, act16, out32, out16, sm, g_sum, parts
+
+
 # ------------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------------

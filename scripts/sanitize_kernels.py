@@ -22,6 +22,17 @@ if which in ("all", "gemm"):
         o = ops.gemm(a, b, **kw)
         torch.cuda.synchronize()
         print("gemm", M, N, K, kw, float(o.float().abs().mean()))
+if which in ("all", "k3"):
+    # K3: split-K GEMM with the reduction + context-gating tail (two grid-wide barriers inside the kernel)
+    B, Kd, H = 16, 2048, 128
+    a, w = (r(B, Kd) * 0.05).half(), (r(Kd, H) * 0.05).half()
+    p2 = ops.gemm((r(B, Kd) * 0.01).half(), w, splits=4)
+    for training in (True, False):
+        res = ops.gemm_splitk_gated(a, w, splits=16, bias=r(H), wg=r(H, H) / 11, gamma=torch.ones(H, device=dev), beta=torch.zeros(H, device=dev),
+                                    moving_mean=torch.zeros(H, device=dev), moving_var=torch.ones(H, device=dev), training=training,
+                                    save=True, parts2=p2)
+        torch.cuda.synchronize()
+        print("k3", training, float(res[2].abs().mean()))
 if which in ("all", "attn_tc"):
     # tcgen05 / TMEM attention (lpm_attn_tc.cu): one sample, 8 heads of depth 16 at 256 positions = two CTAs per kernel;
     # forward opt-in kernel, both backward kernels

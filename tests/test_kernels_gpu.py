@@ -594,3 +594,56 @@ def test_mha_tcgen05_benchmark_batch(cuda):
     assert torch.equal(a, b)                                   # deterministic
     per_sample = (a.float() - ref.float()).reshape(B, -1).norm(dim=1) / ref.float().reshape(B, -1).norm(dim=1)
     assert float(per_sample.max()) < 1e-4, per_sample.max()
+
+
+@pytest.mark.parametrize("B,Kd,H,splits,training,diag,second", [(80, 270336 // 16, 512, 74, True, False, False),
+                                                               (80, 8192, 512, 74, False, False, True),
+                                                               (5, 1024, 128, 8, True, True, False),
+                                                               (128, 4096, 1024, 37, False, True, True)])
+def test_gemm_splitk_gated_k3(cuda, B, Kd, H, splits, training, diag, second):
+    """K3 (frame_level_models.py:2314-2368) in one launch: hidden projection (+ the partials of a second pass), bias, gate
+    product, gating_bn (batch or moving statistics), sigmoid, product -- against fp64 torch on the same fp16 operands."""
+    from learnablepoolingmethods_b200 import ops
+    g = torch.Generator().manual_seed(B + H + splits)
+    a = (torch.randn(B, Kd, generator=g) * 0.05).half()
+    w = (torch.randn(Kd, H, generator=g) * 0.05).half()
+    bias = torch.randn(H, generator=g) * 0.1
+    wg = torch.randn(H, H, generator=g) / H ** 0.5
+    gamma, beta = torch.rand(H, generator=g) + 0.5, torch.randn(H, generator=g) * 0.2
+    mm, mv = torch.randn(H, generator=g) * 0.1, torch.rand(H, generator=g) + 0.5
+    hidden = a.double() @ w.double() + bias.double()
+    parts2 = None
+    if second:
+        a2 = (torch.randn(B, Kd, generator=g) * 0.01).half()
+        parts2 = ops.gemm(a2.to(cuda), w.to(cuda), splits=4)
+        hidden = hidden + a2.double() @ w.double()
+    gp = hidden @ wg.double()
+    v = gp - (torch.diagonal(wg).double() * hidden if diag else 0)
+    if training:
+        mean, var = v.mean(0), v.var(0, unbiased=False)
+    else:
+        mean, var = mm.double(), mv.double()
+    gates = (v - mean) / torch.sqrt(var + 1e-3) * gamma.double() + beta.double()
+    ref = hidden * torch.sigmoid(gates)
+    mmd, mvd = mm.to(cuda).clone(), mv.to(cuda).clone()
+    act32, a3, out32, g3, st, g_sum, _ = ops.gemm_splitk_gated(
+        a.to(cuda), w.to(cuda), splits=splits, bias=bias.to(cuda), wg=wg.to(cuda), gamma=gamma.to(cuda), beta=beta.to(cuda),
+        moving_mean=mmd, moving_var=mvd, training=training, wg_diag=torch.diagonal(wg).contiguous().to(cuda) if diag else None,
+        save=True, parts2=parts2)
+    torch.cuda.synchronize()
+    assert rel(act32, hidden) < 1e-5
+    assert rel(g_sum, gp) < 1e-5
+    assert rel(out32, ref) < 2e-5
+    assert rel(st[0], mean) < 1e-4 and rel(st[1], 1 / torch.sqrt(var + 1e-3)) < 1e-4
+    # split-precision operands: hi + lo reproduces the fp32 value to 2^-22
+    assert rel(a3[:, :H].float() + a3[:, H:2 * H].float(), act32) < 1e-6 and torch.equal(a3[:, :H], a3[:, 2 * H:])
+    assert rel(g3[:, :H].float() + g3[:, H:2 * H].float(), out32) < 1e-6
+    if training:
+        corr = B / (B - 1)
+        assert rel(mmd, mm.double() * 0.999 + mean * 0.001) < 1e-5 and rel(mvd, mv.double() * 0.999 + var * corr * 0.001) < 1e-5
+    # second launch: the barrier counters were left at zero
+    o2 = ops.gemm_splitk_gated(a.to(cuda), w.to(cuda), splits=splits, bias=bias.to(cuda), wg=wg.to(cuda), gamma=gamma.to(cuda),
+                               beta=beta.to(cuda), moving_mean=mm.to(cuda).clone(), moving_var=mv.to(cuda).clone(),
+                               training=training, wg_diag=torch.diagonal(wg).contiguous().to(cuda) if diag else None, parts2=parts2)[2]
+    torch.cuda.synchronize()
+    assert torch.equal(o2, out32)
