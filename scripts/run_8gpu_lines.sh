@@ -1,16 +1,15 @@
-# Final multi-GPU lines of round 2 (one 8 x B200 box, sequential runs).
+# Multi-GPU bench lines on one 8 x B200 box (sequential runs).  usage: run_8gpu_lines.sh <tag> [all]
 set -x
+TAG=${1:-r2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-registry-e2e > gpurun_out/r2p_bench_n1.json 2> gpurun_out/r2p_bench_n1.err
-for n in 2 4 8; do
-$TR --nproc-per-node $n --master-port 2981$n bench.py --gpus $n --steps 30 --warmup 5 > gpurun_out/r2p_bench_n$n.json 2> gpurun_out/r2p_bench_n$n.err
-done
-$TR --nproc-per-node 8 --master-port 29821 bench.py --gpus 8 --model NetVladV2 --steps 20 --warmup 5 > gpurun_out/r2p_bench_v2_n8.json 2> gpurun_out/r2p_bench_v2_n8.err
-python bench.py --model NetVladV2 --steps 20 --warmup 5 --no-cpu-baseline --no-registry-e2e > gpurun_out/r2p_bench_v2_n1.json 2> gpurun_out/r2p_bench_v2_n1.err
-$TR --nproc-per-node 8 --master-port 29831 bench.py --gpus 8 --cluster-size 512 --hidden-size 1024 --steps 20 --warmup 5 > gpurun_out/r2p_bench_wide_n8.json 2> gpurun_out/r2p_bench_wide_n8.err
-$TR --nproc-per-node 2 --master-port 29841 scripts/dp_oracle_check.py gpurun_out/r2p_dp_oracle_check_n2.json > gpurun_out/r2p_dp_oracle.log 2>&1; tail -3 gpurun_out/r2p_dp_oracle.log
-for f in gpurun_out/r2p_bench_*.json; do python - "$f" <<'PY'
+$TR --nproc-per-node 8 --master-port 29818 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/${TAG}_bench_n8.json 2> gpurun_out/${TAG}_bench_n8.err
+$TR --nproc-per-node 4 --master-port 29814 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/${TAG}_bench_n4.json 2> gpurun_out/${TAG}_bench_n4.err
+if [ "$2" = "all" ]; then
+$TR --nproc-per-node 8 --master-port 29821 bench.py --gpus 8 --model NetVladV2 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_v2_n8.json 2> gpurun_out/${TAG}_bench_v2_n8.err
+$TR --nproc-per-node 8 --master-port 29831 bench.py --gpus 8 --cluster-size 512 --hidden-size 1024 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_wide_n8.json 2> gpurun_out/${TAG}_bench_wide_n8.err
+fi
+for f in gpurun_out/${TAG}_bench_*.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1]))
