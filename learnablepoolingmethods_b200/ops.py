@@ -135,7 +135,10 @@ def gemm_splitk_gated(a, w, *, splits, bias, wg, gamma, beta, moving_mean, movin
     d.M, d.N, d.K, d.batch, d.splits, d.force_bn = B, H, Kd, 1, eff, 0
     d.out, d.out_f32, d.ldc, d.out_batch_stride, d.out_split_stride = ptr(parts), 1, H, 0, parts.stride(0)
     d.alpha = 1.0
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream if False else 0)
+    # grid-barrier scratch, one buffer per device: the kernel leaves the counters at zero, so consecutive launches can share
+    # them; two gated products must not run CONCURRENTLY on one device (the engine runs one head at a time; the buffer is
+    # created by the first eager call, i.e. before any graph capture)
+    key = dev.index
     if key not in _gated_counters:
         _gated_counters[key] = torch.zeros(4, dtype=torch.int32, device=dev)
     act32, out32, g_sum = _f32((B, H), dev), _f32((B, H), dev), _f32((B, H), dev)
