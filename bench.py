@@ -386,6 +386,14 @@ def main():
         g_ms = time_cuda(lambda: ops.gemm(a, w, out=o), 20)
         g_tf = 2.0 * M * N * K / g_ms / 1e9
         g_traffic, g_traffic_src = ncu_traffic("gemm_f16_ffn_20480x4096x1024")
+        # yardstick only (never on the product path): cuBLAS through torch.matmul at the SAME shape, same timing loop -- the
+        # burst peak in MEASURED_PEAKS.json is cuBLAS at a much larger product
+        lib_tf = None
+        try:
+            lib_ms = time_cuda(lambda: torch.matmul(a, w, out=o), 20)
+            lib_tf = 2.0 * M * N * K / lib_ms / 1e9
+        except Exception as e:
+            print(f"cuBLAS yardstick unavailable: {e!r}", file=sys.stderr)
         # north-star kernel: fused NetVLAD pooling (rgb), 4*T*D*K FLOPs per video
         T, D, Kc = CFG["iterations"], 1024, 256
         xb = torch.randn(B * T, D, device=dev).half()
@@ -414,6 +422,7 @@ def main():
                              "frac_of_sustained_peak": g_tf / sustained,
                              "traffic": g_traffic, "traffic_source": g_traffic_src,
                              "algorithmic_bytes": 2.0 * (M * K + K * N + M * N),
+                             "cublas_same_shape": lib_tf, "frac_of_cublas_same_shape": (g_tf / lib_tf) if lib_tf else None,
                              "peak_source": f"{src} bf16 burst (the kernel is timed alone: 20 back-to-back launches, ~3 ms)"},
                    roofline_pool={"kernel": "netvlad_pool_fwd_kernel<256> (rgb, fused)", "bound": "tensor",
                                   "achieved": p_tf, "peak": burst, "unit": "TFLOP/s", "frac": p_tf / burst,
