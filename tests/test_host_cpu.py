@@ -185,6 +185,28 @@ def _worker_split_allreduce(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_head_tensor_range_for_ranged_optimizer_steps():
+    """trainer.head_tensor_range: the leading tensors / chunks of the flat layout that lpm_adam_clip_step_range may update
+    as soon as the head of the backward is done (per-tensor clipping, utils.py:181-188)."""
+    from learnablepoolingmethods_b200.trainer import FlatState, head_tensor_range
+    store = _cpu_store("WillowModelReg")
+    tr = store.trainable()
+    head = [n for n in tr if not n.startswith(("video_", "audio_", "input_bn")) and n != "hidden1_weights"]
+    body = [n for n in tr if n.startswith(("video_", "audio_", "input_bn"))]
+    flat = FlatState(store, head + body, {}, factored=("hidden1_weights",))
+    nt, nc = head_tensor_range(flat)
+    assert nt == len(head) and flat.order[:nt] == head
+    assert nc == flat.chunk_begin_host[nt] and 0 < nc < flat.chunk_begin_host[-1]
+    # the chunks of the range are exactly the chunks of its tensors (table rows carry absolute tensor ids)
+    table = flat.table.cpu()
+    assert int(table[:nc, 0].max()) == nt - 1 and int(table[nc:, 0].min()) == nt
+    assert flat.chunk_begin.cpu().tolist() == flat.chunk_begin_host
+    # a layout that does not start with the head's tensors has no such range
+    store2 = _cpu_store("WillowModelReg")
+    flat2 = FlatState(store2, body[:2] + head + body[2:], {}, factored=("hidden1_weights",))
+    assert head_tensor_range(flat2) is None
+
+
 def test_head_gradient_span_and_split_allreduce_world2_gloo():
     import torch.multiprocessing as mp
     from learnablepoolingmethods_b200.trainer import FlatState, head_gradient_span
