@@ -754,10 +754,20 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
+  // Smallest grid that needs the same number of rounds (LPM_GEMM_MIN_GRID=0: always every SM): 320 pair tiles take five
+  // rounds on 74 pairs and on 64, and the SMs left free go to whatever runs next to the product (the forked optimiser
+  // branch, the column sums of the bias gradients).  Same tiles, same results.
+  static const bool min_grid = !(getenv("LPM_GEMM_MIN_GRID") != nullptr && getenv("LPM_GEMM_MIN_GRID")[0] == '0');
+  auto fit = [&](int slots) {
+    if (total <= slots) return total;
+    if (!min_grid || p.gated) return slots;
+    const int rounds = (total + slots - 1) / slots;
+    return (total + rounds - 1) / rounds;
+  };
   if (!TWO) {
-    cfg.gridDim = dim3(total < num_sms() ? total : num_sms());
+    cfg.gridDim = dim3(fit(num_sms()));
   } else {
-    const int pairs = total < num_sms() / 2 ? total : num_sms() / 2;
+    const int pairs = fit(num_sms() / 2);
     cfg.gridDim = dim3(2 * pairs);
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
